@@ -1,0 +1,1195 @@
+// b200_kernels.cu -- hand-written sm_100a kernels + the C-ABI of include/b200_sts.h.
+//
+// Everything on this path is FP64 and HBM-bound (~0.5 flop/byte): no tensor cores.
+// What matters is (i) one pass over memory per STS stage, (ii) 16-byte coalesced
+// loads with enough of them in flight, (iii) re-using each input row for its three
+// vertical uses from registers, (iv) deterministic reductions, and (v) bit-faithful
+// arithmetic: explicit __dmul_rn/__dadd_rn in the reference's association order
+// so no FMA contraction can change a result.
+//
+// Reference behaviour restated (paths relative to /root/reference):
+//   stencil            diffusion_2D/diffusion.cpp:34-55 (+ faces :68-205)
+//   linear combination deps/sundials/src/sundials/sundials_nvector.c:557-565
+//   vector ops         deps/sundials/src/nvector/parallel/nvector_parallel.c:424-730
+//   halo pack          diffusion_2D/buffers.cpp:20-43
+//   Jacobi setup       diffusion_2D/preconditioner_jacobi.cpp:9-46
+//   adr callbacks      adr/advection_diffusion_reaction_2d.cpp:1406-1520
+
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include "b200_sts.h"
+
+// --------------------------------------------------------------------- errors
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+#define CU_TRY(expr)                                                          \
+  do {                                                                        \
+    cudaError_t e_ = (expr);                                                  \
+    if (e_ != cudaSuccess)                                                    \
+    {                                                                         \
+      snprintf(g_err, sizeof(g_err), "%s:%d: %s -> %s", __FILE__, __LINE__,   \
+               #expr, cudaGetErrorString(e_));                                \
+      return (int)e_ ? (int)e_ : -1;                                          \
+    }                                                                         \
+  }                                                                           \
+  while (0)
+
+#define NCCL_TRY(expr)                                                        \
+  do {                                                                        \
+    ncclResult_t r_ = (expr);                                                 \
+    if (r_ != ncclSuccess)                                                    \
+    {                                                                         \
+      snprintf(g_err, sizeof(g_err), "%s:%d: %s -> %s", __FILE__, __LINE__,   \
+               #expr, ncclGetErrorString(r_));                                \
+      return 10000 + (int)r_;                                                 \
+    }                                                                         \
+  }                                                                           \
+  while (0)
+
+#define LAUNCH_CHECK()                                                        \
+  do {                                                                        \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                       \
+    CU_TRY(cudaGetLastError());                                               \
+  }                                                                           \
+  while (0)
+
+static int fail(const char* msg)
+{
+  snprintf(g_err, sizeof(g_err), "%s", msg);
+  return -1;
+}
+
+extern "C" const char* b200_last_error(void) { return g_err; }
+extern "C" uint64_t b200_launch_count(void) { return g_launches.load(); }
+
+// -------------------------------------------------------------------- context
+static const int kMaxPartials = 1 << 18;
+
+struct b200_ctx
+{
+  int device          = 0;
+  int sm_count        = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream     = false;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_compute   = nullptr;
+  cudaEvent_t ev_comm      = nullptr;
+  bool comm_pending        = false;
+  double* partials    = nullptr; // [kMaxPartials] block partials
+  unsigned* ticket    = nullptr; // last-block-done counter
+  double* dev_result  = nullptr; // [8] device scalars
+  double* host_result = nullptr; // [8] pinned mirror
+  ncclComm_t comm     = nullptr;
+  int rank = 0, nranks = 1;
+};
+
+extern "C" int b200_ctx_create(int device, void* stream, b200_ctx** out)
+{
+  int ndev = 0;
+  CU_TRY(cudaGetDeviceCount(&ndev));
+  if (ndev <= 0) return fail("b200_ctx_create: no CUDA device (there is no CPU fallback)");
+  CU_TRY(cudaSetDevice(device));
+  b200_ctx* c = new b200_ctx();
+  c->device   = device;
+  CU_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+  if (stream) { c->stream = (cudaStream_t)stream; }
+  else
+  {
+    CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+  }
+  CU_TRY(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+  CU_TRY(cudaEventCreateWithFlags(&c->ev_compute, cudaEventDisableTiming));
+  CU_TRY(cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming));
+  CU_TRY(cudaMalloc(&c->partials, sizeof(double) * kMaxPartials));
+  CU_TRY(cudaMalloc(&c->ticket, sizeof(unsigned) * 4));
+  CU_TRY(cudaMemset(c->ticket, 0, sizeof(unsigned) * 4));
+  CU_TRY(cudaMalloc(&c->dev_result, sizeof(double) * 8));
+  CU_TRY(cudaMallocHost(&c->host_result, sizeof(double) * 8));
+  *out = c;
+  return 0;
+}
+
+extern "C" int b200_ctx_destroy(b200_ctx* c)
+{
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  cudaStreamSynchronize(c->comm_stream);
+  if (c->comm) ncclCommDestroy(c->comm);
+  cudaFree(c->partials);
+  cudaFree(c->ticket);
+  cudaFree(c->dev_result);
+  cudaFreeHost(c->host_result);
+  cudaEventDestroy(c->ev_compute);
+  cudaEventDestroy(c->ev_comm);
+  cudaStreamDestroy(c->comm_stream);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+
+extern "C" void* b200_ctx_stream(b200_ctx* c) { return (void*)c->stream; }
+
+extern "C" int b200_ctx_sync(b200_ctx* c)
+{
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int b200_malloc(b200_ctx* c, int64_t n, double** dptr)
+{
+  CU_TRY(cudaSetDevice(c->device));
+  CU_TRY(cudaMalloc((void**)dptr, sizeof(double) * (size_t)(n > 0 ? n : 1)));
+  return 0;
+}
+
+extern "C" int b200_free(b200_ctx* c, double* dptr)
+{
+  CU_TRY(cudaSetDevice(c->device));
+  CU_TRY(cudaFree(dptr));
+  return 0;
+}
+
+extern "C" int b200_host_alloc(int64_t n, double** hptr)
+{
+  CU_TRY(cudaMallocHost((void**)hptr, sizeof(double) * (size_t)(n > 0 ? n : 1)));
+  return 0;
+}
+
+extern "C" int b200_host_free(double* hptr)
+{
+  CU_TRY(cudaFreeHost(hptr));
+  return 0;
+}
+
+extern "C" int b200_h2d(b200_ctx* c, double* dst, const double* src, int64_t n)
+{
+  CU_TRY(cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int b200_d2h(b200_ctx* c, double* dst, const double* src, int64_t n)
+{
+  CU_TRY(cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// ------------------------------------------------------------ device helpers
+#define DMUL(a, b) __dmul_rn((a), (b))
+#define DADD(a, b) __dadd_rn((a), (b))
+#define DSUB(a, b) __dsub_rn((a), (b))
+
+// streaming (read-once) loads: keep them out of L1, evict-first in L2
+__device__ __forceinline__ double2 ld_stream2(const double* p)
+{
+  double2 r;
+  asm volatile("ld.global.cs.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ double2 ld_keep2(const double* p)
+{
+  return *reinterpret_cast<const double2*>(p);
+}
+
+struct LinTerms
+{
+  int n;
+  int src[B200_MAX_TERMS];
+  double c[B200_MAX_TERMS];
+  const double* v[B200_MAX_TERMS];
+};
+
+static const int kThreads = 256;
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = DADD(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_min(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+enum RedOp { RED_SUM = 0, RED_MAX = 1, RED_MIN = 2 };
+
+template <int ROP>
+__device__ __forceinline__ double red_combine(double a, double b)
+{
+  if (ROP == RED_SUM) return DADD(a, b);
+  if (ROP == RED_MAX) return fmax(a, b);
+  return fmin(a, b);
+}
+template <int ROP>
+__device__ __forceinline__ double red_identity()
+{
+  if (ROP == RED_SUM) return 0.0;
+  if (ROP == RED_MAX) return 0.0; // max-norm of |x| >= 0
+  return __longlong_as_double(0x7ff0000000000000LL);
+}
+
+// Block-level reduce (fixed shuffle tree -> deterministic), result valid in thread 0.
+template <int ROP>
+__device__ __forceinline__ double block_reduce(double v, double* smem /* >= 32 */)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarp = (blockDim.x * blockDim.y + 31) >> 5;
+  if (ROP == RED_SUM) v = warp_sum(v);
+  else if (ROP == RED_MAX) v = warp_max(v);
+  else v = warp_min(v);
+  __syncthreads();
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  if (warp == 0)
+  {
+    v = (lane < nwarp) ? smem[lane] : red_identity<ROP>();
+    if (ROP == RED_SUM) v = warp_sum(v);
+    else if (ROP == RED_MAX) v = warp_max(v);
+    else v = warp_min(v);
+  }
+  return v;
+}
+
+// Grid-level finish: every block stores its partial; the block that takes the
+// last ticket re-reduces all partials in index order (so the result does not
+// depend on which block happens to be last) and resets the ticket.
+template <int ROP>
+__device__ __forceinline__ void grid_finish(double block_val, unsigned nblocks,
+                                            unsigned bid, double* partials,
+                                            unsigned* ticket, double* result,
+                                            double* smem)
+{
+  __shared__ bool is_last;
+  if (threadIdx.x == 0)
+  {
+    partials[bid] = block_val;
+    __threadfence();
+    unsigned t = atomicAdd(ticket, 1u);
+    is_last    = (t == nblocks - 1);
+  }
+  __syncthreads();
+  if (is_last)
+  {
+    __threadfence();
+    double acc = red_identity<ROP>();
+    for (unsigned k = threadIdx.x; k < nblocks; k += blockDim.x)
+      acc = red_combine<ROP>(acc, ((volatile double*)partials)[k]);
+    acc = block_reduce<ROP>(acc, smem);
+    if (threadIdx.x == 0)
+    {
+      *result = acc;
+      *ticket = 0;
+    }
+  }
+}
+
+// ------------------------------------------------------ elementwise kernels
+enum EwOp
+{
+  EW_LINCOMB = 0,
+  EW_SCALESUM,
+  EW_SCALEDIFF,
+  EW_CONST,
+  EW_PROD,
+  EW_DIV,
+  EW_ABS,
+  EW_INV,
+  EW_ADDCONST,
+  EW_EWT
+};
+
+struct EwArgs
+{
+  LinTerms t;   // LINCOMB
+  const double* x;
+  const double* y;
+  double a, b;
+  double* z;
+  int64_t n;
+};
+
+template <int OP>
+__device__ __forceinline__ double ew_apply(const EwArgs& a, int64_t i)
+{
+  if (OP == EW_LINCOMB)
+  {
+    double acc = DMUL(a.t.c[0], a.t.v[0][i]);
+#pragma unroll
+    for (int k = 1; k < B200_MAX_TERMS; k++)
+      if (k < a.t.n) acc = DADD(acc, DMUL(a.t.c[k], a.t.v[k][i]));
+    return acc;
+  }
+  if (OP == EW_SCALESUM) return DMUL(a.a, DADD(a.x[i], a.y[i]));
+  if (OP == EW_SCALEDIFF) return DMUL(a.a, DSUB(a.x[i], a.y[i]));
+  if (OP == EW_CONST) return a.a;
+  if (OP == EW_PROD) return DMUL(a.x[i], a.y[i]);
+  if (OP == EW_DIV) return __ddiv_rn(a.x[i], a.y[i]);
+  if (OP == EW_ABS) return fabs(a.x[i]);
+  if (OP == EW_INV) return __ddiv_rn(1.0, a.x[i]);
+  if (OP == EW_ADDCONST) return DADD(a.x[i], a.b);
+  // EW_EWT: N_VAbs, N_VScale(rtol), N_VAddConst(atol), N_VInv
+  return __ddiv_rn(1.0, DADD(DMUL(a.a, fabs(a.x[i])), a.b));
+}
+
+template <int OP>
+__device__ __forceinline__ double2 ew_apply2(const EwArgs& a, int64_t i)
+{
+  double2 r;
+  if (OP == EW_LINCOMB)
+  {
+    double2 v = ld_keep2(a.t.v[0] + i);
+    r.x = DMUL(a.t.c[0], v.x);
+    r.y = DMUL(a.t.c[0], v.y);
+#pragma unroll
+    for (int k = 1; k < B200_MAX_TERMS; k++)
+      if (k < a.t.n)
+      {
+        v   = ld_keep2(a.t.v[k] + i);
+        r.x = DADD(r.x, DMUL(a.t.c[k], v.x));
+        r.y = DADD(r.y, DMUL(a.t.c[k], v.y));
+      }
+    return r;
+  }
+  if (OP == EW_CONST) { r.x = a.a; r.y = a.a; return r; }
+  double2 x = ld_keep2(a.x + i);
+  if (OP == EW_SCALESUM || OP == EW_SCALEDIFF || OP == EW_PROD || OP == EW_DIV)
+  {
+    double2 y = ld_keep2(a.y + i);
+    if (OP == EW_SCALESUM) { r.x = DMUL(a.a, DADD(x.x, y.x)); r.y = DMUL(a.a, DADD(x.y, y.y)); }
+    if (OP == EW_SCALEDIFF) { r.x = DMUL(a.a, DSUB(x.x, y.x)); r.y = DMUL(a.a, DSUB(x.y, y.y)); }
+    if (OP == EW_PROD) { r.x = DMUL(x.x, y.x); r.y = DMUL(x.y, y.y); }
+    if (OP == EW_DIV) { r.x = __ddiv_rn(x.x, y.x); r.y = __ddiv_rn(x.y, y.y); }
+    return r;
+  }
+  if (OP == EW_ABS) { r.x = fabs(x.x); r.y = fabs(x.y); }
+  if (OP == EW_INV) { r.x = __ddiv_rn(1.0, x.x); r.y = __ddiv_rn(1.0, x.y); }
+  if (OP == EW_ADDCONST) { r.x = DADD(x.x, a.b); r.y = DADD(x.y, a.b); }
+  if (OP == EW_EWT)
+  {
+    r.x = __ddiv_rn(1.0, DADD(DMUL(a.a, fabs(x.x)), a.b));
+    r.y = __ddiv_rn(1.0, DADD(DMUL(a.a, fabs(x.y)), a.b));
+  }
+  return r;
+}
+
+// grid-stride, 2 x double2 per thread per trip (4 independent 16-byte loads / vector)
+template <int OP>
+__global__ void __launch_bounds__(kThreads) k_elementwise(const EwArgs a)
+{
+  const int64_t n2     = a.n >> 1; // number of double2
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t p            = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; p + stride < n2; p += 2 * stride)
+  {
+    double2 r0 = ew_apply2<OP>(a, 2 * p);
+    double2 r1 = ew_apply2<OP>(a, 2 * (p + stride));
+    *reinterpret_cast<double2*>(a.z + 2 * p)            = r0;
+    *reinterpret_cast<double2*>(a.z + 2 * (p + stride)) = r1;
+  }
+  if (p < n2) { *reinterpret_cast<double2*>(a.z + 2 * p) = ew_apply2<OP>(a, 2 * p); }
+  if ((a.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) a.z[a.n - 1] = ew_apply<OP>(a, a.n - 1);
+}
+
+template <int OP>
+static int launch_ew(b200_ctx* c, const EwArgs& a)
+{
+  if (a.n <= 0) return 0;
+  int64_t n2     = (a.n + 1) >> 1;
+  int64_t blocks = (n2 + 2 * kThreads - 1) / (2 * kThreads);
+  int64_t cap    = (int64_t)c->sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  k_elementwise<OP><<<(unsigned)blocks, kThreads, 0, c->stream>>>(a);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+static bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+
+extern "C" int b200_lincomb(b200_ctx* c, int nterms, const double* cf,
+                            const double* const* v, double* z, int64_t n)
+{
+  if (nterms < 1 || nterms > B200_MAX_TERMS) return fail("b200_lincomb: nterms out of range");
+  EwArgs a;
+  memset(&a, 0, sizeof(a));
+  a.t.n = nterms;
+  for (int k = 0; k < nterms; k++)
+  {
+    a.t.c[k] = cf[k];
+    a.t.v[k] = v[k];
+    if (!aligned16(v[k])) return fail("b200_lincomb: operand not 16-byte aligned");
+  }
+  if (!aligned16(z)) return fail("b200_lincomb: output not 16-byte aligned");
+  a.z = z;
+  a.n = n;
+  return launch_ew<EW_LINCOMB>(c, a);
+}
+
+#define EW_ENTRY_CHECK(ptr) \
+  if (!aligned16(ptr)) return fail("b200 elementwise: pointer not 16-byte aligned")
+
+extern "C" int b200_scale_sumdiff(b200_ctx* c, double s, const double* x, const double* y,
+                                  int sign, double* z, int64_t n)
+{
+  EW_ENTRY_CHECK(x); EW_ENTRY_CHECK(y); EW_ENTRY_CHECK(z);
+  EwArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x = x; a.y = y; a.a = s; a.z = z; a.n = n;
+  return sign >= 0 ? launch_ew<EW_SCALESUM>(c, a) : launch_ew<EW_SCALEDIFF>(c, a);
+}
+extern "C" int b200_const(b200_ctx* c, double v, double* z, int64_t n)
+{
+  EW_ENTRY_CHECK(z);
+  EwArgs a;
+  memset(&a, 0, sizeof(a));
+  a.a = v; a.z = z; a.n = n;
+  return launch_ew<EW_CONST>(c, a);
+}
+#define EW_BINARY(NAME, OP)                                                          \
+  extern "C" int NAME(b200_ctx* c, const double* x, const double* y, double* z, int64_t n) \
+  {                                                                                  \
+    EW_ENTRY_CHECK(x); EW_ENTRY_CHECK(y); EW_ENTRY_CHECK(z);                         \
+    EwArgs a;                                                                        \
+    memset(&a, 0, sizeof(a));                                                        \
+    a.x = x; a.y = y; a.z = z; a.n = n;                                              \
+    return launch_ew<OP>(c, a);                                                      \
+  }
+EW_BINARY(b200_prod, EW_PROD)
+EW_BINARY(b200_div, EW_DIV)
+#define EW_UNARY(NAME, OP)                                                \
+  extern "C" int NAME(b200_ctx* c, const double* x, double* z, int64_t n) \
+  {                                                                       \
+    EW_ENTRY_CHECK(x); EW_ENTRY_CHECK(z);                                 \
+    EwArgs a;                                                             \
+    memset(&a, 0, sizeof(a));                                             \
+    a.x = x; a.z = z; a.n = n;                                            \
+    return launch_ew<OP>(c, a);                                           \
+  }
+EW_UNARY(b200_abs, EW_ABS)
+EW_UNARY(b200_inv, EW_INV)
+extern "C" int b200_addconst(b200_ctx* c, const double* x, double b, double* z, int64_t n)
+{
+  EW_ENTRY_CHECK(x); EW_ENTRY_CHECK(z);
+  EwArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x = x; a.b = b; a.z = z; a.n = n;
+  return launch_ew<EW_ADDCONST>(c, a);
+}
+extern "C" int b200_ewt_ss(b200_ctx* c, const double* y, double rtol, double atol,
+                           double* ewt, int64_t n)
+{
+  EW_ENTRY_CHECK(y); EW_ENTRY_CHECK(ewt);
+  EwArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x = y; a.a = rtol; a.b = atol; a.z = ewt; a.n = n;
+  return launch_ew<EW_EWT>(c, a);
+}
+
+// ---------------------------------------------------------------- reductions
+enum RdKind { RD_DOT = 0, RD_WSQR, RD_MAXNORM, RD_MIN, RD_L1 };
+
+template <int KIND>
+__device__ __forceinline__ double rd_term(double x, double y)
+{
+  if (KIND == RD_DOT) return DMUL(x, y);
+  if (KIND == RD_WSQR) { double p = DMUL(x, y); return DMUL(p, p); }
+  if (KIND == RD_MAXNORM) return fabs(x);
+  if (KIND == RD_MIN) return x;
+  return fabs(x);
+}
+
+template <int KIND, int ROP>
+__global__ void __launch_bounds__(kThreads)
+  k_reduce(const double* __restrict__ x, const double* __restrict__ y, int64_t n,
+           double* partials, unsigned* ticket, double* result)
+{
+  __shared__ double smem[32];
+  const bool two       = (KIND == RD_DOT || KIND == RD_WSQR);
+  const int64_t n2     = n >> 1;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  double acc0 = red_identity<ROP>(), acc1 = red_identity<ROP>();
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n2; p += stride)
+  {
+    double2 a = ld_keep2(x + 2 * p);
+    double2 b = two ? ld_keep2(y + 2 * p) : make_double2(0.0, 0.0);
+    acc0      = red_combine<ROP>(acc0, rd_term<KIND>(a.x, b.x));
+    acc1      = red_combine<ROP>(acc1, rd_term<KIND>(a.y, b.y));
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0)
+    acc0 = red_combine<ROP>(acc0, rd_term<KIND>(x[n - 1], two ? y[n - 1] : 0.0));
+  double v = block_reduce<ROP>(red_combine<ROP>(acc0, acc1), smem);
+  grid_finish<ROP>(v, gridDim.x, blockIdx.x, partials, ticket, result, smem);
+}
+
+static int nccl_allreduce_inplace(b200_ctx* c, double* buf, int n, int op);
+
+template <int KIND, int ROP>
+static int run_reduce(b200_ctx* c, const double* x, const double* y, int64_t n, double* result)
+{
+  if (!aligned16(x) || (y && !aligned16(y))) return fail("b200 reduce: pointer not 16-byte aligned");
+  int64_t n2     = (n + 1) >> 1;
+  int64_t blocks = (n2 + 4 * kThreads - 1) / (4 * kThreads);
+  int64_t cap    = (int64_t)c->sm_count * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  k_reduce<KIND, ROP><<<(unsigned)blocks, kThreads, 0, c->stream>>>(x, y, n, c->partials, c->ticket, c->dev_result);
+  LAUNCH_CHECK();
+  if (c->comm && c->nranks > 1)
+  {
+    int rc = nccl_allreduce_inplace(c, c->dev_result, 1, ROP);
+    if (rc) return rc;
+  }
+  CU_TRY(cudaMemcpyAsync(c->host_result, c->dev_result, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  *result = c->host_result[0];
+  return 0;
+}
+
+extern "C" int b200_dot(b200_ctx* c, const double* x, const double* y, int64_t n, double* r)
+{
+  return run_reduce<RD_DOT, RED_SUM>(c, x, y, n, r);
+}
+extern "C" int b200_wsqrsum(b200_ctx* c, const double* x, const double* w, int64_t n, double* r)
+{
+  return run_reduce<RD_WSQR, RED_SUM>(c, x, w, n, r);
+}
+extern "C" int b200_maxnorm(b200_ctx* c, const double* x, int64_t n, double* r)
+{
+  return run_reduce<RD_MAXNORM, RED_MAX>(c, x, nullptr, n, r);
+}
+extern "C" int b200_min(b200_ctx* c, const double* x, int64_t n, double* r)
+{
+  return run_reduce<RD_MIN, RED_MIN>(c, x, nullptr, n, r);
+}
+extern "C" int b200_l1norm(b200_ctx* c, const double* x, int64_t n, double* r)
+{
+  return run_reduce<RD_L1, RED_SUM>(c, x, nullptr, n, r);
+}
+
+// ------------------------------------------------------- fused stage kernels
+struct StageArgs
+{
+  int64_t nx, ny;
+  const double *cxw, *cxe, *cys, *cyn;
+  const double *hw, *he, *hs, *hn;
+  const double* x;
+  LinTerms t;
+  double* z;
+  double* f_out;
+  double *send_w, *send_e, *send_s, *send_n;
+  const double* rw;
+  double* partials;
+  unsigned* ticket;
+  double* result;
+  int rows;   // rows marched per block
+  int region; // 0 all, 1 ring, 2 interior
+};
+
+// 5-point operator in the reference's association order
+// (diffusion_2D/diffusion.cpp:48-53; f starts at 0 and is "+="-ed):
+//   0 + (((( -((Dxw+Dxe)+(Dys+Dyn)) * uc + Dxw*uw ) + Dxe*ue ) + Dys*us ) + Dyn*un )
+__device__ __forceinline__ double lap5(double dxw, double dxe, double dys, double dyn,
+                                       double uc, double uw, double ue, double us, double un)
+{
+  const double dc = -DADD(DADD(dxw, dxe), DADD(dys, dyn));
+  double r        = DMUL(dc, uc);
+  r               = DADD(r, DMUL(dxw, uw));
+  r               = DADD(r, DMUL(dxe, ue));
+  r               = DADD(r, DMUL(dys, us));
+  r               = DADD(r, DMUL(dyn, un));
+  return DADD(0.0, r);
+}
+
+// one cell, generic neighbour access (ring kernel, odd-width fallback)
+__device__ __forceinline__ void stage_cell(const StageArgs& a, int64_t i, int64_t j, double* wr_acc)
+{
+  const int64_t nx = a.nx, ny = a.ny;
+  const int64_t id = j * nx + i;
+  const double uc  = a.x[id];
+  const double uw  = (i > 0) ? a.x[id - 1] : (a.hw ? a.hw[j] : a.x[id + nx - 1]);
+  const double ue  = (i < nx - 1) ? a.x[id + 1] : (a.he ? a.he[j] : a.x[id - (nx - 1)]);
+  const double us  = (j > 0) ? a.x[id - nx] : (a.hs ? a.hs[i] : a.x[(ny - 1) * nx + i]);
+  const double un  = (j < ny - 1) ? a.x[id + nx] : (a.hn ? a.hn[i] : a.x[i]);
+  const double L   = lap5(a.cxw[i], a.cxe[i], a.cys[j], a.cyn[j], uc, uw, ue, us, un);
+  double acc       = 0.0;
+#pragma unroll
+  for (int k = 0; k < B200_MAX_TERMS; k++)
+    if (k < a.t.n)
+    {
+      const double tv = (a.t.src[k] == B200_SRC_STENCIL) ? L
+                        : (a.t.src[k] == B200_SRC_CENTRE) ? uc
+                                                          : a.t.v[k][id];
+      const double pr = DMUL(a.t.c[k], tv);
+      acc             = (k == 0) ? pr : DADD(acc, pr);
+    }
+  a.z[id] = acc;
+  if (a.f_out) a.f_out[id] = L;
+  if (a.send_w && i == 0) a.send_w[j] = acc;
+  if (a.send_e && i == nx - 1) a.send_e[j] = acc;
+  if (a.send_s && j == 0) a.send_s[i] = acc;
+  if (a.send_n && j == ny - 1) a.send_n[i] = acc;
+  if (wr_acc)
+  {
+    const double p = DMUL(acc, a.rw[id]);
+    *wr_acc        = DADD(*wr_acc, DMUL(p, p));
+  }
+}
+
+// Generic kernel: one thread per cell, any nx/ny; region-aware.
+__global__ void __launch_bounds__(kThreads) k_stage_generic(const StageArgs a)
+{
+  __shared__ double smem[32];
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t j = blockIdx.y;
+  double wr       = 0.0;
+  if (i < a.nx)
+  {
+    const bool ring = (i == 0 || i == a.nx - 1 || j == 0 || j == a.ny - 1);
+    if (a.region == 0 || (a.region == 1 && ring) || (a.region == 2 && !ring))
+      stage_cell(a, i, j, a.rw ? &wr : nullptr);
+  }
+  if (a.rw)
+  {
+    double v = block_reduce<RED_SUM>(wr, smem);
+    grid_finish<RED_SUM>(v, gridDim.x * gridDim.y, blockIdx.y * gridDim.x + blockIdx.x,
+                         a.partials, a.ticket, a.result, smem);
+  }
+}
+
+// Ring kernel: the 2*nx + 2*(ny-2) boundary cells only (they are the only ones
+// that read halos and the only ones that are packed for the neighbours).
+__global__ void __launch_bounds__(kThreads) k_stage_ring(const StageArgs a)
+{
+  const int64_t t  = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nx = a.nx, ny = a.ny;
+  int64_t i, j;
+  if (t < nx) { i = t; j = 0; }
+  else if (t < 2 * nx) { i = t - nx; j = ny - 1; }
+  else if (t < 2 * nx + (ny - 2)) { i = 0; j = t - 2 * nx + 1; }
+  else if (t < 2 * nx + 2 * (ny - 2)) { i = nx - 1; j = t - 2 * nx - (ny - 2) + 1; }
+  else return;
+  if (ny == 1 && t >= nx) return;
+  stage_cell(a, i, j, nullptr);
+}
+
+// Fast path (nx even): each thread owns two adjacent cells (one double2) of a
+// 512-cell-wide strip and marches down `rows` rows keeping the three live rows of
+// x in registers, so every x row is loaded from L2/HBM once per block.  West/east
+// neighbours come from warp shuffles; only lanes 0 / 31 (and the strip ends) issue
+// an extra scalar load.  Per cell-update: 4 x 8 B streamed in + 8 B out.
+template <int NT, bool HAS_RED>
+__global__ void __launch_bounds__(kThreads, 4) k_stage_march(const StageArgs a)
+{
+  __shared__ double smem[32];
+  const int64_t nx = a.nx, ny = a.ny;
+  const int lane    = threadIdx.x & 31;
+  const int64_t i0  = 2 * ((int64_t)blockIdx.x * kThreads + threadIdx.x);
+  const bool active = (i0 < nx);
+  const int64_t ic  = active ? i0 : 0; // clamp so address arithmetic stays in range
+  int64_t j0        = (int64_t)blockIdx.y * a.rows;
+  int64_t j1        = j0 + a.rows;
+  if (j1 > ny) j1 = ny;
+  if (a.region == 2)
+  {
+    if (j0 < 1) j0 = 1;
+    if (j1 > ny - 1) j1 = ny - 1;
+  }
+
+  const bool wedge = (i0 == 0);          // west neighbour is outside the field
+  const bool eedge = (i0 + 2 >= nx);     // east neighbour is outside the field
+  const bool wload = active && (lane == 0 || wedge);
+  const bool eload = active && (lane == 31 || eedge);
+  const bool skip_halo_cols = (a.region == 2);
+
+  double cw0 = 0, cw1 = 0, ce0 = 0, ce1 = 0;
+  if (active)
+  {
+    double2 w = ld_keep2(a.cxw + ic), e = ld_keep2(a.cxe + ic);
+    cw0 = w.x; cw1 = w.y; ce0 = e.x; ce1 = e.y;
+  }
+
+  // row pointer with periodic wrap / halo rows
+  auto rowp = [&](int64_t j) -> const double* {
+    if (j < 0) return a.hs ? a.hs : a.x + (ny - 1) * nx;
+    if (j >= ny) return a.hn ? a.hn : a.x;
+    return a.x + j * nx;
+  };
+
+  double2 xm = make_double2(0, 0), xc = make_double2(0, 0);
+  if (active && j0 < j1)
+  {
+    xm = ld_keep2(rowp(j0 - 1) + ic);
+    xc = ld_keep2(rowp(j0) + ic);
+  }
+  double wr = 0.0;
+
+#pragma unroll 1
+  for (int64_t j = j0; j < j1; j++)
+  {
+    const int64_t id = j * nx + ic;
+    double2 xp = make_double2(0, 0);
+    double uw_edge = 0.0, ue_edge = 0.0;
+    double2 tv[NT];
+    if (active)
+    {
+      xp = ld_keep2(rowp(j + 1) + ic);
+      if (wload)
+      {
+        if (!wedge) uw_edge = a.x[id - 1];
+        else if (!skip_halo_cols) uw_edge = a.hw ? a.hw[j] : a.x[j * nx + nx - 1];
+      }
+      if (eload)
+      {
+        if (!eedge) ue_edge = a.x[id + 2];
+        else if (!skip_halo_cols) ue_edge = a.he ? a.he[j] : a.x[j * nx];
+      }
+#pragma unroll
+      for (int k = 0; k < NT; k++)
+        if (a.t.src[k] == B200_SRC_VECTOR) tv[k] = ld_stream2(a.t.v[k] + id);
+    }
+    const double dys = a.cys[j], dyn = a.cyn[j];
+    // west of cell0 = previous lane's cell1 ; east of cell1 = next lane's cell0
+    double uw0 = __shfl_up_sync(0xffffffffu, xc.y, 1);
+    double ue1 = __shfl_down_sync(0xffffffffu, xc.x, 1);
+    if (wload) uw0 = uw_edge;
+    if (eload) ue1 = ue_edge;
+    if (active)
+    {
+      const double L0 = lap5(cw0, ce0, dys, dyn, xc.x, uw0, xc.y, xm.x, xp.x);
+      const double L1 = lap5(cw1, ce1, dys, dyn, xc.y, xc.x, ue1, xm.y, xp.y);
+      double2 acc     = make_double2(0, 0);
+#pragma unroll
+      for (int k = 0; k < NT; k++)
+        {
+          double2 v;
+          if (a.t.src[k] == B200_SRC_STENCIL) v = make_double2(L0, L1);
+          else if (a.t.src[k] == B200_SRC_CENTRE) v = xc;
+          else v = tv[k];
+          const double p0 = DMUL(a.t.c[k], v.x), p1 = DMUL(a.t.c[k], v.y);
+          acc.x = (k == 0) ? p0 : DADD(acc.x, p0);
+          acc.y = (k == 0) ? p1 : DADD(acc.y, p1);
+        }
+      bool st0 = true, st1 = true;
+      if (a.region == 2)
+      {
+        st0 = !wedge;
+        st1 = !eedge;
+      }
+      if (st0 && st1) *reinterpret_cast<double2*>(a.z + id) = acc;
+      else if (st0) a.z[id] = acc.x;
+      else if (st1) a.z[id + 1] = acc.y;
+      if (a.f_out)
+      {
+        if (st0 && st1) *reinterpret_cast<double2*>(a.f_out + id) = make_double2(L0, L1);
+        else if (st0) a.f_out[id] = L0;
+        else if (st1) a.f_out[id + 1] = L1;
+      }
+      if (a.region == 0)
+      {
+        if (a.send_w && wedge) a.send_w[j] = acc.x;
+        if (a.send_e && eedge) a.send_e[j] = acc.y;
+        if (a.send_s && j == 0) *reinterpret_cast<double2*>(a.send_s + ic) = acc;
+        if (a.send_n && j == ny - 1) *reinterpret_cast<double2*>(a.send_n + ic) = acc;
+      }
+      if (HAS_RED)
+      {
+        const double2 w = ld_stream2(a.rw + id);
+        const double q0 = DMUL(acc.x, w.x), q1 = DMUL(acc.y, w.y);
+        wr = DADD(wr, DADD(DMUL(q0, q0), DMUL(q1, q1)));
+      }
+    }
+    xm = xc;
+    xc = xp;
+  }
+  if (HAS_RED)
+  {
+    double v = block_reduce<RED_SUM>(wr, smem);
+    grid_finish<RED_SUM>(v, gridDim.x * gridDim.y, blockIdx.y * gridDim.x + blockIdx.x,
+                         a.partials, a.ticket, a.result, smem);
+  }
+}
+
+static int g_rows_per_block = 32;
+
+extern "C" int b200_set_rows_per_block(int r)
+{
+  if (r < 1) return -1;
+  g_rows_per_block = r;
+  return 0;
+}
+
+extern "C" int b200_stencil_lincomb(b200_ctx* c, const b200_stencil_geom* g, const double* x,
+                                    int nterms, const double* cf, const int* src,
+                                    const double* const* v, double* z,
+                                    const b200_stage_extras* ex, int region)
+{
+  if (nterms < 1 || nterms > B200_MAX_TERMS) return fail("b200_stencil_lincomb: nterms out of range");
+  if (z == x) return fail("b200_stencil_lincomb: z must not alias the stencil input");
+  if (g->nx < 2 || g->ny < 2) return fail("b200_stencil_lincomb: sub-domain must be at least 2x2");
+  StageArgs a;
+  memset(&a, 0, sizeof(a));
+  a.nx = g->nx; a.ny = g->ny;
+  a.cxw = g->cxw; a.cxe = g->cxe; a.cys = g->cys; a.cyn = g->cyn;
+  a.hw = g->halo_w; a.he = g->halo_e; a.hs = g->halo_s; a.hn = g->halo_n;
+  a.x = x; a.z = z;
+  a.t.n = nterms;
+  int nst = 0;
+  for (int k = 0; k < nterms; k++)
+  {
+    a.t.c[k]   = cf[k];
+    a.t.src[k] = src[k];
+    a.t.v[k]   = (src[k] == B200_SRC_VECTOR) ? v[k] : nullptr;
+    if (src[k] == B200_SRC_STENCIL) nst++;
+    if (src[k] == B200_SRC_VECTOR && !v[k]) return fail("b200_stencil_lincomb: NULL operand");
+  }
+  if (nst > 1) return fail("b200_stencil_lincomb: more than one stencil term");
+  if (ex)
+  {
+    a.f_out = ex->f_out;
+    a.send_w = ex->send_w; a.send_e = ex->send_e; a.send_s = ex->send_s; a.send_n = ex->send_n;
+    a.rw = ex->wrms_w;
+    a.result = ex->wrms_result;
+    if (a.f_out == x) return fail("b200_stencil_lincomb: f_out must not alias the stencil input");
+  }
+  if (a.rw && region != 0) return fail("b200_stencil_lincomb: fused WRMS needs region 0");
+  if (a.rw && !a.result) return fail("b200_stencil_lincomb: wrms_result missing");
+  a.partials = c->partials;
+  a.ticket   = c->ticket;
+  a.region   = region;
+
+  if (region == 1)
+  {
+    int64_t cells  = 2 * a.nx + 2 * (a.ny - 2);
+    unsigned blocks = (unsigned)((cells + kThreads - 1) / kThreads);
+    k_stage_ring<<<blocks, kThreads, 0, c->stream>>>(a);
+    LAUNCH_CHECK();
+    return 0;
+  }
+
+  bool fast = (a.nx % 2 == 0) && aligned16(x) && aligned16(z) && (!a.f_out || aligned16(a.f_out)) &&
+              aligned16(a.cxw) && aligned16(a.cxe) && (!a.rw || aligned16(a.rw)) &&
+              (!a.hs || aligned16(a.hs)) && (!a.hn || aligned16(a.hn)) &&
+              (!a.send_s || aligned16(a.send_s)) && (!a.send_n || aligned16(a.send_n));
+  for (int k = 0; k < nterms; k++)
+    if (a.t.v[k] && !aligned16(a.t.v[k])) fast = false;
+
+  if (fast)
+  {
+    a.rows        = g_rows_per_block;
+    int64_t gx    = (a.nx / 2 + kThreads - 1) / kThreads;
+    int64_t gy    = (a.ny + a.rows - 1) / a.rows;
+    if (gy > 65535)
+    {
+      a.rows = (int)((a.ny + 65534) / 65535);
+      gy     = (a.ny + a.rows - 1) / a.rows;
+    }
+    if (a.rw && gx * gy > kMaxPartials) return fail("b200_stencil_lincomb: too many blocks for fused WRMS");
+    dim3 grid((unsigned)gx, (unsigned)gy);
+#define MARCH_CASE(N)                                                          \
+  case N:                                                                      \
+    if (a.rw) k_stage_march<N, true><<<grid, kThreads, 0, c->stream>>>(a);     \
+    else k_stage_march<N, false><<<grid, kThreads, 0, c->stream>>>(a);         \
+    break;
+    switch (nterms)
+    {
+      MARCH_CASE(1) MARCH_CASE(2) MARCH_CASE(3) MARCH_CASE(4)
+      MARCH_CASE(5) MARCH_CASE(6) MARCH_CASE(7) MARCH_CASE(8)
+    }
+#undef MARCH_CASE
+    LAUNCH_CHECK();
+  }
+  else
+  {
+    int64_t gx = (a.nx + kThreads - 1) / kThreads;
+    if (a.ny > 65535) return fail("b200_stencil_lincomb: generic path supports ny <= 65535");
+    if (a.rw && gx * a.ny > kMaxPartials) return fail("b200_stencil_lincomb: too many blocks for fused WRMS");
+    dim3 grid((unsigned)gx, (unsigned)a.ny);
+    k_stage_generic<<<grid, kThreads, 0, c->stream>>>(a);
+    LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ halo pack
+__global__ void __launch_bounds__(kThreads)
+  k_pack(const double* __restrict__ u, int64_t nx, int64_t ny, double* sw, double* se,
+         double* ss, double* sn)
+{
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < ny)
+  {
+    if (sw) sw[t] = u[t * nx];
+    if (se) se[t] = u[t * nx + nx - 1];
+  }
+  if (t < nx)
+  {
+    if (ss) ss[t] = u[t];
+    if (sn) sn[t] = u[(ny - 1) * nx + t];
+  }
+}
+
+extern "C" int b200_pack_halo(b200_ctx* c, const double* u, int64_t nx, int64_t ny,
+                              double* sw, double* se, double* ss, double* sn)
+{
+  int64_t m = nx > ny ? nx : ny;
+  k_pack<<<(unsigned)((m + kThreads - 1) / kThreads), kThreads, 0, c->stream>>>(u, nx, ny, sw, se, ss, sn);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// --------------------------------------------------------------- Jacobi setup
+__global__ void __launch_bounds__(kThreads)
+  k_jacobi(int64_t nx, int64_t ny, const double* __restrict__ pxw, const double* __restrict__ pxe,
+           const double* __restrict__ pys, const double* __restrict__ pyn, double gamma, double* diag)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t j = blockIdx.y;
+  if (i >= nx) return;
+  // preconditioner_jacobi.cpp:41-42: diag = -((Dx_w+Dx_e)+(Dy_s+Dy_n)); 1/(1 - gamma*diag)
+  const double d   = -DADD(DADD(pxw[i], pxe[i]), DADD(pys[j], pyn[j]));
+  diag[j * nx + i] = __ddiv_rn(1.0, DSUB(1.0, DMUL(gamma, d)));
+}
+
+extern "C" int b200_jacobi_setup(b200_ctx* c, int64_t nx, int64_t ny, const double* pxw,
+                                 const double* pxe, const double* pys, const double* pyn,
+                                 double gamma, double* diag)
+{
+  if (ny > 65535) return fail("b200_jacobi_setup: ny <= 65535");
+  dim3 grid((unsigned)((nx + kThreads - 1) / kThreads), (unsigned)ny);
+  k_jacobi<<<grid, kThreads, 0, c->stream>>>(nx, ny, pxw, pxe, pys, pyn, gamma, diag);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// -------------------------------------------------------------- adr kernels
+struct AdrArgs
+{
+  b200_adr_params p;
+  int mode;
+  const double* y;
+  double* f;     // plain RHS output (b200_adr_rhs) or f_out
+  LinTerms t;    // fused combination (b200_adr_diffusion_lincomb)
+  double* z;
+};
+
+// one thread per grid point, both species (one 16-byte access per neighbour)
+__device__ __forceinline__ void adr_point(const AdrArgs& a, int64_t i, int64_t j,
+                                          double2* fadv, double2* fdif, double2* frx, double2* yc_out)
+{
+  const int64_t nx = a.p.nx, ny = a.p.ny;
+  const int64_t il = (i > 0) ? i - 1 : nx - 1, ir = (i < nx - 1) ? i + 1 : 0;
+  const int64_t jb = (j > 0) ? j - 1 : ny - 1, jt = (j < ny - 1) ? j + 1 : 0;
+  const double2 c  = ld_keep2(a.y + 2 * (i + j * nx));
+  *yc_out          = c;
+  if (a.mode & 3)
+  {
+    const double2 l = ld_keep2(a.y + 2 * (il + j * nx));
+    const double2 r = ld_keep2(a.y + 2 * (ir + j * nx));
+    const double2 b = ld_keep2(a.y + 2 * (i + jb * nx));
+    const double2 t = ld_keep2(a.y + 2 * (i + jt * nx));
+    if (a.mode & 1)
+    {
+      // …2d.cpp:1417-1420,1440-1441: c = ONE*cu/(TWO*dx); f = cx*(r-l) + cy*(t-b)
+      const double cux = __ddiv_rn(DMUL(1.0, a.p.cux), DMUL(2.0, a.p.dx));
+      const double cuy = __ddiv_rn(DMUL(1.0, a.p.cuy), DMUL(2.0, a.p.dy));
+      const double cvx = __ddiv_rn(DMUL(1.0, a.p.cvx), DMUL(2.0, a.p.dx));
+      const double cvy = __ddiv_rn(DMUL(1.0, a.p.cvy), DMUL(2.0, a.p.dy));
+      fadv->x = DADD(DMUL(cux, DSUB(r.x, l.x)), DMUL(cuy, DSUB(t.x, b.x)));
+      fadv->y = DADD(DMUL(cvx, DSUB(r.y, l.y)), DMUL(cvy, DSUB(t.y, b.y)));
+    }
+    if (a.mode & 2)
+    {
+      // …2d.cpp:1461-1462,1483-1486: d*dxinv2*(l + r - 2c) + d*dyinv2*(b + t - 2c)
+      const double kx = DMUL(a.p.d, __ddiv_rn(1.0, DMUL(a.p.dx, a.p.dx)));
+      const double ky = DMUL(a.p.d, __ddiv_rn(1.0, DMUL(a.p.dy, a.p.dy)));
+      fdif->x = DADD(DMUL(kx, DSUB(DADD(l.x, r.x), DMUL(2.0, c.x))),
+                     DMUL(ky, DSUB(DADD(b.x, t.x), DMUL(2.0, c.x))));
+      fdif->y = DADD(DMUL(kx, DSUB(DADD(l.y, r.y), DMUL(2.0, c.y))),
+                     DMUL(ky, DSUB(DADD(b.y, t.y), DMUL(2.0, c.y))));
+    }
+  }
+  if (a.mode & 4)
+  {
+    // …2d.cpp:1515-1516: A + u*u*v - (B+1)*u ; B*u - u*u*v
+    const double uuv = DMUL(DMUL(c.x, c.x), c.y);
+    frx->x = DSUB(DADD(a.p.A, uuv), DMUL(DADD(a.p.B, 1.0), c.x));
+    frx->y = DSUB(DMUL(a.p.B, c.x), uuv);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_adr_rhs(const AdrArgs a)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t j = blockIdx.y;
+  if (i >= a.p.nx) return;
+  double2 fa = make_double2(0, 0), fd = make_double2(0, 0), fr = make_double2(0, 0), yc;
+  adr_point(a, i, j, &fa, &fd, &fr, &yc);
+  // composite callbacks add in the order advection, diffusion, reaction
+  // (f_adv_react …2d.cpp:1602-1619, f_adv_diff_react :1622-1646; VSum = x + y)
+  double2 r  = make_double2(0, 0);
+  bool first = true;
+  if (a.mode & 1) { r = fa; first = false; }
+  if (a.mode & 2) { r = first ? fd : make_double2(DADD(r.x, fd.x), DADD(r.y, fd.y)); first = false; }
+  if (a.mode & 4) { r = first ? fr : make_double2(DADD(r.x, fr.x), DADD(r.y, fr.y)); }
+  *reinterpret_cast<double2*>(a.f + 2 * (i + j * a.p.nx)) = r;
+}
+
+__global__ void __launch_bounds__(kThreads) k_adr_diff_lincomb(const AdrArgs a)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t j = blockIdx.y;
+  if (i >= a.p.nx) return;
+  double2 fa, fd = make_double2(0, 0), fr, yc;
+  adr_point(a, i, j, &fa, &fd, &fr, &yc);
+  const int64_t id = 2 * (i + j * a.p.nx);
+  double2 acc      = make_double2(0, 0);
+#pragma unroll
+  for (int k = 0; k < B200_MAX_TERMS; k++)
+    if (k < a.t.n)
+    {
+      double2 v;
+      if (a.t.src[k] == B200_SRC_STENCIL) v = fd;
+      else if (a.t.src[k] == B200_SRC_CENTRE) v = yc;
+      else v = ld_stream2(a.t.v[k] + id);
+      const double p0 = DMUL(a.t.c[k], v.x), p1 = DMUL(a.t.c[k], v.y);
+      acc.x = (k == 0) ? p0 : DADD(acc.x, p0);
+      acc.y = (k == 0) ? p1 : DADD(acc.y, p1);
+    }
+  *reinterpret_cast<double2*>(a.z + id) = acc;
+  if (a.f) *reinterpret_cast<double2*>(a.f + id) = fd;
+}
+
+extern "C" int b200_adr_rhs(b200_ctx* c, const b200_adr_params* p, int mode,
+                            const double* y, double* f)
+{
+  if (mode < 1 || mode > 7) return fail("b200_adr_rhs: mode must be in 1..7");
+  if (y == f) return fail("b200_adr_rhs: f must not alias y");
+  if (p->ny > 65535) return fail("b200_adr_rhs: ny <= 65535");
+  AdrArgs a;
+  memset(&a, 0, sizeof(a));
+  a.p = *p; a.mode = mode; a.y = y; a.f = f;
+  dim3 grid((unsigned)((p->nx + kThreads - 1) / kThreads), (unsigned)p->ny);
+  k_adr_rhs<<<grid, kThreads, 0, c->stream>>>(a);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200_adr_diffusion_lincomb(b200_ctx* c, const b200_adr_params* p, const double* y,
+                                          int nterms, const double* cf, const int* src,
+                                          const double* const* v, double* z, double* f_out)
+{
+  if (nterms < 1 || nterms > B200_MAX_TERMS) return fail("b200_adr_diffusion_lincomb: nterms out of range");
+  if (z == y || f_out == y) return fail("b200_adr_diffusion_lincomb: output aliases the stencil input");
+  if (p->ny > 65535) return fail("b200_adr_diffusion_lincomb: ny <= 65535");
+  AdrArgs a;
+  memset(&a, 0, sizeof(a));
+  a.p = *p; a.mode = 2; a.y = y; a.f = f_out; a.z = z;
+  a.t.n = nterms;
+  for (int k = 0; k < nterms; k++)
+  {
+    a.t.c[k] = cf[k]; a.t.src[k] = src[k];
+    a.t.v[k] = (src[k] == B200_SRC_VECTOR) ? v[k] : nullptr;
+  }
+  dim3 grid((unsigned)((p->nx + kThreads - 1) / kThreads), (unsigned)p->ny);
+  k_adr_diff_lincomb<<<grid, kThreads, 0, c->stream>>>(a);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// --------------------------------------------------------------------- NCCL
+extern "C" int b200_comm_unique_id(unsigned char id[128])
+{
+  ncclUniqueId u;
+  NCCL_TRY(ncclGetUniqueId(&u));
+  static_assert(sizeof(u) == 128, "ncclUniqueId is 128 bytes");
+  memcpy(id, &u, 128);
+  return 0;
+}
+
+extern "C" int b200_comm_init(b200_ctx* c, int rank, int nranks, const unsigned char id[128])
+{
+  CU_TRY(cudaSetDevice(c->device));
+  ncclUniqueId u;
+  memcpy(&u, id, 128);
+  NCCL_TRY(ncclCommInitRank(&c->comm, nranks, u, rank));
+  c->rank   = rank;
+  c->nranks = nranks;
+  return 0;
+}
+
+extern "C" int b200_comm_rank(b200_ctx* c, int* rank, int* nranks)
+{
+  *rank   = c->rank;
+  *nranks = c->nranks;
+  return 0;
+}
+
+static int nccl_allreduce_inplace(b200_ctx* c, double* buf, int n, int op)
+{
+  ncclRedOp_t o = (op == RED_SUM) ? ncclSum : (op == RED_MAX) ? ncclMax : ncclMin;
+  NCCL_TRY(ncclAllReduce(buf, buf, (size_t)n, ncclDouble, o, c->comm, c->stream));
+  return 0;
+}
+
+extern "C" int b200_allreduce(b200_ctx* c, double* dev_buf, int n, int op)
+{
+  if (!c->comm || c->nranks == 1) return 0;
+  return nccl_allreduce_inplace(c, dev_buf, n, op);
+}
+
+extern "C" int b200_halo_exchange(b200_ctx* c, const int peers[4], const double* sw,
+                                  const double* se, const double* ss, const double* sn,
+                                  double* rw, double* re, double* rs, double* rn,
+                                  int64_t nx, int64_t ny)
+{
+  if (!c->comm) return fail("b200_halo_exchange: communicator not initialised");
+  // comm stream picks up after everything enqueued so far on the compute stream
+  CU_TRY(cudaEventRecord(c->ev_compute, c->stream));
+  CU_TRY(cudaStreamWaitEvent(c->comm_stream, c->ev_compute, 0));
+  // The reference pairs messages by tag (diffusion_2D.cpp:421-503): what I send west
+  // is my west neighbour's "from east" halo, and so on.  Within one NCCL group the
+  // per-peer send/recv order must match on both sides: every rank posts
+  // W-send, E-recv, E-send, W-recv, S-send, N-recv, N-send, S-recv.
+  NCCL_TRY(ncclGroupStart());
+  if (sw) NCCL_TRY(ncclSend(sw, (size_t)ny, ncclDouble, peers[0], c->comm, c->comm_stream));
+  if (re) NCCL_TRY(ncclRecv(re, (size_t)ny, ncclDouble, peers[1], c->comm, c->comm_stream));
+  if (se) NCCL_TRY(ncclSend(se, (size_t)ny, ncclDouble, peers[1], c->comm, c->comm_stream));
+  if (rw) NCCL_TRY(ncclRecv(rw, (size_t)ny, ncclDouble, peers[0], c->comm, c->comm_stream));
+  if (ss) NCCL_TRY(ncclSend(ss, (size_t)nx, ncclDouble, peers[2], c->comm, c->comm_stream));
+  if (rn) NCCL_TRY(ncclRecv(rn, (size_t)nx, ncclDouble, peers[3], c->comm, c->comm_stream));
+  if (sn) NCCL_TRY(ncclSend(sn, (size_t)nx, ncclDouble, peers[3], c->comm, c->comm_stream));
+  if (rs) NCCL_TRY(ncclRecv(rs, (size_t)nx, ncclDouble, peers[2], c->comm, c->comm_stream));
+  NCCL_TRY(ncclGroupEnd());
+  CU_TRY(cudaEventRecord(c->ev_comm, c->comm_stream));
+  c->comm_pending = true;
+  return 0;
+}
+
+extern "C" int b200_halo_wait(b200_ctx* c)
+{
+  if (c->comm_pending)
+  {
+    CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
+    c->comm_pending = false;
+  }
+  return 0;
+}

@@ -1,0 +1,206 @@
+/* b200_sts.h -- C-ABI of libb200sts.so: the B200 (sm_100a) device layer of the
+ * explicit super-time-stepping hot path of ceda-demonstrations' diffusion_2D / adr.
+ *
+ * Plain C: raw DEVICE pointers (double*), sizes (int64_t), scalars, an opaque
+ * context handle and a CUDA stream passed as void*.  No torch types, no CUDA
+ * headers, no SUNDIALS headers -- host code (C++, Python/ctypes, cgo ...) binds
+ * these directly.  Every function returns 0 on success and a non-zero
+ * cudaError_t / ncclResult_t-derived code otherwise (b200_last_error() gives text).
+ * There is NO CPU fallback: without a CUDA device every entry fails loudly.
+ *
+ * Each entry cites the reference interface it stands in for
+ * (paths relative to /root/reference; SUN = deps/sundials).
+ *
+ * Arithmetic contract: IEEE-754 binary64, round-to-nearest, NO fused
+ * multiply-add, and the reference's own association order, so that elementwise
+ * results are bit-identical to the reference's CPU build (gcc -O2, baseline
+ * x86-64).  Reductions are deterministic (fixed tree) but not sequential.
+ */
+#ifndef B200_STS_H
+#define B200_STS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_MAX_TERMS 8
+
+typedef struct b200_ctx b200_ctx; /* opaque: device, stream, scratch, NCCL comm */
+
+/* ------------------------------------------------------------------ context */
+/* Create a context on CUDA device `device` (one process per GPU).  `stream` may
+   be NULL (the context creates its own non-blocking stream) or an existing
+   cudaStream_t (e.g. torch's current stream) so that callers can bracket work
+   with their own events. */
+int b200_ctx_create(int device, void* stream, b200_ctx** out);
+int b200_ctx_destroy(b200_ctx* ctx);
+void* b200_ctx_stream(b200_ctx* ctx);
+int b200_ctx_sync(b200_ctx* ctx);
+const char* b200_last_error(void);
+/* number of kernels this library has launched since load (bench "gpu_launches") */
+uint64_t b200_launch_count(void);
+
+/* device / pinned-host memory (stands in for N_VNew_Parallel's malloc,
+   SUN/src/nvector/parallel/nvector_parallel.c:189-221) */
+int b200_malloc(b200_ctx* ctx, int64_t n_doubles, double** dptr);
+int b200_free(b200_ctx* ctx, double* dptr);
+int b200_host_alloc(int64_t n_doubles, double** hptr);
+int b200_host_free(double* hptr);
+int b200_h2d(b200_ctx* ctx, double* dst_dev, const double* src_host, int64_t n);
+int b200_d2h(b200_ctx* ctx, double* dst_host, const double* src_dev, int64_t n);
+
+/* ------------------------------------------------- elementwise vector kernels */
+/* z = sum_k c[k]*v[k] evaluated left to right:  acc = c0*v0; acc = acc + ck*vk.
+   This is SUNDIALS' generic N_VLinearCombination fallback
+   (SUN/src/sundials/sundials_nvector.c:557-565 -> N_VScale + Vaxpy,
+   SUN/src/nvector/parallel/nvector_parallel.c:568-592,1909-1926) and, with
+   nterms<=2, every N_VLinearSum / N_VScale case except a==+-b
+   (nvector_parallel.c:424-517).  z may alias any v[k].  1 <= nterms <= 8. */
+int b200_lincomb(b200_ctx* ctx, int nterms, const double* c,
+                 const double* const* v, double* z, int64_t n);
+/* z = a*(x + y)  (sign=+1, VScaleSum nvector_parallel.c:1839) or
+   z = a*(x - y)  (sign=-1, VScaleDiff :1855) */
+int b200_scale_sumdiff(b200_ctx* ctx, double a, const double* x, const double* y,
+                       int sign, double* z, int64_t n);
+int b200_const(b200_ctx* ctx, double c, double* z, int64_t n);  /* N_VConst :519 */
+int b200_prod(b200_ctx* ctx, const double* x, const double* y, double* z, int64_t n); /* N_VProd :534 */
+int b200_div(b200_ctx* ctx, const double* x, const double* y, double* z, int64_t n);  /* N_VDiv :551 */
+int b200_abs(b200_ctx* ctx, const double* x, double* z, int64_t n);   /* N_VAbs :594 */
+int b200_inv(b200_ctx* ctx, const double* x, double* z, int64_t n);   /* N_VInv :610 */
+int b200_addconst(b200_ctx* ctx, const double* x, double b, double* z, int64_t n); /* N_VAddConst :626 */
+/* ewt = 1 / (rtol*|y| + atol): the four-op sequence of arkEwtSetSS
+   (SUN/src/arkode/arkode.c:2932-2944) in one pass, same rounding sequence. */
+int b200_ewt_ss(b200_ctx* ctx, const double* y, double rtol, double atol,
+                double* ewt, int64_t n);
+
+/* ------------------------------------------------------------- reductions */
+/* Each writes the LOCAL result to *result (host) after a stream sync; with an
+   initialised communicator (b200_comm_init) the value is all-reduced over the
+   ranks first (SUM / MAX / MIN), standing in for the MPI_Allreduce in
+   nvector_parallel.c:658-730. */
+int b200_dot(b200_ctx* ctx, const double* x, const double* y, int64_t n, double* result);      /* N_VDotProd :658 */
+int b200_wsqrsum(b200_ctx* ctx, const double* x, const double* w, int64_t n, double* result);  /* N_VWSqrSumLocal :700 + Allreduce :728 */
+int b200_maxnorm(b200_ctx* ctx, const double* x, int64_t n, double* result);                   /* N_VMaxNorm :689 */
+int b200_min(b200_ctx* ctx, const double* x, int64_t n, double* result);                       /* N_VMin :780 */
+int b200_l1norm(b200_ctx* ctx, const double* x, int64_t n, double* result);                    /* N_VL1Norm :815 */
+
+/* ------------------------------------------------- diffusion_2D RHS stencil */
+/* Local sub-domain of the anisotropic / inhomogeneous 5-point operator
+   f = d/dx(Dx du/dx) + d/dy(Dy du/dy) of diffusion_2D/diffusion.cpp:9-209.
+   Fields are row-major nx*ny doubles, x fastest (IDX, diffusion_2D.hpp:55).
+   The four face-coefficient tables hold exactly the values diffusion.cpp:36-46
+   computes per cell -- Diffusion_Coeff_X(xl+(is+i-+0.5)dx)/(dx*dx) etc. -- and
+   are computed ON THE HOST (libm sin) and uploaded, so coefficients are
+   bit-identical to the reference.  halo_* are the neighbour columns / rows
+   received from the W/E/S/N ranks (the Wrecv..Nrecv buffers of
+   diffusion_2D.hpp:156-159); a NULL halo pointer means "this direction is
+   periodic onto my own field" (one rank in that direction), and the kernel
+   wraps the index instead of reading a buffer. */
+typedef struct b200_stencil_geom
+{
+  int64_t nx, ny;          /* local extents nx_loc, ny_loc */
+  const double* cxw;       /* [nx] Dx_w(i) */
+  const double* cxe;       /* [nx] Dx_e(i) */
+  const double* cys;       /* [ny] Dy_s(j) */
+  const double* cyn;       /* [ny] Dy_n(j) */
+  const double* halo_w;    /* [ny] or NULL */
+  const double* halo_e;    /* [ny] or NULL */
+  const double* halo_s;    /* [nx] or NULL */
+  const double* halo_n;    /* [nx] or NULL */
+} b200_stencil_geom;
+
+/* term sources for b200_stencil_lincomb */
+#define B200_SRC_VECTOR  0 /* v[k] is a device vector */
+#define B200_SRC_CENTRE  1 /* term k is the stencil input x itself (no second load) */
+#define B200_SRC_STENCIL 2 /* term k is L(x), computed on the fly */
+
+/* What to do besides z (all optional, NULL = off) */
+typedef struct b200_stage_extras
+{
+  double* f_out;        /* also store L(x) (the plain ARKRhsFn result) */
+  double* send_w;       /* [ny] pack z's west column   (buffers.cpp:28-30)  */
+  double* send_e;       /* [ny] pack z's east column   (buffers.cpp:32-34)  */
+  double* send_s;       /* [nx] pack z's south row     (buffers.cpp:36-38)  */
+  double* send_n;       /* [nx] pack z's north row     (buffers.cpp:40-42)  */
+  const double* wrms_w; /* fuse sum_i (z_i*w_i)^2 (N_VWSqrSumLocal) ...      */
+  double* wrms_result;  /* ... into this DEVICE double                       */
+} b200_stage_extras;
+
+/* The fused STS stage:  z = sum_k c[k]*T_k, left to right, where T_k is a
+   device vector, the stencil input x, or L(x) (exactly one term should be
+   B200_SRC_STENCIL).  One HBM pass realises the reference's
+   `fe(x -> F)` + `N_VLinearCombination(5, ...)` of
+   SUN/src/arkode/arkode_lsrkstep.c:686-717 (RKC), :985-1020 (RKL), the closing
+   `fe` + embedding LC4 of :768-789, the SSP `fe` + `N_VLinearSum(1,y,c,F,y)`
+   of :1213-1231, and plain f = L(x) (nterms=1, c=1).
+   z must NOT alias x (neighbours are read while z is written); it may alias v[k].
+   region: 0 = whole sub-domain, 1 = boundary ring only, 2 = interior only
+   (ring first / interior after lets the halo exchange overlap the interior). */
+int b200_stencil_lincomb(b200_ctx* ctx, const b200_stencil_geom* g,
+                         const double* x, int nterms, const double* c,
+                         const int* src, const double* const* v, double* z,
+                         const b200_stage_extras* extras, int region);
+
+/* Standalone halo pack of a materialised field (buffers.cpp:20-43). */
+int b200_pack_halo(b200_ctx* ctx, const double* u, int64_t nx, int64_t ny,
+                   double* send_w, double* send_e, double* send_s, double* send_n);
+
+/* Jacobi preconditioner setup: diag = 1/(1 - gamma*d_ij),
+   d_ij = -((pxw[i]+pxe[i]) + (pys[j]+pyn[j])), tables host-computed with the
+   reference's (different) coordinates (preconditioner_jacobi.cpp:9-46). */
+int b200_jacobi_setup(b200_ctx* ctx, int64_t nx, int64_t ny, const double* pxw,
+                      const double* pxe, const double* pys, const double* pyn,
+                      double gamma, double* diag);
+
+/* ------------------------------------------------ adr 2-D Brusselator kernels */
+/* Periodic nx*ny grid, two interleaved species y[2*(i+j*nx)+s]
+   (adr/advection_diffusion_reaction_2d.hpp:44-45). */
+typedef struct b200_adr_params
+{
+  int64_t nx, ny;
+  double dx, dy;
+  double cux, cuy, cvx, cvy; /* advection speeds        (…2d.hpp UserData) */
+  double d;                  /* diffusion coefficient                      */
+  double A, B;               /* Brusselator parameters                     */
+} b200_adr_params;
+/* mode bits: 1 = advection (f_advection …2d.cpp:1406-1445),
+              2 = diffusion (f_diffusion :1448-1491),
+              4 = reaction  (f_reaction  :1494-1520);
+   3/5/6/7 realise the composite callbacks (f_adv_react :1602-1619 etc.) in the
+   reference's summation order.  f must not alias y. */
+int b200_adr_rhs(b200_ctx* ctx, const b200_adr_params* p, int mode,
+                 const double* y, double* f);
+/* fused  z = sum_k c[k]*T_k  with T_k possibly = f_diffusion(y) (STS stages of
+   the Strang / ExtSTS diffusion partition) */
+int b200_adr_diffusion_lincomb(b200_ctx* ctx, const b200_adr_params* p,
+                               const double* y, int nterms, const double* c,
+                               const int* src, const double* const* v, double* z,
+                               double* f_out);
+
+/* --------------------------------------------------- multi-GPU (NCCL, NVLink) */
+/* One process per GPU.  rank 0 calls b200_comm_unique_id and distributes the 128
+   bytes out of band (torch.distributed / a file); every rank then calls
+   b200_comm_init.  Replaces MPI_Init + MPI_Cart_create of
+   diffusion_2D/diffusion_2D.cpp:223-394. */
+int b200_comm_unique_id(unsigned char id[128]);
+int b200_comm_init(b200_ctx* ctx, int rank, int nranks, const unsigned char id[128]);
+int b200_comm_rank(b200_ctx* ctx, int* rank, int* nranks);
+/* Halo exchange: one grouped ncclSend/ncclRecv per neighbour and direction on the
+   context's communication stream (start_exchange/end_exchange,
+   diffusion_2D.cpp:400-584).  peers: ranks of the W,E,S,N neighbours.  The call
+   makes the comm stream wait for everything enqueued so far on the compute
+   stream, and b200_halo_wait makes the compute stream wait for the exchange. */
+int b200_halo_exchange(b200_ctx* ctx, const int peers[4], const double* send_w,
+                       const double* send_e, const double* send_s,
+                       const double* send_n, double* recv_w, double* recv_e,
+                       double* recv_s, double* recv_n, int64_t nx, int64_t ny);
+int b200_halo_wait(b200_ctx* ctx);
+/* all-reduce n doubles in place on the device (op: 0 sum, 1 max, 2 min) */
+int b200_allreduce(b200_ctx* ctx, double* dev_buf, int n, int op);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_STS_H */
