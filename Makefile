@@ -1,0 +1,65 @@
+# Top-level build: everything is compiled in-tree so the artefacts travel with gpurun.
+#
+#   make            product: SUNDIALS host lib (from /root/reference), CUDA kernel lib,
+#                   N_Vector/problem lib, driver executables
+#   make oracle     oracle/liboracle_sts.so (C restatement) and, when /root/reference is
+#                   present, oracle/_ref/* (the unmodified reference CPU binaries)
+#
+# Layout of the outputs (all git-ignored):
+#   ceda-demonstrations_b200/_sundials/   libsundials_host.so + generated config headers
+#   ceda-demonstrations_b200/lib/         libb200sts.so  libb200sts_sundials.so
+#   ceda-demonstrations_b200/bin/         diffusion_2D_b200  adr2d_b200
+
+REF    ?= /root/reference
+SUN    := $(REF)/deps/sundials
+PKG    := ceda-demonstrations_b200
+SRC    := $(PKG)/csrc
+LIB    := $(PKG)/lib
+BIN    := $(PKG)/bin
+SUNOUT := $(PKG)/_sundials
+NVCC   ?= nvcc
+CXX    ?= g++
+NVFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC
+CXXFLAGS := -O2 -std=c++17 -fPIC -Wall -Wno-unused-function
+SUNINC := -I$(SUNOUT)/include -I$(SUN)/include
+
+HAVE_REF := $(wildcard $(SUN)/src/arkode/arkode.c)
+
+.PHONY: all product oracle sundials clean
+all: product
+
+ifneq ($(HAVE_REF),)
+sundials:
+	@$(MAKE) -s -f scripts/sundials_host.mk SUN_OUT=$(SUNOUT)
+product: sundials $(LIB)/libb200sts.so $(LIB)/libb200sts_sundials.so $(BIN)/diffusion_2D_b200
+else
+sundials:
+	@test -f $(SUNOUT)/lib/libsundials_host.so || (echo "no /root/reference and no prebuilt SUNDIALS host lib" && false)
+product: $(LIB)/libb200sts.so
+endif
+
+$(LIB)/libb200sts.so: $(SRC)/b200_kernels.cu include/b200_sts.h
+	@mkdir -p $(LIB)
+	$(NVCC) $(NVFLAGS) -shared -Iinclude $< -o $@ -lnccl
+
+HOST_SRC := $(SRC)/nvector_b200.cpp $(SRC)/diffusion_b200.cpp
+$(LIB)/libb200sts_sundials.so: $(HOST_SRC) include/nvector_b200.h include/b200_diffusion2d.h include/b200_sts.h $(LIB)/libb200sts.so
+	@mkdir -p $(LIB)
+	$(CXX) $(CXXFLAGS) -shared -Iinclude $(SUNINC) $(HOST_SRC) -o $@ \
+	  -L$(LIB) -lb200sts -L$(SUNOUT)/lib -lsundials_host \
+	  -Wl,-rpath,'$$ORIGIN' -Wl,-rpath,'$$ORIGIN/../_sundials/lib'
+
+$(BIN)/diffusion_2D_b200: $(SRC)/main_diffusion.cpp $(LIB)/libb200sts_sundials.so
+	@mkdir -p $(BIN)
+	$(CXX) $(CXXFLAGS) -Iinclude $< -o $@ -L$(LIB) -lb200sts_sundials -lb200sts \
+	  -L$(SUNOUT)/lib -lsundials_host \
+	  -Wl,-rpath,'$$ORIGIN/../lib' -Wl,-rpath,'$$ORIGIN/../_sundials/lib'
+
+oracle:
+	@$(MAKE) -s -C oracle all
+ifneq ($(HAVE_REF),)
+	@$(MAKE) -s -C oracle ref
+endif
+
+clean:
+	rm -rf build $(LIB) $(BIN) $(SUNOUT) oracle/_ref oracle/liboracle_sts.so

@@ -1,0 +1,856 @@
+// diffusion_b200.cpp -- the diffusion_2D problem layer on the B200 vector.
+//
+// Host C++ mirror of /root/reference/diffusion_2D (UserData / UserOptions /
+// UserOutput, the four callbacks, and the main() call sequence) with the data path
+// moved to the GPU: callbacks enqueue work through include/b200_sts.h and never loop
+// over cells on the host.  ARKODE (LSRKStep RKC/RKL/SSP, ARKStep DIRK/ERK, PCG, the
+// power-iteration estimator) is linked UNCHANGED and drives everything through the
+// N_Vector ops table and these callbacks.
+//
+// What stays on the host on purpose ("floating-point parity"):
+//   * the 1-D face-coefficient tables (libm sin) -- diffusion.cpp:36-46,
+//   * the initial condition (libm sin/exp/sqrt) -- initial.cpp:42-43,
+//   * the Jacobi preconditioner's tables -- preconditioner_jacobi.cpp:23-37,
+// each computed exactly as the reference does and uploaded once.
+
+#include <arkode/arkode_arkstep.h>
+#include <arkode/arkode_lsrkstep.h>
+#include <sunadaptcontroller/sunadaptcontroller_imexgus.h>
+#include <sunadaptcontroller/sunadaptcontroller_soderlind.h>
+#include <sundials/sundials_core.h>
+#include <sundomeigest/sundomeigest_power.h>
+#include <sunlinsol/sunlinsol_pcg.h>
+#include <sunlinsol/sunlinsol_spgmr.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "b200_diffusion2d.h"
+#include "b200_sts.h"
+#include "nvector_b200.h"
+
+namespace {
+
+double wall_seconds()
+{
+  using namespace std::chrono;
+  return duration<double>(steady_clock::now().time_since_epoch()).count();
+}
+
+// ------------------------------------------------------------------ UserData
+// Field names follow diffusion_2D/diffusion_2D.hpp:66-216.
+struct UserData
+{
+  // problem (diffusion_2D.hpp:71-93)
+  double kx = 1.0, ky = 1.0;
+  bool inhomogeneous = false;
+  double tf = 1.0;
+  double xl = -M_PI, yl = -6.0, xu = M_PI, yu = 6.0;
+  int64_t nx = 64, ny = 64, nodes = 64 * 64;
+  double dx = 0.0, dy = 0.0;
+  // decomposition (diffusion_2D.hpp:96-133)
+  int64_t qx = 0, qy = 0, rx = 0, ry = 0;
+  int64_t nx_loc = 0, ny_loc = 0, nodes_loc = 0;
+  int64_t is = 0, ie = 0, js = 0, je = 0;
+  int np = 1, npx = 0, npy = 0, myid_c = 0, idx = 0, idy = 0;
+  int ipW = -1, ipE = -1, ipS = -1, ipN = -1;
+  N_Vector diag = nullptr; // Jacobi preconditioner (diffusion_2D.hpp:190)
+
+  // device side
+  b200_ctx* ctx = nullptr;
+  double *cxw = nullptr, *cxe = nullptr, *cys = nullptr, *cyn = nullptr; // stencil tables
+  double *pxw = nullptr, *pxe = nullptr, *pys = nullptr, *pyn = nullptr; // PSetup tables
+  double *Wsend = nullptr, *Esend = nullptr, *Ssend = nullptr, *Nsend = nullptr;
+  double *Wrecv = nullptr, *Erecv = nullptr, *Srecv = nullptr, *Nrecv = nullptr;
+  B200RhsOp rhs_op{};
+  bool overlap = true; // interior kernel overlaps the NCCL exchange
+  long rhs_calls = 0;
+
+  double coeff_x(double x) const
+  { // Diffusion_Coeff_X, diffusion_2D.cpp:887-891
+    return inhomogeneous ? (kx * (1.0 + 0.99 * std::sin(x))) : kx;
+  }
+  double coeff_y(double y) const
+  { // Diffusion_Coeff_Y, diffusion_2D.cpp:893-897
+    return inhomogeneous ? (ky * (1.0 + 0.99 * std::sin(y))) : ky;
+  }
+
+  int setup(int rank, int nranks);
+  int upload_tables();
+  void free_device();
+};
+
+// MPI_Dims_create(np, 2, dims) + MPI_Cart_create/Cart_get/Cart_rank with periodic
+// wrap, row-major rank order (diffusion_2D.cpp:243-394).
+void dims_create(int np, int& px, int& py)
+{
+  if (px > 0 && py > 0) return;
+  if (px > 0) { py = np / px; return; }
+  if (py > 0) { px = np / py; return; }
+  int b = 1;
+  for (int f = 1; f * f <= np; f++)
+    if (np % f == 0) b = f;
+  px = np / b;
+  py = b;
+}
+
+int cart_rank(int cx, int cy, int px, int py)
+{
+  cx = ((cx % px) + px) % px;
+  cy = ((cy % py) + py) % py;
+  return cx * py + cy;
+}
+
+void block_extent(int64_t n, int nproc, int coord, int64_t& q, int64_t& r, int64_t& s, int64_t& e)
+{ // diffusion_2D.cpp:286-317
+  q = n / nproc;
+  r = n % nproc;
+  s = q * coord + (coord < r ? coord : r);
+  e = s + q - 1 + (coord < r ? 1 : 0);
+}
+
+int UserData::setup(int rank, int nranks)
+{
+  np     = nranks;
+  myid_c = rank;
+  dims_create(np, npx, npy);
+  if (npx * npy != np)
+  {
+    fprintf(stderr, "Error: npx*npy = %d*%d does not match the number of ranks %d\n", npx, npy, np);
+    return -1;
+  }
+  idx = rank / npy;
+  idy = rank % npy;
+  block_extent(nx, npx, idx, qx, rx, is, ie);
+  block_extent(ny, npy, idy, qy, ry, js, je);
+  if (ie > nx - 1 || je > ny - 1) return -1;
+  nx_loc    = ie - is + 1;
+  ny_loc    = je - js + 1;
+  nodes     = nx * ny;
+  nodes_loc = nx_loc * ny_loc;
+  ipW       = cart_rank(idx - 1, idy, npx, npy);
+  ipE       = cart_rank(idx + 1, idy, npx, npy);
+  ipS       = cart_rank(idx, idy - 1, npx, npy);
+  ipN       = cart_rank(idx, idy + 1, npx, npy);
+  return 0;
+}
+
+#define DEVRC(call)                                                                   \
+  do {                                                                                \
+    int rc_ = (call);                                                                 \
+    if (rc_ != 0)                                                                     \
+    {                                                                                 \
+      fprintf(stderr, "diffusion_b200: %s failed (%d): %s\n", #call, rc_, b200_last_error()); \
+      return -1;                                                                      \
+    }                                                                                 \
+  }                                                                                   \
+  while (0)
+
+int upload(b200_ctx* ctx, const std::vector<double>& h, double** d)
+{
+  DEVRC(b200_malloc(ctx, (int64_t)h.size() + 2, d));
+  DEVRC(b200_h2d(ctx, *d, h.data(), (int64_t)h.size()));
+  return 0;
+}
+
+int UserData::upload_tables()
+{
+  // stencil tables: diffusion.cpp:36-46 evaluated once per index instead of per cell
+  std::vector<double> xw(nx_loc), xe(nx_loc), ys(ny_loc), yn(ny_loc);
+  for (int64_t j = 0; j < ny_loc; j++)
+  {
+    const double ylo = yl + (js + j - 0.5) * dy;
+    const double yhi = yl + (js + j + 0.5) * dy;
+    ys[j]            = coeff_y(ylo) / (dy * dy);
+    yn[j]            = coeff_y(yhi) / (dy * dy);
+  }
+  for (int64_t i = 0; i < nx_loc; i++)
+  {
+    const double xlo = xl + (is + i - 0.5) * dx;
+    const double xhi = xl + (is + i + 0.5) * dx;
+    xw[i]            = coeff_x(xlo) / (dx * dx);
+    xe[i]            = coeff_x(xhi) / (dx * dx);
+  }
+  if (upload(ctx, xw, &cxw) || upload(ctx, xe, &cxe) || upload(ctx, ys, &cys) || upload(ctx, yn, &cyn)) return -1;
+  // preconditioner tables: preconditioner_jacobi.cpp:23-37 -- (is+i)*dx, no xl, no half cell
+  for (int64_t j = 0; j < ny_loc; j++)
+  {
+    ys[j] = coeff_y((js + j) * dy) / (dy * dy);
+    yn[j] = coeff_y((js + j + 1) * dy) / (dy * dy);
+  }
+  for (int64_t i = 0; i < nx_loc; i++)
+  {
+    xw[i] = coeff_x((is + i) * dx) / (dx * dx);
+    xe[i] = coeff_x((is + i + 1) * dx) / (dx * dx);
+  }
+  if (upload(ctx, xw, &pxw) || upload(ctx, xe, &pxe) || upload(ctx, ys, &pys) || upload(ctx, yn, &pyn)) return -1;
+  // exchange buffers (buffers.cpp:46-73), only for directions that really have a peer
+  if (npx > 1)
+  {
+    DEVRC(b200_malloc(ctx, ny_loc, &Wsend)); DEVRC(b200_malloc(ctx, ny_loc, &Esend));
+    DEVRC(b200_malloc(ctx, ny_loc, &Wrecv)); DEVRC(b200_malloc(ctx, ny_loc, &Erecv));
+  }
+  if (npy > 1)
+  {
+    DEVRC(b200_malloc(ctx, nx_loc, &Ssend)); DEVRC(b200_malloc(ctx, nx_loc, &Nsend));
+    DEVRC(b200_malloc(ctx, nx_loc, &Srecv)); DEVRC(b200_malloc(ctx, nx_loc, &Nrecv));
+  }
+  return 0;
+}
+
+void UserData::free_device()
+{
+  double* all[] = {cxw, cxe, cys, cyn, pxw, pxe, pys, pyn, Wsend, Esend, Ssend, Nsend, Wrecv, Erecv, Srecv, Nrecv};
+  for (double* p : all)
+    if (p) b200_free(ctx, p);
+}
+
+// ----------------------------------------------------------------- callbacks
+// The deferred operator behind diffusion(): start_exchange + interior + end_exchange
+// + faces of diffusion.cpp:9-209, fused with whatever linear combination consumes f.
+int rhs_fused(void* self, b200_ctx* ctx, const double* y, int nterms, const double* c,
+              const int* src, const double* const* v, double* z, double* f_out,
+              const double* wrms_w, double* wrms_result, int* wrms_done)
+{
+  UserData* ud = static_cast<UserData*>(self);
+  b200_stencil_geom g;
+  memset(&g, 0, sizeof(g));
+  g.nx = ud->nx_loc; g.ny = ud->ny_loc;
+  g.cxw = ud->cxw; g.cxe = ud->cxe; g.cys = ud->cys; g.cyn = ud->cyn;
+  b200_stage_extras ex;
+  memset(&ex, 0, sizeof(ex));
+  ex.f_out = f_out;
+  *wrms_done = 0;
+  ud->rhs_calls++;
+  const bool xs = ud->npx > 1, ys = ud->npy > 1;
+  if (!xs && !ys)
+  { // one periodic rank: the halo is this rank's own opposite edge -> index wrap
+    if (wrms_w) { ex.wrms_w = wrms_w; ex.wrms_result = wrms_result; *wrms_done = 1; }
+    return b200_stencil_lincomb(ctx, &g, y, nterms, c, src, v, z, &ex, 0);
+  }
+  // pack_buffers + start_exchange (buffers.cpp:20-43, diffusion_2D.cpp:400-507)
+  int rc = b200_pack_halo(ctx, y, g.nx, g.ny, xs ? ud->Wsend : nullptr, xs ? ud->Esend : nullptr,
+                          ys ? ud->Ssend : nullptr, ys ? ud->Nsend : nullptr);
+  if (rc) return rc;
+  const int peers[4] = {ud->ipW, ud->ipE, ud->ipS, ud->ipN};
+  rc = b200_halo_exchange(ctx, peers, xs ? ud->Wsend : nullptr, xs ? ud->Esend : nullptr,
+                          ys ? ud->Ssend : nullptr, ys ? ud->Nsend : nullptr,
+                          xs ? ud->Wrecv : nullptr, xs ? ud->Erecv : nullptr,
+                          ys ? ud->Srecv : nullptr, ys ? ud->Nrecv : nullptr, g.nx, g.ny);
+  if (rc) return rc;
+  g.halo_w = xs ? ud->Wrecv : nullptr; g.halo_e = xs ? ud->Erecv : nullptr;
+  g.halo_s = ys ? ud->Srecv : nullptr; g.halo_n = ys ? ud->Nrecv : nullptr;
+  if (ud->overlap && g.nx >= 4 && g.ny >= 4)
+  {
+    // interior (no halo reads) runs while NCCL moves the edges; the ring follows
+    rc = b200_stencil_lincomb(ctx, &g, y, nterms, c, src, v, z, &ex, 2);
+    if (rc) return rc;
+    rc = b200_halo_wait(ctx); // end_exchange, diffusion_2D.cpp:509-584
+    if (rc) return rc;
+    return b200_stencil_lincomb(ctx, &g, y, nterms, c, src, v, z, &ex, 1);
+  }
+  rc = b200_halo_wait(ctx);
+  if (rc) return rc;
+  return b200_stencil_lincomb(ctx, &g, y, nterms, c, src, v, z, &ex, 0);
+}
+
+} // namespace
+
+extern "C" {
+
+// ARKRhsFn (SUN/include/arkode/arkode.h:163) -- diffusion(), diffusion_2D.cpp:23-35
+int b200_diffusion_rhs(sunrealtype t, N_Vector u, N_Vector f, void* user_data)
+{
+  (void)t;
+  UserData* ud = static_cast<UserData*>(user_data);
+  return N_VSetDeferredRhs_B200(f, &ud->rhs_op, u) ? -1 : 0;
+}
+
+// ARKDomEigFn (arkode_lsrkstep.h:26-29) -- dom_eig(), main.cpp:536-550
+int b200_diffusion_domeig(sunrealtype t, N_Vector y, N_Vector fn, sunrealtype* lambdaR,
+                          sunrealtype* lambdaI, void* user_data, N_Vector t1, N_Vector t2, N_Vector t3)
+{
+  (void)t; (void)y; (void)fn; (void)t1; (void)t2; (void)t3;
+  UserData* ud = static_cast<UserData*>(user_data);
+  *lambdaR = -8.0 * std::max(ud->kx / ud->dx / ud->dx, ud->ky / ud->dy / ud->dy);
+  *lambdaI = 0.0;
+  return 0;
+}
+
+// ARKLsPrecSetupFn -- PSetup, preconditioner_jacobi.cpp:9-46
+int b200_diffusion_psetup(sunrealtype t, N_Vector u, N_Vector f, sunbooleantype jok,
+                          sunbooleantype* jcurPtr, sunrealtype gamma, void* user_data)
+{
+  (void)t; (void)u; (void)f; (void)jok; (void)jcurPtr;
+  UserData* ud = static_cast<UserData*>(user_data);
+  double* d    = N_VGetDeviceArrayPointerForWrite_B200(ud->diag);
+  return b200_jacobi_setup(ud->ctx, ud->nx_loc, ud->ny_loc, ud->pxw, ud->pxe, ud->pys, ud->pyn, gamma, d) ? -1 : 0;
+}
+
+// ARKLsPrecSolveFn -- PSolve, preconditioner_jacobi.cpp:49-62
+int b200_diffusion_psolve(sunrealtype t, N_Vector u, N_Vector f, N_Vector r, N_Vector z,
+                          sunrealtype gamma, sunrealtype delta, int lr, void* user_data)
+{
+  (void)t; (void)u; (void)f; (void)gamma; (void)delta; (void)lr;
+  UserData* ud = static_cast<UserData*>(user_data);
+  N_VProd(ud->diag, r, z);
+  return 0;
+}
+
+} // extern "C"
+
+namespace {
+
+// Initial(), initial.cpp:20-48: host libm, then one upload
+int initial_condition(N_Vector u, const UserData& ud)
+{
+  std::vector<double> h((size_t)ud.nodes_loc);
+  for (int64_t j = 0; j < ud.ny_loc; j++)
+    for (int64_t i = 0; i < ud.nx_loc; i++)
+    {
+      const double x = ud.xl + (ud.is + i) * ud.dx;
+      const double y = ud.yl + (ud.js + j) * ud.dy;
+      h[(size_t)(ud.nx_loc * j + i)] =
+        (1.0 + 0.3 * std::sin(2.0 * x)) / std::sqrt(5.5 * M_PI) * std::exp(-(y * y) / 5.5);
+    }
+  return N_VCopyFromHost_B200(u, h.data());
+}
+
+// ------------------------------------------------------------------ options
+struct UserOptions
+{ // main.cpp:24-52
+  std::string integrator = "dirk";
+  double rtol = 1.0e-5, atol = 1.0e-10, hfixed = 0.0;
+  int order = 2, controller = 0, maxsteps = 0, onestep = 0;
+  bool error = false, linear = true;
+  std::string ls = "cg";
+  bool preconditioning = true, lsinfo = false;
+  int liniters = 20, msbp = 0;
+  double epslin = 0.0;
+  bool internaleig = false;
+  // UserOutput, diffusion_2D.hpp:223-243
+  int output = 1, nout = 20;
+  // B200 extras (not reference flags)
+  bool no_overlap = false, no_fusion = false;
+  int rows_per_block = 0;
+};
+
+// One pass over argv; unknown flags are an error like main.cpp:116-132.
+int parse_args(std::vector<std::string> args, UserData& ud, UserOptions& uo, bool outproc)
+{
+  for (size_t k = 0; k < args.size(); k++)
+  {
+    const std::string& a = args[k];
+    auto need = [&](const char* what) -> const std::string* {
+      if (k + 1 >= args.size())
+      {
+        if (outproc) fprintf(stderr, "ERROR: %s needs a value\n", what);
+        return nullptr;
+      }
+      return &args[++k];
+    };
+#define ARG_D(flag, dst) if (a == flag) { auto s = need(flag); if (!s) return -1; dst = std::stod(*s); continue; }
+#define ARG_I(flag, dst) if (a == flag) { auto s = need(flag); if (!s) return -1; dst = std::stoi(*s); continue; }
+#define ARG_L(flag, dst) if (a == flag) { auto s = need(flag); if (!s) return -1; dst = std::stoll(*s); continue; }
+#define ARG_S(flag, dst) if (a == flag) { auto s = need(flag); if (!s) return -1; dst = *s; continue; }
+#define ARG_B(flag, dst, val) if (a == flag) { dst = val; continue; }
+    ARG_I("--npx", ud.npx) ARG_I("--npy", ud.npy) ARG_L("--nx", ud.nx) ARG_L("--ny", ud.ny)
+    ARG_D("--xl", ud.xl) ARG_D("--xu", ud.xu)
+    // the reference stores --yl into yu (diffusion_2D.cpp:95-99); kept for parity
+    ARG_D("--yl", ud.yu) ARG_D("--yu", ud.yu)
+    ARG_D("--kx", ud.kx) ARG_D("--ky", ud.ky) ARG_B("--inhomogeneous", ud.inhomogeneous, true)
+    ARG_D("--tf", ud.tf)
+    ARG_S("--integrator", uo.integrator) ARG_D("--rtol", uo.rtol) ARG_D("--atol", uo.atol)
+    ARG_D("--fixedstep", uo.hfixed) ARG_I("--order", uo.order) ARG_I("--controller", uo.controller)
+    ARG_I("--maxsteps", uo.maxsteps) ARG_I("--onestep", uo.onestep) ARG_B("--error", uo.error, true)
+    ARG_B("--nonlinear", uo.linear, false) ARG_S("--ls", uo.ls) ARG_B("--lsinfo", uo.lsinfo, true)
+    ARG_I("--liniters", uo.liniters) ARG_I("--msbp", uo.msbp) ARG_D("--epslin", uo.epslin)
+    ARG_B("--noprec", uo.preconditioning, false) ARG_B("--internaleig", uo.internaleig, true)
+    ARG_I("--output", uo.output) ARG_I("--nout", uo.nout)
+    ARG_B("--no-overlap", uo.no_overlap, true) ARG_B("--no-fusion", uo.no_fusion, true)
+    ARG_I("--rows-per-block", uo.rows_per_block)
+    if (outproc) fprintf(stderr, "ERROR: Unknown inputs: %s\n", a.c_str());
+    return -1;
+  }
+  ud.nodes = ud.nx * ud.ny;                 // diffusion_2D.cpp:156-160
+  ud.dx    = (ud.xu - ud.xl) / (ud.nx - 1);
+  ud.dy    = (ud.yu - ud.yl) / (ud.ny - 1);
+  return 0;
+}
+
+} // namespace
+
+extern "C" int b200_set_rows_per_block(int r);
+
+// ------------------------------------------------------------------- session
+struct b200_d2d
+{
+  UserData ud;
+  UserOptions uo;
+  SUNContext sunctx       = nullptr;
+  b200_ctx* ctx           = nullptr;
+  N_Vector u              = nullptr, uref = nullptr, uerr = nullptr;
+  void* arkode_mem        = nullptr;
+  void* arkref_mem        = nullptr;
+  SUNLinearSolver LS      = nullptr;
+  SUNDomEigEstimator DEE  = nullptr;
+  SUNAdaptController Ctrl = nullptr;
+  double t = 0.0, t2 = 0.0, errtot = 0.0, evolve_seconds = 0.0;
+  bool impl = false, expl = false, sts = false;
+  FILE* uout = nullptr;
+};
+
+#define CHK(call, name)                                                       \
+  do {                                                                        \
+    int flag_ = (call);                                                       \
+    if (flag_ < 0)                                                            \
+    {                                                                         \
+      fprintf(stderr, "ERROR: %s returned %d\n", name, flag_);                \
+      return -1;                                                              \
+    }                                                                         \
+  }                                                                           \
+  while (0)
+#define CHKP(ptr, name)                                                       \
+  do {                                                                        \
+    if ((ptr) == nullptr)                                                     \
+    {                                                                         \
+      fprintf(stderr, "ERROR: %s returned NULL\n", name);                     \
+      return -1;                                                              \
+    }                                                                         \
+  }                                                                           \
+  while (0)
+
+// main.cpp:176-400: vectors, integrator, tolerances, method, eigenvalue source, step control
+static int configure(b200_d2d* p)
+{
+  UserData& ud    = p->ud;
+  UserOptions& uo = p->uo;
+  SUNContext ctx  = p->sunctx;
+  p->impl = (uo.integrator == "dirk");
+  p->expl = (uo.integrator == "erk");
+  p->sts  = (uo.integrator == "rkc" || uo.integrator == "rkl");
+  if (!p->impl && !p->expl && !p->sts)
+  {
+    fprintf(stderr, "ERROR: illegal integrator\n");
+    return -1;
+  }
+
+  p->u = N_VNew_B200(p->ctx, ud.nodes_loc, ud.nodes, ctx); // main.cpp:176
+  CHKP(p->u, "N_VNew_B200");
+  if (initial_condition(p->u, ud)) return -1;              // main.cpp:180
+  if (uo.error)
+  {
+    p->uref = N_VClone(p->u);
+    p->uerr = N_VClone(p->u);
+    N_VScale(1.0, p->u, p->uref);
+    N_VConst(0.0, p->uerr);
+  }
+
+  if (p->impl)
+  { // main.cpp:196-229
+    const int prectype = uo.preconditioning ? SUN_PREC_RIGHT : SUN_PREC_NONE;
+    if (uo.ls == "cg") p->LS = SUNLinSol_PCG(p->u, prectype, uo.liniters, ctx);
+    else if (uo.ls == "gmres") p->LS = SUNLinSol_SPGMR(p->u, prectype, uo.liniters, ctx);
+    CHKP(p->LS, "SUNLinSol");
+    if (uo.preconditioning)
+    {
+      ud.diag = N_VClone(p->u);
+      CHKP(ud.diag, "N_VClone");
+    }
+  }
+
+  ARKRhsFn rhs = b200_diffusion_rhs;
+  if (p->impl) p->arkode_mem = ARKStepCreate(nullptr, rhs, 0.0, p->u, ctx);
+  else if (p->expl && uo.order >= 0) p->arkode_mem = ARKStepCreate(rhs, nullptr, 0.0, p->u, ctx);
+  else if (p->expl) p->arkode_mem = LSRKStepCreateSSP(rhs, 0.0, p->u, ctx);
+  else p->arkode_mem = LSRKStepCreateSTS(rhs, 0.0, p->u, ctx);
+  CHKP(p->arkode_mem, "ARKStep/LSRKStepCreate");
+  void* mem = p->arkode_mem;
+
+  CHK(ARKodeSStolerances(mem, uo.rtol, uo.atol), "ARKodeSStolerances");
+  CHK(ARKodeSetUserData(mem, (void*)&ud), "ARKodeSetUserData");
+  if (p->impl) CHK(ARKodeSetOrder(mem, uo.order), "ARKodeSetOrder");
+  if (p->expl)
+  { // main.cpp:275-300: negative orders select the SSP methods
+    if (uo.order < 0)
+    {
+      ARKODE_LSRKMethodType type;
+      int num_stages;
+      switch (uo.order)
+      {
+      case -2: type = ARKODE_LSRK_SSP_S_2; num_stages = 2; break;
+      case -3: type = ARKODE_LSRK_SSP_S_3; num_stages = 4; break;
+      case -4: type = ARKODE_LSRK_SSP_10_4; num_stages = 10; break;
+      default: fprintf(stderr, "ERROR: illegal SSPRK order\n"); return -1;
+      }
+      CHK(LSRKStepSetSSPMethod(mem, type), "LSRKStepSetSSPMethod");
+      CHK(LSRKStepSetNumSSPStages(mem, num_stages), "LSRKStepSetNumSSPStages");
+    }
+    else CHK(ARKodeSetOrder(mem, uo.order), "ARKodeSetOrder");
+  }
+  if (p->impl)
+  { // main.cpp:302-331
+    CHK(ARKodeSetLinearSolver(mem, p->LS, nullptr), "ARKodeSetLinearSolver");
+    if (uo.preconditioning)
+    {
+      CHK(ARKodeSetPreconditioner(mem, b200_diffusion_psetup, b200_diffusion_psolve), "ARKodeSetPreconditioner");
+      CHK(ARKodeSetLSetupFrequency(mem, uo.msbp), "ARKodeSetLSetupFrequency");
+    }
+    CHK(ARKodeSetEpsLin(mem, uo.epslin), "ARKodeSetEpsLin");
+    if (uo.linear) CHK(ARKodeSetLinear(mem, 0), "ARKodeSetLinear");
+  }
+  if (p->sts)
+  { // main.cpp:333-355
+    ARKODE_LSRKMethodType type = (uo.integrator == "rkc") ? ARKODE_LSRK_RKC_2 : ARKODE_LSRK_RKL_2;
+    CHK(LSRKStepSetSTSMethod(mem, type), "LSRKStepSetSTSMethod");
+    if (uo.internaleig)
+    {
+      p->DEE = SUNDomEigEstimator_Power(p->u, 100, 0.01, ctx);
+      CHKP(p->DEE, "SUNDomEigEstimator_Power");
+      CHK(LSRKStepSetDomEigEstimator(mem, p->DEE), "LSRKStepSetDomEigEstimator");
+    }
+    else CHK(LSRKStepSetDomEigFn(mem, b200_diffusion_domeig), "LSRKStepSetDomEigFn");
+  }
+  if (uo.hfixed > 0.0) CHK(ARKodeSetFixedStep(mem, uo.hfixed), "ARKodeSetFixedStep");
+  else
+  { // main.cpp:364-376
+    switch (uo.controller)
+    {
+    case (ARK_ADAPT_PID): p->Ctrl = SUNAdaptController_PID(ctx); break;
+    case (ARK_ADAPT_PI): p->Ctrl = SUNAdaptController_PI(ctx); break;
+    case (ARK_ADAPT_I): p->Ctrl = SUNAdaptController_I(ctx); break;
+    case (ARK_ADAPT_EXP_GUS): p->Ctrl = SUNAdaptController_ExpGus(ctx); break;
+    case (ARK_ADAPT_IMP_GUS): p->Ctrl = SUNAdaptController_ImpGus(ctx); break;
+    case (ARK_ADAPT_IMEX_GUS): p->Ctrl = SUNAdaptController_ImExGus(ctx); break;
+    }
+    CHK(ARKodeSetAdaptController(mem, p->Ctrl), "ARKodeSetAdaptController");
+  }
+  CHK(ARKodeSetMaxNumSteps(mem, uo.maxsteps), "ARKodeSetMaxNumSteps");
+  CHK(ARKodeSetStopTime(mem, ud.tf), "ARKodeSetStopTime");
+
+  if (uo.error)
+  { // main.cpp:386-400: reference integrator at rtol 1e-12
+    p->arkref_mem = LSRKStepCreateSTS(rhs, 0.0, p->u, ctx);
+    CHKP(p->arkref_mem, "LSRKStepCreateSTS");
+    CHK(ARKodeSStolerances(p->arkref_mem, 1.e-12, uo.atol), "ARKodeSStolerances");
+    CHK(ARKodeSetUserData(p->arkref_mem, (void*)&ud), "ARKodeSetUserData");
+    CHK(LSRKStepSetDomEigFn(p->arkref_mem, b200_diffusion_domeig), "LSRKStepSetDomEigFn");
+    CHK(ARKodeSetMaxNumSteps(p->arkref_mem, 100000 * uo.maxsteps), "ARKodeSetMaxNumSteps");
+  }
+  return 0;
+}
+
+extern "C" int b200_d2d_create(int argc, const char* const* argv, int rank, int nranks,
+                               const unsigned char* nccl_id, int device, void* stream, b200_d2d** out)
+{
+  b200_d2d* p = new b200_d2d();
+  std::vector<std::string> args(argv, argv + argc);
+  if (parse_args(args, p->ud, p->uo, rank == 0)) { delete p; return -1; }
+  if (p->ud.setup(rank, nranks)) { delete p; return -1; }
+  if (b200_ctx_create(device, stream, &p->ctx))
+  {
+    fprintf(stderr, "b200_d2d_create: %s\n", b200_last_error());
+    delete p;
+    return -1;
+  }
+  if (nranks > 1)
+  {
+    if (!nccl_id) { fprintf(stderr, "b200_d2d_create: nranks > 1 needs an NCCL id\n"); return -1; }
+    if (b200_comm_init(p->ctx, rank, nranks, nccl_id))
+    {
+      fprintf(stderr, "b200_d2d_create: %s\n", b200_last_error());
+      return -1;
+    }
+  }
+  p->ud.ctx         = p->ctx;
+  p->ud.overlap     = !p->uo.no_overlap;
+  p->ud.rhs_op.self = &p->ud;
+  p->ud.rhs_op.fused = rhs_fused;
+  if (p->uo.rows_per_block > 0) b200_set_rows_per_block(p->uo.rows_per_block);
+  N_VSetLazyFusion_B200(p->uo.no_fusion ? 0 : 1);
+  if (p->ud.upload_tables()) return -1;
+  if (SUNContext_Create(SUN_COMM_NULL, &p->sunctx)) return -1;
+  if (configure(p)) return -1;
+  *out = p;
+  return 0;
+}
+
+extern "C" int b200_d2d_destroy(b200_d2d* p)
+{
+  if (!p) return 0;
+  if (p->uout) fclose(p->uout);
+  if (p->Ctrl) SUNAdaptController_Destroy(p->Ctrl);
+  if (p->arkode_mem) ARKodeFree(&p->arkode_mem);
+  if (p->arkref_mem) ARKodeFree(&p->arkref_mem);
+  if (p->LS) SUNLinSolFree(p->LS);
+  if (p->DEE) SUNDomEigEstimator_Destroy(&p->DEE);
+  if (p->ud.diag) N_VDestroy(p->ud.diag);
+  if (p->uref) N_VDestroy(p->uref);
+  if (p->uerr) N_VDestroy(p->uerr);
+  if (p->u) N_VDestroy(p->u);
+  p->ud.free_device();
+  if (p->sunctx) SUNContext_Free(&p->sunctx);
+  if (p->ctx) b200_ctx_destroy(p->ctx);
+  delete p;
+  return 0;
+}
+
+extern "C" int b200_d2d_evolve(b200_d2d* p, double tout)
+{
+  CHK(ARKodeSetStopTime(p->arkode_mem, tout), "ARKodeSetStopTime");
+  const double t0 = wall_seconds();
+  int flag        = ARKodeEvolve(p->arkode_mem, tout, p->u, &p->t, ARK_NORMAL);
+  b200_ctx_sync(p->ctx);
+  p->evolve_seconds += wall_seconds() - t0;
+  CHK(flag, "ARKodeEvolve");
+  return 0;
+}
+
+extern "C" int b200_d2d_step(b200_d2d* p, int nsteps)
+{
+  const double t0 = wall_seconds();
+  for (int k = 0; k < nsteps; k++)
+  {
+    int flag = ARKodeEvolve(p->arkode_mem, p->ud.tf, p->u, &p->t, ARK_ONE_STEP);
+    if (flag < 0)
+    {
+      fprintf(stderr, "ERROR: ARKodeEvolve returned %d\n", flag);
+      return -1;
+    }
+  }
+  p->evolve_seconds += wall_seconds() - t0;
+  return 0;
+}
+
+extern "C" int b200_d2d_get_state(b200_d2d* p, double* host) { return N_VCopyToHost_B200(p->u, host); }
+
+extern "C" int b200_d2d_set_state(b200_d2d* p, const double* host, double t)
+{
+  if (N_VCopyFromHost_B200(p->u, host)) return -1;
+  CHK(ARKodeReset(p->arkode_mem, t, p->u), "ARKodeReset");
+  p->t = t;
+  return 0;
+}
+
+extern "C" int b200_d2d_get_stats(b200_d2d* p, b200_d2d_stats* s)
+{
+  memset(s, 0, sizeof(*s));
+  void* mem = p->arkode_mem;
+  s->t      = p->t;
+  ARKodeGetLastStep(mem, &s->h_last);
+  ARKodeGetNumSteps(mem, &s->steps);
+  ARKodeGetNumStepAttempts(mem, &s->step_attempts);
+  ARKodeGetNumErrTestFails(mem, &s->err_test_fails);
+  ARKodeGetNumRhsEvals(mem, p->impl ? 1 : 0, &s->rhs_evals);
+  if (p->sts)
+  {
+    int ms = 0;
+    LSRKStepGetNumDomEigUpdates(mem, &s->dom_eig_updates);
+    LSRKStepGetMaxNumStages(mem, &ms);
+    s->max_stages = ms;
+    LSRKStepGetNumDomEigEstRhsEvals(mem, &s->dee_rhs_evals);
+  }
+  if (p->impl)
+  {
+    ARKodeGetNumLinIters(mem, &s->lin_iters);
+    ARKodeGetNumLinRhsEvals(mem, &s->lin_rhs_evals);
+    ARKodeGetNumPrecSolves(mem, &s->prec_solves);
+    ARKodeGetNumNonlinSolvIters(mem, &s->nonlin_iters);
+  }
+  s->urms = std::sqrt(N_VDotProd(p->u, p->u) / p->ud.nx / p->ud.ny); // diffusion_2D.cpp:801
+  s->evolve_seconds = p->evolve_seconds;
+  B200VecStats vs;
+  N_VGetStats_B200(&vs);
+  s->fused_launches = vs.fused_launches; s->plain_rhs_launches = vs.plain_rhs_launches;
+  s->aliased_copies = vs.aliased_copies; s->wrms_fused = vs.wrms_fused;
+  s->buffers_allocated = vs.buffers_allocated;
+  s->kernel_launches = b200_launch_count();
+  s->nx = p->ud.nx; s->ny = p->ud.ny; s->nx_loc = p->ud.nx_loc; s->ny_loc = p->ud.ny_loc;
+  s->is = p->ud.is; s->js = p->ud.js; s->npx = p->ud.npx; s->npy = p->ud.npy;
+  s->rank = p->ud.myid_c; s->nranks = p->ud.np;
+  return 0;
+}
+
+extern "C" int b200_d2d_print_stats(b200_d2d* p)
+{
+  return ARKodePrintAllStats(p->arkode_mem, stdout, SUN_OUTPUTFORMAT_TABLE);
+}
+
+extern "C" int b200_d2d_local_extent(int64_t nx, int64_t ny, int rank, int nranks, int npx, int npy,
+                                     int64_t* is, int64_t* nx_loc, int64_t* js, int64_t* ny_loc,
+                                     int* npx_out, int* npy_out)
+{
+  UserData ud;
+  ud.nx = nx; ud.ny = ny; ud.npx = npx; ud.npy = npy;
+  if (ud.setup(rank, nranks)) return -1;
+  *is = ud.is; *nx_loc = ud.nx_loc; *js = ud.js; *ny_loc = ud.ny_loc;
+  *npx_out = ud.npx; *npy_out = ud.npy;
+  return 0;
+}
+
+// -------------------------------------------------------------------- main()
+namespace {
+
+// UserOutput::open / write, diffusion_2D.cpp:723-830 (same file name and layout)
+int output_open(b200_d2d* p)
+{
+  if (p->uo.output != 2) return 0;
+  char name[64];
+  snprintf(name, sizeof(name), "diffusion_2d_solution.%05d.txt", p->ud.myid_c);
+  p->uout = fopen(name, "w");
+  if (!p->uout) return -1;
+  const UserData& u = p->ud;
+  fprintf(p->uout, "# title Diffusion 2D\n# nvar 1\n# vars u\n# nt  %d\n", p->uo.nout + 1);
+  fprintf(p->uout, "# nx  %lld\n# xl  %g\n# xu  %g\n# ny  %lld\n# yl  %g\n# yu  %g\n", (long long)u.nx,
+          u.xl, u.xu, (long long)u.ny, u.yl, u.yu);
+  fprintf(p->uout, "# px  %d\n# py  %d\n# np  %d\n# is  %lld\n# ie  %lld\n# js  %lld\n# je  %lld\n",
+          u.npx, u.npy, u.np, (long long)u.is, (long long)u.ie, (long long)u.js, (long long)u.je);
+  return 0;
+}
+
+int output_write(b200_d2d* p, double t, bool outproc)
+{
+  if (p->uo.output <= 0) return 0;
+  const double urms = std::sqrt(N_VDotProd(p->u, p->u) / p->ud.nx / p->ud.ny);
+  if (outproc)
+  {
+    if (p->uo.error) printf("%22.15e%25.15e%25.15e\n", t, urms, 0.0);
+    else printf("%22.15e%25.15e\n", t, urms);
+  }
+  if (p->uo.output == 2)
+  {
+    std::vector<double> h((size_t)p->ud.nodes_loc);
+    if (N_VCopyToHost_B200(p->u, h.data())) return -1;
+    fprintf(p->uout, "%.15e ", t);
+    for (double v : h) fprintf(p->uout, "%.15e ", v);
+    fprintf(p->uout, "\n");
+  }
+  return 0;
+}
+
+int env_int(const char* a, const char* b, int dflt)
+{
+  const char* s = getenv(a);
+  if (!s && b) s = getenv(b);
+  return s ? atoi(s) : dflt;
+}
+
+// rank 0 writes the 128-byte NCCL id to a file, the others poll for it
+int share_nccl_id(int rank, unsigned char id[128])
+{
+  const char* path = getenv("B200_NCCL_ID_FILE");
+  if (!path) { fprintf(stderr, "B200_NCCL_ID_FILE must be set for multi-rank runs\n"); return -1; }
+  std::string tmp = std::string(path) + ".tmp";
+  if (rank == 0)
+  {
+    if (b200_comm_unique_id(id)) return -1;
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) return -1;
+    fwrite(id, 1, 128, f);
+    fclose(f);
+    rename(tmp.c_str(), path);
+    return 0;
+  }
+  for (int tries = 0; tries < 6000; tries++)
+  {
+    FILE* f = fopen(path, "rb");
+    if (f)
+    {
+      size_t n = fread(id, 1, 128, f);
+      fclose(f);
+      if (n == 128) return 0;
+    }
+    std::this_thread::sleep_for(std::chrono::milliseconds(10));
+  }
+  return -1;
+}
+
+} // namespace
+
+extern "C" int b200_d2d_main(int argc, char** argv)
+{
+  const int rank   = env_int("RANK", "B200_RANK", 0);
+  const int nranks = env_int("WORLD_SIZE", "B200_NP", 1);
+  const int device = env_int("LOCAL_RANK", "B200_DEVICE", rank);
+  unsigned char id[128];
+  if (nranks > 1 && share_nccl_id(rank, id)) return 1;
+  for (int k = 1; k < argc; k++)
+    if (std::string(argv[k]) == "--help")
+    {
+      if (rank == 0) printf("options: see /root/reference/diffusion_2D (same flags) plus --no-overlap --no-fusion --rows-per-block N\n");
+      return 0;
+    }
+  b200_d2d* p = nullptr;
+  if (b200_d2d_create(argc - 1, argv + 1, rank, nranks, nranks > 1 ? id : nullptr, device, nullptr, &p)) return 1;
+  const bool outproc = (rank == 0);
+  UserData& ud       = p->ud;
+  UserOptions& uo    = p->uo;
+  if (outproc)
+  {
+    printf("\n2D Heat PDE test problem on B200 (N_Vector_B200, lazy stage fusion %s)\n", uo.no_fusion ? "off" : "on");
+    printf("  nprocs = %d  npx = %d  npy = %d\n  kx = %g  ky = %g  inhomogeneous = %d  tf = %g\n", ud.np,
+           ud.npx, ud.npy, ud.kx, ud.ky, (int)ud.inhomogeneous, ud.tf);
+    printf("  nx = %lld  ny = %lld  dx = %.17g  dy = %.17g  nx_loc = %lld  ny_loc = %lld\n", (long long)ud.nx,
+           (long long)ud.ny, ud.dx, ud.dy, (long long)ud.nx_loc, (long long)ud.ny_loc);
+    printf("  integrator = %s  rtol = %g  atol = %g  hfixed = %g  order = %d  controller = %d\n\n",
+           uo.integrator.c_str(), uo.rtol, uo.atol, uo.hfixed, uo.order, uo.controller);
+  }
+  // main.cpp:402-476: loop over output times
+  int nout = uo.nout;
+  const bool onestep = uo.onestep > 0;
+  if (onestep) nout = uo.onestep;
+  const double dTout = ud.tf / nout;
+  double tout        = dTout;
+  if (output_open(p)) return 1;
+  if (outproc && uo.output > 0)
+    printf("          t                     ||u||_rms      \n ----------------------------------------------\n");
+  if (output_write(p, p->t, outproc)) return 1;
+  for (int iout = 0; iout < nout; iout++)
+  {
+    const double t0 = wall_seconds();
+    if (uo.error) ARKodeSetStopTime(p->arkode_mem, tout);
+    int flag = ARKodeEvolve(p->arkode_mem, tout, p->u, &p->t, onestep ? ARK_ONE_STEP : ARK_NORMAL);
+    b200_ctx_sync(p->ctx);
+    p->evolve_seconds += wall_seconds() - t0;
+    if (flag < 0) { fprintf(stderr, "ERROR: ARKodeEvolve returned %d\n", flag); return 1; }
+    if (uo.error)
+    {
+      ARKodeSetStopTime(p->arkref_mem, p->t);
+      flag = ARKodeEvolve(p->arkref_mem, tout, p->uref, &p->t2, ARK_NORMAL);
+      if (flag < 0) break;
+    }
+    if (output_write(p, p->t, outproc)) return 1;
+    if (uo.error)
+    {
+      N_VLinearSum(1.0, p->uref, -1.0, p->u, p->uerr);
+      p->errtot = std::max(p->errtot, N_VMaxNorm(p->uerr) / N_VMaxNorm(p->uref));
+    }
+    tout += dTout;
+    tout = (tout > ud.tf) ? ud.tf : tout;
+  }
+  if (outproc)
+  {
+    if (uo.output > 0) printf(" ----------------------------------------------\n\n");
+    if (uo.error) printf("Maximum relative error = %.16g\n", p->errtot);
+    printf("Total simulation time = %.15e\n\n", p->evolve_seconds);
+    printf("Final integrator statistics:\n");
+    b200_d2d_print_stats(p);
+    b200_d2d_stats s;
+    b200_d2d_get_stats(p, &s);
+    printf("B200 fused stage launches     = %ld\n", s.fused_launches);
+    printf("B200 plain RHS launches       = %ld\n", s.plain_rhs_launches);
+    printf("B200 aliased copies           = %ld\n", s.aliased_copies);
+    printf("B200 fused WRMS norms         = %ld\n", s.wrms_fused);
+    printf("B200 kernel launches          = %llu\n", (unsigned long long)s.kernel_launches);
+    printf("B200 vector buffers allocated = %ld\n", s.buffers_allocated);
+  }
+  b200_d2d_destroy(p);
+  return 0;
+}

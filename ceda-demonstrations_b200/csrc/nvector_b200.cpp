@@ -1,0 +1,646 @@
+// nvector_b200.cpp -- N_Vector ops table over B200 HBM with lazy stage fusion.
+//
+// Replaces SUN/src/nvector/parallel/nvector_parallel.c (the reference's backend for
+// diffusion_2D) and nvector_serial.c (adr) behind the unchanged ops table
+// (SUN/include/sundials/sundials_nvector.h:98-192).  Host C++ only; all device work
+// goes through the C-ABI in include/b200_sts.h.  There is no CPU fallback: a failed
+// device call aborts loudly.
+//
+// Value model: every vector points at an immutable, reference-counted Value that is
+// either materialised (device buffer from a per-length pool) or deferred (op applied
+// to another Value).  All N_V* ops that write z build a NEW Value and re-point z, so
+//   * N_VScale(1,x,z) is a handle share (arkode_lsrkstep.c:642,746,2242; arkode.c:2737),
+//   * in-place forms such as N_VLinearSum(1,y,c,F,y) with F = L(y) (SSP stages,
+//     arkode_lsrkstep.c:1213-1231) are automatically ping-ponged,
+//   * ARKODE swapping its tempv1/tempv2 handles (arkode_lsrkstep.c:742-744) is harmless.
+
+#include "nvector_b200.h"
+
+#include <sundials/sundials_core.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+namespace {
+
+[[noreturn]] void die(const char* what, int rc)
+{
+  fprintf(stderr, "nvector_b200: FATAL: %s failed (code %d): %s\n", what, rc, b200_last_error());
+  abort();
+}
+#define DEV(call)                       \
+  do {                                  \
+    int rc_ = (call);                   \
+    if (rc_ != 0) die(#call, rc_);      \
+  }                                     \
+  while (0)
+
+B200VecStats g_stats = {0, 0, 0, 0, 0};
+bool g_lazy          = true;
+
+// buffers of one local length on one context, shared by all clones
+struct Shared
+{
+  b200_ctx* ctx;
+  sunindextype nloc, nglob;
+  int refs;
+  std::vector<double*> free_bufs;
+  double* wrms_slots; // device scalars for fused WRMS partial sums
+  int next_slot;
+  bool spec_sigs[96]; // fused-launch signatures whose result a matching WRMS norm followed
+};
+const int kSlots = 8;
+
+struct Value
+{
+  int refs;
+  double* d;           // device data, nullptr while deferred
+  const B200RhsOp* op; // deferred: value = op(src)
+  Value* src;
+  // fused WRMS partial: sum (this_i * w_i)^2 already sits in slot
+  Value* wrms_w;
+  int wrms_slot;
+  int sig;  // signature of the fused launch that produced it (0 = none)
+  long seq; // creation order
+};
+
+struct Content
+{
+  Shared* sh;
+  Value* val;
+  double* host;    // pinned mirror for N_VGetArrayPointer
+  bool host_dirty; // host mirror may have been written since it was handed out
+};
+
+inline Content* C(N_Vector v) { return static_cast<Content*>(v->content); }
+
+// weight value of the most recent WRMS norm (one reference held) and when it was set
+Value* g_last_weight     = nullptr;
+Shared* g_last_weight_sh = nullptr;
+long g_last_weight_seq   = 0;
+long g_seq               = 0;
+
+double* pool_get(Shared* sh)
+{
+  if (!sh->free_bufs.empty())
+  {
+    double* p = sh->free_bufs.back();
+    sh->free_bufs.pop_back();
+    return p;
+  }
+  double* p = nullptr;
+  DEV(b200_malloc(sh->ctx, sh->nloc, &p));
+  g_stats.buffers_allocated++;
+  return p;
+}
+
+void value_release(Shared* sh, Value* v)
+{
+  while (v)
+  {
+    if (--v->refs > 0) return;
+    if (v->d) sh->free_bufs.push_back(v->d);
+    if (v->wrms_w) value_release(sh, v->wrms_w);
+    Value* next = v->src; // a deferred value owns a reference on its source
+    delete v;
+    v = next;
+  }
+}
+
+Value* value_new(Shared* sh, bool with_buffer)
+{
+  Value* v     = new Value();
+  v->refs      = 1;
+  v->d         = with_buffer ? pool_get(sh) : nullptr;
+  v->op        = nullptr;
+  v->src       = nullptr;
+  v->wrms_w    = nullptr;
+  v->wrms_slot = -1;
+  v->sig       = 0;
+  v->seq       = ++g_seq;
+  return v;
+}
+
+void assign(Content* c, Value* nv) // takes ownership of one reference on nv
+{
+  Value* old = c->val;
+  c->val     = nv;
+  if (old) value_release(c->sh, old);
+  c->host_dirty = false;
+}
+
+void materialise(Shared* sh, Value* v);
+
+// make sure the host mirror (if it was handed out) is reflected on the device
+void sync_from_host(Content* c)
+{
+  if (c->host_dirty)
+  {
+    Value* nv = value_new(c->sh, true);
+    DEV(b200_h2d(c->sh->ctx, nv->d, c->host, c->sh->nloc));
+    assign(c, nv);
+  }
+  if (!c->val)
+  { // never written: SUNDIALS would read uninitialised memory; give zeros
+    Value* nv = value_new(c->sh, true);
+    DEV(b200_const(c->sh->ctx, 0.0, nv->d, c->sh->nloc));
+    assign(c, nv);
+  }
+}
+
+// launch the deferred operator (optionally fused with a linear combination)
+//   out = sum_k cf[k] * T_k ; terms equal to L become the stencil term
+void launch_fused(Shared* sh, Value* L, int nterms, const double* cf, Value* const* X,
+                  Value* out, bool store_f)
+{
+  Value* src = L->src;
+  materialise(sh, src);
+  int srcs[B200_MAX_TERMS];
+  const double* vp[B200_MAX_TERMS];
+  int lpos = -1;
+  for (int k = 0; k < nterms; k++)
+  {
+    if (X[k] == L) { srcs[k] = B200_SRC_STENCIL; vp[k] = nullptr; if (lpos < 0) lpos = k; }
+    else if (X[k] == src) { srcs[k] = B200_SRC_CENTRE; vp[k] = nullptr; }
+    else { srcs[k] = B200_SRC_VECTOR; vp[k] = X[k]->d; }
+  }
+  double* f_out = nullptr;
+  if (store_f) { L->d = pool_get(sh); f_out = L->d; }
+  // speculative WRMS: only for launch signatures a norm has followed before
+  const int sig        = 1 + nterms * 8 + lpos;
+  const double* w      = nullptr;
+  double* wres         = nullptr;
+  Value* wv            = nullptr;
+  int slot             = -1;
+  if (out && sh->spec_sigs[sig] && sh->wrms_slots)
+  {
+    // weight guess: the value the most recent N_VWrmsNorm used, kept alive by a ref
+    if (g_last_weight && g_last_weight_sh == sh && g_last_weight->d)
+    {
+      wv   = g_last_weight;
+      w    = wv->d;
+      slot = sh->next_slot;
+      sh->next_slot = (sh->next_slot + 1) % kSlots;
+      wres = sh->wrms_slots + slot;
+    }
+  }
+  int wdone = 0;
+  DEV(L->op->fused(L->op->self, sh->ctx, src->d, nterms, cf, srcs, vp, out ? out->d : nullptr, f_out,
+                   w, wres, &wdone));
+  if (out)
+  {
+    out->sig = sig;
+    if (wdone)
+    {
+      out->wrms_w = wv;
+      wv->refs++;
+      out->wrms_slot = slot;
+    }
+  }
+  if (store_f)
+  { // L is now a plain materialised value
+    L->op  = nullptr;
+    L->src = nullptr;
+    value_release(sh, src);
+  }
+}
+
+void materialise(Shared* sh, Value* v)
+{
+  if (v->d) return;
+  if (!v->op) die("materialise: value has neither data nor operator", -1);
+  // f = 1 * L(src), stored through the f_out path so v itself becomes plain
+  const double one = 1.0;
+  Value* X[1]      = {v};
+  Value* src       = v->src;
+  materialise(sh, src);
+  int srcs[1]          = {B200_SRC_STENCIL};
+  const double* vp[1]  = {nullptr};
+  v->d                 = pool_get(sh);
+  int wdone            = 0;
+  DEV(v->op->fused(v->op->self, sh->ctx, src->d, 1, &one, srcs, vp, v->d, nullptr, nullptr, nullptr, &wdone));
+  (void)X;
+  v->op  = nullptr;
+  v->src = nullptr;
+  value_release(sh, src);
+  g_stats.plain_rhs_launches++;
+}
+
+// z = sum_k cf[k]*X[k], left to right; handles deferred operands by fusion
+void eval_lincomb(int nterms, const double* cf, N_Vector* Xv, N_Vector zv)
+{
+  Content* zc = C(zv);
+  Shared* sh  = zc->sh;
+  Value* X[B200_MAX_TERMS];
+  for (int k = 0; k < nterms; k++)
+  {
+    sync_from_host(C(Xv[k]));
+    X[k] = C(Xv[k])->val;
+  }
+  // pick the deferred operand to fuse (first one); others are materialised
+  Value* L = nullptr;
+  for (int k = 0; k < nterms; k++)
+  {
+    if (!X[k]->d)
+    {
+      if (!L) L = X[k];
+      else if (X[k] != L) materialise(sh, X[k]);
+    }
+  }
+  if (L)
+  {
+    int uses = 0;
+    for (int k = 0; k < nterms; k++) uses += (X[k] == L);
+    if (uses > 1 || !g_lazy) { materialise(sh, L); L = nullptr; }
+  }
+  Value* out = value_new(sh, true);
+  if (L)
+  {
+    // F itself must be kept if anything other than z will still point at it
+    const bool store_f = (L->refs - (zc->val == L ? 1 : 0)) > 0;
+    launch_fused(sh, L, nterms, cf, X, out, store_f);
+    g_stats.fused_launches++;
+  }
+  else
+  {
+    const double* vp[B200_MAX_TERMS];
+    for (int k = 0; k < nterms; k++) vp[k] = X[k]->d;
+    DEV(b200_lincomb(sh->ctx, nterms, cf, vp, out->d, sh->nloc));
+  }
+  assign(zc, out);
+}
+
+const double* mat(N_Vector v) // materialised device pointer of v
+{
+  Content* c = C(v);
+  sync_from_host(c);
+  materialise(c->sh, c->val);
+  return c->val->d;
+}
+
+// ------------------------------------------------------------------ ops table
+N_Vector_ID op_getvectorid(N_Vector) { return SUNDIALS_NVEC_CUSTOM; }
+
+N_Vector op_clone(N_Vector w);
+
+void op_destroy(N_Vector v)
+{
+  if (!v) return;
+  Content* c = C(v);
+  if (c)
+  {
+    if (c->val) value_release(c->sh, c->val);
+    if (c->host) b200_host_free(c->host);
+    Shared* sh = c->sh;
+    if (--sh->refs == 0)
+    {
+      if (g_last_weight && g_last_weight_sh == sh)
+      {
+        value_release(sh, g_last_weight);
+        g_last_weight = nullptr;
+      }
+      b200_ctx_sync(sh->ctx);
+      for (double* p : sh->free_bufs) b200_free(sh->ctx, p);
+      if (sh->wrms_slots) b200_free(sh->ctx, sh->wrms_slots);
+      delete sh;
+    }
+    delete c;
+  }
+  N_VFreeEmpty(v);
+}
+
+void op_space(N_Vector v, sunindextype* lrw, sunindextype* liw)
+{
+  *lrw = C(v)->sh->nglob;
+  *liw = 2;
+}
+
+sunindextype op_getlength(N_Vector v) { return C(v)->sh->nglob; }
+
+sunrealtype* op_getarraypointer(N_Vector v)
+{
+  Content* c = C(v);
+  if (!c->host) DEV(b200_host_alloc(c->sh->nloc, &c->host));
+  if (!c->host_dirty)
+  {
+    if (c->val)
+    {
+      materialise(c->sh, c->val);
+      DEV(b200_d2h(c->sh->ctx, c->host, c->val->d, c->sh->nloc));
+    }
+    else { memset(c->host, 0, sizeof(double) * (size_t)c->sh->nloc); }
+  }
+  c->host_dirty = true; // caller may write through the pointer
+  return c->host;
+}
+
+void op_linearsum(sunrealtype a, N_Vector x, sunrealtype b, N_Vector y, N_Vector z)
+{
+  // nvector_parallel.c:424-517: every branch except a==+-b (|a| != 1) evaluates
+  // (a*x) + (b*y) with exact +-1 products; those two evaluate a*(x +- y).
+  const bool unit = (a == 1.0 || a == -1.0 || b == 1.0 || b == -1.0);
+  if (!unit && (a == b || a == -b))
+  {
+    const double* xd = mat(x);
+    const double* yd = mat(y);
+    Content* zc      = C(z);
+    Value* out       = value_new(zc->sh, true);
+    DEV(b200_scale_sumdiff(zc->sh->ctx, a, xd, yd, (a == b) ? +1 : -1, out->d, zc->sh->nloc));
+    assign(zc, out);
+    return;
+  }
+  double cf[2]  = {a, b};
+  N_Vector X[2] = {x, y};
+  eval_lincomb(2, cf, X, z);
+}
+
+void op_const(sunrealtype c, N_Vector z)
+{
+  Content* zc = C(z);
+  Value* out  = value_new(zc->sh, true);
+  DEV(b200_const(zc->sh->ctx, c, out->d, zc->sh->nloc));
+  assign(zc, out);
+}
+
+#define BINARY_OP(NAME, KERNEL)                                      \
+  void NAME(N_Vector x, N_Vector y, N_Vector z)                      \
+  {                                                                  \
+    const double* xd = mat(x);                                       \
+    const double* yd = mat(y);                                       \
+    Content* zc      = C(z);                                         \
+    Value* out       = value_new(zc->sh, true);                      \
+    DEV(KERNEL(zc->sh->ctx, xd, yd, out->d, zc->sh->nloc));          \
+    assign(zc, out);                                                 \
+  }
+BINARY_OP(op_prod, b200_prod)
+BINARY_OP(op_div, b200_div)
+
+void op_scale(sunrealtype c, N_Vector x, N_Vector z)
+{
+  if (c == 1.0)
+  { // VCopy (nvector_parallel.c:1771): share the value, deferred or not
+    if (x == z) return;
+    Content* xc = C(x);
+    sync_from_host(xc);
+    xc->val->refs++;
+    assign(C(z), xc->val);
+    g_stats.aliased_copies++;
+    return;
+  }
+  double cf[1]  = {c};
+  N_Vector X[1] = {x};
+  eval_lincomb(1, cf, X, z);
+}
+
+#define UNARY_OP(NAME, KERNEL)                                  \
+  void NAME(N_Vector x, N_Vector z)                             \
+  {                                                             \
+    const double* xd = mat(x);                                  \
+    Content* zc      = C(z);                                    \
+    Value* out       = value_new(zc->sh, true);                 \
+    DEV(KERNEL(zc->sh->ctx, xd, out->d, zc->sh->nloc));         \
+    assign(zc, out);                                            \
+  }
+UNARY_OP(op_abs, b200_abs)
+UNARY_OP(op_inv, b200_inv)
+
+void op_addconst(N_Vector x, sunrealtype b, N_Vector z)
+{
+  const double* xd = mat(x);
+  Content* zc      = C(z);
+  Value* out       = value_new(zc->sh, true);
+  DEV(b200_addconst(zc->sh->ctx, xd, b, out->d, zc->sh->nloc));
+  assign(zc, out);
+}
+
+sunrealtype op_dotprod(N_Vector x, N_Vector y)
+{
+  const double* xd = mat(x);
+  const double* yd = mat(y);
+  double r         = 0.0;
+  DEV(b200_dot(C(x)->sh->ctx, xd, yd, C(x)->sh->nloc, &r));
+  return r;
+}
+
+sunrealtype op_maxnorm(N_Vector x)
+{
+  const double* xd = mat(x);
+  double r         = 0.0;
+  DEV(b200_maxnorm(C(x)->sh->ctx, xd, C(x)->sh->nloc, &r));
+  return r;
+}
+
+sunrealtype wsqrsum(N_Vector x, N_Vector w)
+{
+  Content* xc      = C(x);
+  Shared* sh       = xc->sh;
+  const double* xd = mat(x);
+  const double* wd = mat(w);
+  Value* xv        = xc->val;
+  Value* wv        = C(w)->val;
+  double r         = 0.0;
+  if (xv->wrms_w == wv && xv->wrms_slot >= 0)
+  { // the fused kernel that produced x already reduced sum (x*w)^2
+    double* slot = sh->wrms_slots + xv->wrms_slot;
+    DEV(b200_allreduce(sh->ctx, slot, 1, 0));
+    DEV(b200_d2h(sh->ctx, &r, slot, 1));
+    xv->wrms_slot = -1; // the all-reduce is in place: do not reuse
+    g_stats.wrms_fused++;
+  }
+  else { DEV(b200_wsqrsum(sh->ctx, xd, wd, sh->nloc, &r)); }
+  // learn: x came out of a fused launch issued while w was already the most recent
+  // norm weight, i.e. fusing the norm into that launch would have hit -> do so next time
+  if (xv->sig && g_last_weight == wv && xv->seq > g_last_weight_seq) sh->spec_sigs[xv->sig] = true;
+  if (g_last_weight != wv)
+  {
+    if (g_last_weight) value_release(g_last_weight_sh, g_last_weight);
+    g_last_weight     = wv;
+    g_last_weight_sh  = sh;
+    g_last_weight_seq = g_seq;
+    wv->refs++;
+  }
+  return r;
+}
+
+sunrealtype op_wrmsnorm(N_Vector x, N_Vector w)
+{
+  // nvector_parallel.c:721-730: sqrt(global sum / global length)
+  return std::sqrt(wsqrsum(x, w) / (double)C(x)->sh->nglob);
+}
+
+sunrealtype op_wl2norm(N_Vector x, N_Vector w) { return std::sqrt(wsqrsum(x, w)); }
+
+sunrealtype op_min(N_Vector x)
+{
+  const double* xd = mat(x);
+  double r         = 0.0;
+  DEV(b200_min(C(x)->sh->ctx, xd, C(x)->sh->nloc, &r));
+  return r;
+}
+
+sunrealtype op_l1norm(N_Vector x)
+{
+  const double* xd = mat(x);
+  double r         = 0.0;
+  DEV(b200_l1norm(C(x)->sh->ctx, xd, C(x)->sh->nloc, &r));
+  return r;
+}
+
+SUNErrCode op_linearcombination(int nvec, sunrealtype* c, N_Vector* X, N_Vector z)
+{
+  if (nvec < 1) return SUN_ERR_ARG_OUTOFRANGE;
+  if (nvec <= B200_MAX_TERMS)
+  {
+    if (nvec == 1 && c[0] == 1.0) { op_scale(1.0, X[0], z); return SUN_SUCCESS; }
+    eval_lincomb(nvec, c, X, z);
+    return SUN_SUCCESS;
+  }
+  // more than 8 terms: z = first 8, then z = 1*z + next 7, ... (same left-to-right sums)
+  eval_lincomb(B200_MAX_TERMS, c, X, z);
+  int done = B200_MAX_TERMS;
+  while (done < nvec)
+  {
+    int m = nvec - done;
+    if (m > B200_MAX_TERMS - 1) m = B200_MAX_TERMS - 1;
+    double cf[B200_MAX_TERMS];
+    N_Vector Xs[B200_MAX_TERMS];
+    cf[0] = 1.0;
+    Xs[0] = z;
+    for (int k = 0; k < m; k++) { cf[k + 1] = c[done + k]; Xs[k + 1] = X[done + k]; }
+    eval_lincomb(m + 1, cf, Xs, z);
+    done += m;
+  }
+  return SUN_SUCCESS;
+}
+
+void op_print(N_Vector v)
+{
+  sunrealtype* h = op_getarraypointer(v);
+  C(v)->host_dirty = false;
+  for (sunindextype i = 0; i < C(v)->sh->nloc; i++) printf("%.16e\n", h[i]);
+}
+
+void fill_ops(N_Vector v)
+{
+  v->ops->nvgetvectorid       = op_getvectorid;
+  v->ops->nvclone             = op_clone;
+  v->ops->nvcloneempty        = op_clone;
+  v->ops->nvdestroy           = op_destroy;
+  v->ops->nvspace             = op_space;
+  v->ops->nvgetarraypointer   = op_getarraypointer;
+  v->ops->nvgetlength         = op_getlength;
+  v->ops->nvlinearsum         = op_linearsum;
+  v->ops->nvconst             = op_const;
+  v->ops->nvprod              = op_prod;
+  v->ops->nvdiv               = op_div;
+  v->ops->nvscale             = op_scale;
+  v->ops->nvabs               = op_abs;
+  v->ops->nvinv               = op_inv;
+  v->ops->nvaddconst          = op_addconst;
+  v->ops->nvdotprod           = op_dotprod;
+  v->ops->nvmaxnorm           = op_maxnorm;
+  v->ops->nvwrmsnorm          = op_wrmsnorm;
+  v->ops->nvwl2norm           = op_wl2norm;
+  v->ops->nvmin               = op_min;
+  v->ops->nvl1norm            = op_l1norm;
+  v->ops->nvlinearcombination = op_linearcombination;
+  v->ops->nvprint             = op_print;
+}
+
+N_Vector op_clone(N_Vector w)
+{
+  N_Vector v = N_VNewEmpty(w->sunctx);
+  if (!v) return nullptr;
+  fill_ops(v);
+  Content* c    = new Content();
+  c->sh         = C(w)->sh;
+  c->sh->refs++;
+  c->val        = nullptr;
+  c->host       = nullptr;
+  c->host_dirty = false;
+  v->content    = c;
+  return v;
+}
+
+} // namespace
+
+// ------------------------------------------------------------------ public API
+extern "C" {
+
+N_Vector N_VNew_B200(b200_ctx* ctx, sunindextype local_length, sunindextype global_length,
+                     SUNContext sunctx)
+{
+  if (!ctx)
+  {
+    fprintf(stderr, "N_VNew_B200: a device context is required (no CPU fallback)\n");
+    return nullptr;
+  }
+  N_Vector v = N_VNewEmpty(sunctx);
+  if (!v) return nullptr;
+  fill_ops(v);
+  Shared* sh     = new Shared();
+  sh->ctx        = ctx;
+  sh->nloc       = local_length;
+  sh->nglob      = global_length;
+  sh->refs       = 1;
+  sh->wrms_slots = nullptr;
+  sh->next_slot  = 0;
+  memset(sh->spec_sigs, 0, sizeof(sh->spec_sigs));
+  DEV(b200_malloc(ctx, kSlots, &sh->wrms_slots));
+  Content* c    = new Content();
+  c->sh         = sh;
+  c->val        = nullptr;
+  c->host       = nullptr;
+  c->host_dirty = false;
+  v->content    = c;
+  return v;
+}
+
+b200_ctx* N_VGetContext_B200(N_Vector v) { return C(v)->sh->ctx; }
+sunindextype N_VGetLocalLength_B200(N_Vector v) { return C(v)->sh->nloc; }
+
+const double* N_VGetDeviceArrayPointer_B200(N_Vector v) { return mat(v); }
+
+double* N_VGetDeviceArrayPointerForWrite_B200(N_Vector v)
+{
+  Content* c = C(v);
+  Value* out = value_new(c->sh, true);
+  assign(c, out);
+  return out->d;
+}
+
+int N_VCopyFromHost_B200(N_Vector v, const double* host)
+{
+  double* d = N_VGetDeviceArrayPointerForWrite_B200(v);
+  return b200_h2d(C(v)->sh->ctx, d, host, C(v)->sh->nloc);
+}
+
+int N_VCopyToHost_B200(N_Vector v, double* host)
+{
+  const double* d = mat(v);
+  return b200_d2h(C(v)->sh->ctx, host, d, C(v)->sh->nloc);
+}
+
+int N_VSetDeferredRhs_B200(N_Vector f, const B200RhsOp* op, N_Vector y)
+{
+  Content* fc = C(f);
+  Content* yc = C(y);
+  if (fc->sh != yc->sh && fc->sh->nloc != yc->sh->nloc) return -1;
+  sync_from_host(yc);
+  Value* L = value_new(fc->sh, false);
+  L->op    = op;
+  L->src   = yc->val;
+  yc->val->refs++;
+  assign(fc, L);
+  if (!g_lazy) materialise(fc->sh, L);
+  return 0;
+}
+
+int N_VIsDeferred_B200(N_Vector v) { return (C(v)->val && !C(v)->val->d) ? 1 : 0; }
+void N_VSetLazyFusion_B200(int on) { g_lazy = (on != 0); }
+void N_VGetStats_B200(B200VecStats* s) { *s = g_stats; }
+
+} // extern "C"

@@ -1,0 +1,83 @@
+/* nvector_b200.h -- a SUNDIALS N_Vector whose data lives in B200 HBM.
+ *
+ * Drop-in for the one constructor call that selects the vector backend in the
+ * reference drivers:
+ *     N_VNew_Parallel(comm, local_length, global_length, ctx)   diffusion_2D/main.cpp:176
+ *     N_VNew_Serial(neq, ctx)                                    adr/advection_diffusion_reaction_2d.cpp:83
+ * Every other vector (ARKODE's ewt/yn/fn/tempv*, the Lagrange history, the power
+ * iteration's V/q, PCG's r/p/z/Ap, udata.diag) is an N_VClone and inherits the ops
+ * table (struct _generic_N_Vector_Ops, SUN/include/sundials/sundials_nvector.h:98-192).
+ *
+ * Host code only: no CUDA headers.  The ops call the C-ABI of b200_sts.h.
+ *
+ * Lazy fusion.  A vector's value is an immutable, reference
+ * counted object that is either materialised (a device buffer) or DEFERRED
+ * ("the RHS operator applied to that other value").  An ARKRhsFn written for this
+ * vector does not launch anything: it calls N_VSetDeferredRhs_B200(f, op, y).  The
+ * next N_VLinearCombination / N_VLinearSum / N_VScale that consumes f launches ONE
+ * fused kernel (stencil + recurrence), so an STS stage makes one pass over HBM;
+ * N_VScale(1, x, z) only shares the value.  Any other consumer materialises first.
+ */
+#ifndef NVECTOR_B200_H
+#define NVECTOR_B200_H
+
+#include <sundials/sundials_nvector.h>
+
+#include "b200_sts.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* A deferred right-hand-side operator F(y).  `fused` must enqueue, on the context's
+   stream, one kernel (group) that computes
+       z = sum_k c[k] * T_k   (left to right),  T_k in { v[k], y, F(y) } per src[k]
+   and, if f_out != NULL, also stores F(y) there.  If wrms_w != NULL it may fuse
+   sum_i (z_i w_i)^2 into wrms_result (device) and set *wrms_done = 1.
+   y, v[k], z, f_out are device pointers of the vector's local length. */
+typedef struct B200RhsOp
+{
+  void* self;
+  int (*fused)(void* self, b200_ctx* ctx, const double* y, int nterms, const double* c,
+               const int* src, const double* const* v, double* z, double* f_out,
+               const double* wrms_w, double* wrms_result, int* wrms_done);
+} B200RhsOp;
+
+/* Create a vector: local_length entries on this rank's GPU, global_length overall
+   (N_VWrmsNorm divides by it, nvector_parallel.c:729; N_VGetLength returns it). */
+SUNDIALS_EXPORT N_Vector N_VNew_B200(b200_ctx* ctx, sunindextype local_length,
+                                     sunindextype global_length, SUNContext sunctx);
+
+SUNDIALS_EXPORT b200_ctx* N_VGetContext_B200(N_Vector v);
+SUNDIALS_EXPORT sunindextype N_VGetLocalLength_B200(N_Vector v);
+
+/* Read access to the (materialised) device data. */
+SUNDIALS_EXPORT const double* N_VGetDeviceArrayPointer_B200(N_Vector v);
+/* Give v a fresh, writable device buffer (previous value is dropped, not copied). */
+SUNDIALS_EXPORT double* N_VGetDeviceArrayPointerForWrite_B200(N_Vector v);
+/* Explicit host <-> device copies (n = local length). */
+SUNDIALS_EXPORT int N_VCopyFromHost_B200(N_Vector v, const double* host);
+SUNDIALS_EXPORT int N_VCopyToHost_B200(N_Vector v, double* host);
+
+/* Called from an ARKRhsFn: f := F(y), deferred.  op must outlive the vectors. */
+SUNDIALS_EXPORT int N_VSetDeferredRhs_B200(N_Vector f, const B200RhsOp* op, N_Vector y);
+/* 1 if v currently holds a deferred value (tests / diagnostics) */
+SUNDIALS_EXPORT int N_VIsDeferred_B200(N_Vector v);
+/* Turn lazy fusion off (every RHS materialises immediately) / on; default on. */
+SUNDIALS_EXPORT void N_VSetLazyFusion_B200(int on);
+
+/* statistics since process start: fused launches, aliased copies, device buffers */
+typedef struct B200VecStats
+{
+  long fused_launches;    /* stencil+combination kernels launched from the ops */
+  long plain_rhs_launches;/* deferred values materialised on their own */
+  long aliased_copies;    /* N_VScale(1,x,z) turned into a handle share */
+  long buffers_allocated; /* cudaMalloc'd vector buffers */
+  long wrms_fused;        /* WRMS norms answered from a fused partial */
+} B200VecStats;
+SUNDIALS_EXPORT void N_VGetStats_B200(B200VecStats* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
