@@ -40,7 +40,7 @@ endif
 
 $(LIB)/libb200sts.so: $(SRC)/b200_kernels.cu include/b200_sts.h
 	@mkdir -p $(LIB)
-	$(NVCC) $(NVFLAGS) -shared -Iinclude $< -o $@ -lnccl
+	$(NVCC) $(NVFLAGS) -shared -Iinclude $< -o $@ -ldl
 
 HOST_SRC := $(SRC)/nvector_b200.cpp $(SRC)/diffusion_b200.cpp
 $(LIB)/libb200sts_sundials.so: $(HOST_SRC) include/nvector_b200.h include/b200_diffusion2d.h include/b200_sts.h $(LIB)/libb200sts.so

@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- cell-updates/s of the explicit STS hot path (diffusion_2D, RKC, 16384^2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    torchrun ... bench.py --gpus N --steps K --warmup W        (one rank per GPU)
+
+Workload (BASELINE.json configs[2], SURVEY.md section 8d "C3 throughput"):
+    diffusion_2D --nx 16384 --ny 16384 --integrator rkc --fixedstep 1e-4
+    => rho = 1.01*8/dx^2, s = 92 RKC stages per step, one "step" = one LSRKStep time step
+       (92 stage evaluations + the closing RHS evaluation = 93 RHS evals).
+Weak scaling: every GPU owns a 16384 x 16384 block; the global grid is
+(16384*npx) x (16384*npy) with dims = MPI_Dims_create(N) (2->2x1, 4->2x2, 8->4x2) and the
+domain enlarged so dx, dy and therefore the stage count stay fixed.
+
+metric  cell-updates/s = RHS evaluations (counted by ARKODE) x global cells / device time.
+value   state resident in HBM, timed with CUDA events on the launching stream, max over ranks.
+e2e     every step: pinned-host state -> device (H2D), ARKodeReset, one time step, device -> pinned
+        host (D2H), through the public session API (b200_d2d_*), host wall clock.
+roofline dominant kernel = k_stage_march (fused stencil + 5-term RKC recurrence), 40 algorithmic
+        bytes per cell-update (4 FP64 reads + 1 write).
+"""
+import argparse
+import ctypes
+import importlib
+import json
+import os
+import re
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALG_BYTES_PER_UPDATE = 40.0
+H_FIXED = 1.0e-4
+XL, XU0, YL, YU0 = -3.141592653589793, 3.141592653589793, -6.0, 6.0
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def dims_create(n):
+    b, f = 1, 1
+    while f * f <= n:
+        if n % f == 0:
+            b = f
+        f += 1
+    return n // b, b
+
+
+def workload_args(local_n, npx, npy, method="rkc", base_n=None):
+    """Reference-style flags for a (local_n*npx) x (local_n*npy) grid whose spacing equals that of
+    the single-GPU base_n^2 grid on the default domain (so rho, hence the stage count, is fixed)."""
+    base_n = base_n or local_n
+    dx = (XU0 - XL) / (base_n - 1)
+    dy = (YU0 - YL) / (base_n - 1)
+    nx, ny = local_n * npx, local_n * npy
+    xu = XL + dx * (nx - 1)
+    yu = YL + dy * (ny - 1)
+    return ["--nx", str(nx), "--ny", str(ny), "--xu", repr(xu), "--yu", repr(yu),
+            "--integrator", method, "--fixedstep", repr(H_FIXED), "--tf", "1.0", "--nout", "1",
+            "--output", "0", "--npx", str(npx), "--npy", str(npy)]
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(int(float(s[0])) for s in self.samples if s[0].replace(".", "").isdigit())
+        mx = [int(float(s[1])) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(s[3 + k].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------ reference arm
+def parse_ref(out):
+    t = float(re.search(r"Total simulation time\s*=\s*([-+0-9.eE]+)", out).group(1))
+    evals = int(re.search(r"RHS fn evals\s*=\s*(\d+)", out).group(1))
+    return t, evals
+
+
+def run_reference_sample(nsteps, sample_n, cores, base_n=16384):
+    """The reference's own MPI CPU path (oracle/_ref/diffusion_2D_ref: unmodified sources +
+    the in-tree MPI shim) on `cores` ranks, on a sample_n^2 block of the workload (same dx, dy,
+    h => same 92 stages)."""
+    binary = os.path.join(ROOT, "oracle", "_ref", "diffusion_2D_ref")
+    if not os.path.exists(binary):
+        raise RuntimeError("oracle/_ref/diffusion_2D_ref missing (built by __graft_entry__.build())")
+    args = workload_args(sample_n, 1, 1, base_n=base_n)
+    args[args.index("--tf") + 1] = repr(nsteps * H_FIXED)
+    args = [a for a in args]
+    # let the reference pick its own process grid for `cores` ranks
+    for flag in ("--npx", "--npy"):
+        k = args.index(flag)
+        del args[k:k + 2]
+    env = dict(os.environ, MPISHIM_NP=str(cores))
+    out = subprocess.run([binary] + args, env=env, capture_output=True, text=True, timeout=3000).stdout
+    t, evals = parse_ref(out)
+    return evals * sample_n * sample_n / t, t, evals
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    ranks = 1
+    while ranks * 2 <= min(cores, 64):
+        ranks *= 2
+    sample_n = 4096 if ranks >= 8 else 2048
+    if args.warmup > 0:
+        run_reference_sample(1, sample_n, ranks)
+    t0 = time.time()
+    value, t, evals = run_reference_sample(max(args.steps, 1), sample_n, ranks)
+    npx, npy = dims_create(args.gpus)
+    sample = ("%d^2 block of the workload grid (same dx, dy, h=1e-4 => 92 RKC stages/step), %d steps, "
+              "%d shared-memory MPI ranks of the unmodified reference build" % (sample_n, max(args.steps, 1), ranks))
+    line = {
+        "impl": "reference", "metric": "cell-updates/s (RHS evals x cells / s), diffusion_2D 16384^2 RKC",
+        "value": value, "unit": "cell-updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "diffusion_2D 16384x16384 per GPU, LSRKStep RKC, fixedstep 1e-4 (92 stages/step)",
+                   "global_grid": [16384 * npx, 16384 * npy], "parallelism": "%dx%d blocks" % (npx, npy)},
+        "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": ranks, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.time() - t0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--local-n", type=int, default=16384, help="per-GPU block edge (default: the headline 16384)")
+    ap.add_argument("--method", default="rkc")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
+    b200 = importlib.import_module("ceda-demonstrations_b200")
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d does not match WORLD_SIZE %d" % (args.gpus, world))
+    torch.cuda.set_device(local_rank)
+    dist = None
+    nccl_id = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.tensor(list(b200.nccl_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(idt, 0)
+        nccl_id = bytes(idt.cpu().tolist())
+
+    npx, npy = dims_create(world)
+    n = args.local_n
+    wargs = workload_args(n, npx, npy, method=args.method, base_n=n)
+    prob = b200.Diffusion2D(wargs, rank=rank, nranks=world, nccl_id=nccl_id, device=local_rank)
+    ncell_global = (n * npx) * (n * npy)
+    ncell_local = n * n
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: state resident in HBM -------------------------------------------------------
+    prob.step(max(args.warmup, 3))
+    barrier()
+    s0 = prob.stats()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    prob.step(args.steps)
+    ev1.record()
+    barrier()
+    sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    s1 = prob.stats()
+    evals = s1["rhs_evals"] - s0["rhs_evals"]
+    fused = s1["fused_launches"] - s0["fused_launches"]
+    launches = s1["kernel_launches"] - s0["kernel_launches"]
+    tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_max = float(tms.item())
+    value = evals * ncell_global / (ms_max * 1e-3)
+
+    # ---- e2e: host buffers, H2D + step + D2H every step ---------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        h_in = torch.empty(ncell_local, dtype=torch.float64, pin_memory=True)
+        h_out = torch.empty(ncell_local, dtype=torch.float64, pin_memory=True)
+        prob.get_state(h_in)
+        e_s0 = prob.stats()
+        t_cur = e_s0["t"]
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            prob.set_state(h_in, t_cur)  # H2D + ARKodeReset
+            prob.step(1)
+            prob.get_state(h_out)  # D2H (synchronises)
+            h_in, h_out = h_out, h_in
+            t_cur += H_FIXED
+        barrier()
+        dt = time.perf_counter() - t0
+        e_s1 = prob.stats()
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e_evals = e_s1["rhs_evals"] - e_s0["rhs_evals"]
+        e2e = {"value": e_evals * ncell_global / float(tt.item()), "unit": "cell-updates/s",
+               "h2d_bytes_per_step": 8 * ncell_local * world, "d2h_bytes_per_step": 8 * ncell_local * world,
+               "ms_per_step": 1e3 * float(tt.item()) / args.steps}
+        del h_in, h_out
+
+    stats_final = prob.stats()
+    prob.close()
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (fused stage kernel) ----------------------------------
+    peak, peak_src = measured_peak()
+    # every fused launch updates every local cell once; avg duration = timed region / launches
+    # (an upper bound on the kernel's own duration: the few per-step vector kernels are inside)
+    avg_launch_s = (ms_max * 1e-3) / max(fused, 1)
+    achieved = ALG_BYTES_PER_UPDATE * ncell_local / avg_launch_s / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "stage_kernel_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            with open(tpath) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch_16384")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "kernel": "k_stage_march<5,false>",
+                "alg_bytes_per_cell_update": ALG_BYTES_PER_UPDATE, "launches_timed": fused,
+                "frac_of_nominal_8TBs": achieved / 8000.0}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = host_cores()
+        ranks = 1
+        while ranks * 2 <= min(cores, 64):
+            ranks *= 2
+        try:
+            sample_n = 2048
+            v, t, ev = run_reference_sample(1, sample_n, ranks)
+            cpu_baseline = {"value": v, "unit": "cell-updates/s", "cores": ranks, "kind": "reference",
+                            "sample": "%d^2 block of the workload (same dx, dy, h => 92 RKC stages), 1 step = %d RHS evals, "
+                                      "%d shared-memory MPI ranks, %.1f s" % (sample_n, ev, ranks, t)}
+        except Exception as exc:  # the reference binary is test infrastructure; report, do not hide
+            cpu_baseline = {"value": None, "unit": "cell-updates/s", "cores": 0, "kind": "reference",
+                            "sample": "unavailable: %s" % exc}
+
+    line = {
+        "metric": "cell-updates/s (RHS evals x cells / s), diffusion_2D 16384^2 RKC",
+        "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "diffusion_2D %dx%d per GPU, LSRKStep %s, fixedstep 1e-4 (%d stages/step)"
+                               % (n, n, args.method.upper(), stats_final["max_stages"]),
+                   "global_grid": [n * npx, n * npy], "parallelism": "%dx%d blocks, NCCL halo exchange" % (npx, npy),
+                   "l2_note": "per-stage working set %.1f GiB >> 126 MB L2 (inputs larger than L2, no flush needed)"
+                              % (5 * 8 * ncell_local / 2**30),
+                   "rhs_evals_timed": evals},
+        "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "clocks": sampler.summary(),
+        "achieved_hbm_gbs_per_gpu": value * ALG_BYTES_PER_UPDATE / 1e9 / world,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

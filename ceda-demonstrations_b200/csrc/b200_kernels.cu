@@ -16,7 +16,8 @@
 //   adr callbacks      adr/advection_diffusion_reaction_2d.cpp:1406-1520
 
 #include <cuda_runtime.h>
-#include <nccl.h>
+#include <dlfcn.h>
+#include <nccl.h> // types only: the library is bound with dlopen (see nccl_api below)
 
 #include <atomic>
 #include <cstdint>
@@ -71,6 +72,7 @@ extern "C" uint64_t b200_launch_count(void) { return g_launches.load(); }
 
 // -------------------------------------------------------------------- context
 static const int kMaxPartials = 1 << 18;
+static ncclResult_t (*g_nccl_destroy)(ncclComm_t) = nullptr; // set once NCCL is bound
 
 struct b200_ctx
 {
@@ -123,7 +125,7 @@ extern "C" int b200_ctx_destroy(b200_ctx* c)
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   cudaStreamSynchronize(c->comm_stream);
-  if (c->comm) ncclCommDestroy(c->comm);
+  if (c->comm && g_nccl_destroy) g_nccl_destroy(c->comm);
   cudaFree(c->partials);
   cudaFree(c->ticket);
   cudaFree(c->dev_result);
@@ -696,7 +698,19 @@ __global__ void __launch_bounds__(kThreads) k_stage_ring(const StageArgs a)
 // x in registers, so every x row is loaded from L2/HBM once per block.  West/east
 // neighbours come from warp shuffles; only lanes 0 / 31 (and the strip ends) issue
 // an extra scalar load.  Per cell-update: 4 x 8 B streamed in + 8 B out.
-template <int NT, bool HAS_RED>
+//
+// The term pattern (which of the NT terms is a vector / the stencil input / L(x))
+// is a template parameter for the sequences LSRKStep actually issues, so the row
+// loop carries no dispatch; PAT_RUNTIME keeps a fully general fallback.  All
+// addresses are running pointers (one add per row).
+#define PAT_RUNTIME 0xffffffffu
+#define PAT1(a) (uint32_t)(a)
+#define PAT2(a, b) (uint32_t)((a) | ((b) << 2))
+#define PAT3(a, b, c) (uint32_t)((a) | ((b) << 2) | ((c) << 4))
+#define PAT4(a, b, c, d) (uint32_t)((a) | ((b) << 2) | ((c) << 4) | ((d) << 6))
+#define PAT5(a, b, c, d, e) (uint32_t)((a) | ((b) << 2) | ((c) << 4) | ((d) << 6) | ((e) << 8))
+
+template <int NT, uint32_t PAT, int REGION, bool HAS_RED>
 __global__ void __launch_bounds__(kThreads, 4) k_stage_march(const StageArgs a)
 {
   __shared__ double smem[32];
@@ -705,68 +719,81 @@ __global__ void __launch_bounds__(kThreads, 4) k_stage_march(const StageArgs a)
   const int64_t i0  = 2 * ((int64_t)blockIdx.x * kThreads + threadIdx.x);
   const bool active = (i0 < nx);
   const int64_t ic  = active ? i0 : 0; // clamp so address arithmetic stays in range
-  int64_t j0        = (int64_t)blockIdx.y * a.rows;
-  int64_t j1        = j0 + a.rows;
-  if (j1 > ny) j1 = ny;
-  if (a.region == 2)
+  int j0            = (int)blockIdx.y * a.rows; // ny < 2^31 (checked by the launcher)
+  int j1            = j0 + a.rows;
+  if (j1 > (int)ny) j1 = (int)ny;
+  if (REGION == 2)
   {
     if (j0 < 1) j0 = 1;
-    if (j1 > ny - 1) j1 = ny - 1;
+    if (j1 > (int)ny - 1) j1 = (int)ny - 1;
   }
+  const int jlast = (int)ny - 1;
+  const int nt = (PAT == PAT_RUNTIME) ? a.t.n : NT;
+#define SRC_OF(k) ((PAT == PAT_RUNTIME) ? a.t.src[k] : (int)((PAT >> (2 * (k))) & 3u))
 
-  const bool wedge = (i0 == 0);          // west neighbour is outside the field
-  const bool eedge = (i0 + 2 >= nx);     // east neighbour is outside the field
+  const bool wedge = (i0 == 0);      // west neighbour lies outside the field
+  const bool eedge = (i0 + 2 >= nx); // east neighbour lies outside the field
   const bool wload = active && (lane == 0 || wedge);
   const bool eload = active && (lane == 31 || eedge);
-  const bool skip_halo_cols = (a.region == 2);
 
+  // x-direction face coefficients of my two cells, and their sums (diffusion.cpp:48)
   double cw0 = 0, cw1 = 0, ce0 = 0, ce1 = 0;
   if (active)
   {
-    double2 w = ld_keep2(a.cxw + ic), e = ld_keep2(a.cxe + ic);
+    const double2 w = ld_keep2(a.cxw + ic), e = ld_keep2(a.cxe + ic);
     cw0 = w.x; cw1 = w.y; ce0 = e.x; ce1 = e.y;
   }
+  const double sx0 = DADD(cw0, ce0), sx1 = DADD(cw1, ce1);
 
-  // row pointer with periodic wrap / halo rows
-  auto rowp = [&](int64_t j) -> const double* {
-    if (j < 0) return a.hs ? a.hs : a.x + (ny - 1) * nx;
-    if (j >= ny) return a.hn ? a.hn : a.x;
-    return a.x + j * nx;
-  };
+  // running pointers: current x row, west/east edge values, and the element offset
+  int64_t off        = (int64_t)j0 * nx + ic;
+  const double* xrow = a.x + off;
+  const double* wptr;
+  const double* eptr;
+  int64_t wstep = nx, estep = nx;
+  if (!wedge) wptr = xrow - 1;
+  else if (a.hw) { wptr = a.hw + j0; wstep = 1; }
+  else wptr = xrow + (nx - 1);
+  if (!eedge) eptr = xrow + 2;
+  else if (a.he) { eptr = a.he + j0; estep = 1; }
+  else eptr = a.x + (int64_t)j0 * nx;
+  const bool wvalid = wload && !(REGION == 2 && wedge);
+  const bool evalid = eload && !(REGION == 2 && eedge);
 
   double2 xm = make_double2(0, 0), xc = make_double2(0, 0);
   if (active && j0 < j1)
   {
-    xm = ld_keep2(rowp(j0 - 1) + ic);
-    xc = ld_keep2(rowp(j0) + ic);
+    const double* below = (j0 > 0) ? (xrow - nx) : (a.hs ? a.hs + ic : a.x + (ny - 1) * nx + ic);
+    xm = ld_keep2(below);
+    xc = ld_keep2(xrow);
   }
   double wr = 0.0;
+  // loop-invariant switches (all uniform or per-thread constants)
+  const bool has_f  = (a.f_out != nullptr);
+  const bool do_sw  = (REGION == 0) && a.send_w && wedge;
+  const bool do_se  = (REGION == 0) && a.send_e && eedge;
+  const bool do_ss  = (REGION == 0) && a.send_s && (j0 == 0);
+  const bool do_sn  = (REGION == 0) && a.send_n && (j1 == (int)ny);
+  const double* wrapn = a.hn ? a.hn + ic : a.x + ic; // row "ny": north halo or periodic wrap
 
 #pragma unroll 1
-  for (int64_t j = j0; j < j1; j++)
+  for (int j = j0; j < j1; j++)
   {
-    const int64_t id = j * nx + ic;
     double2 xp = make_double2(0, 0);
     double uw_edge = 0.0, ue_edge = 0.0;
     double2 tv[NT];
     if (active)
     {
-      xp = ld_keep2(rowp(j + 1) + ic);
-      if (wload)
-      {
-        if (!wedge) uw_edge = a.x[id - 1];
-        else if (!skip_halo_cols) uw_edge = a.hw ? a.hw[j] : a.x[j * nx + nx - 1];
-      }
-      if (eload)
-      {
-        if (!eedge) ue_edge = a.x[id + 2];
-        else if (!skip_halo_cols) ue_edge = a.he ? a.he[j] : a.x[j * nx];
-      }
+      const double* above = (j < jlast) ? (xrow + nx) : wrapn;
+      xp = ld_keep2(above);
+      if (wvalid) uw_edge = *wptr;
+      if (evalid) ue_edge = *eptr;
 #pragma unroll
       for (int k = 0; k < NT; k++)
-        if (a.t.src[k] == B200_SRC_VECTOR) tv[k] = ld_stream2(a.t.v[k] + id);
+        if (k < nt && SRC_OF(k) == B200_SRC_VECTOR) tv[k] = ld_stream2(a.t.v[k] + off);
     }
     const double dys = a.cys[j], dyn = a.cyn[j];
+    const double sy  = DADD(dys, dyn);
     // west of cell0 = previous lane's cell1 ; east of cell1 = next lane's cell0
     double uw0 = __shfl_up_sync(0xffffffffu, xc.y, 1);
     double ue1 = __shfl_down_sync(0xffffffffu, xc.x, 1);
@@ -774,58 +801,109 @@ __global__ void __launch_bounds__(kThreads, 4) k_stage_march(const StageArgs a)
     if (eload) ue1 = ue_edge;
     if (active)
     {
-      const double L0 = lap5(cw0, ce0, dys, dyn, xc.x, uw0, xc.y, xm.x, xp.x);
-      const double L1 = lap5(cw1, ce1, dys, dyn, xc.y, xc.x, ue1, xm.y, xp.y);
-      double2 acc     = make_double2(0, 0);
+      // diffusion.cpp:48-53, same association: ((((dc*uc + Dxw*uw) + Dxe*ue) + Dys*us) + Dyn*un)
+      double L0 = DMUL(-DADD(sx0, sy), xc.x);
+      double L1 = DMUL(-DADD(sx1, sy), xc.y);
+      L0 = DADD(L0, DMUL(cw0, uw0));  L1 = DADD(L1, DMUL(cw1, xc.x));
+      L0 = DADD(L0, DMUL(ce0, xc.y)); L1 = DADD(L1, DMUL(ce1, ue1));
+      L0 = DADD(L0, DMUL(dys, xm.x)); L1 = DADD(L1, DMUL(dys, xm.y));
+      L0 = DADD(L0, DMUL(dyn, xp.x)); L1 = DADD(L1, DMUL(dyn, xp.y));
+      L0 = DADD(0.0, L0);             L1 = DADD(0.0, L1);
+      double2 acc = make_double2(0, 0);
 #pragma unroll
       for (int k = 0; k < NT; k++)
+        if (k < nt)
         {
           double2 v;
-          if (a.t.src[k] == B200_SRC_STENCIL) v = make_double2(L0, L1);
-          else if (a.t.src[k] == B200_SRC_CENTRE) v = xc;
+          const int sk = SRC_OF(k);
+          if (sk == B200_SRC_STENCIL) v = make_double2(L0, L1);
+          else if (sk == B200_SRC_CENTRE) v = xc;
           else v = tv[k];
           const double p0 = DMUL(a.t.c[k], v.x), p1 = DMUL(a.t.c[k], v.y);
           acc.x = (k == 0) ? p0 : DADD(acc.x, p0);
           acc.y = (k == 0) ? p1 : DADD(acc.y, p1);
         }
-      bool st0 = true, st1 = true;
-      if (a.region == 2)
-      {
-        st0 = !wedge;
-        st1 = !eedge;
+      double* zp = a.z + off;
+      if (REGION == 2 && (wedge || eedge))
+      { // ring cells belong to the ring kernel
+        if (!wedge) zp[0] = acc.x;
+        if (!eedge) zp[1] = acc.y;
+        if (has_f)
+        {
+          if (!wedge) a.f_out[off] = L0;
+          if (!eedge) a.f_out[off + 1] = L1;
+        }
       }
-      if (st0 && st1) *reinterpret_cast<double2*>(a.z + id) = acc;
-      else if (st0) a.z[id] = acc.x;
-      else if (st1) a.z[id + 1] = acc.y;
-      if (a.f_out)
+      else
       {
-        if (st0 && st1) *reinterpret_cast<double2*>(a.f_out + id) = make_double2(L0, L1);
-        else if (st0) a.f_out[id] = L0;
-        else if (st1) a.f_out[id + 1] = L1;
+        *reinterpret_cast<double2*>(zp) = acc;
+        if (has_f) *reinterpret_cast<double2*>(a.f_out + off) = make_double2(L0, L1);
       }
-      if (a.region == 0)
+      if (REGION == 0)
       {
-        if (a.send_w && wedge) a.send_w[j] = acc.x;
-        if (a.send_e && eedge) a.send_e[j] = acc.y;
-        if (a.send_s && j == 0) *reinterpret_cast<double2*>(a.send_s + ic) = acc;
-        if (a.send_n && j == ny - 1) *reinterpret_cast<double2*>(a.send_n + ic) = acc;
+        if (do_sw) a.send_w[j] = acc.x;
+        if (do_se) a.send_e[j] = acc.y;
+        if (do_ss && j == 0) *reinterpret_cast<double2*>(a.send_s + ic) = acc;
+        if (do_sn && j == jlast) *reinterpret_cast<double2*>(a.send_n + ic) = acc;
       }
       if (HAS_RED)
       {
-        const double2 w = ld_stream2(a.rw + id);
+        const double2 w = ld_stream2(a.rw + off);
         const double q0 = DMUL(acc.x, w.x), q1 = DMUL(acc.y, w.y);
         wr = DADD(wr, DADD(DMUL(q0, q0), DMUL(q1, q1)));
       }
     }
     xm = xc;
     xc = xp;
+    xrow += nx;
+    off += nx;
+    wptr += wstep;
+    eptr += estep;
   }
+#undef SRC_OF
   if (HAS_RED)
   {
     double v = block_reduce<RED_SUM>(wr, smem);
     grid_finish<RED_SUM>(v, gridDim.x * gridDim.y, blockIdx.y * gridDim.x + blockIdx.x,
                          a.partials, a.ticket, a.result, smem);
   }
+}
+
+template <int NT, uint32_t PAT>
+static void launch_march(const StageArgs& a, dim3 grid, cudaStream_t st)
+{
+  if (a.region == 2) k_stage_march<NT, PAT, 2, false><<<grid, kThreads, 0, st>>>(a);
+  else if (a.rw) k_stage_march<NT, PAT, 0, true><<<grid, kThreads, 0, st>>>(a);
+  else k_stage_march<NT, PAT, 0, false><<<grid, kThreads, 0, st>>>(a);
+}
+
+// pick the compiled pattern for the term sequence, else the general kernel
+static void dispatch_march(const StageArgs& a, dim3 grid, cudaStream_t st)
+{
+  uint32_t pat = 0;
+  for (int k = 0; k < a.t.n; k++) pat |= (uint32_t)a.t.src[k] << (2 * k);
+  const int V = B200_SRC_VECTOR, C = B200_SRC_CENTRE, S = B200_SRC_STENCIL;
+  switch (a.t.n)
+  {
+  case 1:
+    if (pat == PAT1(S)) return launch_march<1, PAT1(S)>(a, grid, st);                       // f = L(x)
+    break;
+  case 2:
+    if (pat == PAT2(C, S)) return launch_march<2, PAT2(C, S)>(a, grid, st);                 // y + c L(y): SSP stage, STS stage 1
+    if (pat == PAT2(V, S)) return launch_march<2, PAT2(V, S)>(a, grid, st);
+    if (pat == PAT2(S, V)) return launch_march<2, PAT2(S, V)>(a, grid, st);                 // DQ: sig*v + y style sums
+    break;
+  case 3:
+    if (pat == PAT3(C, V, S)) return launch_march<3, PAT3(C, V, S)>(a, grid, st);           // SSP closing LC3
+    break;
+  case 4:
+    if (pat == PAT4(V, C, V, S)) return launch_march<4, PAT4(V, C, V, S)>(a, grid, st);     // STS embedding LC4
+    break;
+  case 5:
+    if (pat == PAT5(S, V, V, C, V)) return launch_march<5, PAT5(S, V, V, C, V)>(a, grid, st); // RKC/RKL stage
+    break;
+  }
+  return launch_march<B200_MAX_TERMS, PAT_RUNTIME>(a, grid, st);
 }
 
 static int g_rows_per_block = 32;
@@ -897,6 +975,7 @@ extern "C" int b200_stencil_lincomb(b200_ctx* c, const b200_stencil_geom* g, con
     a.rows        = g_rows_per_block;
     int64_t gx    = (a.nx / 2 + kThreads - 1) / kThreads;
     int64_t gy    = (a.ny + a.rows - 1) / a.rows;
+    if (a.ny >= (int64_t)1 << 31) return fail("b200_stencil_lincomb: ny must be below 2^31");
     if (gy > 65535)
     {
       a.rows = (int)((a.ny + 65534) / 65535);
@@ -904,17 +983,7 @@ extern "C" int b200_stencil_lincomb(b200_ctx* c, const b200_stencil_geom* g, con
     }
     if (a.rw && gx * gy > kMaxPartials) return fail("b200_stencil_lincomb: too many blocks for fused WRMS");
     dim3 grid((unsigned)gx, (unsigned)gy);
-#define MARCH_CASE(N)                                                          \
-  case N:                                                                      \
-    if (a.rw) k_stage_march<N, true><<<grid, kThreads, 0, c->stream>>>(a);     \
-    else k_stage_march<N, false><<<grid, kThreads, 0, c->stream>>>(a);         \
-    break;
-    switch (nterms)
-    {
-      MARCH_CASE(1) MARCH_CASE(2) MARCH_CASE(3) MARCH_CASE(4)
-      MARCH_CASE(5) MARCH_CASE(6) MARCH_CASE(7) MARCH_CASE(8)
-    }
-#undef MARCH_CASE
+    dispatch_march(a, grid, c->stream);
     LAUNCH_CHECK();
   }
   else
@@ -1116,8 +1185,59 @@ extern "C" int b200_adr_diffusion_lincomb(b200_ctx* c, const b200_adr_params* p,
 }
 
 // --------------------------------------------------------------------- NCCL
+// NCCL is resolved at first use with dlopen("libnccl.so.2") instead of being a link-time
+// dependency: inside a Python process torch has usually loaded its own bundled NCCL
+// already (same SONAME -> the same handle is returned), in the standalone C++ driver
+// the system library is used.  Either way one NCCL per process.
+struct NcclApi
+{
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+  ncclResult_t (*CommDestroy)(ncclComm_t);
+  const char* (*GetErrorString)(ncclResult_t);
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*GroupStart)();
+  ncclResult_t (*GroupEnd)();
+  bool ok = false;
+};
+static NcclApi g_nccl;
+
+static int nccl_load()
+{
+  if (g_nccl.ok) return 0;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return fail("cannot dlopen libnccl.so.2 (needed for multi-GPU runs)");
+#define NCCL_SYM(field, name)                                  \
+  *(void**)(&g_nccl.field) = dlsym(h, name);                   \
+  if (!g_nccl.field) return fail("libnccl: missing symbol " name);
+  NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+  NCCL_SYM(CommInitRank, "ncclCommInitRank")
+  NCCL_SYM(CommDestroy, "ncclCommDestroy")
+  NCCL_SYM(GetErrorString, "ncclGetErrorString")
+  NCCL_SYM(AllReduce, "ncclAllReduce")
+  NCCL_SYM(Send, "ncclSend")
+  NCCL_SYM(Recv, "ncclRecv")
+  NCCL_SYM(GroupStart, "ncclGroupStart")
+  NCCL_SYM(GroupEnd, "ncclGroupEnd")
+#undef NCCL_SYM
+  g_nccl_destroy = g_nccl.CommDestroy;
+  g_nccl.ok = true;
+  return 0;
+}
+#define ncclGetUniqueId g_nccl.GetUniqueId
+#define ncclCommInitRank g_nccl.CommInitRank
+#define ncclGetErrorString g_nccl.GetErrorString
+#define ncclAllReduce g_nccl.AllReduce
+#define ncclSend g_nccl.Send
+#define ncclRecv g_nccl.Recv
+#define ncclGroupStart g_nccl.GroupStart
+#define ncclGroupEnd g_nccl.GroupEnd
 extern "C" int b200_comm_unique_id(unsigned char id[128])
 {
+  if (nccl_load()) return -1;
   ncclUniqueId u;
   NCCL_TRY(ncclGetUniqueId(&u));
   static_assert(sizeof(u) == 128, "ncclUniqueId is 128 bytes");
@@ -1127,6 +1247,7 @@ extern "C" int b200_comm_unique_id(unsigned char id[128])
 
 extern "C" int b200_comm_init(b200_ctx* c, int rank, int nranks, const unsigned char id[128])
 {
+  if (nccl_load()) return -1;
   CU_TRY(cudaSetDevice(c->device));
   ncclUniqueId u;
   memcpy(&u, id, 128);
