@@ -906,7 +906,7 @@ static void dispatch_march(const StageArgs& a, dim3 grid, cudaStream_t st)
   return launch_march<B200_MAX_TERMS, PAT_RUNTIME>(a, grid, st);
 }
 
-static int g_rows_per_block = 32;
+static int g_rows_per_block = 8; // measured best on B200 at 4096^2 and 16384^2 (profiles/)
 
 extern "C" int b200_set_rows_per_block(int r)
 {

@@ -405,6 +405,8 @@ struct b200_d2d
   double t = 0.0, t2 = 0.0, errtot = 0.0, evolve_seconds = 0.0;
   bool impl = false, expl = false, sts = false;
   FILE* uout = nullptr;
+  B200VecStats vs0{};          // process-wide counters at creation (stats are reported per session)
+  uint64_t launches0 = 0;
 };
 
 #define CHK(call, name)                                                       \
@@ -551,6 +553,8 @@ extern "C" int b200_d2d_create(int argc, const char* const* argv, int rank, int 
                                const unsigned char* nccl_id, int device, void* stream, b200_d2d** out)
 {
   b200_d2d* p = new b200_d2d();
+  N_VGetStats_B200(&p->vs0);
+  p->launches0 = b200_launch_count();
   std::vector<std::string> args(argv, argv + argc);
   if (parse_args(args, p->ud, p->uo, rank == 0)) { delete p; return -1; }
   if (p->ud.setup(rank, nranks)) { delete p; return -1; }
@@ -668,10 +672,12 @@ extern "C" int b200_d2d_get_stats(b200_d2d* p, b200_d2d_stats* s)
   s->evolve_seconds = p->evolve_seconds;
   B200VecStats vs;
   N_VGetStats_B200(&vs);
-  s->fused_launches = vs.fused_launches; s->plain_rhs_launches = vs.plain_rhs_launches;
-  s->aliased_copies = vs.aliased_copies; s->wrms_fused = vs.wrms_fused;
-  s->buffers_allocated = vs.buffers_allocated;
-  s->kernel_launches = b200_launch_count();
+  s->fused_launches     = vs.fused_launches - p->vs0.fused_launches;
+  s->plain_rhs_launches = vs.plain_rhs_launches - p->vs0.plain_rhs_launches;
+  s->aliased_copies     = vs.aliased_copies - p->vs0.aliased_copies;
+  s->wrms_fused         = vs.wrms_fused - p->vs0.wrms_fused;
+  s->buffers_allocated  = vs.buffers_allocated - p->vs0.buffers_allocated;
+  s->kernel_launches    = b200_launch_count() - p->launches0;
   s->nx = p->ud.nx; s->ny = p->ud.ny; s->nx_loc = p->ud.nx_loc; s->ny_loc = p->ud.ny_loc;
   s->is = p->ud.is; s->js = p->ud.js; s->npx = p->ud.npx; s->npy = p->ud.npy;
   s->rank = p->ud.myid_c; s->nranks = p->ud.np;

@@ -143,6 +143,10 @@ int b200_stencil_lincomb(b200_ctx* ctx, const b200_stencil_geom* g,
                          const int* src, const double* const* v, double* z,
                          const b200_stage_extras* extras, int region);
 
+/* Tuning knob: rows of the sub-domain each thread block of the fused kernel marches over
+   (default 8).  Results do not depend on it. */
+int b200_set_rows_per_block(int rows);
+
 /* Standalone halo pack of a materialised field (buffers.cpp:20-43). */
 int b200_pack_halo(b200_ctx* ctx, const double* u, int64_t nx, int64_t ny,
                    double* send_w, double* send_e, double* send_s, double* send_n);

@@ -1,0 +1,128 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ (run HERE, where /root/reference exists).
+
+Two sources, both the reference's own:
+
+1. SUNDIALS' committed known-answer logs for the LSRKStep stage recurrences
+   /root/reference/deps/sundials/test/unit_tests/logging/test_logging_arkode_lsrkstep_lvl5_{0..3}.out
+   (RKC2, RKL2, SSP(s,2), SSP(s,3) on the scalar Prothero-Robinson problem prv.hpp).  Only the
+   numbers are extracted -> lsrk_logging_golden.json.
+
+2. Outputs of the UNMODIFIED reference driver compiled into oracle/_ref/diffusion_2D_ref
+   (make -C oracle ref): integrator statistics and the final state (the reference's own
+   `--output 2` text, 16 significant digits) for a handful of small configurations
+   -> d2d_<name>.json / d2d_<name>.npy.   The np=1 vs np=4 spread of the reference itself is
+   recorded too: it is the reference's own sensitivity to the reduction order.
+
+    python tests/golden/make_golden.py
+"""
+import json
+import os
+import re
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "scripts"))
+import compare_runs as cr  # noqa: E402
+
+LOGDIR = "/root/reference/deps/sundials/test/unit_tests/logging"
+
+# name -> reference command line (all --nout 1 --output 2)
+D2D_CASES = {
+    # BASELINE.json configs[0]: the reference's own CPU-runnable case
+    "c1_rkc_128": ["--nx", "128", "--ny", "128", "--integrator", "rkc", "--tf", "1"],
+    "rkc_fixed_aniso_inhom_96x64": ["--nx", "96", "--ny", "64", "--kx", "1.0", "--ky", "0.5", "--inhomogeneous",
+                                    "--integrator", "rkc", "--fixedstep", "0.0009765625", "--tf", "0.00390625"],
+    "rkl_fixed_aniso_inhom_96x64": ["--nx", "96", "--ny", "64", "--kx", "1.0", "--ky", "0.1", "--inhomogeneous",
+                                    "--integrator", "rkl", "--fixedstep", "0.0009765625", "--tf", "0.0078125"],
+    "rkl_adaptive_inhom_64": ["--nx", "64", "--ny", "64", "--kx", "1.0", "--ky", "0.1", "--inhomogeneous",
+                              "--integrator", "rkl", "--tf", "0.1"],
+    "rkl_internaleig_64": ["--nx", "64", "--ny", "64", "--kx", "1.0", "--ky", "0.1", "--inhomogeneous",
+                           "--integrator", "rkl", "--internaleig", "--tf", "0.1"],
+    "rkc_odd_75x51": ["--nx", "75", "--ny", "51", "--integrator", "rkc", "--tf", "0.1"],
+    "ssp2_fixed_64": ["--nx", "64", "--ny", "64", "--integrator", "erk", "--order", "-2",
+                      "--fixedstep", "0.0001220703125", "--tf", "0.0009765625"],
+    "ssp3_fixed_64": ["--nx", "64", "--ny", "64", "--integrator", "erk", "--order", "-3",
+                      "--fixedstep", "0.0001220703125", "--tf", "0.0009765625"],
+    "ssp104_fixed_64": ["--nx", "64", "--ny", "64", "--integrator", "erk", "--order", "-4",
+                        "--fixedstep", "0.0001220703125", "--tf", "0.0009765625"],
+    "ssp104_adaptive_64": ["--nx", "64", "--ny", "64", "--integrator", "erk", "--order", "-4", "--tf", "0.05"],
+    "erk3_adaptive_64": ["--nx", "64", "--ny", "64", "--integrator", "erk", "--order", "3", "--tf", "0.02"],
+    "dirk3_pcg_64": ["--nx", "64", "--ny", "64", "--integrator", "dirk", "--order", "3", "--tf", "0.1"],
+    "dirk2_pcg_inhom_noprec_48": ["--nx", "48", "--ny", "48", "--inhomogeneous", "--integrator", "dirk",
+                                  "--order", "2", "--noprec", "--tf", "0.05"],
+}
+
+
+def parse_lsrk_log(path):
+    steps = []
+    cur = None
+    lines = open(path).read().split("\n")
+    k = 0
+
+    def nextval():
+        return float(lines[k + 1].strip())
+
+    while k < len(lines):
+        ln = lines[k]
+        m = re.search(r"begin-step-attempt\] step = (\d+), tn = ([-+0-9.eE]+), h = ([-+0-9.eE]+)", ln)
+        if m:
+            cur = {"step": int(m.group(1)), "tn": float(m.group(2)), "h": float(m.group(3)), "F": {}, "stages": None,
+                   "spectral_radius": None}
+            steps.append(cur)
+        m = re.search(r"spectral radius = ([-+0-9.eE]+), num stages = (\d+)", ln)
+        if m and cur is not None:
+            cur["spectral_radius"] = float(m.group(1))
+            cur["stages"] = int(m.group(2))
+        if cur is not None:
+            if "z_0(:) =" in ln:
+                cur["z0"] = nextval()
+            m = re.search(r"F_(\d+)\(:\) =", ln)
+            if m:
+                cur["F"][int(m.group(1))] = nextval()
+            if "F_n(:) =" in ln:
+                cur["Fn"] = nextval()
+            if "ycur(:) =" in ln:
+                cur["ycur"] = nextval()
+            m = re.search(r"end-step-attempt\] status = success, dsm = ([-+0-9.eE]+)", ln)
+            if m:
+                cur["dsm"] = float(m.group(1))
+        k += 1
+    for s in steps:
+        s["F"] = [s["F"][i] for i in sorted(s["F"])]
+    return steps
+
+
+def main():
+    out = {"source": "deps/sundials/test/unit_tests/logging/test_logging_arkode_lsrkstep_lvl5_{0..3}.out",
+           "problem": "prv.hpp: y' = L(t)(y - atan t) + 1/(1+t^2), L(t) = -1000 - 10 cos((10-t)/10 pi); dom_eig = L(t)",
+           "rtol": 1e-6, "atol": 1e-10, "methods": {}}
+    for idx, name in enumerate(["rkc", "rkl", "ssps2", "ssps3"]):
+        out["methods"][name] = parse_lsrk_log(os.path.join(LOGDIR, "test_logging_arkode_lsrkstep_lvl5_%d.out" % idx))
+    with open(os.path.join(HERE, "lsrk_logging_golden.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("lsrk_logging_golden.json:", {k: len(v) for k, v in out["methods"].items()})
+
+    for name, args in D2D_CASES.items():
+        full = args + ["--nout", "1", "--output", "2"]
+        nx, ny = int(cr.get_arg(full, "--nx", 64)), int(cr.get_arg(full, "--ny", 64))
+        wd, text = cr.run(cr.REF_BIN, full, 1)
+        t, u = cr.read_solution(wd, nx, ny)
+        stats = cr.parse_stats(text)
+        stats.pop("sim_time", None)
+        wd4, text4 = cr.run(cr.REF_BIN, full, 4)
+        t4, u4 = cr.read_solution(wd4, nx, ny)
+        spread = float(np.linalg.norm(u - u4) / np.linalg.norm(u))
+        np.save(os.path.join(HERE, "d2d_%s.npy" % name), u)
+        meta = {"args": args, "t_final": t, "stats": stats, "stats_np4": {k: v for k, v in cr.parse_stats(text4).items() if k != "sim_time"},
+                "ref_np1_vs_np4_rel_l2": spread, "state_digits": 16}
+        with open(os.path.join(HERE, "d2d_%s.json" % name), "w") as f:
+            json.dump(meta, f, indent=1)
+        print("%-32s steps=%s evals=%s np1-vs-np4=%.2e" % (name, stats.get("steps"), stats.get("rhs_evals", stats.get("rhs_evals_i")), spread))
+
+
+if __name__ == "__main__":
+    main()

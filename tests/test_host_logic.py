@@ -1,0 +1,174 @@
+"""CPU-side checks: the C-ABI libraries load and export every declared symbol, the host mirror of
+the reference's decomposition agrees with the oracle and with the C++ driver, the oracle's vector
+ops honour the reference's special cases, and the product refuses to run without a GPU."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+from conftest import ROOT, P, has_gpu, make_grid
+
+INCLUDE = os.path.join(ROOT, "include")
+
+
+def declared_functions(header):
+    text = open(os.path.join(INCLUDE, header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = set(re.findall(r"\b((?:b200|N_V)\w*)\s*\(", text))
+    return sorted(n for n in names if not n.isupper())
+
+
+def exported(lib_path):
+    out = subprocess.run(["nm", "-D", "--defined-only", lib_path], capture_output=True, text=True, check=True).stdout
+    return {ln.split()[-1] for ln in out.splitlines() if ln.strip()}
+
+
+def test_kernel_library_exports_every_declared_symbol(b200):
+    syms = exported(b200.KERNEL_LIB)
+    missing = [f for f in declared_functions("b200_sts.h") if f not in syms]
+    assert not missing, missing
+    b200.kernel_lib()  # dlopen succeeds without a GPU and without NCCL being loaded
+
+
+def test_sundials_library_exports_every_declared_symbol(b200):
+    if not os.path.exists(b200.SUNDIALS_LIB):
+        pytest.skip("libb200sts_sundials.so not built (no SUNDIALS host library)")
+    syms = exported(b200.SUNDIALS_LIB)
+    want = declared_functions("nvector_b200.h") + declared_functions("b200_diffusion2d.h")
+    want += ["b200_diffusion_rhs", "b200_diffusion_domeig", "b200_diffusion_psetup", "b200_diffusion_psolve"]
+    missing = [f for f in want if f not in syms and not f.startswith("b200_ctx") and f in want]
+    missing = [f for f in missing if f.startswith(("N_V", "b200_d2d", "b200_diffusion", "b200_adr2d", "b200_adr_"))]
+    assert not missing, missing
+    b200.sundials_lib()
+
+
+def test_kernel_library_has_sm100a_code_and_no_nccl_link_dependency(b200):
+    out = subprocess.run(["cuobjdump", "-lelf", b200.KERNEL_LIB], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    ldd = subprocess.run(["ldd", b200.KERNEL_LIB], capture_output=True, text=True).stdout
+    assert "nccl" not in ldd  # bound with dlopen at first multi-GPU use
+
+
+@pytest.mark.skipif(has_gpu(), reason="only meaningful where there is no GPU")
+def test_product_fails_loudly_without_a_gpu(b200):
+    lib = b200.kernel_lib()
+    h = ctypes.c_void_p()
+    rc = lib.b200_ctx_create(0, None, ctypes.byref(h))
+    assert rc != 0 and lib.b200_last_error()
+    if os.path.exists(b200.DRIVER_BIN):
+        r = subprocess.run([b200.DRIVER_BIN, "--nx", "32", "--ny", "32", "--integrator", "rkc"], capture_output=True, text=True)
+        assert r.returncode != 0
+
+
+def test_product_does_not_reference_the_oracle():
+    """oracle/ is test infrastructure: nothing under the package or include/ may mention it."""
+    bad = []
+    for base in ("ceda-demonstrations_b200", "include"):
+        for dp, _, files in os.walk(os.path.join(ROOT, base)):
+            if "_sundials" in dp or dp.endswith(("lib", "bin", "__pycache__")):
+                continue
+            for fn in files:
+                if fn.endswith((".py", ".cpp", ".cu", ".h", ".hpp")):
+                    txt = open(os.path.join(dp, fn)).read()
+                    if re.search(r"liboracle|sts_oracle|orc_|oracle/", txt):
+                        bad.append(os.path.join(dp, fn))
+    assert not bad, bad
+
+
+# ---- decomposition: diffusion_2D.cpp:243-317 ----------------------------------------------------
+@pytest.mark.parametrize("nranks", [1, 2, 3, 4, 6, 8, 12, 16])
+@pytest.mark.parametrize("nx,ny", [(128, 128), (101, 77), (16384, 16384), (10, 7)])
+def test_block_decomposition_matches_oracle_and_driver(b200, orc, nranks, nx, ny):
+    dims = (ctypes.c_int * 2)()
+    orc.orc_dims_create(nranks, dims)
+    covered = np.zeros((ny, nx), dtype=np.int32)
+    for rank in range(nranks):
+        d = b200.block_decomposition(nx, ny, rank, nranks)
+        assert (d["npx"], d["npy"]) == (dims[0], dims[1])
+        s, c = ctypes.c_int64(), ctypes.c_int64()
+        orc.orc_decompose(ctypes.c_int64(nx), d["npx"], d["idx"], ctypes.byref(s), ctypes.byref(c))
+        assert (d["is"], d["nx_loc"]) == (s.value, c.value)
+        orc.orc_decompose(ctypes.c_int64(ny), d["npy"], d["idy"], ctypes.byref(s), ctypes.byref(c))
+        assert (d["js"], d["ny_loc"]) == (s.value, c.value)
+        covered[d["js"] : d["js"] + d["ny_loc"], d["is"] : d["is"] + d["nx_loc"]] += 1
+        # periodic neighbours are mutual
+        for a, bk in (("ipW", "ipE"), ("ipS", "ipN")):
+            nb = b200.block_decomposition(nx, ny, d[a], nranks)
+            assert nb[bk] == rank
+        if os.path.exists(b200.SUNDIALS_LIB):
+            lib = b200.sundials_lib()
+            out = [ctypes.c_int64() for _ in range(4)]
+            px, py = ctypes.c_int(), ctypes.c_int()
+            rc = lib.b200_d2d_local_extent(ctypes.c_int64(nx), ctypes.c_int64(ny), rank, nranks, 0, 0,
+                                           *[ctypes.byref(o) for o in out], ctypes.byref(px), ctypes.byref(py))
+            assert rc == 0
+            assert [o.value for o in out] == [d["is"], d["nx_loc"], d["js"], d["ny_loc"]]
+            assert (px.value, py.value) == (d["npx"], d["npy"])
+    assert np.all(covered == 1)
+
+
+def test_mpi_dims_create_known_values(orc):
+    want = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2), 16: (4, 4), 64: (8, 8), 6: (3, 2), 7: (7, 1)}
+    dims = (ctypes.c_int * 2)()
+    for n, d in want.items():
+        orc.orc_dims_create(n, dims)
+        assert (dims[0], dims[1]) == d
+
+
+# ---- oracle vector ops: the special cases of N_VLinearSum (nvector_parallel.c:424-517) ------------
+def test_oracle_linear_sum_special_cases(orc):
+    rng = np.random.default_rng(7)
+    x, y = rng.standard_normal(257), rng.standard_normal(257)
+    cases = [(1.0, 1.0), (1.0, -1.0), (-1.0, 1.0), (1.0, 0.37), (0.37, 1.0), (-1.0, 0.37), (0.37, -1.0),
+             (0.37, 0.37), (0.37, -0.37), (0.37, 2.5)]
+    for a, b in cases:
+        z = np.zeros_like(x)
+        orc.orc_linear_sum(ctypes.c_double(a), P(x), ctypes.c_double(b), P(y), P(z), ctypes.c_int64(x.size))
+        if a == b and abs(a) != 1.0:
+            want = a * (x + y)
+        elif a == -b and abs(a) != 1.0:
+            want = a * (x - y)
+        else:
+            want = (a * x) + (b * y)
+        assert np.array_equal(z, want), (a, b)
+    # in-place axpy forms
+    z = y.copy()
+    orc.orc_linear_sum(ctypes.c_double(0.37), P(x), ctypes.c_double(1.0), P(z), P(z), ctypes.c_int64(x.size))
+    assert np.array_equal(z, y + 0.37 * x)
+
+
+def test_oracle_linear_combination_is_left_to_right(orc):
+    rng = np.random.default_rng(3)
+    X = [rng.standard_normal(100) for _ in range(5)]
+    c = [1e-4, -0.31, 0.2, 1.11, -3e-5]
+    z = np.zeros(100)
+    arr = (ctypes.c_void_p * 5)(*[v.ctypes.data for v in X])
+    orc.orc_linear_combination(5, (ctypes.c_double * 5)(*c), arr, P(z), ctypes.c_int64(100))
+    want = c[0] * X[0]
+    for k in range(1, 5):
+        want = want + c[k] * X[k]
+    assert np.array_equal(z, want)
+
+
+def test_oracle_laplacian_halo_equals_periodic_wrap(orc):
+    """One periodic rank: feeding the rank's own opposite edges as halos must equal the wrap path."""
+    nx, ny = 23, 17
+    g = make_grid(nx, ny, kx=0.9, ky=1.7, inhom=True)
+    rng = np.random.default_rng(11)
+    u = rng.standard_normal(nx * ny)
+    f1, f2 = np.zeros(nx * ny), np.zeros(nx * ny)
+    orc.orc_laplacian(ctypes.byref(g), P(u), P(f1), None, None, None, None)
+    W, E, S, N = np.zeros(ny), np.zeros(ny), np.zeros(nx), np.zeros(nx)
+    orc.orc_pack(ctypes.byref(g), P(u), P(W), P(E), P(S), P(N))
+    # what I send west arrives as my east neighbour's "from west"... with one rank: Wrecv = Esend
+    orc.orc_laplacian(ctypes.byref(g), P(u), P(f2), P(E), P(W), P(N), P(S))
+    assert np.array_equal(f1, f2)
+
+
+def test_python_and_header_struct_sizes_agree(b200):
+    """ctypes mirrors must match the C structs (sizes are checked against known layouts)."""
+    assert ctypes.sizeof(b200.StencilGeom) == 2 * 8 + 8 * 8
+    assert ctypes.sizeof(b200.StageExtras) == 7 * 8
+    assert ctypes.sizeof(b200.AdrParams) == 2 * 8 + 9 * 8
