@@ -31,7 +31,7 @@ all: product
 ifneq ($(HAVE_REF),)
 sundials:
 	@$(MAKE) -s -f scripts/sundials_host.mk SUN_OUT=$(SUNOUT)
-product: sundials $(LIB)/libb200sts.so $(LIB)/libb200sts_sundials.so $(BIN)/diffusion_2D_b200
+product: sundials $(LIB)/libb200sts.so $(LIB)/libb200sts_sundials.so $(BIN)/diffusion_2D_b200 $(BIN)/adr2d_b200
 else
 sundials:
 	@test -f $(SUNOUT)/lib/libsundials_host.so || (echo "no /root/reference and no prebuilt SUNDIALS host lib" && false)
@@ -42,14 +42,20 @@ $(LIB)/libb200sts.so: $(SRC)/b200_kernels.cu include/b200_sts.h
 	@mkdir -p $(LIB)
 	$(NVCC) $(NVFLAGS) -shared -Iinclude $< -o $@ -ldl
 
-HOST_SRC := $(SRC)/nvector_b200.cpp $(SRC)/diffusion_b200.cpp
-$(LIB)/libb200sts_sundials.so: $(HOST_SRC) include/nvector_b200.h include/b200_diffusion2d.h include/b200_sts.h $(LIB)/libb200sts.so
+HOST_SRC := $(SRC)/nvector_b200.cpp $(SRC)/diffusion_b200.cpp $(SRC)/adr_b200.cpp
+$(LIB)/libb200sts_sundials.so: $(HOST_SRC) include/nvector_b200.h include/b200_diffusion2d.h include/b200_adr2d.h include/b200_callbacks.h include/b200_sts.h $(LIB)/libb200sts.so
 	@mkdir -p $(LIB)
 	$(CXX) $(CXXFLAGS) -shared -Iinclude $(SUNINC) $(HOST_SRC) -o $@ \
 	  -L$(LIB) -lb200sts -L$(SUNOUT)/lib -lsundials_host \
 	  -Wl,-rpath,'$$ORIGIN' -Wl,-rpath,'$$ORIGIN/../_sundials/lib'
 
 $(BIN)/diffusion_2D_b200: $(SRC)/main_diffusion.cpp $(LIB)/libb200sts_sundials.so
+	@mkdir -p $(BIN)
+	$(CXX) $(CXXFLAGS) -Iinclude $< -o $@ -L$(LIB) -lb200sts_sundials -lb200sts \
+	  -L$(SUNOUT)/lib -lsundials_host \
+	  -Wl,-rpath,'$$ORIGIN/../lib' -Wl,-rpath,'$$ORIGIN/../_sundials/lib'
+
+$(BIN)/adr2d_b200: $(SRC)/main_adr.cpp $(LIB)/libb200sts_sundials.so
 	@mkdir -p $(BIN)
 	$(CXX) $(CXXFLAGS) -Iinclude $< -o $@ -L$(LIB) -lb200sts_sundials -lb200sts \
 	  -L$(SUNOUT)/lib -lsundials_host \

@@ -24,6 +24,7 @@ BIN_DIR = os.path.join(_HERE, "bin")
 KERNEL_LIB = os.path.join(LIB_DIR, "libb200sts.so")
 SUNDIALS_LIB = os.path.join(LIB_DIR, "libb200sts_sundials.so")
 DRIVER_BIN = os.path.join(BIN_DIR, "diffusion_2D_b200")
+ADR_DRIVER_BIN = os.path.join(BIN_DIR, "adr2d_b200")
 
 MAX_TERMS = 8
 SRC_VECTOR, SRC_CENTRE, SRC_STENCIL = 0, 1, 2
@@ -88,6 +89,25 @@ class D2DStats(ctypes.Structure):
 
     def as_dict(self):
         return {name.rstrip("_"): getattr(self, name) for name, _ in self._fields_}
+
+
+class AdrStats(ctypes.Structure):
+    """b200_adr_stats (include/b200_adr2d.h)."""
+
+    _fields_ = [
+        ("t", ctypes.c_double), ("evolve_seconds", ctypes.c_double),
+        ("steps", ctypes.c_long), ("step_attempts", ctypes.c_long),
+        ("rhs_evals_explicit", ctypes.c_long), ("rhs_evals_implicit", ctypes.c_long),
+        ("lsrk_steps", ctypes.c_long), ("lsrk_rhs_evals", ctypes.c_long), ("lsrk_max_stages", ctypes.c_long),
+        ("ark_steps", ctypes.c_long), ("ark_rhs_evals", ctypes.c_long),
+        ("fused_launches", ctypes.c_long), ("plain_rhs_launches", ctypes.c_long),
+        ("aliased_copies", ctypes.c_long), ("buffers_allocated", ctypes.c_long),
+        ("kernel_launches", ctypes.c_uint64),
+        ("nx", ctypes.c_int64), ("ny", ctypes.c_int64), ("neq", ctypes.c_int64),
+    ]
+
+    def as_dict(self):
+        return {name: getattr(self, name) for name, _ in self._fields_}
 
 
 _kernel_lib = None
@@ -283,6 +303,56 @@ class Diffusion2D:
     def close(self):
         if self.handle:
             self._lib.b200_d2d_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+
+class Adr2D:
+    """One adr 2-D Brusselator problem + ARKODE integrator on one GPU (b200_adr).
+
+    ``args`` are the reference driver's command-line flags
+    (adr/advection_diffusion_reaction_2d.hpp InputHelp)."""
+
+    def __init__(self, args, device=0, stream="torch"):
+        lib = sundials_lib()
+        self._lib = lib
+        self.handle = ctypes.c_void_p()
+        argv = (ctypes.c_char_p * len(args))(*[str(a).encode() for a in args])
+        sptr = None
+        if stream == "torch":
+            import torch
+
+            torch.cuda.set_device(device)
+            self._tstream = torch.cuda.Stream(device)
+            torch.cuda.set_stream(self._tstream)
+            sptr = ctypes.c_void_p(self._tstream.cuda_stream)
+        rc = lib.b200_adr_create(len(args), argv, int(device), sptr, ctypes.byref(self.handle))
+        if rc != 0:
+            raise RuntimeError("b200_adr_create failed: %s" % kernel_lib().b200_last_error().decode())
+
+    def evolve(self, tout):
+        if self._lib.b200_adr_evolve(self.handle, ctypes.c_double(tout)) != 0:
+            raise RuntimeError("b200_adr_evolve failed")
+
+    def step(self, nsteps=1):
+        if self._lib.b200_adr_step(self.handle, int(nsteps)) != 0:
+            raise RuntimeError("b200_adr_step failed")
+
+    def get_state(self, host):
+        if self._lib.b200_adr_get_state(self.handle, _ptr(host)) != 0:
+            raise RuntimeError("b200_adr_get_state failed")
+
+    def set_state(self, host, t=0.0):
+        if self._lib.b200_adr_set_state(self.handle, _ptr(host), ctypes.c_double(t)) != 0:
+            raise RuntimeError("b200_adr_set_state failed")
+
+    def stats(self):
+        s = AdrStats()
+        self._lib.b200_adr_get_stats(self.handle, ctypes.byref(s))
+        return s.as_dict()
+
+    def close(self):
+        if self.handle:
+            self._lib.b200_adr_destroy(self.handle)
             self.handle = ctypes.c_void_p()
 
 

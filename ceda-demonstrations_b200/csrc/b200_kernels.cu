@@ -1105,30 +1105,39 @@ __device__ __forceinline__ void adr_point(const AdrArgs& a, int64_t i, int64_t j
   }
 }
 
-__global__ void __launch_bounds__(kThreads) k_adr_rhs(const AdrArgs a)
+// composite callbacks add in the order advection, diffusion, reaction
+// (f_adv_react ...2d.cpp:1602-1619, f_adv_diff_react :1622-1646, f_diff_react, f_adv_diff;
+// the N_VLinearSum(1,f,1,temp,f) there is Vaxpy: f += temp)
+__device__ __forceinline__ double2 adr_composite(const AdrArgs& a, int64_t i, int64_t j, double2* yc)
 {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t j = blockIdx.y;
-  if (i >= a.p.nx) return;
-  double2 fa = make_double2(0, 0), fd = make_double2(0, 0), fr = make_double2(0, 0), yc;
-  adr_point(a, i, j, &fa, &fd, &fr, &yc);
-  // composite callbacks add in the order advection, diffusion, reaction
-  // (f_adv_react …2d.cpp:1602-1619, f_adv_diff_react :1622-1646; VSum = x + y)
+  double2 fa = make_double2(0, 0), fd = make_double2(0, 0), fr = make_double2(0, 0);
+  adr_point(a, i, j, &fa, &fd, &fr, yc);
   double2 r  = make_double2(0, 0);
   bool first = true;
   if (a.mode & 1) { r = fa; first = false; }
   if (a.mode & 2) { r = first ? fd : make_double2(DADD(r.x, fd.x), DADD(r.y, fd.y)); first = false; }
   if (a.mode & 4) { r = first ? fr : make_double2(DADD(r.x, fr.x), DADD(r.y, fr.y)); }
-  *reinterpret_cast<double2*>(a.f + 2 * (i + j * a.p.nx)) = r;
+  return r;
 }
 
-__global__ void __launch_bounds__(kThreads) k_adr_diff_lincomb(const AdrArgs a)
+__global__ void __launch_bounds__(kThreads) k_adr_rhs(const AdrArgs a)
 {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t j = blockIdx.y;
   if (i >= a.p.nx) return;
-  double2 fa, fd = make_double2(0, 0), fr, yc;
-  adr_point(a, i, j, &fa, &fd, &fr, &yc);
+  double2 yc;
+  const double2 r = adr_composite(a, i, j, &yc);
+  *reinterpret_cast<double2*>(a.f + 2 * (i + j * a.p.nx)) = r;
+}
+
+// z = sum_k c[k]*T_k with T_k in {vector, y, F_mode(y)}; optionally also stores F_mode(y)
+__global__ void __launch_bounds__(kThreads) k_adr_lincomb(const AdrArgs a)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t j = blockIdx.y;
+  if (i >= a.p.nx) return;
+  double2 yc;
+  const double2 F  = adr_composite(a, i, j, &yc);
   const int64_t id = 2 * (i + j * a.p.nx);
   double2 acc      = make_double2(0, 0);
 #pragma unroll
@@ -1136,7 +1145,7 @@ __global__ void __launch_bounds__(kThreads) k_adr_diff_lincomb(const AdrArgs a)
     if (k < a.t.n)
     {
       double2 v;
-      if (a.t.src[k] == B200_SRC_STENCIL) v = fd;
+      if (a.t.src[k] == B200_SRC_STENCIL) v = F;
       else if (a.t.src[k] == B200_SRC_CENTRE) v = yc;
       else v = ld_stream2(a.t.v[k] + id);
       const double p0 = DMUL(a.t.c[k], v.x), p1 = DMUL(a.t.c[k], v.y);
@@ -1144,7 +1153,7 @@ __global__ void __launch_bounds__(kThreads) k_adr_diff_lincomb(const AdrArgs a)
       acc.y = (k == 0) ? p1 : DADD(acc.y, p1);
     }
   *reinterpret_cast<double2*>(a.z + id) = acc;
-  if (a.f) *reinterpret_cast<double2*>(a.f + id) = fd;
+  if (a.f) *reinterpret_cast<double2*>(a.f + id) = F;
 }
 
 extern "C" int b200_adr_rhs(b200_ctx* c, const b200_adr_params* p, int mode,
@@ -1162,26 +1171,35 @@ extern "C" int b200_adr_rhs(b200_ctx* c, const b200_adr_params* p, int mode,
   return 0;
 }
 
-extern "C" int b200_adr_diffusion_lincomb(b200_ctx* c, const b200_adr_params* p, const double* y,
-                                          int nterms, const double* cf, const int* src,
-                                          const double* const* v, double* z, double* f_out)
+extern "C" int b200_adr_lincomb(b200_ctx* c, const b200_adr_params* p, int mode, const double* y,
+                                int nterms, const double* cf, const int* src,
+                                const double* const* v, double* z, double* f_out)
 {
-  if (nterms < 1 || nterms > B200_MAX_TERMS) return fail("b200_adr_diffusion_lincomb: nterms out of range");
-  if (z == y || f_out == y) return fail("b200_adr_diffusion_lincomb: output aliases the stencil input");
-  if (p->ny > 65535) return fail("b200_adr_diffusion_lincomb: ny <= 65535");
+  if (mode < 1 || mode > 7) return fail("b200_adr_lincomb: mode must be in 1..7");
+  if (nterms < 1 || nterms > B200_MAX_TERMS) return fail("b200_adr_lincomb: nterms out of range");
+  if (z == y || f_out == y) return fail("b200_adr_lincomb: output aliases the stencil input");
+  if (p->ny > 65535) return fail("b200_adr_lincomb: ny <= 65535");
   AdrArgs a;
   memset(&a, 0, sizeof(a));
-  a.p = *p; a.mode = 2; a.y = y; a.f = f_out; a.z = z;
+  a.p = *p; a.mode = mode; a.y = y; a.f = f_out; a.z = z;
   a.t.n = nterms;
   for (int k = 0; k < nterms; k++)
   {
     a.t.c[k] = cf[k]; a.t.src[k] = src[k];
     a.t.v[k] = (src[k] == B200_SRC_VECTOR) ? v[k] : nullptr;
+    if (src[k] == B200_SRC_VECTOR && !v[k]) return fail("b200_adr_lincomb: NULL operand");
   }
   dim3 grid((unsigned)((p->nx + kThreads - 1) / kThreads), (unsigned)p->ny);
-  k_adr_diff_lincomb<<<grid, kThreads, 0, c->stream>>>(a);
+  k_adr_lincomb<<<grid, kThreads, 0, c->stream>>>(a);
   LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int b200_adr_diffusion_lincomb(b200_ctx* c, const b200_adr_params* p, const double* y,
+                                          int nterms, const double* cf, const int* src,
+                                          const double* const* v, double* z, double* f_out)
+{
+  return b200_adr_lincomb(c, p, 2, y, nterms, cf, src, v, z, f_out);
 }
 
 // --------------------------------------------------------------------- NCCL

@@ -1,0 +1,52 @@
+/* b200_callbacks.h -- the user-supplied ARKODE callbacks of the two reference drivers,
+ * re-implemented for N_Vector_B200.  Same signatures (SUNDIALS types), same return
+ * convention (0 ok, <0 fatal), registered with the same ARKODE calls -- see
+ * INTEGRATION.md.  `user_data` must be the B200 problem object the matching session
+ * constructor built (b200_d2d_create / b200_adr_create), which is what those
+ * constructors pass to ARKodeSetUserData.
+ *
+ * None of the RHS callbacks launches a kernel: each marks `f` as the deferred value
+ * "operator applied to y" (N_VSetDeferredRhs_B200); the vector fuses the operator into
+ * the N_VLinearCombination / N_VLinearSum that consumes it (nvector_b200.h).
+ */
+#ifndef B200_CALLBACKS_H
+#define B200_CALLBACKS_H
+
+#include <sundials/sundials_nvector.h>
+#include <sundials/sundials_types.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- diffusion_2D ---------------------------------------------------------------- */
+/* ARKRhsFn: diffusion(), diffusion_2D/diffusion_2D.cpp:23-35 -> laplacian(), diffusion.cpp:9-209 */
+int b200_diffusion_rhs(sunrealtype t, N_Vector u, N_Vector f, void* user_data);
+/* ARKDomEigFn: dom_eig(), diffusion_2D/main.cpp:536-550 */
+int b200_diffusion_domeig(sunrealtype t, N_Vector y, N_Vector fn, sunrealtype* lambdaR,
+                          sunrealtype* lambdaI, void* user_data, N_Vector temp1,
+                          N_Vector temp2, N_Vector temp3);
+/* ARKLsPrecSetupFn / ARKLsPrecSolveFn: diffusion_2D/preconditioner_jacobi.cpp:9-46 / 49-62 */
+int b200_diffusion_psetup(sunrealtype t, N_Vector u, N_Vector f, sunbooleantype jok,
+                          sunbooleantype* jcurPtr, sunrealtype gamma, void* user_data);
+int b200_diffusion_psolve(sunrealtype t, N_Vector u, N_Vector f, N_Vector r, N_Vector z,
+                          sunrealtype gamma, sunrealtype delta, int lr, void* user_data);
+
+/* ---- adr 2-D: adr/advection_diffusion_reaction_2d.cpp ------------------------------ */
+int b200_adr_f_advection(sunrealtype t, N_Vector y, N_Vector f, void* user_data);      /* :1406-1445 */
+int b200_adr_f_diffusion(sunrealtype t, N_Vector y, N_Vector f, void* user_data);      /* :1448-1491 */
+int b200_adr_f_reaction(sunrealtype t, N_Vector y, N_Vector f, void* user_data);       /* :1494-1520 */
+int b200_adr_f_adv_diff(sunrealtype t, N_Vector y, N_Vector f, void* user_data);       /* :1562-1579 */
+int b200_adr_f_adv_react(sunrealtype t, N_Vector y, N_Vector f, void* user_data);      /* :1602-1619 */
+int b200_adr_f_diff_react(sunrealtype t, N_Vector y, N_Vector f, void* user_data);     /* :1582-1599 */
+int b200_adr_f_adv_diff_react(sunrealtype t, N_Vector y, N_Vector f, void* user_data); /* :1622-1646 */
+int b200_adr_f_diffusion_forcing(sunrealtype t, N_Vector y, N_Vector f, void* user_data); /* :1649-1663 */
+/* ARKDomEigFn: diffusion_domeig(), :1666-1679 */
+int b200_adr_domeig(sunrealtype t, N_Vector y, N_Vector fn, sunrealtype* lambdaR,
+                    sunrealtype* lambdaI, void* user_data, N_Vector temp1, N_Vector temp2,
+                    N_Vector temp3);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

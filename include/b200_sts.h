@@ -176,8 +176,15 @@ typedef struct b200_adr_params
    reference's summation order.  f must not alias y. */
 int b200_adr_rhs(b200_ctx* ctx, const b200_adr_params* p, int mode,
                  const double* y, double* f);
-/* fused  z = sum_k c[k]*T_k  with T_k possibly = f_diffusion(y) (STS stages of
-   the Strang / ExtSTS diffusion partition) */
+/* fused  z = sum_k c[k]*T_k  with T_k in { v[k], y, F_mode(y) } per src[k], F_mode the
+   (composite) callback selected by the mode bits above; f_out != NULL also stores
+   F_mode(y).  Realises the RHS call + the N_VLinearCombination / N_VLinearSum that
+   consumes it (LSRKStep stages of the diffusion partition, ARKStep/ERKStep stages of
+   the advection-reaction partition) in one pass. */
+int b200_adr_lincomb(b200_ctx* ctx, const b200_adr_params* p, int mode, const double* y,
+                     int nterms, const double* c, const int* src,
+                     const double* const* v, double* z, double* f_out);
+/* mode = 2 (f_diffusion) shorthand */
 int b200_adr_diffusion_lincomb(b200_ctx* ctx, const b200_adr_params* p,
                                const double* y, int nterms, const double* c,
                                const int* src, const double* const* v, double* z,

@@ -57,6 +57,26 @@ D2D_CASES = {
 }
 
 
+# adr 2-D (oracle/_ref/adr2d_ref): name -> reference command line (all --nout 1 --output 1)
+ADR_CASES = {
+    "strang_rkc_64": ["--nx", "64", "--ny", "64", "--integrator", "3", "--sts_method", "0", "--fixed_h", "0.01", "--tf", "0.1"],
+    "strang_rkl_96x48_d": ["--nx", "96", "--ny", "48", "--integrator", "3", "--sts_method", "1", "--d", "0.05",
+                           "--fixed_h", "0.005", "--tf", "0.05"],
+    "strang_rkc_noadv_64": ["--nx", "64", "--ny", "64", "--integrator", "3", "--sts_method", "0", "--no-advection",
+                            "--fixed_h", "0.01", "--tf", "0.05"],
+    "extsts_ars_rkc_64": ["--nx", "64", "--ny", "64", "--integrator", "2", "--sts_method", "0", "--extsts_method", "0",
+                          "--fixed_h", "0.005", "--tf", "0.05"],
+    "extsts_ralston_rkl_fixed_48": ["--nx", "48", "--ny", "48", "--integrator", "2", "--sts_method", "1",
+                                    "--extsts_method", "2", "--fixed_h", "0.004", "--tf", "0.04"],
+    "erk2_adaptive_48": ["--nx", "48", "--ny", "48", "--integrator", "0", "--order", "2", "--rtol", "1e-4", "--tf", "0.02"],
+    "erk3_fixed_64x32": ["--nx", "64", "--ny", "32", "--integrator", "0", "--order", "3", "--fixed_h", "1e-4", "--tf", "2e-3"],
+    "extsts_heun_rkc_fixed_64x48": ["--nx", "64", "--ny", "48", "--integrator", "2", "--sts_method", "0",
+                                    "--extsts_method", "3", "--d", "0.1", "--fixed_h", "0.002", "--tf", "0.02"],
+    "ark_ars_adaptive_48": ["--nx", "48", "--ny", "48", "--integrator", "1", "--table_id", "1", "--rtol", "1e-4", "--tf", "0.02"],
+    "ark_default_adaptive_48": ["--nx", "48", "--ny", "48", "--integrator", "1", "--order", "3", "--rtol", "1e-5", "--tf", "0.02"],
+}
+
+
 def parse_lsrk_log(path):
     steps = []
     cur = None
@@ -124,5 +144,24 @@ def main():
         print("%-32s steps=%s evals=%s np1-vs-np4=%.2e" % (name, stats.get("steps"), stats.get("rhs_evals", stats.get("rhs_evals_i")), spread))
 
 
+def main_adr():
+    import compare_adr as ca
+
+    for name, args in ADR_CASES.items():
+        full = args + ["--nout", "1", "--output", "1"]
+        nx, ny = int(ca.get_arg(full, "--nx", 400)), int(ca.get_arg(full, "--ny", 400))
+        wd, text = ca.run(ca.REF_BIN, full)
+        t, y = ca.read_solution(wd, nx, ny)
+        np.save(os.path.join(HERE, "adr_%s.npy" % name), y)
+        meta = {"args": args, "t_final": t, "stats": ca.parse_stats(text), "state_digits": 15}
+        with open(os.path.join(HERE, "adr_%s.json" % name), "w") as f:
+            json.dump(meta, f, indent=1)
+        print("%-34s %s" % (name, meta["stats"]))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "adr":
+        main_adr()
+    else:
+        main()
+        main_adr()
