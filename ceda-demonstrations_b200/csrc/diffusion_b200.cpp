@@ -841,6 +841,9 @@ extern "C" int b200_d2d_main(int argc, char** argv)
     tout += dTout;
     tout = (tout > ud.tf) ? ud.tf : tout;
   }
+  // collective: the statistics include ||u||_rms, i.e. an all-reduce every rank must join
+  b200_d2d_stats s;
+  b200_d2d_get_stats(p, &s);
   if (outproc)
   {
     if (uo.output > 0) printf(" ----------------------------------------------\n\n");
@@ -848,8 +851,6 @@ extern "C" int b200_d2d_main(int argc, char** argv)
     printf("Total simulation time = %.15e\n\n", p->evolve_seconds);
     printf("Final integrator statistics:\n");
     b200_d2d_print_stats(p);
-    b200_d2d_stats s;
-    b200_d2d_get_stats(p, &s);
     printf("B200 fused stage launches     = %ld\n", s.fused_launches);
     printf("B200 plain RHS launches       = %ld\n", s.plain_rhs_launches);
     printf("B200 aliased copies           = %ld\n", s.aliased_copies);

@@ -59,6 +59,7 @@ int b200_d2d_step(b200_d2d* p, int nsteps);
 int b200_d2d_get_state(b200_d2d* p, double* host);
 /* overwrite the state from host memory and ARKodeReset to time t */
 int b200_d2d_set_state(b200_d2d* p, const double* host, double t);
+/* COLLECTIVE when nranks > 1 (urms is an all-reduced dot product): call on every rank. */
 int b200_d2d_get_stats(b200_d2d* p, b200_d2d_stats* s);
 /* print ARKodePrintAllStats exactly as the reference main.cpp:486 does */
 int b200_d2d_print_stats(b200_d2d* p);

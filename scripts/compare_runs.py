@@ -76,7 +76,7 @@ def read_solution(workdir, nx, ny):
     return t_final, u
 
 
-def run(binary, args, np_ranks=1, env_extra=None, timeout=3600):
+def run(binary, args, np_ranks=1, env_extra=None, timeout=600):
     workdir = tempfile.mkdtemp(prefix="d2d_")
     env = dict(os.environ)
     if env_extra:
@@ -94,7 +94,12 @@ def run(binary, args, np_ranks=1, env_extra=None, timeout=3600):
             e.pop("WORLD_SIZE", None)
             e.pop("LOCAL_RANK", None)
             procs.append(subprocess.Popen([binary] + args, cwd=workdir, env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
-    outs = [p.communicate(timeout=timeout)[0] for p in procs]
+    try:
+        outs = [p.communicate(timeout=timeout)[0] for p in procs]
+    except subprocess.TimeoutExpired:
+        for p in procs:  # a hung rank must not outlive the test (exact PIDs we started)
+            p.kill()
+        raise
     rcs = [p.returncode for p in procs]
     if any(rcs):
         raise RuntimeError("%s failed rc=%s\n%s" % (binary, rcs, "\n".join(outs)[-4000:]))
