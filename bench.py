@@ -169,11 +169,24 @@ def reference_arm(args):
         "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.time() - t0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------ our arm
+def emit(line):
+    """The contract is ONE JSON line on stdout: libraries (NCCL prints its version banner to stdout)
+    write to the process' fd 1, which main() points at stderr; the result goes to the real stdout."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -336,7 +349,7 @@ def main():
         "clocks": sampler.summary(),
         "achieved_hbm_gbs_per_gpu": value * ALG_BYTES_PER_UPDATE / 1e9 / world,
     }
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
