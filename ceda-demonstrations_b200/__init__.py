@@ -85,6 +85,7 @@ class D2DStats(ctypes.Structure):
         ("nx", ctypes.c_int64), ("ny", ctypes.c_int64), ("nx_loc", ctypes.c_int64),
         ("ny_loc", ctypes.c_int64), ("is_", ctypes.c_int64), ("js", ctypes.c_int64),
         ("npx", ctypes.c_int), ("npy", ctypes.c_int), ("rank", ctypes.c_int), ("nranks", ctypes.c_int),
+        ("chain_launches", ctypes.c_long), ("chain_stages", ctypes.c_long),
     ]
 
     def as_dict(self):
@@ -202,6 +203,15 @@ class Context:
         check(self._lib.b200_stencil_lincomb(self.handle, ctypes.byref(geom), _ptr(x), n, c, s, v, _ptr(z),
                                              ctypes.byref(extras) if extras is not None else None, int(region)),
               "b200_stencil_lincomb")
+
+    def stencil_chain(self, geom, x, prev2, yn, fn, coeffs, outs):
+        """b200_stencil_chain: len(coeffs) temporally blocked stages; outs[l] may be None."""
+        k = len(coeffs)
+        flat = [v for row in coeffs for v in row]
+        c = (ctypes.c_double * (5 * k))(*flat)
+        o = (ctypes.c_void_p * k)(*[(t.data_ptr() if t is not None else 0) for t in outs])
+        check(self._lib.b200_stencil_chain(self.handle, ctypes.byref(geom), k, _ptr(x), _ptr(prev2), _ptr(yn),
+                                           _ptr(fn), c, o), "b200_stencil_chain")
 
     def reduce(self, name, x, y=None):
         out = ctypes.c_double()

@@ -998,6 +998,340 @@ extern "C" int b200_stencil_lincomb(b200_ctx* c, const b200_stencil_geom* g, con
   return 0;
 }
 
+// ------------------------------------------- temporally blocked STS stages
+// K consecutive RKC/RKL stages (arkode_lsrkstep.c:674-750 / :960-1050) in ONE pass:
+//   z_1 = c1[0] L(x)   + c1[1] p   + c1[2] yn + c1[3] x   + c1[4] fn      (x = z_{j-1}, p = z_{j-2})
+//   z_2 = c2[0] L(z_1) + c2[1] x   + c2[2] yn + c2[3] z_1 + c2[4] fn
+//   z_l = cl[0] L(z_{l-1}) + cl[1] z_{l-2} + cl[2] yn + cl[3] z_{l-1} + cl[4] fn
+// Every cell value is produced by exactly the instruction sequence of the one-stage kernel, so
+// the result is bit-identical; only the traffic changes: 4 streamed reads + (usually) 2 writes
+// per K cell-updates instead of per one (48/K bytes instead of 40).
+//
+// Overlapped tiling, no block-level sync: a warp owns a 64-cell window of which the outer HL
+// lanes on each side are halo (level l is valid on cells [l, 63-l] of the window; halo lanes
+// never store); a block marches down `rows` output rows and starts K-1 rows early.  Level l lags
+// level l-1 by one row; each level keeps a 3-row window of the level below in registers and gets
+// west/east neighbours by warp shuffle.  One periodic rank (index wrap) only.
+struct ChainArgs
+{
+  int64_t nx, ny;
+  const double *cxw, *cxe, *cys, *cyn;
+  const double* x;
+  const double* prev2;
+  const double* yn;
+  const double* fn;
+  double c[B200_MAX_CHAIN][5];
+  double* out[B200_MAX_CHAIN];
+  int rows;
+};
+
+static const int kChainThreads = 256;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
+{
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// Operands are staged through a thread-private shared-memory ring filled with cp.async
+// (LDGSTS, 16 B per thread per operand per row) PF rows ahead: the bytes in flight that keep HBM
+// busy cost no registers, and the FP64 pipe works on row r while rows r+1..r+PF stream in.
+// Every thread reads back only the slots it filled itself, so cp.async.wait_group is the only
+// synchronisation in the row loop.  Ring depths: x and prev2 PF+1 rows, yn and fn PF+K rows
+// (level l consumes yn/fn of row r-(l-1)).  The y-direction coefficients of the block's rows
+// sit in a small shared table (one __syncthreads before the loop).
+//
+// The row loop is issue-bound once HBM is no longer the limit, so the steady state is unrolled
+// by 3 with the 3-row register windows addressed by a compile-time phase (no rotation moves),
+// carries no row-range predicates, and uses running offsets instead of index multiplies; the
+// 2(K-1) warm-up rows and the K-1 drain rows run through the same body with CHECK = true.
+struct ChainState
+{
+  int64_t soff;      // r1*nx + ic (unwrapped; valid whenever a store can happen)
+  int64_t ioff0;     // wrapped row offset of the next group's row r      (prev2, yn, fn)
+  int64_t ioff1;     // wrapped row offset of the next group's row r + 1  (x)
+  int sx_issue, sy_issue, sx_use, sy_use; // ring slots (byte offsets / 16 / threads)
+  int trow;          // index of row r1 in the y-coefficient table
+};
+
+template <int K, int PF, int PH, bool CHECK>
+__device__ __forceinline__ void chain_row(const ChainArgs& a, ChainState& st, double2 (&W)[K][3],
+                                          double2* rx, double2* rp, double2* ry, double2* rf,
+                                          const double2* ytab, const double* gx, const double* gp,
+                                          const double* gy, const double* gf, int64_t nx, int64_t ntot,
+                                          double2 cw, double2 ce, double sx0, double sx1,
+                                          unsigned smask, int r1, int j0, int j1, bool issue)
+{
+  constexpr int DX = PF + 1, DY = PF + K;
+  constexpr int IO = PH % 3, IM = (PH + 1) % 3, IC = (PH + 2) % 3; // oldest (overwritten), then um, uc ; up = IO
+  // ---- issue group(r1 + PF): x row +1, prev2 / yn / fn row +0
+  if (issue)
+  {
+    cp_async16(rx + st.sx_issue * kChainThreads, gx + st.ioff1);
+    cp_async16(rp + st.sx_issue * kChainThreads, gp + st.ioff0);
+    cp_async16(ry + st.sy_issue * kChainThreads, gy + st.ioff0);
+    cp_async16(rf + st.sy_issue * kChainThreads, gf + st.ioff0);
+  }
+  cp_async_commit();
+  st.sx_issue = (st.sx_issue + 1 == DX) ? 0 : st.sx_issue + 1;
+  st.sy_issue = (st.sy_issue + 1 == DY) ? 0 : st.sy_issue + 1;
+  st.ioff0    = st.ioff1;
+  st.ioff1 += nx;
+  if (st.ioff1 == ntot) st.ioff1 = 0;
+  cp_async_wait<PF>(); // all but the PF newest groups have landed: group(r1) is ready
+
+  W[0][IO]        = rx[st.sx_use * kChainThreads]; // x row r1+1 replaces the oldest row
+  const double2 P = rp[st.sx_use * kChainThreads];
+  int64_t so      = st.soff;
+#pragma unroll
+  for (int l = 1; l <= K; l++)
+  {
+    const double2 dy = ytab[st.trow - (l - 1)]; // (Dy_s, Dy_n) of row r1-(l-1)
+    const double sy  = DADD(dy.x, dy.y);
+    const double2 um = W[l - 1][IM], uc = W[l - 1][IC], up = W[l - 1][IO];
+    const double uw0 = __shfl_up_sync(0xffffffffu, uc.y, 1);
+    const double ue1 = __shfl_down_sync(0xffffffffu, uc.x, 1);
+    // diffusion.cpp:48-53, same association as k_stage_march
+    double L0 = DMUL(-DADD(sx0, sy), uc.x);
+    double L1 = DMUL(-DADD(sx1, sy), uc.y);
+    L0 = DADD(L0, DMUL(cw.x, uw0));  L1 = DADD(L1, DMUL(cw.y, uc.x));
+    L0 = DADD(L0, DMUL(ce.x, uc.y)); L1 = DADD(L1, DMUL(ce.y, ue1));
+    L0 = DADD(L0, DMUL(dy.x, um.x)); L1 = DADD(L1, DMUL(dy.x, um.y));
+    L0 = DADD(L0, DMUL(dy.y, up.x)); L1 = DADD(L1, DMUL(dy.y, up.y));
+    L0 = DADD(0.0, L0);              L1 = DADD(0.0, L1);
+    // z_{l-2} at this row: prev2 for the first stage, else the oldest row of level l-2's window
+    const double2 p2 = (l == 1) ? P : W[(l >= 2) ? l - 2 : 0][IM];
+    int sl = st.sy_use - (l - 1); // yn / fn of row r1-(l-1)
+    if (sl < 0) sl += DY;
+    const double2 yv = ry[sl * kChainThreads], fv = rf[sl * kChainThreads];
+    const double* cf = a.c[l - 1];
+    double2 z;
+    z.x = DMUL(cf[0], L0);               z.y = DMUL(cf[0], L1);
+    z.x = DADD(z.x, DMUL(cf[1], p2.x));  z.y = DADD(z.y, DMUL(cf[1], p2.y));
+    z.x = DADD(z.x, DMUL(cf[2], yv.x));  z.y = DADD(z.y, DMUL(cf[2], yv.y));
+    z.x = DADD(z.x, DMUL(cf[3], uc.x));  z.y = DADD(z.y, DMUL(cf[3], uc.y));
+    z.x = DADD(z.x, DMUL(cf[4], fv.x));  z.y = DADD(z.y, DMUL(cf[4], fv.y));
+    bool doit = (smask >> (l - 1)) & 1u;
+    if (CHECK)
+    {
+      const int rl = r1 - (l - 1);
+      doit         = doit && rl >= j0 && rl < j1;
+    }
+    if (doit) *reinterpret_cast<double2*>(a.out[l - 1] + so) = z;
+    so -= nx;
+    if (l < K) W[l][IO] = z; // newest row of level l replaces its oldest
+  }
+  st.soff += nx;
+  st.trow += 1;
+  st.sx_use = (st.sx_use + 1 == DX) ? 0 : st.sx_use + 1;
+  st.sy_use = (st.sy_use + 1 == DY) ? 0 : st.sy_use + 1;
+}
+
+template <int K, int PF>
+__global__ void __launch_bounds__(kChainThreads, 2) k_chain_march(const ChainArgs a)
+{
+  constexpr int HL   = (K + 1) / 2;  // halo lanes per side (2 cells each): 2*HL >= K
+  constexpr int WUSE = 64 - 4 * HL;  // cells a warp stores per row
+  constexpr int DX   = PF + 1;       // ring depth of x and prev2
+  constexpr int DY   = PF + K;       // ring depth of yn and fn
+  extern __shared__ double2 ring[];
+  double2* rx   = ring + threadIdx.x;                                         // [DX][threads]
+  double2* rp   = ring + (size_t)DX * kChainThreads + threadIdx.x;            // [DX][threads]
+  double2* ry   = ring + (size_t)2 * DX * kChainThreads + threadIdx.x;        // [DY][threads]
+  double2* rf   = ring + (size_t)(2 * DX + DY) * kChainThreads + threadIdx.x; // [DY][threads]
+  double2* ytab = ring + (size_t)(2 * DX + 2 * DY) * kChainThreads;           // [rows + 3(K-1) + 2]
+
+  const int lane   = threadIdx.x & 31;
+  const int64_t nx = a.nx;
+  const int ny     = (int)a.ny;
+  const int j0     = (int)blockIdx.y * a.rows;
+  int j1           = j0 + a.rows;
+  if (j1 > ny) j1 = ny;
+  const int rstart = j0 - (K - 1), rend = j1 + (K - 1); // level-1 rows [rstart, rend)
+#define WROW(r) ((r) < 0 ? (r) + ny : ((r) >= ny ? (r) - ny : (r)))
+  // y-direction face coefficients of rows rstart-(K-1) .. rend+1 (table index 0 = row rstart-(K-1))
+  for (int t = threadIdx.x; t < (rend - rstart) + (K - 1) + 2; t += kChainThreads)
+  {
+    const int rw = WROW(rstart - (K - 1) + t);
+    ytab[t]      = make_double2(a.cys[rw], a.cyn[rw]);
+  }
+  __syncthreads();
+
+  const int64_t wg = (int64_t)blockIdx.x * (kChainThreads / 32) + (threadIdx.x >> 5);
+  if (wg * WUSE >= nx) return; // window entirely outside the field (no block-level sync below)
+  const int64_t col_u = wg * WUSE - 2 * HL + 2 * lane; // unwrapped column of my first cell
+  int64_t ic          = col_u;
+  if (ic < 0) ic += nx;
+  else if (ic >= nx) ic -= nx;
+  const bool store_ok = (lane >= HL) && (lane < 32 - HL) && (col_u < nx);
+  unsigned smask      = 0;
+#pragma unroll
+  for (int l = 0; l < K; l++)
+    if (store_ok && a.out[l]) smask |= 1u << l;
+
+  const double2 cw = ld_keep2(a.cxw + ic), ce = ld_keep2(a.cxe + ic);
+  const double sx0 = DADD(cw.x, ce.x), sx1 = DADD(cw.y, ce.y);
+  const double* gx = a.x + ic;
+  const double* gp = a.prev2 + ic;
+  const double* gy = a.yn + ic;
+  const double* gf = a.fn + ic;
+  const int64_t ntot = (int64_t)ny * nx;
+
+  ChainState st;
+  st.soff     = (int64_t)rstart * nx + ic;
+  st.ioff0    = (int64_t)WROW(rstart) * nx;
+  st.ioff1    = (int64_t)WROW(rstart + 1) * nx;
+  st.sx_issue = st.sy_issue = st.sx_use = st.sy_use = 0;
+  st.trow     = K - 1;
+
+  double2 W[K][3];
+#pragma unroll
+  for (int l = 0; l < K; l++) W[l][0] = W[l][1] = W[l][2] = make_double2(0.0, 0.0);
+  // canonical layout at phase 0: index 0 oldest (about to be overwritten), 1 = um, 2 = uc
+  W[0][1] = ld_keep2(gx + (int64_t)WROW(rstart - 1) * nx);
+  W[0][2] = ld_keep2(gx + (int64_t)WROW(rstart) * nx);
+
+  // prologue of the pipeline: groups rstart .. rstart+PF-1
+#pragma unroll
+  for (int q = 0; q < PF; q++)
+  {
+    cp_async16(rx + st.sx_issue * kChainThreads, gx + st.ioff1);
+    cp_async16(rp + st.sx_issue * kChainThreads, gp + st.ioff0);
+    cp_async16(ry + st.sy_issue * kChainThreads, gy + st.ioff0);
+    cp_async16(rf + st.sy_issue * kChainThreads, gf + st.ioff0);
+    cp_async_commit();
+    st.sx_issue = (st.sx_issue + 1 == DX) ? 0 : st.sx_issue + 1;
+    st.sy_issue = (st.sy_issue + 1 == DY) ? 0 : st.sy_issue + 1;
+    st.ioff0    = st.ioff1;
+    st.ioff1 += nx;
+    if (st.ioff1 == ntot) st.ioff1 = 0;
+  }
+
+#define ROW(PH, CHECK, R1) \
+  chain_row<K, PF, PH, CHECK>(a, st, W, rx, rp, ry, rf, ytab, gx, gp, gy, gf, nx, ntot, cw, ce, sx0, sx1, smask, R1, j0, j1, (R1) + PF < rend)
+
+  // phases: [rstart, s0) checked warm-up in whole triples, [s0, s1) unchecked steady state in
+  // triples, [s1, rend3) checked drain; rend3 rounds the trip count up to a multiple of 3 (the
+  // extra rows compute garbage that is never stored and load wrapped, in-range rows).
+  const int total3 = ((rend - rstart + 2) / 3) * 3;
+  int warm         = 2 * (K - 1);
+  warm             = ((warm + 2) / 3) * 3;
+  int steady       = (j1 - (rstart + warm)) / 3 * 3;
+  if (steady < 0) steady = 0;
+  int r1 = rstart;
+#pragma unroll 1
+  for (; r1 < rstart + warm && r1 < rstart + total3; r1 += 3)
+  {
+    ROW(0, true, r1);
+    ROW(1, true, r1 + 1);
+    ROW(2, true, r1 + 2);
+  }
+  const int s1 = r1 + steady;
+#pragma unroll 1
+  for (; r1 < s1; r1 += 3)
+  {
+    ROW(0, false, r1);
+    ROW(1, false, r1 + 1);
+    ROW(2, false, r1 + 2);
+  }
+#pragma unroll 1
+  for (; r1 < rstart + total3; r1 += 3)
+  {
+    ROW(0, true, r1);
+    ROW(1, true, r1 + 1);
+    ROW(2, true, r1 + 2);
+  }
+  cp_async_wait<0>();
+#undef ROW
+#undef WROW
+}
+
+template <int K, int PF>
+static int launch_chain(const ChainArgs& a, dim3 grid, cudaStream_t st)
+{
+  const size_t smem = (size_t)(2 * (PF + 1) + 2 * (PF + K)) * kChainThreads * sizeof(double2) +
+                      (size_t)(a.rows + 3 * (K - 1) + 2) * sizeof(double2);
+  static size_t configured = 0;
+  if (smem > configured)
+  {
+    CU_TRY(cudaFuncSetAttribute(k_chain_march<K, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  k_chain_march<K, PF><<<grid, kChainThreads, smem, st>>>(a);
+  return 0;
+}
+
+static int g_chain_rows = 64;
+
+extern "C" int b200_set_chain_rows(int r)
+{
+  if (r < 1) return -1;
+  g_chain_rows = r;
+  return 0;
+}
+
+extern "C" int b200_stencil_chain(b200_ctx* c, const b200_stencil_geom* g, int nstages,
+                                  const double* x, const double* prev2, const double* yn,
+                                  const double* fn, const double* coeffs, double* const* z_out)
+{
+  if (nstages < 2 || nstages > B200_MAX_CHAIN) return fail("b200_stencil_chain: nstages must be 2..B200_MAX_CHAIN");
+  if (g->halo_w || g->halo_e || g->halo_s || g->halo_n)
+    return fail("b200_stencil_chain: one periodic rank only (no halo buffers)");
+  if ((g->nx & 1) || g->nx < 128 || g->ny < 16) return fail("b200_stencil_chain: needs even nx >= 128 and ny >= 16");
+  if (g->ny >= (int64_t)1 << 30) return fail("b200_stencil_chain: ny too large");
+  ChainArgs a;
+  memset(&a, 0, sizeof(a));
+  a.nx = g->nx; a.ny = g->ny;
+  a.cxw = g->cxw; a.cxe = g->cxe; a.cys = g->cys; a.cyn = g->cyn;
+  a.x = x; a.prev2 = prev2; a.yn = yn; a.fn = fn;
+  if (!aligned16(x) || !aligned16(prev2) || !aligned16(yn) || !aligned16(fn) || !aligned16(a.cxw) || !aligned16(a.cxe))
+    return fail("b200_stencil_chain: operand not 16-byte aligned");
+  bool any = false;
+  for (int l = 0; l < nstages; l++)
+  {
+    for (int k = 0; k < 5; k++) a.c[l][k] = coeffs[5 * l + k];
+    a.out[l] = z_out[l];
+    if (a.out[l])
+    {
+      any = true;
+      if (!aligned16(a.out[l])) return fail("b200_stencil_chain: output not 16-byte aligned");
+      if (a.out[l] == x || a.out[l] == prev2 || a.out[l] == yn || a.out[l] == fn)
+        return fail("b200_stencil_chain: an output aliases an input");
+    }
+  }
+  if (!any || !a.out[nstages - 1]) return fail("b200_stencil_chain: the last stage must be stored");
+  a.rows        = g_chain_rows;
+  const int hl  = (nstages + 1) / 2;
+  const int use = 64 - 4 * hl;
+  int64_t warps = (a.nx + use - 1) / use;
+  int64_t gx    = (warps + kChainThreads / 32 - 1) / (kChainThreads / 32);
+  int64_t gy    = (a.ny + a.rows - 1) / a.rows;
+  if (gy > 65535)
+  {
+    a.rows = (int)((a.ny + 65534) / 65535);
+    gy     = (a.ny + a.rows - 1) / a.rows;
+  }
+  dim3 grid((unsigned)gx, (unsigned)gy);
+  int rc = 0;
+  switch (nstages)
+  {
+  case 2: rc = launch_chain<2, 4>(a, grid, c->stream); break;
+  case 3: rc = launch_chain<3, 4>(a, grid, c->stream); break;
+  case 4: rc = launch_chain<4, 3>(a, grid, c->stream); break;
+  case 5: rc = launch_chain<5, 3>(a, grid, c->stream); break;
+  default: rc = launch_chain<6, 3>(a, grid, c->stream); break;
+  }
+  if (rc) return rc;
+  LAUNCH_CHECK();
+  return 0;
+}
+
 // ------------------------------------------------------------------ halo pack
 __global__ void __launch_bounds__(kThreads)
   k_pack(const double* __restrict__ u, int64_t nx, int64_t ny, double* sw, double* se,

@@ -261,6 +261,19 @@ int rhs_fused(void* self, b200_ctx* ctx, const double* y, int nterms, const doub
   return b200_stencil_lincomb(ctx, &g, y, nterms, c, src, v, z, &ex, 0);
 }
 
+// K consecutive STS stages in one pass (temporal blocking); single periodic rank only
+int rhs_chain(void* self, b200_ctx* ctx, int nstages, const double* x, const double* prev2, const double* yn,
+              const double* fn, const double* coeffs, double* const* z_out)
+{
+  UserData* ud = static_cast<UserData*>(self);
+  b200_stencil_geom g;
+  memset(&g, 0, sizeof(g));
+  g.nx = ud->nx_loc; g.ny = ud->ny_loc;
+  g.cxw = ud->cxw; g.cxe = ud->cxe; g.cys = ud->cys; g.cyn = ud->cyn;
+  ud->rhs_calls += nstages;
+  return b200_stencil_chain(ctx, &g, nstages, x, prev2, yn, fn, coeffs, z_out);
+}
+
 } // namespace
 
 extern "C" {
@@ -340,6 +353,7 @@ struct UserOptions
   // B200 extras (not reference flags)
   bool no_overlap = false, no_fusion = false;
   int rows_per_block = 0;
+  int chain = 0; // temporal-blocking depth (0 = default / B200_CHAIN, 1 = off)
 };
 
 // One pass over argv; unknown flags are an error like main.cpp:116-132.
@@ -375,7 +389,7 @@ int parse_args(std::vector<std::string> args, UserData& ud, UserOptions& uo, boo
     ARG_B("--noprec", uo.preconditioning, false) ARG_B("--internaleig", uo.internaleig, true)
     ARG_I("--output", uo.output) ARG_I("--nout", uo.nout)
     ARG_B("--no-overlap", uo.no_overlap, true) ARG_B("--no-fusion", uo.no_fusion, true)
-    ARG_I("--rows-per-block", uo.rows_per_block)
+    ARG_I("--rows-per-block", uo.rows_per_block) ARG_I("--chain", uo.chain)
     if (outproc) fprintf(stderr, "ERROR: Unknown inputs: %s\n", a.c_str());
     return -1;
   }
@@ -577,6 +591,18 @@ extern "C" int b200_d2d_create(int argc, const char* const* argv, int rank, int 
   p->ud.overlap     = !p->uo.no_overlap;
   p->ud.rhs_op.self = &p->ud;
   p->ud.rhs_op.fused = rhs_fused;
+  p->ud.rhs_op.chain = nullptr;
+  p->ud.rhs_op.chain_max = 0;
+  if (nranks == 1 && p->ud.nx_loc % 2 == 0 && p->ud.nx_loc >= 128 && p->ud.ny_loc >= 16)
+  { // temporal blocking needs the periodic index wrap of a single rank (b200_stencil_chain)
+    p->ud.rhs_op.chain     = rhs_chain;
+    p->ud.rhs_op.chain_max = B200_MAX_CHAIN;
+  }
+  {
+    int depth = p->uo.chain;
+    if (depth <= 0) { const char* e = getenv("B200_CHAIN"); depth = e ? atoi(e) : 4; }
+    N_VSetStageChain_B200(depth);
+  }
   if (p->uo.rows_per_block > 0) b200_set_rows_per_block(p->uo.rows_per_block);
   N_VSetLazyFusion_B200(p->uo.no_fusion ? 0 : 1);
   if (p->ud.upload_tables()) return -1;
@@ -677,6 +703,8 @@ extern "C" int b200_d2d_get_stats(b200_d2d* p, b200_d2d_stats* s)
   s->aliased_copies     = vs.aliased_copies - p->vs0.aliased_copies;
   s->wrms_fused         = vs.wrms_fused - p->vs0.wrms_fused;
   s->buffers_allocated  = vs.buffers_allocated - p->vs0.buffers_allocated;
+  s->chain_launches     = vs.chain_launches - p->vs0.chain_launches;
+  s->chain_stages       = vs.chain_stages - p->vs0.chain_stages;
   s->kernel_launches    = b200_launch_count() - p->launches0;
   s->nx = p->ud.nx; s->ny = p->ud.ny; s->nx_loc = p->ud.nx_loc; s->ny_loc = p->ud.ny_loc;
   s->is = p->ud.is; s->js = p->ud.js; s->npx = p->ud.npx; s->npy = p->ud.npy;
@@ -790,7 +818,7 @@ extern "C" int b200_d2d_main(int argc, char** argv)
   for (int k = 1; k < argc; k++)
     if (std::string(argv[k]) == "--help")
     {
-      if (rank == 0) printf("options: see /root/reference/diffusion_2D (same flags) plus --no-overlap --no-fusion --rows-per-block N\n");
+      if (rank == 0) printf("options: see /root/reference/diffusion_2D (same flags) plus --no-overlap --no-fusion --rows-per-block N --chain K\n");
       return 0;
     }
   b200_d2d* p = nullptr;
@@ -851,7 +879,8 @@ extern "C" int b200_d2d_main(int argc, char** argv)
     printf("Total simulation time = %.15e\n\n", p->evolve_seconds);
     printf("Final integrator statistics:\n");
     b200_d2d_print_stats(p);
-    printf("B200 fused stage launches     = %ld\n", s.fused_launches);
+    printf("B200 fused stage evaluations  = %ld\n", s.fused_launches);
+    printf("B200 chained launches/stages  = %ld / %ld\n", s.chain_launches, s.chain_stages);
     printf("B200 plain RHS launches       = %ld\n", s.plain_rhs_launches);
     printf("B200 aliased copies           = %ld\n", s.aliased_copies);
     printf("B200 fused WRMS norms         = %ld\n", s.wrms_fused);

@@ -13,6 +13,13 @@
 //   * in-place forms such as N_VLinearSum(1,y,c,F,y) with F = L(y) (SSP stages,
 //     arkode_lsrkstep.c:1213-1231) are automatically ping-ponged,
 //   * ARKODE swapping its tempv1/tempv2 handles (arkode_lsrkstep.c:742-744) is harmless.
+//
+// Temporal blocking.  An STS stage  z = c0 L(x) + c1 p + c2 yn + c3 x + c4 fn
+// (arkode_lsrkstep.c:706-717 RKC, :1001-1012 RKL) is not launched when it is requested either: z
+// becomes a PENDING STAGE value.  If the next stage is built on it with the matching operands
+// (its p is this stage's x, same yn / fn) the chain grows; at the configured depth, or as soon
+// as anything else needs one of the values, the whole chain goes out as ONE kernel
+// (B200RhsOp::chain -> b200_stencil_chain) that stores only the levels somebody still points at.
 
 #include "nvector_b200.h"
 
@@ -38,8 +45,9 @@ namespace {
   }                                     \
   while (0)
 
-B200VecStats g_stats = {0, 0, 0, 0, 0};
+B200VecStats g_stats = {0, 0, 0, 0, 0, 0, 0};
 bool g_lazy          = true;
+int g_chain_max      = 4; // stages per temporally blocked launch (1 = off)
 
 // buffers of one local length on one context, shared by all clones
 struct Shared
@@ -54,12 +62,24 @@ struct Shared
 };
 const int kSlots = 8;
 
+struct Value;
+
+// a requested-but-not-launched STS stage:  c[0] L(x) + c[1] p2 + c[2] yn + c[3] x + c[4] fn
+struct StageRec
+{
+  const B200RhsOp* op;
+  Value *x, *p2, *yn, *fn; // one reference held on each
+  double c[5];
+  int depth;               // 1 for the first stage of a chain
+};
+
 struct Value
 {
   int refs;
-  double* d;           // device data, nullptr while deferred
+  double* d;           // device data, nullptr while deferred / pending
   const B200RhsOp* op; // deferred: value = op(src)
   Value* src;
+  StageRec* st;        // pending stage (d == nullptr, op == nullptr)
   // fused WRMS partial: sum (this_i * w_i)^2 already sits in slot
   Value* wrms_w;
   int wrms_slot;
@@ -105,6 +125,15 @@ void value_release(Shared* sh, Value* v)
     if (v->d) sh->free_bufs.push_back(v->d);
     if (v->wrms_w) value_release(sh, v->wrms_w);
     Value* next = v->src; // a deferred value owns a reference on its source
+    if (v->st)
+    { // a pending stage that was never needed: drop its operands
+      StageRec* r = v->st;
+      value_release(sh, r->p2);
+      value_release(sh, r->yn);
+      value_release(sh, r->fn);
+      next = r->x; // (src is null for a pending stage)
+      delete r;
+    }
     delete v;
     v = next;
   }
@@ -117,6 +146,7 @@ Value* value_new(Shared* sh, bool with_buffer)
   v->d         = with_buffer ? pool_get(sh) : nullptr;
   v->op        = nullptr;
   v->src       = nullptr;
+  v->st        = nullptr;
   v->wrms_w    = nullptr;
   v->wrms_slot = -1;
   v->sig       = 0;
@@ -208,9 +238,74 @@ void launch_fused(Shared* sh, Value* L, int nterms, const double* cf, Value* con
   }
 }
 
+// Launch the chain of pending stages that ends in `top` as one kernel (or, for a single
+// stage, as the ordinary fused stage launch).
+void launch_chain(Shared* sh, Value* top)
+{
+  Value* lv[B200_MAX_CHAIN]; // lv[0] = first stage of the chain ... lv[n-1] = top
+  int n = 0;
+  {
+    Value* rev[B200_MAX_CHAIN];
+    Value* u = top;
+    while (u && !u->d && u->st && n < B200_MAX_CHAIN) { rev[n++] = u; u = u->st->x; }
+    for (int k = 0; k < n; k++) lv[k] = rev[n - 1 - k];
+  }
+  StageRec* first = lv[0]->st;
+  materialise(sh, first->x); // (only reachable if a chain longer than B200_MAX_CHAIN was built)
+  materialise(sh, first->p2);
+  materialise(sh, first->yn);
+  materialise(sh, first->fn);
+  // a level must be stored iff somebody outside this chain still points at it: chain-internal
+  // references are the next stage's x and the stage after that's p2
+  double* outs[B200_MAX_CHAIN];
+  double cf[B200_MAX_CHAIN * 5];
+  for (int k = 0; k < n; k++)
+  {
+    int internal = 0;
+    if (k + 1 < n) internal++;
+    if (k + 2 < n) internal++;
+    const bool keep = (k == n - 1) || (lv[k]->refs - internal > 0);
+    outs[k]         = keep ? pool_get(sh) : nullptr;
+    for (int q = 0; q < 5; q++) cf[5 * k + q] = lv[k]->st->c[q];
+  }
+  if (n == 1)
+  {
+    int srcs[5]         = {B200_SRC_STENCIL, B200_SRC_VECTOR, B200_SRC_VECTOR, B200_SRC_CENTRE, B200_SRC_VECTOR};
+    const double* vp[5] = {nullptr, first->p2->d, first->yn->d, nullptr, first->fn->d};
+    int wdone           = 0;
+    DEV(first->op->fused(first->op->self, sh->ctx, first->x->d, 5, cf, srcs, vp, outs[0], nullptr, nullptr, nullptr,
+                         &wdone));
+  }
+  else
+  {
+    DEV(first->op->chain(first->op->self, sh->ctx, n, first->x->d, first->p2->d, first->yn->d, first->fn->d, cf, outs));
+    g_stats.chain_launches++;
+    g_stats.chain_stages += n;
+  }
+  // retire the records bottom-up; values nobody points at any more disappear with them
+  for (int k = 0; k < n; k++) lv[k]->refs++; // pin while we rewire
+  for (int k = 0; k < n; k++)
+  {
+    StageRec* r = lv[k]->st;
+    lv[k]->st   = nullptr;
+    lv[k]->d    = outs[k];
+    value_release(sh, r->x);
+    value_release(sh, r->p2);
+    value_release(sh, r->yn);
+    value_release(sh, r->fn);
+    delete r;
+  }
+  for (int k = 0; k < n; k++)
+  {
+    if (lv[k]->refs == 1 && !lv[k]->d) { delete lv[k]; } // unpinned, never stored, unreachable
+    else value_release(sh, lv[k]);
+  }
+}
+
 void materialise(Shared* sh, Value* v)
 {
   if (v->d) return;
+  if (v->st) { launch_chain(sh, v); return; }
   if (!v->op) die("materialise: value has neither data nor operator", -1);
   // f = 1 * L(src), stored through the f_out path so v itself becomes plain
   const double one = 1.0;
@@ -240,27 +335,57 @@ void eval_lincomb(int nterms, const double* cf, N_Vector* Xv, N_Vector zv)
     sync_from_host(C(Xv[k]));
     X[k] = C(Xv[k])->val;
   }
-  // pick the deferred operand to fuse (first one); others are materialised
+  // pick the deferred RHS operand to fuse (first one)
   Value* L = nullptr;
   for (int k = 0; k < nterms; k++)
-  {
-    if (!X[k]->d)
-    {
-      if (!L) L = X[k];
-      else if (X[k] != L) materialise(sh, X[k]);
-    }
-  }
+    if (!X[k]->d && X[k]->op && !L) L = X[k];
   if (L)
   {
     int uses = 0;
     for (int k = 0; k < nterms; k++) uses += (X[k] == L);
     if (uses > 1 || !g_lazy) { materialise(sh, L); L = nullptr; }
   }
+  // F itself must be kept if anything other than z will still point at it
+  const bool store_f = L && (L->refs - (zc->val == L ? 1 : 0)) > 0;
+
+  // STS stage pattern [L(x), p, yn, x, fn]: defer it as a pending stage (temporal blocking)
+  if (L && g_chain_max >= 2 && nterms == 5 && !store_f && L->op->chain && L->op->chain_max >= 2 && X[0] == L &&
+      X[3] == L->src && X[1] != L && X[2] != L && X[4] != L && X[1] != X[3])
+  {
+    const int cmax = g_chain_max < L->op->chain_max ? g_chain_max : L->op->chain_max;
+    Value* xin     = L->src;
+    int depth      = 1;
+    if (!xin->d && xin->st)
+    { // the input is itself a pending stage: extend its chain if the operands line up
+      StageRec* pr = xin->st;
+      if (pr->op == L->op && X[1] == pr->x && X[2] == pr->yn && X[4] == pr->fn && pr->depth < cmax) depth = pr->depth + 1;
+      else materialise(sh, xin);
+    }
+    else materialise(sh, xin);
+    if (depth == 1) materialise(sh, X[1]);
+    materialise(sh, X[2]);
+    materialise(sh, X[4]);
+    Value* out  = value_new(sh, false);
+    StageRec* r = new StageRec();
+    r->op = L->op; r->x = xin; r->p2 = X[1]; r->yn = X[2]; r->fn = X[4];
+    r->x->refs++; r->p2->refs++; r->yn->refs++; r->fn->refs++;
+    for (int q = 0; q < 5; q++) r->c[q] = cf[q];
+    r->depth = depth;
+    out->st  = r;
+    out->refs++;      // keep it alive across the assignment below
+    assign(zc, out);  // (drops L, which releases its reference on xin)
+    g_stats.fused_launches++;
+    if (depth >= cmax) launch_chain(sh, out);
+    value_release(sh, out);
+    return;
+  }
+
+  for (int k = 0; k < nterms; k++)
+    if (!X[k]->d && X[k] != L) materialise(sh, X[k]);
+  if (L) materialise(sh, L->src);
   Value* out = value_new(sh, true);
   if (L)
   {
-    // F itself must be kept if anything other than z will still point at it
-    const bool store_f = (L->refs - (zc->val == L ? 1 : 0)) > 0;
     launch_fused(sh, L, nterms, cf, X, out, store_f);
     g_stats.fused_launches++;
   }
@@ -641,6 +766,13 @@ int N_VSetDeferredRhs_B200(N_Vector f, const B200RhsOp* op, N_Vector y)
 
 int N_VIsDeferred_B200(N_Vector v) { return (C(v)->val && !C(v)->val->d) ? 1 : 0; }
 void N_VSetLazyFusion_B200(int on) { g_lazy = (on != 0); }
+void N_VSetStageChain_B200(int depth)
+{
+  if (depth < 1) depth = 1;
+  if (depth > B200_MAX_CHAIN) depth = B200_MAX_CHAIN;
+  g_chain_max = depth;
+}
+int N_VGetStageChain_B200(void) { return g_chain_max; }
 void N_VGetStats_B200(B200VecStats* s) { *s = g_stats; }
 
 } // extern "C"

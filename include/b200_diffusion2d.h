@@ -40,6 +40,7 @@ typedef struct b200_d2d_stats
   uint64_t kernel_launches; /* b200_launch_count() */
   int64_t nx, ny, nx_loc, ny_loc, is, js;
   int npx, npy, rank, nranks;
+  long chain_launches, chain_stages; /* temporally blocked launches and the stages they covered */
 } b200_d2d_stats;
 
 /* Build the problem from reference-style arguments, e.g.

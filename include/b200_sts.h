@@ -143,6 +143,22 @@ int b200_stencil_lincomb(b200_ctx* ctx, const b200_stencil_geom* g,
                          const int* src, const double* const* v, double* z,
                          const b200_stage_extras* extras, int region);
 
+/* Temporal blocking: `nstages` (2..B200_MAX_CHAIN) consecutive
+   RKC/RKL stages of SUN/src/arkode/arkode_lsrkstep.c:674-750 (RKC) / :960-1050 (RKL)
+   in one pass.  Stage l (1-based) computes
+       z_l = c[l][0]*L(z_{l-1}) + c[l][1]*z_{l-2} + c[l][2]*yn + c[l][3]*z_{l-1} + c[l][4]*fn
+   with z_0 = x and z_{-1} = prev2, evaluated left to right exactly as
+   b200_stencil_lincomb would, so results are bit-identical to nstages separate
+   launches.  coeffs is [nstages][5] row-major; z_out[l] receives z_{l+1} or may be
+   NULL for an intermediate stage nobody reads (the last stage must be stored).
+   One periodic rank only (all halo_* NULL), nx even >= 128, ny >= 16. */
+#define B200_MAX_CHAIN 6
+int b200_stencil_chain(b200_ctx* ctx, const b200_stencil_geom* g, int nstages,
+                       const double* x, const double* prev2, const double* yn,
+                       const double* fn, const double* coeffs, double* const* z_out);
+/* rows of output each thread block of the chain kernel marches over (default 64) */
+int b200_set_chain_rows(int rows);
+
 /* Tuning knob: rows of the sub-domain each thread block of the fused kernel marches over
    (default 8).  Results do not depend on it. */
 int b200_set_rows_per_block(int rows);

@@ -41,6 +41,13 @@ typedef struct B200RhsOp
   int (*fused)(void* self, b200_ctx* ctx, const double* y, int nterms, const double* c,
                const int* src, const double* const* v, double* z, double* f_out,
                const double* wrms_w, double* wrms_result, int* wrms_done);
+  /* Optional (NULL / 0 = not available): temporal blocking of `nstages` <= chain_max
+     consecutive STS stages  z_l = c[l][0] F(z_{l-1}) + c[l][1] z_{l-2} + c[l][2] yn +
+     c[l][3] z_{l-1} + c[l][4] fn  (z_0 = x, z_{-1} = prev2) in one kernel; coeffs is
+     [nstages][5], z_out[l] == NULL means "stage l+1 need not be stored". */
+  int (*chain)(void* self, b200_ctx* ctx, int nstages, const double* x, const double* prev2,
+               const double* yn, const double* fn, const double* coeffs, double* const* z_out);
+  int chain_max;
 } B200RhsOp;
 
 /* Create a vector: local_length entries on this rank's GPU, global_length overall
@@ -65,15 +72,22 @@ SUNDIALS_EXPORT int N_VSetDeferredRhs_B200(N_Vector f, const B200RhsOp* op, N_Ve
 SUNDIALS_EXPORT int N_VIsDeferred_B200(N_Vector v);
 /* Turn lazy fusion off (every RHS materialises immediately) / on; default on. */
 SUNDIALS_EXPORT void N_VSetLazyFusion_B200(int on);
+/* Temporal blocking depth: how many consecutive STS stages one kernel launch may cover
+   (1 = off, default 4, at most B200_MAX_CHAIN and what the RHS operator supports).
+   Results do not depend on it (bit-identical). */
+SUNDIALS_EXPORT void N_VSetStageChain_B200(int depth);
+SUNDIALS_EXPORT int N_VGetStageChain_B200(void);
 
 /* statistics since process start: fused launches, aliased copies, device buffers */
 typedef struct B200VecStats
 {
-  long fused_launches;    /* stencil+combination kernels launched from the ops */
+  long fused_launches;    /* RHS evaluations realised inside a fused (stencil+combination) kernel */
   long plain_rhs_launches;/* deferred values materialised on their own */
   long aliased_copies;    /* N_VScale(1,x,z) turned into a handle share */
   long buffers_allocated; /* cudaMalloc'd vector buffers */
   long wrms_fused;        /* WRMS norms answered from a fused partial */
+  long chain_launches;    /* temporally blocked launches (>= 2 stages each) */
+  long chain_stages;      /* stages covered by those launches */
 } B200VecStats;
 SUNDIALS_EXPORT void N_VGetStats_B200(B200VecStats* s);
 

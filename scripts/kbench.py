@@ -43,6 +43,8 @@ def main():
     out = {}
     for rows in [int(r) for r in args.rows.split(",")]:
         lib.b200_set_rows_per_block(rows)
+        if args.pattern.startswith("chain"):
+            lib.b200_set_chain_rows(rows)
 
         def launch(k):
             x, v1, yn, fn, z = bufs[k % 3], bufs[(k + 1) % 3], bufs[3], bufs[4], bufs[(k + 2) % 3]
@@ -56,6 +58,14 @@ def main():
                 ex = b200.StageExtras(bufs[5].data_ptr(), None, None, None, None, None, None)
                 ctx.stencil_lincomb(g, x, [0.8, -0.8, 0.4e-4, 0.4e-4], [0, 1, 0, 2], [yn, None, fn, None], z, ex)
                 return 40.0
+            if args.pattern.startswith("chain"):
+                kk = int(args.pattern[5:])
+                cs = [[1e-7 * (l + 1), -0.3, 0.2, 1.1, -2e-8] for l in range(kk)]
+                outs = [None] * kk
+                outs[kk - 1] = z
+                outs[kk - 2] = bufs[5]
+                ctx.stencil_chain(g, x, v1, yn, fn, cs, outs)
+                return 40.0 * kk
             raise SystemExit("unknown pattern")
 
         for k in range(5):

@@ -362,3 +362,45 @@ def test_full_size_shift_equivariance_and_conservation(ctx, b200, n):
     ctx.lincomb(c, [f, v1, u], z2)
     torch.cuda.synchronize()
     assert torch.equal(z, z2)
+
+
+# --------------------------------------------------------------- temporally blocked stage chains
+@pytest.mark.parametrize("size", [(128, 16), (192, 70), (1024, 96), (2050, 33)], ids=lambda s: "%dx%d" % s)
+@pytest.mark.parametrize("k", [2, 3, 4, 5, 6])
+@pytest.mark.parametrize("rows", [64, 5])
+def test_stencil_chain_equals_single_stage_launches(ctx, b200, size, k, rows):
+    """b200_stencil_chain (K stages in one pass) must be bit-identical to K b200_stencil_lincomb launches
+    (which are themselves pinned against the oracle above), including periodic wrap in x and y, partial
+    windows (nx not a multiple of 60/56) and partial row blocks."""
+    nx, ny = size
+    n = nx * ny
+    rng = np.random.default_rng(nx * 7 + ny + k)
+    lib = b200.kernel_lib()
+    lib.b200_set_chain_rows(rows)
+    cx = [dev(rng.random(nx) + 0.5) for _ in range(2)]
+    cy = [dev(rng.random(ny) + 0.5) for _ in range(2)]
+    g = b200.StencilGeom(nx, ny, cx[0].data_ptr(), cx[1].data_ptr(), cy[0].data_ptr(), cy[1].data_ptr(), None, None, None, None)
+    x, p2, yn, fn = (dev(rng.standard_normal(n)) for _ in range(4))
+    coeffs = [[1e-3 * (l + 1), -0.3 + 0.1 * l, 0.2, 1.1 - 0.05 * l, -2e-4] for l in range(k)]
+    # reference: one launch per stage
+    zs = []
+    prev, cur = p2, x
+    for l in range(k):
+        z = torch.empty(n, dtype=torch.float64, device="cuda")
+        ctx.stencil_lincomb(g, cur, coeffs[l], [2, 0, 0, 1, 0], [None, prev, yn, None, fn], z)
+        zs.append(z)
+        prev, cur = cur, z
+    # chain: all levels stored
+    outs = [torch.full((n,), np.nan, dtype=torch.float64, device="cuda") for _ in range(k)]
+    ctx.stencil_chain(g, x, p2, yn, fn, coeffs, outs)
+    ctx.sync()
+    for l in range(k):
+        assert np.array_equal(host(outs[l]), host(zs[l])), "level %d" % (l + 1)
+    # chain: only the last two levels stored (what LSRKStep needs)
+    outs2 = [None] * k
+    outs2[k - 1] = torch.full((n,), np.nan, dtype=torch.float64, device="cuda")
+    outs2[k - 2] = torch.full((n,), np.nan, dtype=torch.float64, device="cuda")
+    ctx.stencil_chain(g, x, p2, yn, fn, coeffs, outs2)
+    ctx.sync()
+    assert np.array_equal(host(outs2[k - 1]), host(zs[k - 1])) and np.array_equal(host(outs2[k - 2]), host(zs[k - 2]))
+    lib.b200_set_chain_rows(64)
