@@ -90,6 +90,8 @@ struct b200_ctx
   double* host_result = nullptr; // [8] pinned mirror
   ncclComm_t comm     = nullptr;
   int rank = 0, nranks = 1;
+  double* strips      = nullptr; // W/E send staging of b200_deep_halo_exchange
+  size_t strip_cap    = 0;
 };
 
 extern "C" int b200_ctx_create(int device, void* stream, b200_ctx** out)
@@ -126,6 +128,7 @@ extern "C" int b200_ctx_destroy(b200_ctx* c)
   cudaStreamSynchronize(c->stream);
   cudaStreamSynchronize(c->comm_stream);
   if (c->comm && g_nccl_destroy) g_nccl_destroy(c->comm);
+  if (c->strips) cudaFree(c->strips);
   cudaFree(c->partials);
   cudaFree(c->ticket);
   cudaFree(c->dev_result);
@@ -1023,9 +1026,33 @@ struct ChainArgs
   double c[B200_MAX_CHAIN][5];
   double* out[B200_MAX_CHAIN];
   int rows;
+  // multi-rank (HALO = true): per-operand deep-halo buffers, layout of b200_deep_halo_exchange
+  const double *hx, *hp, *hy, *hf;
+  int g, g2; // halo depth in rows / in columns (g >= K, g2 even >= 2*ceil(K/2))
 };
 
 static const int kChainThreads = 256;
+
+// address of (row r, this lane's column), r in [-g, ny+g):
+//   wrap mode: rows outside [0, ny) wrap periodically onto the field itself;
+//   halo mode: they come from the field's deep halo
+//     halo = [ S: g rows x nx | N: g rows x nx | W: (ny+2g) rows x g2 | E: (ny+2g) rows x g2 ]
+//     (S = rows -g..-1, N = rows ny..ny+g-1, W / E = columns -g2..-1 / nx..nx+g2-1 of rows
+//     -g..ny+g-1); we = this lane lies in a W/E strip (lane_col then includes the strip offset).
+template <bool HALO>
+__device__ __forceinline__ const double* row_ptr(const double* field, const double* halo, int r, bool we,
+                                                 int64_t lane_col, int64_t nx, int ny, int g, int g2)
+{
+  if (!HALO)
+  {
+    const int rw = (r < 0) ? r + ny : ((r >= ny) ? r - ny : r);
+    return field + (int64_t)rw * nx + lane_col;
+  }
+  if (we) return halo + lane_col + (int64_t)(r + g) * g2;
+  if (r >= 0 && r < ny) return field + (int64_t)r * nx + lane_col;
+  const int hr = (r < 0) ? r + g : g + (r - ny);
+  return halo + (int64_t)hr * nx + lane_col;
+}
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
 {
@@ -1054,36 +1081,55 @@ __device__ __forceinline__ void cp_async_wait()
 struct ChainState
 {
   int64_t soff;      // r1*nx + ic (unwrapped; valid whenever a store can happen)
-  int64_t ioff0;     // wrapped row offset of the next group's row r      (prev2, yn, fn)
-  int64_t ioff1;     // wrapped row offset of the next group's row r + 1  (x)
-  int sx_issue, sy_issue, sx_use, sy_use; // ring slots (byte offsets / 16 / threads)
+  const double *px, *pp, *py, *pf; // next group: x at row ir+1 ; prev2 / yn / fn at row ir
+  int64_t pstep;     // row stride of this lane's source (nx, or g2 in a W/E halo strip)
+  int ir;            // unwrapped row of the next group
+  int sx_issue, sy_issue, sx_use, sy_use; // ring slots
   int trow;          // index of row r1 in the y-coefficient table
+  bool we;           // halo mode: this lane reads the W/E halo strips
+  int64_t lane_col;  // column (halo mode: strip offset + column) of this lane
 };
 
-template <int K, int PF, int PH, bool CHECK>
+// issue group(ir) = { x row ir+1, prev2 / yn / fn row ir } into the ring and advance the running
+// source pointers by one row; the pointers are recomputed only where the source changes
+// (rows 0 and ny: wrap-around, or field <-> S/N halo)
+template <int K, int PF, bool HALO>
+__device__ __forceinline__ void chain_issue(const ChainArgs& a, ChainState& st, double2* rx, double2* rp,
+                                            double2* ry, double2* rf, int64_t nx, int ny, bool issue)
+{
+  constexpr int DX = PF + 1, DY = PF + K;
+  if (issue)
+  {
+    cp_async16(rx + st.sx_issue * kChainThreads, st.px);
+    cp_async16(rp + st.sx_issue * kChainThreads, st.pp);
+    cp_async16(ry + st.sy_issue * kChainThreads, st.py);
+    cp_async16(rf + st.sy_issue * kChainThreads, st.pf);
+  }
+  cp_async_commit();
+  st.sx_issue = (st.sx_issue + 1 == DX) ? 0 : st.sx_issue + 1;
+  st.sy_issue = (st.sy_issue + 1 == DY) ? 0 : st.sy_issue + 1;
+  const int r = ++st.ir;
+  if (r == 0 || r == ny)
+  {
+    st.pp = row_ptr<HALO>(a.prev2, a.hp, r, st.we, st.lane_col, nx, ny, a.g, a.g2);
+    st.py = row_ptr<HALO>(a.yn, a.hy, r, st.we, st.lane_col, nx, ny, a.g, a.g2);
+    st.pf = row_ptr<HALO>(a.fn, a.hf, r, st.we, st.lane_col, nx, ny, a.g, a.g2);
+  }
+  else { st.pp += st.pstep; st.py += st.pstep; st.pf += st.pstep; }
+  if (r + 1 == 0 || r + 1 == ny) st.px = row_ptr<HALO>(a.x, a.hx, r + 1, st.we, st.lane_col, nx, ny, a.g, a.g2);
+  else st.px += st.pstep;
+}
+
+template <int K, int PF, int PH, bool CHECK, bool HALO>
 __device__ __forceinline__ void chain_row(const ChainArgs& a, ChainState& st, double2 (&W)[K][3],
                                           double2* rx, double2* rp, double2* ry, double2* rf,
-                                          const double2* ytab, const double* gx, const double* gp,
-                                          const double* gy, const double* gf, int64_t nx, int64_t ntot,
+                                          const double2* ytab, int64_t nx, int ny,
                                           double2 cw, double2 ce, double sx0, double sx1,
                                           unsigned smask, int r1, int j0, int j1, bool issue)
 {
   constexpr int DX = PF + 1, DY = PF + K;
   constexpr int IO = PH % 3, IM = (PH + 1) % 3, IC = (PH + 2) % 3; // oldest (overwritten), then um, uc ; up = IO
-  // ---- issue group(r1 + PF): x row +1, prev2 / yn / fn row +0
-  if (issue)
-  {
-    cp_async16(rx + st.sx_issue * kChainThreads, gx + st.ioff1);
-    cp_async16(rp + st.sx_issue * kChainThreads, gp + st.ioff0);
-    cp_async16(ry + st.sy_issue * kChainThreads, gy + st.ioff0);
-    cp_async16(rf + st.sy_issue * kChainThreads, gf + st.ioff0);
-  }
-  cp_async_commit();
-  st.sx_issue = (st.sx_issue + 1 == DX) ? 0 : st.sx_issue + 1;
-  st.sy_issue = (st.sy_issue + 1 == DY) ? 0 : st.sy_issue + 1;
-  st.ioff0    = st.ioff1;
-  st.ioff1 += nx;
-  if (st.ioff1 == ntot) st.ioff1 = 0;
+  chain_issue<K, PF, HALO>(a, st, rx, rp, ry, rf, nx, ny, issue); // group(r1 + PF)
   cp_async_wait<PF>(); // all but the PF newest groups have landed: group(r1) is ready
 
   W[0][IO]        = rx[st.sx_use * kChainThreads]; // x row r1+1 replaces the oldest row
@@ -1133,7 +1179,7 @@ __device__ __forceinline__ void chain_row(const ChainArgs& a, ChainState& st, do
   st.sy_use = (st.sy_use + 1 == DY) ? 0 : st.sy_use + 1;
 }
 
-template <int K, int PF>
+template <int K, int PF, bool HALO>
 __global__ void __launch_bounds__(kChainThreads, 2) k_chain_march(const ChainArgs a)
 {
   constexpr int HL   = (K + 1) / 2;  // halo lanes per side (2 cells each): 2*HL >= K
@@ -1157,8 +1203,8 @@ __global__ void __launch_bounds__(kChainThreads, 2) k_chain_march(const ChainArg
 #define WROW(r) ((r) < 0 ? (r) + ny : ((r) >= ny ? (r) - ny : (r)))
   // y-direction face coefficients of rows rstart-(K-1) .. rend+1 (table index 0 = row rstart-(K-1))
   for (int t = threadIdx.x; t < (rend - rstart) + (K - 1) + 2; t += kChainThreads)
-  {
-    const int rw = WROW(rstart - (K - 1) + t);
+  { // HALO: the tables are extended by the caller (global periodic index), negative rows are valid
+    const int rw = HALO ? (rstart - (K - 1) + t) : WROW(rstart - (K - 1) + t);
     ytab[t]      = make_double2(a.cys[rw], a.cyn[rw]);
   }
   __syncthreads();
@@ -1166,55 +1212,63 @@ __global__ void __launch_bounds__(kChainThreads, 2) k_chain_march(const ChainArg
   const int64_t wg = (int64_t)blockIdx.x * (kChainThreads / 32) + (threadIdx.x >> 5);
   if (wg * WUSE >= nx) return; // window entirely outside the field (no block-level sync below)
   const int64_t col_u = wg * WUSE - 2 * HL + 2 * lane; // unwrapped column of my first cell
-  int64_t ic          = col_u;
-  if (ic < 0) ic += nx;
-  else if (ic >= nx) ic -= nx;
   const bool store_ok = (lane >= HL) && (lane < 32 - HL) && (col_u < nx);
   unsigned smask      = 0;
 #pragma unroll
   for (int l = 0; l < K; l++)
     if (store_ok && a.out[l]) smask |= 1u << l;
 
-  const double2 cw = ld_keep2(a.cxw + ic), ce = ld_keep2(a.cxe + ic);
-  const double sx0 = DADD(cw.x, ce.x), sx1 = DADD(cw.y, ce.y);
-  const double* gx = a.x + ic;
-  const double* gp = a.prev2 + ic;
-  const double* gy = a.yn + ic;
-  const double* gf = a.fn + ic;
-  const int64_t ntot = (int64_t)ny * nx;
-
   ChainState st;
+  int64_t ic = col_u; // column used for stores and (wrap mode) loads
+  int64_t xc = col_u; // column index into the x-direction coefficient tables
+  st.we      = false;
+  st.pstep   = nx;
+  if (HALO)
+  { // columns outside [0, nx) come from the W / E halo strips; beyond the strips: clamp (never used)
+    const int64_t strip = (int64_t)(ny + 2 * a.g) * a.g2;
+    if (col_u < 0) { st.we = true; st.lane_col = 2 * a.g * nx + (col_u + a.g2); }
+    else if (col_u >= nx)
+    {
+      int64_t c = col_u - nx;
+      if (c > a.g2 - 2) { c = a.g2 - 2; xc = nx + c; }
+      st.we       = true;
+      st.lane_col = 2 * a.g * nx + strip + c;
+    }
+    else st.lane_col = col_u;
+    if (st.we) st.pstep = a.g2;
+  }
+  else
+  {
+    if (ic < 0) ic += nx;
+    else if (ic >= nx) ic -= nx;
+    xc          = ic;
+    st.lane_col = ic;
+  }
+  const double2 cw = ld_keep2(a.cxw + xc), ce = ld_keep2(a.cxe + xc);
+  const double sx0 = DADD(cw.x, ce.x), sx1 = DADD(cw.y, ce.y);
+
   st.soff     = (int64_t)rstart * nx + ic;
-  st.ioff0    = (int64_t)WROW(rstart) * nx;
-  st.ioff1    = (int64_t)WROW(rstart + 1) * nx;
   st.sx_issue = st.sy_issue = st.sx_use = st.sy_use = 0;
   st.trow     = K - 1;
+  st.ir       = rstart;
+  st.px = row_ptr<HALO>(a.x, a.hx, rstart + 1, st.we, st.lane_col, nx, ny, a.g, a.g2);
+  st.pp = row_ptr<HALO>(a.prev2, a.hp, rstart, st.we, st.lane_col, nx, ny, a.g, a.g2);
+  st.py = row_ptr<HALO>(a.yn, a.hy, rstart, st.we, st.lane_col, nx, ny, a.g, a.g2);
+  st.pf = row_ptr<HALO>(a.fn, a.hf, rstart, st.we, st.lane_col, nx, ny, a.g, a.g2);
 
   double2 W[K][3];
 #pragma unroll
   for (int l = 0; l < K; l++) W[l][0] = W[l][1] = W[l][2] = make_double2(0.0, 0.0);
   // canonical layout at phase 0: index 0 oldest (about to be overwritten), 1 = um, 2 = uc
-  W[0][1] = ld_keep2(gx + (int64_t)WROW(rstart - 1) * nx);
-  W[0][2] = ld_keep2(gx + (int64_t)WROW(rstart) * nx);
+  W[0][1] = ld_keep2(row_ptr<HALO>(a.x, a.hx, rstart - 1, st.we, st.lane_col, nx, ny, a.g, a.g2));
+  W[0][2] = ld_keep2(row_ptr<HALO>(a.x, a.hx, rstart, st.we, st.lane_col, nx, ny, a.g, a.g2));
 
   // prologue of the pipeline: groups rstart .. rstart+PF-1
 #pragma unroll
-  for (int q = 0; q < PF; q++)
-  {
-    cp_async16(rx + st.sx_issue * kChainThreads, gx + st.ioff1);
-    cp_async16(rp + st.sx_issue * kChainThreads, gp + st.ioff0);
-    cp_async16(ry + st.sy_issue * kChainThreads, gy + st.ioff0);
-    cp_async16(rf + st.sy_issue * kChainThreads, gf + st.ioff0);
-    cp_async_commit();
-    st.sx_issue = (st.sx_issue + 1 == DX) ? 0 : st.sx_issue + 1;
-    st.sy_issue = (st.sy_issue + 1 == DY) ? 0 : st.sy_issue + 1;
-    st.ioff0    = st.ioff1;
-    st.ioff1 += nx;
-    if (st.ioff1 == ntot) st.ioff1 = 0;
-  }
+  for (int q = 0; q < PF; q++) chain_issue<K, PF, HALO>(a, st, rx, rp, ry, rf, nx, ny, true);
 
 #define ROW(PH, CHECK, R1) \
-  chain_row<K, PF, PH, CHECK>(a, st, W, rx, rp, ry, rf, ytab, gx, gp, gy, gf, nx, ntot, cw, ce, sx0, sx1, smask, R1, j0, j1, (R1) + PF < rend)
+  chain_row<K, PF, PH, CHECK, HALO>(a, st, W, rx, rp, ry, rf, ytab, nx, ny, cw, ce, sx0, sx1, smask, R1, j0, j1, (R1) + PF < rend)
 
   // phases: [rstart, s0) checked warm-up in whole triples, [s0, s1) unchecked steady state in
   // triples, [s1, rend3) checked drain; rend3 rounds the trip count up to a multiple of 3 (the
@@ -1252,19 +1306,24 @@ __global__ void __launch_bounds__(kChainThreads, 2) k_chain_march(const ChainArg
 #undef WROW
 }
 
-template <int K, int PF>
-static int launch_chain(const ChainArgs& a, dim3 grid, cudaStream_t st)
+template <int K, int PF, bool HALO>
+static int launch_chain_k(const ChainArgs& a, dim3 grid, cudaStream_t st)
 {
   const size_t smem = (size_t)(2 * (PF + 1) + 2 * (PF + K)) * kChainThreads * sizeof(double2) +
                       (size_t)(a.rows + 3 * (K - 1) + 2) * sizeof(double2);
   static size_t configured = 0;
   if (smem > configured)
   {
-    CU_TRY(cudaFuncSetAttribute(k_chain_march<K, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_TRY(cudaFuncSetAttribute(k_chain_march<K, PF, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  k_chain_march<K, PF><<<grid, kChainThreads, smem, st>>>(a);
+  k_chain_march<K, PF, HALO><<<grid, kChainThreads, smem, st>>>(a);
   return 0;
+}
+template <int K, int PF>
+static int launch_chain(const ChainArgs& a, dim3 grid, cudaStream_t st)
+{
+  return a.hx ? launch_chain_k<K, PF, true>(a, grid, st) : launch_chain_k<K, PF, false>(a, grid, st);
 }
 
 static int g_chain_rows = 64;
@@ -1276,13 +1335,14 @@ extern "C" int b200_set_chain_rows(int r)
   return 0;
 }
 
-extern "C" int b200_stencil_chain(b200_ctx* c, const b200_stencil_geom* g, int nstages,
-                                  const double* x, const double* prev2, const double* yn,
-                                  const double* fn, const double* coeffs, double* const* z_out)
+static int stencil_chain_common(b200_ctx* c, const b200_stencil_geom* g, int nstages, const double* x,
+                                const double* prev2, const double* yn, const double* fn,
+                                const double* coeffs, double* const* z_out, const double* const* halos,
+                                int hg, int hg2)
 {
   if (nstages < 2 || nstages > B200_MAX_CHAIN) return fail("b200_stencil_chain: nstages must be 2..B200_MAX_CHAIN");
   if (g->halo_w || g->halo_e || g->halo_s || g->halo_n)
-    return fail("b200_stencil_chain: one periodic rank only (no halo buffers)");
+    return fail("b200_stencil_chain: the one-deep halo buffers of b200_stencil_geom are not used here");
   if ((g->nx & 1) || g->nx < 128 || g->ny < 16) return fail("b200_stencil_chain: needs even nx >= 128 and ny >= 16");
   if (g->ny >= (int64_t)1 << 30) return fail("b200_stencil_chain: ny too large");
   ChainArgs a;
@@ -1292,6 +1352,15 @@ extern "C" int b200_stencil_chain(b200_ctx* c, const b200_stencil_geom* g, int n
   a.x = x; a.prev2 = prev2; a.yn = yn; a.fn = fn;
   if (!aligned16(x) || !aligned16(prev2) || !aligned16(yn) || !aligned16(fn) || !aligned16(a.cxw) || !aligned16(a.cxe))
     return fail("b200_stencil_chain: operand not 16-byte aligned");
+  if (halos)
+  {
+    if (hg < nstages || (hg2 & 1) || hg2 < 2 * ((nstages + 1) / 2)) return fail("b200_stencil_chain_halo: halo too shallow");
+    a.hx = halos[0]; a.hp = halos[1]; a.hy = halos[2]; a.hf = halos[3];
+    a.g = hg; a.g2 = hg2;
+    if (!a.hx || !a.hp || !a.hy || !a.hf) return fail("b200_stencil_chain_halo: NULL halo buffer");
+    if (!aligned16(a.hx) || !aligned16(a.hp) || !aligned16(a.hy) || !aligned16(a.hf))
+      return fail("b200_stencil_chain_halo: halo buffer not 16-byte aligned");
+  }
   bool any = false;
   for (int l = 0; l < nstages; l++)
   {
@@ -1329,6 +1398,124 @@ extern "C" int b200_stencil_chain(b200_ctx* c, const b200_stencil_geom* g, int n
   }
   if (rc) return rc;
   LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200_stencil_chain(b200_ctx* c, const b200_stencil_geom* g, int nstages,
+                                  const double* x, const double* prev2, const double* yn,
+                                  const double* fn, const double* coeffs, double* const* z_out)
+{
+  return stencil_chain_common(c, g, nstages, x, prev2, yn, fn, coeffs, z_out, nullptr, 0, 0);
+}
+
+extern "C" int b200_stencil_chain_halo(b200_ctx* c, const b200_stencil_geom* g, int nstages,
+                                       const double* x, const double* prev2, const double* yn,
+                                       const double* fn, const double* coeffs, double* const* z_out,
+                                       const double* const* halos, int halo_rows, int halo_cols)
+{
+  if (!halos) return fail("b200_stencil_chain_halo: halos missing");
+  return stencil_chain_common(c, g, nstages, x, prev2, yn, fn, coeffs, z_out, halos, halo_rows, halo_cols);
+}
+
+// ------------------------------------------------------------ deep halo exchange
+// W / E strips of one field: columns [0, g2) and [nx-g2, nx) over rows -g..ny+g-1, the rows
+// outside the field taken from the S / N halo (so corners travel with the second phase).
+__global__ void __launch_bounds__(kThreads)
+  k_pack_strips(const double* __restrict__ field, const double* __restrict__ halo, int64_t nx, int64_t ny,
+                int g, int g2, double* __restrict__ wstrip, double* __restrict__ estrip)
+{
+  const int64_t t     = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nrows = ny + 2 * g;
+  if (t >= nrows * g2) return;
+  const int64_t rr = t / g2; // 0 .. ny+2g-1  <->  row rr - g
+  const int cc     = (int)(t - rr * g2);
+  const int64_t r  = rr - g;
+  const double* row;
+  if (r < 0) row = halo + (r + g) * nx;
+  else if (r >= ny) row = halo + (g + (r - ny)) * nx;
+  else row = field + r * nx;
+  wstrip[t] = row[cc];
+  estrip[t] = row[nx - g2 + cc];
+}
+
+extern "C" int64_t b200_deep_halo_doubles(int64_t nx, int64_t ny, int g, int g2)
+{
+  return 2 * (int64_t)g * nx + 2 * (ny + 2 * (int64_t)g) * g2;
+}
+
+static int nccl_load();
+static int deep_halo_nccl_phase(b200_ctx* c, int nfields, const int peers[2], const double* const* send_lo,
+                                const double* const* send_hi, double* const* recv_lo, double* const* recv_hi,
+                                size_t count);
+
+extern "C" int b200_deep_halo_exchange(b200_ctx* c, const int peers[4], int x_split, int y_split,
+                                       int64_t nx, int64_t ny, int g, int g2, int nfields,
+                                       const double* const* fields, double* const* halos)
+{
+  if (nfields < 1 || nfields > 4) return fail("b200_deep_halo_exchange: 1..4 fields");
+  if (g < 1 || g > ny || g2 < 2 || (g2 & 1) || g2 > nx) return fail("b200_deep_halo_exchange: bad halo depth");
+  if ((x_split || y_split) && !c->comm) return fail("b200_deep_halo_exchange: communicator not initialised");
+  const int64_t srow  = (int64_t)g * nx;             // doubles in one S / N block
+  const int64_t strip = (ny + 2 * (int64_t)g) * g2;  // doubles in one W / E strip
+  // ---- phase 1: S / N blocks (contiguous rows, no packing)
+  if (y_split)
+  {
+    const double* lo[4]; const double* hi[4]; double* rlo[4]; double* rhi[4];
+    for (int f = 0; f < nfields; f++)
+    {
+      lo[f]  = fields[f];                   // my rows 0..g-1      -> S neighbour's N halo
+      hi[f]  = fields[f] + (ny - g) * nx;   // my rows ny-g..ny-1  -> N neighbour's S halo
+      rlo[f] = halos[f];                    // S halo  <- S neighbour's top rows
+      rhi[f] = halos[f] + srow;             // N halo  <- N neighbour's bottom rows
+    }
+    const int py[2] = {peers[2], peers[3]};
+    int rc = deep_halo_nccl_phase(c, nfields, py, lo, hi, rlo, rhi, (size_t)srow);
+    if (rc) return rc;
+  }
+  else
+  {
+    for (int f = 0; f < nfields; f++)
+    { // one rank in y: the periodic neighbour is this rank itself
+      CU_TRY(cudaMemcpyAsync(halos[f], fields[f] + (ny - g) * nx, sizeof(double) * srow, cudaMemcpyDeviceToDevice, c->stream));
+      CU_TRY(cudaMemcpyAsync(halos[f] + srow, fields[f], sizeof(double) * srow, cudaMemcpyDeviceToDevice, c->stream));
+    }
+  }
+  // ---- phase 2: W / E strips including the corner rows received in phase 1
+  const unsigned blocks = (unsigned)((strip + kThreads - 1) / kThreads);
+  if (x_split)
+  {
+    const size_t need = (size_t)nfields * 2 * strip;
+    if (c->strip_cap < need)
+    {
+      if (c->strips) CU_TRY(cudaFree(c->strips));
+      CU_TRY(cudaMalloc(&c->strips, sizeof(double) * need));
+      c->strip_cap = need;
+    }
+    const double* lo[4]; const double* hi[4]; double* rlo[4]; double* rhi[4];
+    for (int f = 0; f < nfields; f++)
+    {
+      double* ws = c->strips + (size_t)(2 * f) * strip;
+      double* es = ws + strip;
+      k_pack_strips<<<blocks, kThreads, 0, c->stream>>>(fields[f], halos[f], nx, ny, g, g2, ws, es);
+      LAUNCH_CHECK();
+      lo[f]  = ws;                              // my west columns -> W neighbour's E halo
+      hi[f]  = es;                              // my east columns -> E neighbour's W halo
+      rlo[f] = halos[f] + 2 * srow;             // W halo <- W neighbour's east columns
+      rhi[f] = halos[f] + 2 * srow + strip;     // E halo <- E neighbour's west columns
+    }
+    const int px[2] = {peers[0], peers[1]};
+    int rc = deep_halo_nccl_phase(c, nfields, px, lo, hi, rlo, rhi, (size_t)strip);
+    if (rc) return rc;
+  }
+  else
+  {
+    for (int f = 0; f < nfields; f++)
+    { // one rank in x: my own east columns are my W halo and vice versa
+      k_pack_strips<<<blocks, kThreads, 0, c->stream>>>(fields[f], halos[f], nx, ny, g, g2,
+                                                        halos[f] + 2 * srow + strip, halos[f] + 2 * srow);
+      LAUNCH_CHECK();
+    }
+  }
   return 0;
 }
 
@@ -1627,6 +1814,26 @@ extern "C" int b200_allreduce(b200_ctx* c, double* dev_buf, int n, int op)
 {
   if (!c->comm || c->nranks == 1) return 0;
   return nccl_allreduce_inplace(c, dev_buf, n, op);
+}
+
+// one direction pair of the deep halo exchange: "lo" data goes to peers[0] (W or S) and arrives
+// as that rank's "hi" halo; "hi" data goes to peers[1]; per-peer posting order is the same on
+// every rank (send lo, recv hi, send hi, recv lo), which is what NCCL's in-group matching needs.
+static int deep_halo_nccl_phase(b200_ctx* c, int nfields, const int peers[2], const double* const* send_lo,
+                                const double* const* send_hi, double* const* recv_lo, double* const* recv_hi,
+                                size_t count)
+{
+  if (nccl_load()) return -1;
+  NCCL_TRY(ncclGroupStart());
+  for (int f = 0; f < nfields; f++)
+  {
+    NCCL_TRY(ncclSend(send_lo[f], count, ncclDouble, peers[0], c->comm, c->stream));
+    NCCL_TRY(ncclRecv(recv_hi[f], count, ncclDouble, peers[1], c->comm, c->stream));
+    NCCL_TRY(ncclSend(send_hi[f], count, ncclDouble, peers[1], c->comm, c->stream));
+    NCCL_TRY(ncclRecv(recv_lo[f], count, ncclDouble, peers[0], c->comm, c->stream));
+  }
+  NCCL_TRY(ncclGroupEnd());
+  return 0;
 }
 
 extern "C" int b200_halo_exchange(b200_ctx* c, const int peers[4], const double* sw,

@@ -69,6 +69,11 @@ struct UserData
   double *pxw = nullptr, *pxe = nullptr, *pys = nullptr, *pyn = nullptr; // PSetup tables
   double *Wsend = nullptr, *Esend = nullptr, *Ssend = nullptr, *Nsend = nullptr;
   double *Wrecv = nullptr, *Erecv = nullptr, *Srecv = nullptr, *Nrecv = nullptr;
+  // the same four tables extended by kTableMargin entries on both sides with the GLOBAL periodic
+  // index (what the neighbouring ranks use for those cells); pointers address local index 0
+  double *cxw_ext = nullptr, *cxe_ext = nullptr, *cys_ext = nullptr, *cyn_ext = nullptr;
+  double *ext_base[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool force_halo = false; // use the deep-halo path even on one rank (tests)
   B200RhsOp rhs_op{};
   bool overlap = true; // interior kernel overlaps the NCCL exchange
   long rhs_calls = 0;
@@ -86,6 +91,10 @@ struct UserData
   int upload_tables();
   void free_device();
 };
+
+const int kHaloRows    = B200_MAX_CHAIN;                 // deep-halo depth in y (>= chain depth)
+const int kHaloCols    = 2 * ((B200_MAX_CHAIN + 1) / 2); // and in x (even, >= chain depth)
+const int kTableMargin = 16;                             // b200_stencil_chain_halo contract
 
 // MPI_Dims_create(np, 2, dims) + MPI_Cart_create/Cart_get/Cart_rank with periodic
 // wrap, row-major rank order (diffusion_2D.cpp:243-394).
@@ -179,6 +188,28 @@ int UserData::upload_tables()
     xe[i]            = coeff_x(xhi) / (dx * dx);
   }
   if (upload(ctx, xw, &cxw) || upload(ctx, xe, &cxe) || upload(ctx, ys, &cys) || upload(ctx, yn, &cyn)) return -1;
+  if (np > 1 || force_halo)
+  { // extended tables for temporally blocked launches on a sub-domain: entry i (may be negative or
+    // >= n_loc) is the coefficient of global cell (is + i) mod nx, computed as its owner computes it
+    const int M = kTableMargin;
+    std::vector<double> ew(nx_loc + 2 * M), ee(nx_loc + 2 * M), es(ny_loc + 2 * M), en(ny_loc + 2 * M);
+    for (int64_t i = -M; i < nx_loc + M; i++)
+    {
+      const int64_t gi = (((is + i) % nx) + nx) % nx;
+      ew[(size_t)(i + M)] = coeff_x(xl + (gi - 0.5) * dx) / (dx * dx);
+      ee[(size_t)(i + M)] = coeff_x(xl + (gi + 0.5) * dx) / (dx * dx);
+    }
+    for (int64_t j = -M; j < ny_loc + M; j++)
+    {
+      const int64_t gj = (((js + j) % ny) + ny) % ny;
+      es[(size_t)(j + M)] = coeff_y(yl + (gj - 0.5) * dy) / (dy * dy);
+      en[(size_t)(j + M)] = coeff_y(yl + (gj + 0.5) * dy) / (dy * dy);
+    }
+    if (upload(ctx, ew, &ext_base[0]) || upload(ctx, ee, &ext_base[1]) || upload(ctx, es, &ext_base[2]) ||
+        upload(ctx, en, &ext_base[3]))
+      return -1;
+    cxw_ext = ext_base[0] + M; cxe_ext = ext_base[1] + M; cys_ext = ext_base[2] + M; cyn_ext = ext_base[3] + M;
+  }
   // preconditioner tables: preconditioner_jacobi.cpp:23-37 -- (is+i)*dx, no xl, no half cell
   for (int64_t j = 0; j < ny_loc; j++)
   {
@@ -207,7 +238,8 @@ int UserData::upload_tables()
 
 void UserData::free_device()
 {
-  double* all[] = {cxw, cxe, cys, cyn, pxw, pxe, pys, pyn, Wsend, Esend, Ssend, Nsend, Wrecv, Erecv, Srecv, Nrecv};
+  double* all[] = {cxw, cxe, cys, cyn, pxw, pxe, pys, pyn, Wsend, Esend, Ssend, Nsend, Wrecv, Erecv, Srecv, Nrecv,
+                   ext_base[0], ext_base[1], ext_base[2], ext_base[3]};
   for (double* p : all)
     if (p) b200_free(ctx, p);
 }
@@ -263,15 +295,34 @@ int rhs_fused(void* self, b200_ctx* ctx, const double* y, int nterms, const doub
 
 // K consecutive STS stages in one pass (temporal blocking); single periodic rank only
 int rhs_chain(void* self, b200_ctx* ctx, int nstages, const double* x, const double* prev2, const double* yn,
-              const double* fn, const double* coeffs, double* const* z_out)
+              const double* fn, const double* coeffs, double* const* z_out, double* const* halos,
+              const int* halo_valid)
 {
   UserData* ud = static_cast<UserData*>(self);
   b200_stencil_geom g;
   memset(&g, 0, sizeof(g));
   g.nx = ud->nx_loc; g.ny = ud->ny_loc;
-  g.cxw = ud->cxw; g.cxe = ud->cxe; g.cys = ud->cys; g.cyn = ud->cyn;
   ud->rhs_calls += nstages;
-  return b200_stencil_chain(ctx, &g, nstages, x, prev2, yn, fn, coeffs, z_out);
+  if (!halos)
+  { // one periodic rank: index wrap inside the kernel
+    g.cxw = ud->cxw; g.cxe = ud->cxe; g.cys = ud->cys; g.cyn = ud->cyn;
+    return b200_stencil_chain(ctx, &g, nstages, x, prev2, yn, fn, coeffs, z_out);
+  }
+  // a rank of the 2-D decomposition: refresh the stale deep halos in one exchange
+  const double* fields[4] = {x, prev2, yn, fn};
+  const double* xf[4];
+  double* xh[4];
+  int nf = 0;
+  for (int q = 0; q < 4; q++)
+    if (!halo_valid[q]) { xf[nf] = fields[q]; xh[nf] = halos[q]; nf++; }
+  if (nf > 0)
+  {
+    const int peers[4] = {ud->ipW, ud->ipE, ud->ipS, ud->ipN};
+    int rc = b200_deep_halo_exchange(ctx, peers, ud->npx > 1, ud->npy > 1, g.nx, g.ny, kHaloRows, kHaloCols, nf, xf, xh);
+    if (rc) return rc;
+  }
+  g.cxw = ud->cxw_ext; g.cxe = ud->cxe_ext; g.cys = ud->cys_ext; g.cyn = ud->cyn_ext;
+  return b200_stencil_chain_halo(ctx, &g, nstages, x, prev2, yn, fn, coeffs, z_out, halos, kHaloRows, kHaloCols);
 }
 
 } // namespace
@@ -354,6 +405,7 @@ struct UserOptions
   bool no_overlap = false, no_fusion = false;
   int rows_per_block = 0;
   int chain = 0; // temporal-blocking depth (0 = default / B200_CHAIN, 1 = off)
+  bool force_halo = false;
 };
 
 // One pass over argv; unknown flags are an error like main.cpp:116-132.
@@ -389,7 +441,7 @@ int parse_args(std::vector<std::string> args, UserData& ud, UserOptions& uo, boo
     ARG_B("--noprec", uo.preconditioning, false) ARG_B("--internaleig", uo.internaleig, true)
     ARG_I("--output", uo.output) ARG_I("--nout", uo.nout)
     ARG_B("--no-overlap", uo.no_overlap, true) ARG_B("--no-fusion", uo.no_fusion, true)
-    ARG_I("--rows-per-block", uo.rows_per_block) ARG_I("--chain", uo.chain)
+    ARG_I("--rows-per-block", uo.rows_per_block) ARG_I("--chain", uo.chain) ARG_B("--force-halo", uo.force_halo, true)
     if (outproc) fprintf(stderr, "ERROR: Unknown inputs: %s\n", a.c_str());
     return -1;
   }
@@ -593,10 +645,14 @@ extern "C" int b200_d2d_create(int argc, const char* const* argv, int rank, int 
   p->ud.rhs_op.fused = rhs_fused;
   p->ud.rhs_op.chain = nullptr;
   p->ud.rhs_op.chain_max = 0;
-  if (nranks == 1 && p->ud.nx_loc % 2 == 0 && p->ud.nx_loc >= 128 && p->ud.ny_loc >= 16)
-  { // temporal blocking needs the periodic index wrap of a single rank (b200_stencil_chain)
+  p->ud.rhs_op.halo_doubles = 0;
+  p->ud.force_halo          = p->uo.force_halo || getenv("B200_FORCE_HALO") != nullptr;
+  if (p->ud.nx_loc % 2 == 0 && p->ud.nx_loc >= 128 && p->ud.ny_loc >= 16)
+  { // temporal blocking: index wrap on one periodic rank, deep halos on a rank of a decomposition
     p->ud.rhs_op.chain     = rhs_chain;
     p->ud.rhs_op.chain_max = B200_MAX_CHAIN;
+    if (nranks > 1 || p->ud.force_halo)
+      p->ud.rhs_op.halo_doubles = b200_deep_halo_doubles(p->ud.nx_loc, p->ud.ny_loc, kHaloRows, kHaloCols);
   }
   {
     int depth = p->uo.chain;

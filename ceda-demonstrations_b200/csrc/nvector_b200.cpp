@@ -56,6 +56,8 @@ struct Shared
   sunindextype nloc, nglob;
   int refs;
   std::vector<double*> free_bufs;
+  std::vector<double*> free_halos; // deep-halo buffers (one size per problem)
+  int64_t halo_doubles;
   double* wrms_slots; // device scalars for fused WRMS partial sums
   int next_slot;
   bool spec_sigs[96]; // fused-launch signatures whose result a matching WRMS norm followed
@@ -80,6 +82,8 @@ struct Value
   const B200RhsOp* op; // deferred: value = op(src)
   Value* src;
   StageRec* st;        // pending stage (d == nullptr, op == nullptr)
+  double* halo;        // deep halo of this value (multi-rank temporal blocking), filled on demand
+  bool halo_valid;
   // fused WRMS partial: sum (this_i * w_i)^2 already sits in slot
   Value* wrms_w;
   int wrms_slot;
@@ -123,6 +127,7 @@ void value_release(Shared* sh, Value* v)
   {
     if (--v->refs > 0) return;
     if (v->d) sh->free_bufs.push_back(v->d);
+    if (v->halo) sh->free_halos.push_back(v->halo);
     if (v->wrms_w) value_release(sh, v->wrms_w);
     Value* next = v->src; // a deferred value owns a reference on its source
     if (v->st)
@@ -147,6 +152,8 @@ Value* value_new(Shared* sh, bool with_buffer)
   v->op        = nullptr;
   v->src       = nullptr;
   v->st        = nullptr;
+  v->halo      = nullptr;
+  v->halo_valid = false;
   v->wrms_w    = nullptr;
   v->wrms_slot = -1;
   v->sig       = 0;
@@ -278,7 +285,36 @@ void launch_chain(Shared* sh, Value* top)
   }
   else
   {
-    DEV(first->op->chain(first->op->self, sh->ctx, n, first->x->d, first->p2->d, first->yn->d, first->fn->d, cf, outs));
+    double* halos[4] = {nullptr, nullptr, nullptr, nullptr};
+    int valid[4]     = {1, 1, 1, 1};
+    Value* opv[4]    = {first->x, first->p2, first->yn, first->fn};
+    const bool deep  = first->op->halo_doubles > 0;
+    if (deep)
+    { // multi-rank: each operand carries a deep halo, exchanged by the operator when stale
+      if (sh->halo_doubles != first->op->halo_doubles)
+      {
+        for (double* p : sh->free_halos) b200_free(sh->ctx, p);
+        sh->free_halos.clear();
+        sh->halo_doubles = first->op->halo_doubles;
+      }
+      for (int q = 0; q < 4; q++)
+      {
+        if (!opv[q]->halo)
+        {
+          if (!sh->free_halos.empty()) { opv[q]->halo = sh->free_halos.back(); sh->free_halos.pop_back(); }
+          else DEV(b200_malloc(sh->ctx, sh->halo_doubles, &opv[q]->halo));
+          opv[q]->halo_valid = false;
+        }
+        halos[q] = opv[q]->halo;
+        valid[q] = opv[q]->halo_valid ? 1 : 0;
+        for (int e = 0; e < q; e++)
+          if (opv[e] == opv[q]) valid[q] = 1; // same value twice: exchange it once
+      }
+    }
+    DEV(first->op->chain(first->op->self, sh->ctx, n, first->x->d, first->p2->d, first->yn->d, first->fn->d, cf, outs,
+                         deep ? halos : nullptr, valid));
+    if (deep)
+      for (int q = 0; q < 4; q++) opv[q]->halo_valid = true;
     g_stats.chain_launches++;
     g_stats.chain_stages += n;
   }
@@ -429,6 +465,7 @@ void op_destroy(N_Vector v)
       }
       b200_ctx_sync(sh->ctx);
       for (double* p : sh->free_bufs) b200_free(sh->ctx, p);
+      for (double* p : sh->free_halos) b200_free(sh->ctx, p);
       if (sh->wrms_slots) b200_free(sh->ctx, sh->wrms_slots);
       delete sh;
     }
@@ -712,6 +749,7 @@ N_Vector N_VNew_B200(b200_ctx* ctx, sunindextype local_length, sunindextype glob
   sh->nglob      = global_length;
   sh->refs       = 1;
   sh->wrms_slots = nullptr;
+  sh->halo_doubles = 0;
   sh->next_slot  = 0;
   memset(sh->spec_sigs, 0, sizeof(sh->spec_sigs));
   DEV(b200_malloc(ctx, kSlots, &sh->wrms_slots));

@@ -156,6 +156,29 @@ int b200_stencil_lincomb(b200_ctx* ctx, const b200_stencil_geom* g,
 int b200_stencil_chain(b200_ctx* ctx, const b200_stencil_geom* g, int nstages,
                        const double* x, const double* prev2, const double* yn,
                        const double* fn, const double* coeffs, double* const* z_out);
+/* The same on a rank of a 2-D block decomposition: rows / columns outside the local
+   sub-domain come from per-operand deep-halo buffers filled by b200_deep_halo_exchange
+   (layout below), halos[] = { of x, of prev2, of yn, of fn }.  The coefficient tables of
+   `g` must then be valid for indices -16 .. n+15 (global periodic index, i.e. what the
+   neighbouring ranks use for those cells).  halo_rows >= nstages, halo_cols even >=
+   2*ceil(nstages/2). */
+int b200_stencil_chain_halo(b200_ctx* ctx, const b200_stencil_geom* g, int nstages,
+                            const double* x, const double* prev2, const double* yn,
+                            const double* fn, const double* coeffs, double* const* z_out,
+                            const double* const* halos, int halo_rows, int halo_cols);
+/* Deep halo of one nx*ny field, `rows` deep in y and `cols` deep in x, corners included:
+     [ S: rows x nx | N: rows x nx | W: (ny+2 rows) x cols | E: (ny+2 rows) x cols ]
+   S = rows -rows..-1, N = rows ny..ny+rows-1, W / E = columns -cols..-1 / nx..nx+cols-1
+   of rows -rows..ny+rows-1.  b200_deep_halo_doubles gives its size. */
+int64_t b200_deep_halo_doubles(int64_t nx, int64_t ny, int rows, int cols);
+/* Fill the deep halos of `nfields` (<= 4) fields: two NCCL phases on the compute stream
+   (S/N blocks, then W/E strips that carry the corners), replacing the one-deep
+   start_exchange/end_exchange of diffusion_2D.cpp:400-584 for temporally blocked
+   launches.  peers = ranks of the W,E,S,N neighbours; x_split / y_split = 0 means one
+   rank in that direction (the periodic neighbour is this rank: local copies). */
+int b200_deep_halo_exchange(b200_ctx* ctx, const int peers[4], int x_split, int y_split,
+                            int64_t nx, int64_t ny, int rows, int cols, int nfields,
+                            const double* const* fields, double* const* halos);
 /* rows of output each thread block of the chain kernel marches over (default 64) */
 int b200_set_chain_rows(int rows);
 

@@ -46,8 +46,14 @@ typedef struct B200RhsOp
      c[l][3] z_{l-1} + c[l][4] fn  (z_0 = x, z_{-1} = prev2) in one kernel; coeffs is
      [nstages][5], z_out[l] == NULL means "stage l+1 need not be stored". */
   int (*chain)(void* self, b200_ctx* ctx, int nstages, const double* x, const double* prev2,
-               const double* yn, const double* fn, const double* coeffs, double* const* z_out);
+               const double* yn, const double* fn, const double* coeffs, double* const* z_out,
+               double* const* halos, const int* halo_valid);
   int chain_max;
+  /* > 0: the operator runs on one rank of a decomposition and `chain` needs a deep halo
+     (this many doubles) for each of x, prev2, yn, fn.  The vector owns and caches the
+     buffers per value; `chain` receives halos[4] and halo_valid[4] and must fill (exchange)
+     the stale ones before launching.  0: halos == NULL. */
+  int64_t halo_doubles;
 } B200RhsOp;
 
 /* Create a vector: local_length entries on this rank's GPU, global_length overall
