@@ -29,6 +29,8 @@
 // --------------------------------------------------------------------- errors
 static thread_local char g_err[512] = "";
 static std::atomic<uint64_t> g_launches{0};
+static std::atomic<uint64_t> g_alg_bytes{0}; // modelled bytes (full-vector reads + writes) of all launches
+#define ALG_BYTES(nvec_touches, ndoubles) g_alg_bytes.fetch_add((uint64_t)(nvec_touches) * 8ull * (uint64_t)(ndoubles), std::memory_order_relaxed)
 
 #define CU_TRY(expr)                                                          \
   do {                                                                        \
@@ -69,6 +71,7 @@ static int fail(const char* msg)
 
 extern "C" const char* b200_last_error(void) { return g_err; }
 extern "C" uint64_t b200_launch_count(void) { return g_launches.load(); }
+extern "C" uint64_t b200_algorithmic_bytes(void) { return g_alg_bytes.load(); }
 
 // -------------------------------------------------------------------- context
 static const int kMaxPartials = 1 << 18;
@@ -425,6 +428,10 @@ static int launch_ew(b200_ctx* c, const EwArgs& a)
   if (blocks < 1) blocks = 1;
   k_elementwise<OP><<<(unsigned)blocks, kThreads, 0, c->stream>>>(a);
   LAUNCH_CHECK();
+  const int reads = (OP == EW_LINCOMB) ? a.t.n
+                    : (OP == EW_CONST) ? 0
+                    : (OP == EW_SCALESUM || OP == EW_SCALEDIFF || OP == EW_PROD || OP == EW_DIV) ? 2 : 1;
+  ALG_BYTES(reads + 1, a.n);
   return 0;
 }
 
@@ -558,6 +565,7 @@ static int run_reduce(b200_ctx* c, const double* x, const double* y, int64_t n, 
   if (blocks < 1) blocks = 1;
   k_reduce<KIND, ROP><<<(unsigned)blocks, kThreads, 0, c->stream>>>(x, y, n, c->partials, c->ticket, c->dev_result);
   LAUNCH_CHECK();
+  ALG_BYTES((KIND == RD_DOT || KIND == RD_WSQR) ? 2 : 1, n);
   if (c->comm && c->nranks > 1)
   {
     int rc = nccl_allreduce_inplace(c, c->dev_result, 1, ROP);
@@ -998,6 +1006,11 @@ extern "C" int b200_stencil_lincomb(b200_ctx* c, const b200_stencil_geom* g, con
     k_stage_generic<<<grid, kThreads, 0, c->stream>>>(a);
     LAUNCH_CHECK();
   }
+  {
+    int touches = 2 + (a.f_out ? 1 : 0) + (a.rw ? 1 : 0); // x, z
+    for (int k = 0; k < nterms; k++) touches += (src[k] == B200_SRC_VECTOR);
+    ALG_BYTES(touches, a.nx * a.ny);
+  }
   return 0;
 }
 
@@ -1398,6 +1411,11 @@ static int stencil_chain_common(b200_ctx* c, const b200_stencil_geom* g, int nst
   }
   if (rc) return rc;
   LAUNCH_CHECK();
+  {
+    int touches = 4; // x, prev2, yn, fn
+    for (int l = 0; l < nstages; l++) touches += (a.out[l] != nullptr);
+    ALG_BYTES(touches, a.nx * a.ny);
+  }
   return 0;
 }
 
@@ -1567,6 +1585,7 @@ extern "C" int b200_jacobi_setup(b200_ctx* c, int64_t nx, int64_t ny, const doub
   dim3 grid((unsigned)((nx + kThreads - 1) / kThreads), (unsigned)ny);
   k_jacobi<<<grid, kThreads, 0, c->stream>>>(nx, ny, pxw, pxe, pys, pyn, gamma, diag);
   LAUNCH_CHECK();
+  ALG_BYTES(1, nx * ny);
   return 0;
 }
 
@@ -1689,6 +1708,7 @@ extern "C" int b200_adr_rhs(b200_ctx* c, const b200_adr_params* p, int mode,
   dim3 grid((unsigned)((p->nx + kThreads - 1) / kThreads), (unsigned)p->ny);
   k_adr_rhs<<<grid, kThreads, 0, c->stream>>>(a);
   LAUNCH_CHECK();
+  ALG_BYTES(2, 2 * p->nx * p->ny);
   return 0;
 }
 
@@ -1713,6 +1733,11 @@ extern "C" int b200_adr_lincomb(b200_ctx* c, const b200_adr_params* p, int mode,
   dim3 grid((unsigned)((p->nx + kThreads - 1) / kThreads), (unsigned)p->ny);
   k_adr_lincomb<<<grid, kThreads, 0, c->stream>>>(a);
   LAUNCH_CHECK();
+  {
+    int touches = 2 + (f_out ? 1 : 0);
+    for (int k = 0; k < nterms; k++) touches += (src[k] == B200_SRC_VECTOR);
+    ALG_BYTES(touches, 2 * p->nx * p->ny);
+  }
   return 0;
 }
 

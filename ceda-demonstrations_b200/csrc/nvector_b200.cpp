@@ -408,11 +408,11 @@ void eval_lincomb(int nterms, const double* cf, N_Vector* Xv, N_Vector zv)
     for (int q = 0; q < 5; q++) r->c[q] = cf[q];
     r->depth = depth;
     out->st  = r;
-    out->refs++;      // keep it alive across the assignment below
+    // Not launched even at full depth: ARKODE still holds z_{j-2} in tempv1 at this point and
+    // drops it right after (pointer swap + N_VScale, arkode_lsrkstep.c:742-746); launching lazily,
+    // when the next stage or anything else needs the data, stores two levels instead of three.
     assign(zc, out);  // (drops L, which releases its reference on xin)
     g_stats.fused_launches++;
-    if (depth >= cmax) launch_chain(sh, out);
-    value_release(sh, out);
     return;
   }
 

@@ -41,6 +41,11 @@ int b200_ctx_sync(b200_ctx* ctx);
 const char* b200_last_error(void);
 /* number of kernels this library has launched since load (bench "gpu_launches") */
 uint64_t b200_launch_count(void);
+/* modelled ("algorithmic") bytes of all launches since load: 8 B x vector length x the
+   number of full vectors each kernel reads and writes (halo re-reads, coefficient tables and
+   scalars not counted).  bench.py divides its growth over the timed region by the device
+   time to get the achieved-bandwidth side of the roofline. */
+uint64_t b200_algorithmic_bytes(void);
 
 /* device / pinned-host memory (stands in for N_VNew_Parallel's malloc,
    SUN/src/nvector/parallel/nvector_parallel.c:189-221) */

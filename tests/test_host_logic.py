@@ -36,8 +36,9 @@ def test_sundials_library_exports_every_declared_symbol(b200):
     if not os.path.exists(b200.SUNDIALS_LIB):
         pytest.skip("libb200sts_sundials.so not built (no SUNDIALS host library)")
     syms = exported(b200.SUNDIALS_LIB)
-    want = declared_functions("nvector_b200.h") + declared_functions("b200_diffusion2d.h")
-    want += ["b200_diffusion_rhs", "b200_diffusion_domeig", "b200_diffusion_psetup", "b200_diffusion_psolve"]
+    want = (declared_functions("nvector_b200.h") + declared_functions("b200_diffusion2d.h") +
+            declared_functions("b200_adr2d.h") + declared_functions("b200_callbacks.h"))
+    assert "b200_adr_f_diffusion_forcing" in want and "b200_adr_create" in want and "b200_diffusion_rhs" in want
     missing = [f for f in want if f not in syms and not f.startswith("b200_ctx") and f in want]
     missing = [f for f in missing if f.startswith(("N_V", "b200_d2d", "b200_diffusion", "b200_adr2d", "b200_adr_"))]
     assert not missing, missing
