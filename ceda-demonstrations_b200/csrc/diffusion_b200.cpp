@@ -647,8 +647,14 @@ extern "C" int b200_d2d_create(int argc, const char* const* argv, int rank, int 
   p->ud.rhs_op.chain_max = 0;
   p->ud.rhs_op.halo_doubles = 0;
   p->ud.force_halo          = p->uo.force_halo || getenv("B200_FORCE_HALO") != nullptr;
-  if (p->ud.nx_loc % 2 == 0 && p->ud.nx_loc >= 128 && p->ud.ny_loc >= 16)
-  { // temporal blocking: index wrap on one periodic rank, deep halos on a rank of a decomposition
+  // Temporal blocking is a collective decision: a temporally blocked launch is preceded by a deep halo
+  // exchange that every rank must join, so it is enabled only if EVERY block of the decomposition
+  // qualifies (even width >= 128, >= 16 rows) -- judged from the global sizes, which all ranks share,
+  // not from this rank's extent (uneven splits give neighbouring blocks of different parity).
+  const int64_t qx_min = p->ud.nx / p->ud.npx, qy_min = p->ud.ny / p->ud.npy;
+  const bool all_even  = (p->ud.nx % p->ud.npx == 0) && (qx_min % 2 == 0);
+  if (all_even && qx_min >= 128 && qy_min >= 16)
+  { // index wrap on one periodic rank, deep halos on a rank of a decomposition
     p->ud.rhs_op.chain     = rhs_chain;
     p->ud.rhs_op.chain_max = B200_MAX_CHAIN;
     if (nranks > 1 || p->ud.force_halo)
