@@ -1136,7 +1136,7 @@ __device__ __forceinline__ void chain_issue(const ChainArgs& a, ChainState& st, 
 template <int K, int PF, int PH, bool CHECK, bool HALO>
 __device__ __forceinline__ void chain_row(const ChainArgs& a, ChainState& st, double2 (&W)[K][3],
                                           double2* rx, double2* rp, double2* ry, double2* rf,
-                                          const double2* ytab, int64_t nx, int ny,
+                                          const double2* ytab, const double* stab, int64_t nx, int ny,
                                           double2 cw, double2 ce, double sx0, double sx1,
                                           unsigned smask, int r1, int j0, int j1, bool issue)
 {
@@ -1152,7 +1152,7 @@ __device__ __forceinline__ void chain_row(const ChainArgs& a, ChainState& st, do
   for (int l = 1; l <= K; l++)
   {
     const double2 dy = ytab[st.trow - (l - 1)]; // (Dy_s, Dy_n) of row r1-(l-1)
-    const double sy  = DADD(dy.x, dy.y);
+    const double sy  = stab[st.trow - (l - 1)]; // Dy_s + Dy_n, summed once per block when the table is filled
     const double2 um = W[l - 1][IM], uc = W[l - 1][IC], up = W[l - 1][IO];
     const double uw0 = __shfl_up_sync(0xffffffffu, uc.y, 1);
     const double ue1 = __shfl_down_sync(0xffffffffu, uc.x, 1);
@@ -1163,7 +1163,10 @@ __device__ __forceinline__ void chain_row(const ChainArgs& a, ChainState& st, do
     L0 = DADD(L0, DMUL(ce.x, uc.y)); L1 = DADD(L1, DMUL(ce.y, ue1));
     L0 = DADD(L0, DMUL(dy.x, um.x)); L1 = DADD(L1, DMUL(dy.x, um.y));
     L0 = DADD(L0, DMUL(dy.y, up.x)); L1 = DADD(L1, DMUL(dy.y, up.y));
-    L0 = DADD(0.0, L0);              L1 = DADD(0.0, L1);
+    // The reference's "f = 0; f += ..." (k_stage_march: DADD(0.0, L)) is dropped here: 0 + L differs from L only
+    // for L = -0.0, and L is consumed by z = c0*L + ... below and never stored, so the only trace it could
+    // leave is the sign of an exactly-zero z (all five terms zero) -- equal as a number, and the FP64 pipe is
+    // what bounds this kernel.
     // z_{l-2} at this row: prev2 for the first stage, else the oldest row of level l-2's window
     const double2 p2 = (l == 1) ? P : W[(l >= 2) ? l - 2 : 0][IM];
     int sl = st.sy_use - (l - 1); // yn / fn of row r1-(l-1)
@@ -1205,6 +1208,7 @@ __global__ void __launch_bounds__(kChainThreads, 2) k_chain_march(const ChainArg
   double2* ry   = ring + (size_t)2 * DX * kChainThreads + threadIdx.x;        // [DY][threads]
   double2* rf   = ring + (size_t)(2 * DX + DY) * kChainThreads + threadIdx.x; // [DY][threads]
   double2* ytab = ring + (size_t)(2 * DX + 2 * DY) * kChainThreads;           // [rows + 3(K-1) + 2]
+  double* stab  = reinterpret_cast<double*>(ytab + (a.rows + 3 * (K - 1) + 2)); // [rows + 3(K-1) + 2]
 
   const int lane   = threadIdx.x & 31;
   const int64_t nx = a.nx;
@@ -1218,7 +1222,9 @@ __global__ void __launch_bounds__(kChainThreads, 2) k_chain_march(const ChainArg
   for (int t = threadIdx.x; t < (rend - rstart) + (K - 1) + 2; t += kChainThreads)
   { // HALO: the tables are extended by the caller (global periodic index), negative rows are valid
     const int rw = HALO ? (rstart - (K - 1) + t) : WROW(rstart - (K - 1) + t);
-    ytab[t]      = make_double2(a.cys[rw], a.cyn[rw]);
+    const double ds = a.cys[rw], dn = a.cyn[rw];
+    ytab[t]         = make_double2(ds, dn);
+    stab[t]         = DADD(ds, dn); // diffusion.cpp:48: (Dys + Dyn)
   }
   __syncthreads();
 
@@ -1281,7 +1287,7 @@ __global__ void __launch_bounds__(kChainThreads, 2) k_chain_march(const ChainArg
   for (int q = 0; q < PF; q++) chain_issue<K, PF, HALO>(a, st, rx, rp, ry, rf, nx, ny, true);
 
 #define ROW(PH, CHECK, R1) \
-  chain_row<K, PF, PH, CHECK, HALO>(a, st, W, rx, rp, ry, rf, ytab, nx, ny, cw, ce, sx0, sx1, smask, R1, j0, j1, (R1) + PF < rend)
+  chain_row<K, PF, PH, CHECK, HALO>(a, st, W, rx, rp, ry, rf, ytab, stab, nx, ny, cw, ce, sx0, sx1, smask, R1, j0, j1, (R1) + PF < rend)
 
   // phases: [rstart, s0) checked warm-up in whole triples, [s0, s1) unchecked steady state in
   // triples, [s1, rend3) checked drain; rend3 rounds the trip count up to a multiple of 3 (the
@@ -1323,7 +1329,7 @@ template <int K, int PF, bool HALO>
 static int launch_chain_k(const ChainArgs& a, dim3 grid, cudaStream_t st)
 {
   const size_t smem = (size_t)(2 * (PF + 1) + 2 * (PF + K)) * kChainThreads * sizeof(double2) +
-                      (size_t)(a.rows + 3 * (K - 1) + 2) * sizeof(double2);
+                      (size_t)(a.rows + 3 * (K - 1) + 2) * (sizeof(double2) + sizeof(double));
   static size_t configured = 0;
   if (smem > configured)
   {
@@ -1590,110 +1596,183 @@ extern "C" int b200_jacobi_setup(b200_ctx* c, int64_t nx, int64_t ny, const doub
 }
 
 // -------------------------------------------------------------- adr kernels
-struct AdrArgs
+// Scalar factors of the three operators, computed ONCE on the host with the reference's own
+// expressions (IEEE division, so the bits are those of the reference's per-call scalars):
+//   advection  ...2d.cpp:1417-1420: c = ONE*cu/(TWO*dx)
+//   diffusion  ...2d.cpp:1461-1462: d*dxinv2 with dxinv2 = ONE/(dx*dx)
+//   reaction   ...2d.cpp:1515:      (B + 1)
+struct AdrConsts
 {
-  b200_adr_params p;
-  int mode;
-  const double* y;
-  double* f;     // plain RHS output (b200_adr_rhs) or f_out
-  LinTerms t;    // fused combination (b200_adr_diffusion_lincomb)
-  double* z;
+  double cux, cuy, cvx, cvy;
+  double kx, ky;
+  double A, B, Bp1;
 };
 
-// one thread per grid point, both species (one 16-byte access per neighbour)
-__device__ __forceinline__ void adr_point(const AdrArgs& a, int64_t i, int64_t j,
-                                          double2* fadv, double2* fdif, double2* frx, double2* yc_out)
+static AdrConsts adr_consts(const b200_adr_params& p)
 {
-  const int64_t nx = a.p.nx, ny = a.p.ny;
-  const int64_t il = (i > 0) ? i - 1 : nx - 1, ir = (i < nx - 1) ? i + 1 : 0;
-  const int64_t jb = (j > 0) ? j - 1 : ny - 1, jt = (j < ny - 1) ? j + 1 : 0;
-  const double2 c  = ld_keep2(a.y + 2 * (i + j * nx));
-  *yc_out          = c;
-  if (a.mode & 3)
-  {
-    const double2 l = ld_keep2(a.y + 2 * (il + j * nx));
-    const double2 r = ld_keep2(a.y + 2 * (ir + j * nx));
-    const double2 b = ld_keep2(a.y + 2 * (i + jb * nx));
-    const double2 t = ld_keep2(a.y + 2 * (i + jt * nx));
-    if (a.mode & 1)
-    {
-      // …2d.cpp:1417-1420,1440-1441: c = ONE*cu/(TWO*dx); f = cx*(r-l) + cy*(t-b)
-      const double cux = __ddiv_rn(DMUL(1.0, a.p.cux), DMUL(2.0, a.p.dx));
-      const double cuy = __ddiv_rn(DMUL(1.0, a.p.cuy), DMUL(2.0, a.p.dy));
-      const double cvx = __ddiv_rn(DMUL(1.0, a.p.cvx), DMUL(2.0, a.p.dx));
-      const double cvy = __ddiv_rn(DMUL(1.0, a.p.cvy), DMUL(2.0, a.p.dy));
-      fadv->x = DADD(DMUL(cux, DSUB(r.x, l.x)), DMUL(cuy, DSUB(t.x, b.x)));
-      fadv->y = DADD(DMUL(cvx, DSUB(r.y, l.y)), DMUL(cvy, DSUB(t.y, b.y)));
-    }
-    if (a.mode & 2)
-    {
-      // …2d.cpp:1461-1462,1483-1486: d*dxinv2*(l + r - 2c) + d*dyinv2*(b + t - 2c)
-      const double kx = DMUL(a.p.d, __ddiv_rn(1.0, DMUL(a.p.dx, a.p.dx)));
-      const double ky = DMUL(a.p.d, __ddiv_rn(1.0, DMUL(a.p.dy, a.p.dy)));
-      fdif->x = DADD(DMUL(kx, DSUB(DADD(l.x, r.x), DMUL(2.0, c.x))),
-                     DMUL(ky, DSUB(DADD(b.x, t.x), DMUL(2.0, c.x))));
-      fdif->y = DADD(DMUL(kx, DSUB(DADD(l.y, r.y), DMUL(2.0, c.y))),
-                     DMUL(ky, DSUB(DADD(b.y, t.y), DMUL(2.0, c.y))));
-    }
+  AdrConsts k;
+  k.cux = (1.0 * p.cux) / (2.0 * p.dx);
+  k.cuy = (1.0 * p.cuy) / (2.0 * p.dy);
+  k.cvx = (1.0 * p.cvx) / (2.0 * p.dx);
+  k.cvy = (1.0 * p.cvy) / (2.0 * p.dy);
+  k.kx  = p.d * (1.0 / (p.dx * p.dx));
+  k.ky  = p.d * (1.0 / (p.dy * p.dy));
+  k.A   = p.A;
+  k.B   = p.B;
+  k.Bp1 = p.B + 1.0;
+  return k;
+}
+
+struct AdrArgs
+{
+  int64_t nx, ny;
+  AdrConsts k;
+  const double* y;
+  double* f;  // plain RHS output (b200_adr_rhs) or f_out
+  LinTerms t; // fused combination (b200_adr_lincomb); t.n == 0: plain RHS
+  double* z;
+  int rows;   // rows marched per block
+};
+
+// One grid point, both species: c = centre, l/r = west/east, b/t = south/north.  Composite callbacks add in
+// the order advection, diffusion, reaction (f_adv_react ...2d.cpp:1602-1619, f_adv_diff_react :1622-1646,
+// f_diff_react, f_adv_diff; the N_VLinearSum(1,f,1,temp,f) there is Vaxpy: f += temp).
+template <int MODE>
+__device__ __forceinline__ double2 adr_point(const AdrConsts& k, double2 c, double2 l, double2 r, double2 b, double2 t)
+{
+  double2 res = make_double2(0, 0);
+  if (MODE & 1)
+  { // ...2d.cpp:1440-1441: f = cx*(r-l) + cy*(t-b)
+    res.x = DADD(DMUL(k.cux, DSUB(r.x, l.x)), DMUL(k.cuy, DSUB(t.x, b.x)));
+    res.y = DADD(DMUL(k.cvx, DSUB(r.y, l.y)), DMUL(k.cvy, DSUB(t.y, b.y)));
   }
-  if (a.mode & 4)
-  {
-    // …2d.cpp:1515-1516: A + u*u*v - (B+1)*u ; B*u - u*u*v
+  if (MODE & 2)
+  { // ...2d.cpp:1483-1486: d*dxinv2*(l + r - 2c) + d*dyinv2*(b + t - 2c)
+    const double c2x = DMUL(2.0, c.x), c2y = DMUL(2.0, c.y);
+    double2 fd;
+    fd.x = DADD(DMUL(k.kx, DSUB(DADD(l.x, r.x), c2x)), DMUL(k.ky, DSUB(DADD(b.x, t.x), c2x)));
+    fd.y = DADD(DMUL(k.kx, DSUB(DADD(l.y, r.y), c2y)), DMUL(k.ky, DSUB(DADD(b.y, t.y), c2y)));
+    res  = (MODE & 1) ? make_double2(DADD(res.x, fd.x), DADD(res.y, fd.y)) : fd;
+  }
+  if (MODE & 4)
+  { // ...2d.cpp:1515-1516: A + u*u*v - (B+1)*u ; B*u - u*u*v
     const double uuv = DMUL(DMUL(c.x, c.x), c.y);
-    frx->x = DSUB(DADD(a.p.A, uuv), DMUL(DADD(a.p.B, 1.0), c.x));
-    frx->y = DSUB(DMUL(a.p.B, c.x), uuv);
+    double2 fr;
+    fr.x = DSUB(DADD(k.A, uuv), DMUL(k.Bp1, c.x));
+    fr.y = DSUB(DMUL(k.B, c.x), uuv);
+    res  = (MODE & 3) ? make_double2(DADD(res.x, fr.x), DADD(res.y, fr.y)) : fr;
+  }
+  return res;
+}
+
+// Marching kernel: a thread owns one grid point (both species = one 16-byte access) of a 256-point strip and
+// marches down `rows` rows with the three live rows of y in registers, so a row of y is fetched once per
+// block; west/east neighbours come from warp shuffles (lanes 0 / 31 and the strip ends issue one extra
+// load; the domain is periodic, the reference wraps indices the same way, ...2d.cpp:1425-1433).  With
+// t.n > 0 the operator value is consumed in registers by z = sum_k c[k]*T_k, T_k in {vector, y, F(y)}
+// (left to right like SUNDIALS' N_VLinearCombination fallback) and optionally stored as well.
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) k_adr_march(const AdrArgs a)
+{
+  constexpr bool NB = (MODE & 3) != 0; // the reaction alone is pointwise
+  const int64_t nx  = a.nx;
+  const int ny      = (int)a.ny;
+  const int lane    = threadIdx.x & 31;
+  const int64_t i0  = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const bool active = i0 < nx;
+  const int64_t i   = active ? i0 : 0;
+  const int j0      = (int)blockIdx.y * a.rows;
+  int j1            = j0 + a.rows;
+  if (j1 > ny) j1 = ny;
+  const bool wload = NB && active && (lane == 0 || i == 0);
+  const bool eload = NB && active && (lane == 31 || i == nx - 1);
+  const int64_t iw = (i > 0) ? i - 1 : nx - 1, ie = (i < nx - 1) ? i + 1 : 0;
+  const double* yb = a.y;
+  int64_t off      = 2 * ((int64_t)j0 * nx + i);
+  double2 ym = make_double2(0, 0), yc = make_double2(0, 0);
+  if (active && j0 < j1)
+  {
+    yc = ld_keep2(yb + off);
+    if (NB) ym = ld_keep2(yb + 2 * ((int64_t)(j0 > 0 ? j0 - 1 : ny - 1) * nx + i));
+  }
+  const int nt = a.t.n;
+#pragma unroll 1
+  for (int j = j0; j < j1; j++)
+  {
+    double2 yp = make_double2(0, 0), wv = make_double2(0, 0), ev = make_double2(0, 0);
+    double2 tv[B200_MAX_TERMS];
+    if (active)
+    {
+      if (NB) yp = ld_keep2(yb + 2 * ((int64_t)(j < ny - 1 ? j + 1 : 0) * nx + i));
+      else if (j + 1 < j1) yp = ld_keep2(yb + off + 2 * nx);
+      if (wload) wv = ld_keep2(yb + 2 * ((int64_t)j * nx + iw));
+      if (eload) ev = ld_keep2(yb + 2 * ((int64_t)j * nx + ie));
+#pragma unroll
+      for (int k = 0; k < B200_MAX_TERMS; k++)
+        if (k < nt && a.t.src[k] == B200_SRC_VECTOR) tv[k] = ld_stream2(a.t.v[k] + off);
+    }
+    double2 l = make_double2(0, 0), r = make_double2(0, 0);
+    if (NB)
+    {
+      l.x = __shfl_up_sync(0xffffffffu, yc.x, 1);
+      l.y = __shfl_up_sync(0xffffffffu, yc.y, 1);
+      r.x = __shfl_down_sync(0xffffffffu, yc.x, 1);
+      r.y = __shfl_down_sync(0xffffffffu, yc.y, 1);
+      if (wload) l = wv;
+      if (eload) r = ev;
+    }
+    if (active)
+    {
+      const double2 F = adr_point<MODE>(a.k, yc, l, r, ym, yp);
+      if (nt > 0)
+      {
+        double2 acc = make_double2(0, 0);
+#pragma unroll
+        for (int k = 0; k < B200_MAX_TERMS; k++)
+          if (k < nt)
+          {
+            double2 v;
+            if (a.t.src[k] == B200_SRC_STENCIL) v = F;
+            else if (a.t.src[k] == B200_SRC_CENTRE) v = yc;
+            else v = tv[k];
+            const double p0 = DMUL(a.t.c[k], v.x), p1 = DMUL(a.t.c[k], v.y);
+            acc.x = (k == 0) ? p0 : DADD(acc.x, p0);
+            acc.y = (k == 0) ? p1 : DADD(acc.y, p1);
+          }
+        *reinterpret_cast<double2*>(a.z + off) = acc;
+      }
+      if (a.f) *reinterpret_cast<double2*>(a.f + off) = F;
+    }
+    ym = yc;
+    yc = yp;
+    off += 2 * nx;
   }
 }
 
-// composite callbacks add in the order advection, diffusion, reaction
-// (f_adv_react ...2d.cpp:1602-1619, f_adv_diff_react :1622-1646, f_diff_react, f_adv_diff;
-// the N_VLinearSum(1,f,1,temp,f) there is Vaxpy: f += temp)
-__device__ __forceinline__ double2 adr_composite(const AdrArgs& a, int64_t i, int64_t j, double2* yc)
+static int launch_adr(b200_ctx* c, AdrArgs& a, int mode)
 {
-  double2 fa = make_double2(0, 0), fd = make_double2(0, 0), fr = make_double2(0, 0);
-  adr_point(a, i, j, &fa, &fd, &fr, yc);
-  double2 r  = make_double2(0, 0);
-  bool first = true;
-  if (a.mode & 1) { r = fa; first = false; }
-  if (a.mode & 2) { r = first ? fd : make_double2(DADD(r.x, fd.x), DADD(r.y, fd.y)); first = false; }
-  if (a.mode & 4) { r = first ? fr : make_double2(DADD(r.x, fr.x), DADD(r.y, fr.y)); }
-  return r;
-}
-
-__global__ void __launch_bounds__(kThreads) k_adr_rhs(const AdrArgs a)
-{
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t j = blockIdx.y;
-  if (i >= a.p.nx) return;
-  double2 yc;
-  const double2 r = adr_composite(a, i, j, &yc);
-  *reinterpret_cast<double2*>(a.f + 2 * (i + j * a.p.nx)) = r;
-}
-
-// z = sum_k c[k]*T_k with T_k in {vector, y, F_mode(y)}; optionally also stores F_mode(y)
-__global__ void __launch_bounds__(kThreads) k_adr_lincomb(const AdrArgs a)
-{
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t j = blockIdx.y;
-  if (i >= a.p.nx) return;
-  double2 yc;
-  const double2 F  = adr_composite(a, i, j, &yc);
-  const int64_t id = 2 * (i + j * a.p.nx);
-  double2 acc      = make_double2(0, 0);
-#pragma unroll
-  for (int k = 0; k < B200_MAX_TERMS; k++)
-    if (k < a.t.n)
-    {
-      double2 v;
-      if (a.t.src[k] == B200_SRC_STENCIL) v = F;
-      else if (a.t.src[k] == B200_SRC_CENTRE) v = yc;
-      else v = ld_stream2(a.t.v[k] + id);
-      const double p0 = DMUL(a.t.c[k], v.x), p1 = DMUL(a.t.c[k], v.y);
-      acc.x = (k == 0) ? p0 : DADD(acc.x, p0);
-      acc.y = (k == 0) ? p1 : DADD(acc.y, p1);
-    }
-  *reinterpret_cast<double2*>(a.z + id) = acc;
-  if (a.f) *reinterpret_cast<double2*>(a.f + id) = F;
+  const int64_t gx = (a.nx + kThreads - 1) / kThreads;
+  // enough blocks for >= 2 waves of 148 SMs x 3 resident blocks (76-80 registers) before the strips get longer
+  a.rows = (gx * ((a.ny + 15) / 16) >= 2 * 148 * 3) ? 16 : 8;
+  int64_t gy = (a.ny + a.rows - 1) / a.rows;
+  if (gy > 65535)
+  {
+    a.rows = (int)((a.ny + 65534) / 65535);
+    gy     = (a.ny + a.rows - 1) / a.rows;
+  }
+  dim3 grid((unsigned)gx, (unsigned)gy);
+  switch (mode)
+  {
+  case 1: k_adr_march<1><<<grid, kThreads, 0, c->stream>>>(a); break;
+  case 2: k_adr_march<2><<<grid, kThreads, 0, c->stream>>>(a); break;
+  case 3: k_adr_march<3><<<grid, kThreads, 0, c->stream>>>(a); break;
+  case 4: k_adr_march<4><<<grid, kThreads, 0, c->stream>>>(a); break;
+  case 5: k_adr_march<5><<<grid, kThreads, 0, c->stream>>>(a); break;
+  case 6: k_adr_march<6><<<grid, kThreads, 0, c->stream>>>(a); break;
+  default: k_adr_march<7><<<grid, kThreads, 0, c->stream>>>(a); break;
+  }
+  LAUNCH_CHECK();
+  return 0;
 }
 
 extern "C" int b200_adr_rhs(b200_ctx* c, const b200_adr_params* p, int mode,
@@ -1701,13 +1780,12 @@ extern "C" int b200_adr_rhs(b200_ctx* c, const b200_adr_params* p, int mode,
 {
   if (mode < 1 || mode > 7) return fail("b200_adr_rhs: mode must be in 1..7");
   if (y == f) return fail("b200_adr_rhs: f must not alias y");
-  if (p->ny > 65535) return fail("b200_adr_rhs: ny <= 65535");
+  if (p->ny >= (int64_t)1 << 30) return fail("b200_adr_rhs: ny too large");
+  if (!aligned16(y) || !aligned16(f)) return fail("b200_adr_rhs: operand not 16-byte aligned");
   AdrArgs a;
   memset(&a, 0, sizeof(a));
-  a.p = *p; a.mode = mode; a.y = y; a.f = f;
-  dim3 grid((unsigned)((p->nx + kThreads - 1) / kThreads), (unsigned)p->ny);
-  k_adr_rhs<<<grid, kThreads, 0, c->stream>>>(a);
-  LAUNCH_CHECK();
+  a.nx = p->nx; a.ny = p->ny; a.k = adr_consts(*p); a.y = y; a.f = f;
+  if (launch_adr(c, a, mode)) return -1;
   ALG_BYTES(2, 2 * p->nx * p->ny);
   return 0;
 }
@@ -1719,20 +1797,20 @@ extern "C" int b200_adr_lincomb(b200_ctx* c, const b200_adr_params* p, int mode,
   if (mode < 1 || mode > 7) return fail("b200_adr_lincomb: mode must be in 1..7");
   if (nterms < 1 || nterms > B200_MAX_TERMS) return fail("b200_adr_lincomb: nterms out of range");
   if (z == y || f_out == y) return fail("b200_adr_lincomb: output aliases the stencil input");
-  if (p->ny > 65535) return fail("b200_adr_lincomb: ny <= 65535");
+  if (p->ny >= (int64_t)1 << 30) return fail("b200_adr_lincomb: ny too large");
+  if (!aligned16(y) || !aligned16(z) || !aligned16(f_out)) return fail("b200_adr_lincomb: operand not 16-byte aligned");
   AdrArgs a;
   memset(&a, 0, sizeof(a));
-  a.p = *p; a.mode = mode; a.y = y; a.f = f_out; a.z = z;
+  a.nx = p->nx; a.ny = p->ny; a.k = adr_consts(*p); a.y = y; a.f = f_out; a.z = z;
   a.t.n = nterms;
   for (int k = 0; k < nterms; k++)
   {
     a.t.c[k] = cf[k]; a.t.src[k] = src[k];
     a.t.v[k] = (src[k] == B200_SRC_VECTOR) ? v[k] : nullptr;
     if (src[k] == B200_SRC_VECTOR && !v[k]) return fail("b200_adr_lincomb: NULL operand");
+    if (src[k] == B200_SRC_VECTOR && !aligned16(v[k])) return fail("b200_adr_lincomb: operand not 16-byte aligned");
   }
-  dim3 grid((unsigned)((p->nx + kThreads - 1) / kThreads), (unsigned)p->ny);
-  k_adr_lincomb<<<grid, kThreads, 0, c->stream>>>(a);
-  LAUNCH_CHECK();
+  if (launch_adr(c, a, mode)) return -1;
   {
     int touches = 2 + (f_out ? 1 : 0);
     for (int k = 0; k < nterms; k++) touches += (src[k] == B200_SRC_VECTOR);
