@@ -38,7 +38,7 @@ sundials:
 product: $(LIB)/libb200sts.so
 endif
 
-$(LIB)/libb200sts.so: $(SRC)/b200_kernels.cu include/b200_sts.h
+$(LIB)/libb200sts.so: $(SRC)/b200_kernels.cu $(wildcard $(SRC)/*.cuh) include/b200_sts.h
 	@mkdir -p $(LIB)
 	$(NVCC) $(NVFLAGS) -shared -Iinclude $< -o $@ -ldl
 

@@ -1,0 +1,331 @@
+// chain_march.cuh -- k_chain_march: K temporally blocked STS stages per launch, two cells per thread.
+//
+// Included by b200_kernels.cu (nvcc, sm_100a) and -- with B200_HOST_EMU defined -- by the host
+// emulation harness tests/emu (g++), which runs the same source lane by lane on CPU threads so the
+// indexing, tiling, ring and halo logic is tested without a GPU.  The harness is test
+// infrastructure: nothing in the product includes this file with B200_HOST_EMU.
+#pragma once
+#include "kernel_prims.cuh"
+
+// ------------------------------------------- temporally blocked STS stages
+// K consecutive RKC/RKL stages (arkode_lsrkstep.c:674-750 / :960-1050) in ONE pass:
+//   z_1 = c1[0] L(x)   + c1[1] p   + c1[2] yn + c1[3] x   + c1[4] fn      (x = z_{j-1}, p = z_{j-2})
+//   z_2 = c2[0] L(z_1) + c2[1] x   + c2[2] yn + c2[3] z_1 + c2[4] fn
+//   z_l = cl[0] L(z_{l-1}) + cl[1] z_{l-2} + cl[2] yn + cl[3] z_{l-1} + cl[4] fn
+// Every cell value is produced by exactly the instruction sequence of the one-stage kernel, so
+// the result is bit-identical; only the traffic changes: 4 streamed reads + (usually) 2 writes
+// per K cell-updates instead of per one (48/K bytes instead of 40).
+//
+// Overlapped tiling, no block-level sync: a warp owns a 64-cell window of which the outer HL
+// lanes on each side are halo (level l is valid on cells [l, 63-l] of the window; halo lanes
+// never store); a block marches down `rows` output rows and starts K-1 rows early.  Level l lags
+// level l-1 by one row; each level keeps a 3-row window of the level below in registers and gets
+// west/east neighbours by warp shuffle.  One periodic rank (index wrap) only.
+struct ChainArgs
+{
+  int64_t nx, ny;
+  const double *cxw, *cxe, *cys, *cyn;
+  const double* x;
+  const double* prev2;
+  const double* yn;
+  const double* fn;
+  double c[B200_MAX_CHAIN][5];
+  double* out[B200_MAX_CHAIN];
+  int rows;
+  // multi-rank (HALO = true): per-operand deep-halo buffers, layout of b200_deep_halo_exchange
+  const double *hx, *hp, *hy, *hf;
+  int g, g2; // halo depth in rows / in columns (g >= K, g2 even >= 2*ceil(K/2))
+};
+
+static const int kChainThreads = 256;
+
+// address of (row r, this lane's column), r in [-g, ny+g):
+//   wrap mode: rows outside [0, ny) wrap periodically onto the field itself;
+//   halo mode: they come from the field's deep halo
+//     halo = [ S: g rows x nx | N: g rows x nx | W: (ny+2g) rows x g2 | E: (ny+2g) rows x g2 ]
+//     (S = rows -g..-1, N = rows ny..ny+g-1, W / E = columns -g2..-1 / nx..nx+g2-1 of rows
+//     -g..ny+g-1); we = this lane lies in a W/E strip (lane_col then includes the strip offset).
+template <bool HALO>
+__device__ __forceinline__ const double* row_ptr(const double* field, const double* halo, int r, bool we,
+                                                 int64_t lane_col, int64_t nx, int ny, int g, int g2)
+{
+  if (!HALO)
+  {
+    const int rw = (r < 0) ? r + ny : ((r >= ny) ? r - ny : r);
+    return field + (int64_t)rw * nx + lane_col;
+  }
+  if (we) return halo + lane_col + (int64_t)(r + g) * g2;
+  if (r >= 0 && r < ny) return field + (int64_t)r * nx + lane_col;
+  const int hr = (r < 0) ? r + g : g + (r - ny);
+  return halo + (int64_t)hr * nx + lane_col;
+}
+
+// Operands are staged through a thread-private shared-memory ring filled with cp.async
+// (LDGSTS, 16 B per thread per operand per row) PF rows ahead: the bytes in flight that keep HBM
+// busy cost no registers, and the FP64 pipe works on row r while rows r+1..r+PF stream in.
+// Every thread reads back only the slots it filled itself, so cp.async.wait_group is the only
+// synchronisation in the row loop.  Ring depths: x and prev2 PF+1 rows, yn and fn PF+K rows
+// (level l consumes yn/fn of row r-(l-1)).  The y-direction coefficients of the block's rows
+// sit in a small shared table (one __syncthreads before the loop).
+//
+// The row loop is issue-bound once HBM is no longer the limit, so the steady state is unrolled
+// by 3 with the 3-row register windows addressed by a compile-time phase (no rotation moves),
+// carries no row-range predicates, and uses running offsets instead of index multiplies; the
+// 2(K-1) warm-up rows and the K-1 drain rows run through the same body with CHECK = true.
+struct ChainState
+{
+  int64_t soff;      // r1*nx + ic (unwrapped; valid whenever a store can happen)
+  const double *px, *pp, *py, *pf; // next group: x at row ir+1 ; prev2 / yn / fn at row ir
+  int64_t pstep;     // row stride of this lane's source (nx, or g2 in a W/E halo strip)
+  int ir;            // unwrapped row of the next group
+  int sx_issue, sy_issue, sx_use, sy_use; // ring slots
+  int trow;          // index of row r1 in the y-coefficient table
+  bool we;           // halo mode: this lane reads the W/E halo strips
+  int64_t lane_col;  // column (halo mode: strip offset + column) of this lane
+};
+
+// issue group(ir) = { x row ir+1, prev2 / yn / fn row ir } into the ring and advance the running
+// source pointers by one row; the pointers are recomputed only where the source changes
+// (rows 0 and ny: wrap-around, or field <-> S/N halo)
+template <int K, int PF, bool HALO>
+__device__ __forceinline__ void chain_issue(const ChainArgs& a, ChainState& st, double2* rx, double2* rp,
+                                            double2* ry, double2* rf, int64_t nx, int ny, bool issue)
+{
+  constexpr int DX = PF + 1, DY = PF + K;
+  if (issue)
+  {
+    cp_async16(rx + st.sx_issue * kChainThreads, st.px);
+    cp_async16(rp + st.sx_issue * kChainThreads, st.pp);
+    cp_async16(ry + st.sy_issue * kChainThreads, st.py);
+    cp_async16(rf + st.sy_issue * kChainThreads, st.pf);
+  }
+  cp_async_commit();
+  st.sx_issue = (st.sx_issue + 1 == DX) ? 0 : st.sx_issue + 1;
+  st.sy_issue = (st.sy_issue + 1 == DY) ? 0 : st.sy_issue + 1;
+  const int r = ++st.ir;
+  if (r == 0 || r == ny)
+  {
+    st.pp = row_ptr<HALO>(a.prev2, a.hp, r, st.we, st.lane_col, nx, ny, a.g, a.g2);
+    st.py = row_ptr<HALO>(a.yn, a.hy, r, st.we, st.lane_col, nx, ny, a.g, a.g2);
+    st.pf = row_ptr<HALO>(a.fn, a.hf, r, st.we, st.lane_col, nx, ny, a.g, a.g2);
+  }
+  else { st.pp += st.pstep; st.py += st.pstep; st.pf += st.pstep; }
+  if (r + 1 == 0 || r + 1 == ny) st.px = row_ptr<HALO>(a.x, a.hx, r + 1, st.we, st.lane_col, nx, ny, a.g, a.g2);
+  else st.px += st.pstep;
+}
+
+template <int K, int PF, int PH, bool CHECK, bool HALO, bool FMA>
+__device__ __forceinline__ void chain_row(const ChainArgs& a, ChainState& st, double2 (&W)[K][3],
+                                          double2* rx, double2* rp, double2* ry, double2* rf,
+                                          const double2* ytab, const double* stab, int64_t nx, int ny,
+                                          double2 cw, double2 ce, double sx0, double sx1,
+                                          unsigned smask, int r1, int j0, int j1, bool issue)
+{
+  constexpr int DX = PF + 1, DY = PF + K;
+  constexpr int IO = PH % 3, IM = (PH + 1) % 3, IC = (PH + 2) % 3; // oldest (overwritten), then um, uc ; up = IO
+  chain_issue<K, PF, HALO>(a, st, rx, rp, ry, rf, nx, ny, issue); // group(r1 + PF)
+  cp_async_wait<PF>(); // all but the PF newest groups have landed: group(r1) is ready
+
+  W[0][IO]        = rx[st.sx_use * kChainThreads]; // x row r1+1 replaces the oldest row
+  const double2 P = rp[st.sx_use * kChainThreads];
+  int64_t so      = st.soff;
+#pragma unroll
+  for (int l = 1; l <= K; l++)
+  {
+    const double2 dy = ytab[st.trow - (l - 1)]; // (Dy_s, Dy_n) of row r1-(l-1)
+    const double sy  = stab[st.trow - (l - 1)]; // Dy_s + Dy_n, summed once per block when the table is filled
+    const double2 um = W[l - 1][IM], uc = W[l - 1][IC], up = W[l - 1][IO];
+    const double uw0 = __shfl_up_sync(0xffffffffu, uc.y, 1);
+    const double ue1 = __shfl_down_sync(0xffffffffu, uc.x, 1);
+    // diffusion.cpp:48-53, same association as k_stage_march
+    double L0 = DMUL(-DADD(sx0, sy), uc.x);
+    double L1 = DMUL(-DADD(sx1, sy), uc.y);
+    L0 = mad<FMA>(cw.x, uw0, L0);  L1 = mad<FMA>(cw.y, uc.x, L1);
+    L0 = mad<FMA>(ce.x, uc.y, L0); L1 = mad<FMA>(ce.y, ue1, L1);
+    L0 = mad<FMA>(dy.x, um.x, L0); L1 = mad<FMA>(dy.x, um.y, L1);
+    L0 = mad<FMA>(dy.y, up.x, L0); L1 = mad<FMA>(dy.y, up.y, L1);
+    // The reference's "f = 0; f += ..." (k_stage_march: DADD(0.0, L)) is dropped here: 0 + L differs from L only
+    // for L = -0.0, and L is consumed by z = c0*L + ... below and never stored, so the only trace it could
+    // leave is the sign of an exactly-zero z (all five terms zero) -- equal as a number, and the FP64 pipe is
+    // what bounds this kernel.
+    // z_{l-2} at this row: prev2 for the first stage, else the oldest row of level l-2's window
+    const double2 p2 = (l == 1) ? P : W[(l >= 2) ? l - 2 : 0][IM];
+    int sl = st.sy_use - (l - 1); // yn / fn of row r1-(l-1)
+    if (sl < 0) sl += DY;
+    const double2 yv = ry[sl * kChainThreads], fv = rf[sl * kChainThreads];
+    const double* cf = a.c[l - 1];
+    double2 z;
+    z.x = DMUL(cf[0], L0);               z.y = DMUL(cf[0], L1);
+    z.x = mad<FMA>(cf[1], p2.x, z.x);  z.y = mad<FMA>(cf[1], p2.y, z.y);
+    z.x = mad<FMA>(cf[2], yv.x, z.x);  z.y = mad<FMA>(cf[2], yv.y, z.y);
+    z.x = mad<FMA>(cf[3], uc.x, z.x);  z.y = mad<FMA>(cf[3], uc.y, z.y);
+    z.x = mad<FMA>(cf[4], fv.x, z.x);  z.y = mad<FMA>(cf[4], fv.y, z.y);
+    bool doit = (smask >> (l - 1)) & 1u;
+    if (CHECK)
+    {
+      const int rl = r1 - (l - 1);
+      doit         = doit && rl >= j0 && rl < j1;
+    }
+    if (doit) *reinterpret_cast<double2*>(a.out[l - 1] + so) = z;
+    so -= nx;
+    if (l < K) W[l][IO] = z; // newest row of level l replaces its oldest
+  }
+  st.soff += nx;
+  st.trow += 1;
+  st.sx_use = (st.sx_use + 1 == DX) ? 0 : st.sx_use + 1;
+  st.sy_use = (st.sy_use + 1 == DY) ? 0 : st.sy_use + 1;
+}
+
+template <int K, int PF, bool HALO, bool FMA>
+__global__ void __launch_bounds__(kChainThreads, 2) k_chain_march(const ChainArgs a)
+{
+  constexpr int HL   = (K + 1) / 2;  // halo lanes per side (2 cells each): 2*HL >= K
+  constexpr int WUSE = 64 - 4 * HL;  // cells a warp stores per row
+  constexpr int DX   = PF + 1;       // ring depth of x and prev2
+  constexpr int DY   = PF + K;       // ring depth of yn and fn
+  B200_DYN_SMEM(double2, ring);
+  double2* rx   = ring + threadIdx.x;                                         // [DX][threads]
+  double2* rp   = ring + (size_t)DX * kChainThreads + threadIdx.x;            // [DX][threads]
+  double2* ry   = ring + (size_t)2 * DX * kChainThreads + threadIdx.x;        // [DY][threads]
+  double2* rf   = ring + (size_t)(2 * DX + DY) * kChainThreads + threadIdx.x; // [DY][threads]
+  double2* ytab = ring + (size_t)(2 * DX + 2 * DY) * kChainThreads;           // [rows + 3(K-1) + 2]
+  double* stab  = reinterpret_cast<double*>(ytab + (a.rows + 3 * (K - 1) + 2)); // [rows + 3(K-1) + 2]
+
+  const int lane   = threadIdx.x & 31;
+  const int64_t nx = a.nx;
+  const int ny     = (int)a.ny;
+  const int j0     = (int)blockIdx.y * a.rows;
+  int j1           = j0 + a.rows;
+  if (j1 > ny) j1 = ny;
+  const int rstart = j0 - (K - 1), rend = j1 + (K - 1); // level-1 rows [rstart, rend)
+#define WROW(r) ((r) < 0 ? (r) + ny : ((r) >= ny ? (r) - ny : (r)))
+  // y-direction face coefficients of rows rstart-(K-1) .. rend+1 (table index 0 = row rstart-(K-1))
+  for (int t = threadIdx.x; t < (rend - rstart) + (K - 1) + 2; t += kChainThreads)
+  { // HALO: the tables are extended by the caller (global periodic index), negative rows are valid
+    const int rw = HALO ? (rstart - (K - 1) + t) : WROW(rstart - (K - 1) + t);
+    const double ds = a.cys[rw], dn = a.cyn[rw];
+    ytab[t]         = make_double2(ds, dn);
+    stab[t]         = DADD(ds, dn); // diffusion.cpp:48: (Dys + Dyn)
+  }
+  __syncthreads();
+
+  const int64_t wg = (int64_t)blockIdx.x * (kChainThreads / 32) + (threadIdx.x >> 5);
+  if (wg * WUSE >= nx) return; // window entirely outside the field (no block-level sync below)
+  const int64_t col_u = wg * WUSE - 2 * HL + 2 * lane; // unwrapped column of my first cell
+  const bool store_ok = (lane >= HL) && (lane < 32 - HL) && (col_u < nx);
+  unsigned smask      = 0;
+#pragma unroll
+  for (int l = 0; l < K; l++)
+    if (store_ok && a.out[l]) smask |= 1u << l;
+
+  ChainState st;
+  int64_t ic = col_u; // column used for stores and (wrap mode) loads
+  int64_t xc = col_u; // column index into the x-direction coefficient tables
+  st.we      = false;
+  st.pstep   = nx;
+  if (HALO)
+  { // columns outside [0, nx) come from the W / E halo strips; beyond the strips: clamp (never used)
+    const int64_t strip = (int64_t)(ny + 2 * a.g) * a.g2;
+    if (col_u < 0) { st.we = true; st.lane_col = 2 * a.g * nx + (col_u + a.g2); }
+    else if (col_u >= nx)
+    {
+      int64_t c = col_u - nx;
+      if (c > a.g2 - 2) { c = a.g2 - 2; xc = nx + c; }
+      st.we       = true;
+      st.lane_col = 2 * a.g * nx + strip + c;
+    }
+    else st.lane_col = col_u;
+    if (st.we) st.pstep = a.g2;
+  }
+  else
+  {
+    if (ic < 0) ic += nx;
+    else if (ic >= nx) ic -= nx;
+    xc          = ic;
+    st.lane_col = ic;
+  }
+  const double2 cw = ld_keep2(a.cxw + xc), ce = ld_keep2(a.cxe + xc);
+  const double sx0 = DADD(cw.x, ce.x), sx1 = DADD(cw.y, ce.y);
+
+  st.soff     = (int64_t)rstart * nx + ic;
+  st.sx_issue = st.sy_issue = st.sx_use = st.sy_use = 0;
+  st.trow     = K - 1;
+  st.ir       = rstart;
+  st.px = row_ptr<HALO>(a.x, a.hx, rstart + 1, st.we, st.lane_col, nx, ny, a.g, a.g2);
+  st.pp = row_ptr<HALO>(a.prev2, a.hp, rstart, st.we, st.lane_col, nx, ny, a.g, a.g2);
+  st.py = row_ptr<HALO>(a.yn, a.hy, rstart, st.we, st.lane_col, nx, ny, a.g, a.g2);
+  st.pf = row_ptr<HALO>(a.fn, a.hf, rstart, st.we, st.lane_col, nx, ny, a.g, a.g2);
+
+  double2 W[K][3];
+#pragma unroll
+  for (int l = 0; l < K; l++) W[l][0] = W[l][1] = W[l][2] = make_double2(0.0, 0.0);
+  // canonical layout at phase 0: index 0 oldest (about to be overwritten), 1 = um, 2 = uc
+  W[0][1] = ld_keep2(row_ptr<HALO>(a.x, a.hx, rstart - 1, st.we, st.lane_col, nx, ny, a.g, a.g2));
+  W[0][2] = ld_keep2(row_ptr<HALO>(a.x, a.hx, rstart, st.we, st.lane_col, nx, ny, a.g, a.g2));
+
+  // prologue of the pipeline: groups rstart .. rstart+PF-1
+#pragma unroll
+  for (int q = 0; q < PF; q++) chain_issue<K, PF, HALO>(a, st, rx, rp, ry, rf, nx, ny, true);
+
+#define ROW(PH, CHECK, R1) \
+  chain_row<K, PF, PH, CHECK, HALO, FMA>(a, st, W, rx, rp, ry, rf, ytab, stab, nx, ny, cw, ce, sx0, sx1, smask, R1, j0, j1, (R1) + PF < rend)
+
+  // phases: [rstart, s0) checked warm-up in whole triples, [s0, s1) unchecked steady state in
+  // triples, [s1, rend3) checked drain; rend3 rounds the trip count up to a multiple of 3 (the
+  // extra rows compute garbage that is never stored and load wrapped, in-range rows).
+  const int total3 = ((rend - rstart + 2) / 3) * 3;
+  int warm         = 2 * (K - 1);
+  warm             = ((warm + 2) / 3) * 3;
+  int steady       = (j1 - (rstart + warm)) / 3 * 3;
+  if (steady < 0) steady = 0;
+  int r1 = rstart;
+#pragma unroll 1
+  for (; r1 < rstart + warm && r1 < rstart + total3; r1 += 3)
+  {
+    ROW(0, true, r1);
+    ROW(1, true, r1 + 1);
+    ROW(2, true, r1 + 2);
+  }
+  const int s1 = r1 + steady;
+#pragma unroll 1
+  for (; r1 < s1; r1 += 3)
+  {
+    ROW(0, false, r1);
+    ROW(1, false, r1 + 1);
+    ROW(2, false, r1 + 2);
+  }
+#pragma unroll 1
+  for (; r1 < rstart + total3; r1 += 3)
+  {
+    ROW(0, true, r1);
+    ROW(1, true, r1 + 1);
+    ROW(2, true, r1 + 2);
+  }
+  cp_async_wait<0>();
+#undef ROW
+#undef WROW
+}
+
+
+// ---- launch geometry (host side; shared by b200_kernels.cu and the emulation harness)
+static inline size_t chain_march_smem(int K, int PF, int rows)
+{
+  return (size_t)(2 * (PF + 1) + 2 * (PF + K)) * kChainThreads * sizeof(double2) +
+         (size_t)(rows + 3 * (K - 1) + 2) * (sizeof(double2) + sizeof(double));
+}
+static inline int chain_march_pf(int K) { return K <= 3 ? 4 : 3; } // prefetch depth instantiated per K
+// rows may be raised so that grid.y fits 65535
+static inline dim3 chain_march_grid(int64_t nx, int64_t ny, int K, int* rows)
+{
+  const int hl  = (K + 1) / 2;
+  const int use = 64 - 4 * hl;
+  int64_t warps = (nx + use - 1) / use;
+  int64_t gx    = (warps + kChainThreads / 32 - 1) / (kChainThreads / 32);
+  int64_t gy    = (ny + *rows - 1) / *rows;
+  if (gy > 65535)
+  {
+    *rows = (int)((ny + 65534) / 65535);
+    gy    = (ny + *rows - 1) / *rows;
+  }
+  return dim3((unsigned)gx, (unsigned)gy);
+}

@@ -1,0 +1,89 @@
+// emu_chain.cpp -- TEST INFRASTRUCTURE: runs the temporally blocked stage kernels
+// (csrc/chain_march.cuh, csrc/chain_quad.cuh) on CPU threads through cuda_emu.h and exposes one
+// C entry point for the pytest side (tests/test_kernel_emulation.py).  Built by tests/emu/Makefile
+// with -DB200_HOST_EMU; the product never links this.
+#include "b200_sts.h"
+#include "chain_march.cuh"
+#include "chain_quad.cuh"
+
+namespace
+{
+template <int K, int PF, bool HALO, bool FMA>
+void run_march(const ChainArgs& a, dim3 grid)
+{
+  emu::launch(k_chain_march<K, PF, HALO, FMA>, grid, kChainThreads, chain_march_smem(K, PF, a.rows), a);
+}
+template <int K, int PF>
+void run_march_k(const ChainArgs& a, dim3 grid, bool halo, bool fma)
+{
+  if (halo) fma ? run_march<K, PF, true, true>(a, grid) : run_march<K, PF, true, false>(a, grid);
+  else fma ? run_march<K, PF, false, true>(a, grid) : run_march<K, PF, false, false>(a, grid);
+}
+
+template <int K, int PF, bool HALO, bool FMA>
+void run_quad(const ChainArgs& a, dim3 grid)
+{
+  emu::launch(k_chain_quad<K, PF, HALO, FMA>, grid, kQuadThreads, chain_quad_smem(K, PF, a.rows), a);
+}
+template <int K, int PF>
+void run_quad_k(const ChainArgs& a, dim3 grid, bool halo, bool fma)
+{
+  if (halo) fma ? run_quad<K, PF, true, true>(a, grid) : run_quad<K, PF, true, false>(a, grid);
+  else fma ? run_quad<K, PF, false, true>(a, grid) : run_quad<K, PF, false, false>(a, grid);
+}
+} // namespace
+
+// variant: 0 = k_chain_march (2 cells / thread), 1 = k_chain_quad (4 cells / thread)
+// halos: NULL (periodic wrap) or the four deep-halo buffers {x, prev2, yn, fn} (g rows, g2 columns)
+// lazy_cp_async: see cuda_emu.h.  Returns 0, or -1 for an unsupported combination.
+extern "C" int emu_stencil_chain(int variant, int K, int fma, int lazy_cp_async, int64_t nx, int64_t ny,
+                                 const double* cxw, const double* cxe, const double* cys, const double* cyn,
+                                 const double* x, const double* prev2, const double* yn, const double* fn,
+                                 const double* coeffs, double* const* out, int rows,
+                                 const double* const* halos, int g, int g2)
+{
+  ChainArgs a;
+  memset(&a, 0, sizeof(a));
+  a.nx = nx; a.ny = ny;
+  a.cxw = cxw; a.cxe = cxe; a.cys = cys; a.cyn = cyn;
+  a.x = x; a.prev2 = prev2; a.yn = yn; a.fn = fn;
+  for (int l = 0; l < K; l++)
+  {
+    for (int k = 0; k < 5; k++) a.c[l][k] = coeffs[5 * l + k];
+    a.out[l] = out[l];
+  }
+  a.rows = rows;
+  if (halos) { a.hx = halos[0]; a.hp = halos[1]; a.hy = halos[2]; a.hf = halos[3]; a.g = g; a.g2 = g2; }
+  emu::cp_async_lazy = lazy_cp_async != 0;
+  const bool h = halos != nullptr, f = fma != 0;
+  if (variant == 0)
+  {
+    dim3 grid = chain_march_grid(nx, ny, K, &a.rows);
+    switch (K)
+    {
+    case 2: run_march_k<2, 4>(a, grid, h, f); break;
+    case 3: run_march_k<3, 4>(a, grid, h, f); break;
+    case 4: run_march_k<4, 3>(a, grid, h, f); break;
+    case 5: run_march_k<5, 3>(a, grid, h, f); break;
+    case 6: run_march_k<6, 3>(a, grid, h, f); break;
+    default: return -1;
+    }
+    return 0;
+  }
+  if (variant == 1)
+  {
+    if (!chain_quad_supported(nx, ny, K, h ? g2 : -1)) return -1;
+    dim3 grid = chain_quad_grid(nx, ny, K, &a.rows);
+    switch (K)
+    {
+    case 2: run_quad_k<2, kQuadPF>(a, grid, h, f); break;
+    case 3: run_quad_k<3, kQuadPF>(a, grid, h, f); break;
+    case 4: run_quad_k<4, kQuadPF>(a, grid, h, f); break;
+    case 5: run_quad_k<5, kQuadPF>(a, grid, h, f); break;
+    case 6: run_quad_k<6, kQuadPF>(a, grid, h, f); break;
+    default: return -1;
+    }
+    return 0;
+  }
+  return -1;
+}

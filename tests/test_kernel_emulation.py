@@ -1,0 +1,203 @@
+"""CPU tests of the temporally blocked stage kernels' SOURCE (csrc/chain_march.cuh, chain_quad.cuh)
+run through the host emulation harness tests/emu (one OS thread per CUDA thread, warp shuffles,
+cp.async groups in eager and lazy completion order).  They check the tiling / ring / halo / wrap
+indexing and the arithmetic order against a numpy restatement of the stage recurrence
+(diffusion_2D/diffusion.cpp:34-55 + arkode_lsrkstep.c:706-717), which is itself checked against the
+oracle's orc_laplacian here.  Bar: bit-exact (two-rounding arithmetic); the FMA flavour of the two
+kernels must agree with each other bit for bit and with the exact flavour to 1e-13.
+
+The emulation is test infrastructure: the product path never loads it (the GPU tests in
+test_kernels_gpu.py run the same cases on the device)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+from conftest import ROOT, P, make_grid
+
+EMU_DIR = os.path.join(ROOT, "tests", "emu")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.run(["make", "-s", "-C", EMU_DIR], check=True)
+    lib = ctypes.CDLL(os.path.join(EMU_DIR, "_build", "libemu_chain.so"))
+    lib.emu_stencil_chain.restype = ctypes.c_int
+    return lib
+
+
+def stage_np(cxw, cxe, cys, cyn, x, p2, yn, fn, c):
+    """One STS stage on a periodic grid, (ny, nx) arrays, the reference's association order."""
+    uw, ue = np.roll(x, 1, axis=1), np.roll(x, -1, axis=1)
+    us, un = np.roll(x, 1, axis=0), np.roll(x, -1, axis=0)
+    L = (-((cxw + cxe)[None, :] + (cys + cyn)[:, None])) * x
+    L = L + cxw[None, :] * uw
+    L = L + cxe[None, :] * ue
+    L = L + cys[:, None] * us
+    L = L + cyn[:, None] * un
+    z = c[0] * L
+    z = z + c[1] * p2
+    z = z + c[2] * yn
+    z = z + c[3] * x
+    z = z + c[4] * fn
+    return z
+
+
+def chain_np(cxw, cxe, cys, cyn, x, p2, yn, fn, coeffs):
+    zs, prev, cur = [], p2, x
+    for c in coeffs:
+        z = stage_np(cxw, cxe, cys, cyn, cur, prev, yn, fn, c)
+        zs.append(z)
+        prev, cur = cur, z
+    return zs
+
+
+def coeffs_for(k):
+    return [[1e-3 * (l + 1), -0.3 + 0.1 * l, 0.2, 1.1 - 0.05 * l, -2e-4] for l in range(k)]
+
+
+def run_emu(emu, variant, k, fma, lazy, nx, ny, cx, cy, ops, coeffs, rows, store, halos=None, g=0, g2=0):
+    n = nx * ny
+    outs = [np.full(n, np.nan) if store[l] else None for l in range(k)]
+    optr = (ctypes.c_void_p * k)(*[o.ctypes.data if o is not None else None for o in outs])
+    cf = np.ascontiguousarray(np.array(coeffs, dtype=np.float64).ravel())
+    hptr = None
+    if halos is not None:
+        hptr = (ctypes.c_void_p * 4)(*[h.ctypes.data for h in halos])
+    rc = emu.emu_stencil_chain(variant, k, int(fma), int(lazy), ctypes.c_int64(nx), ctypes.c_int64(ny),
+                               ctypes.c_void_p(cx[0]), ctypes.c_void_p(cx[1]), ctypes.c_void_p(cy[0]), ctypes.c_void_p(cy[1]),
+                               P(ops[0]), P(ops[1]), P(ops[2]), P(ops[3]), P(cf), optr, rows, hptr, g, g2)
+    return rc, outs
+
+
+def test_numpy_stage_matches_oracle_laplacian(orc):
+    nx, ny = 64, 48
+    g = make_grid(nx, ny, kx=1.0, ky=0.5, inhom=True)
+    tabs = [np.zeros(nx), np.zeros(nx), np.zeros(ny), np.zeros(ny)]
+    orc.orc_coeff_tables(ctypes.byref(g), *[P(t) for t in tabs])
+    rng = np.random.default_rng(5)
+    u = rng.standard_normal((ny, nx))
+    want = np.zeros(nx * ny)
+    orc.orc_laplacian(ctypes.byref(g), P(np.ascontiguousarray(u.ravel())), P(want), None, None, None, None)
+    zero = np.zeros_like(u)
+    got = stage_np(tabs[0], tabs[1], tabs[2], tabs[3], u, zero, zero, zero, [1.0, 0.0, 0.0, 0.0, 0.0])
+    assert np.array_equal(got.ravel(), want)
+
+
+CASES = [  # (nx, ny, rows)
+    (128, 16, 64),   # smallest supported field: a second warp window that wraps in x
+    (132, 21, 5),    # partial last window, partial row blocks, short blocks (warm-up and drain only)
+    (376, 26, 8),    # > 1 block in x for the quad kernel (4 warps x 120 cells), steady-state rows
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "%dx%d_rows%d" % c)
+@pytest.mark.parametrize("k", [2, 3, 4])
+@pytest.mark.parametrize("variant", [0, 1], ids=["march", "quad"])
+def test_chain_kernels_periodic_wrap_bit_exact(emu, case, k, variant):
+    nx, ny, rows = case
+    rng = np.random.default_rng(nx * 31 + ny + k)
+    tabs = [rng.random(nx) + 0.5, rng.random(nx) + 0.5, rng.random(ny) + 0.5, rng.random(ny) + 0.5]
+    ops = [np.ascontiguousarray(rng.standard_normal(nx * ny)) for _ in range(4)]
+    coeffs = coeffs_for(k)
+    want = chain_np(*tabs, *[o.reshape(ny, nx) for o in ops], coeffs)
+    cx = [tabs[0].ctypes.data, tabs[1].ctypes.data]
+    cy = [tabs[2].ctypes.data, tabs[3].ctypes.data]
+    for lazy in (0, 1):
+        # all levels stored
+        rc, outs = run_emu(emu, variant, k, 0, lazy, nx, ny, cx, cy, ops, coeffs, rows, [True] * k)
+        assert rc == 0
+        for l in range(k):
+            assert np.array_equal(outs[l], want[l].ravel()), "level %d (lazy=%d)" % (l + 1, lazy)
+    # only the last two levels stored (what LSRKStep needs)
+    store = [l >= k - 2 for l in range(k)]
+    rc, outs = run_emu(emu, variant, k, 0, 1, nx, ny, cx, cy, ops, coeffs, rows, store)
+    assert rc == 0
+    assert np.array_equal(outs[k - 1], want[k - 1].ravel()) and np.array_equal(outs[k - 2], want[k - 2].ravel())
+
+
+@pytest.mark.parametrize("k", [5, 6])
+@pytest.mark.parametrize("variant", [0, 1], ids=["march", "quad"])
+def test_chain_kernels_deep_levels_bit_exact(emu, k, variant):
+    nx, ny, rows = 192, 24, 7
+    rng = np.random.default_rng(k)
+    tabs = [rng.random(nx) + 0.5, rng.random(nx) + 0.5, rng.random(ny) + 0.5, rng.random(ny) + 0.5]
+    ops = [np.ascontiguousarray(rng.standard_normal(nx * ny)) for _ in range(4)]
+    coeffs = coeffs_for(k)
+    want = chain_np(*tabs, *[o.reshape(ny, nx) for o in ops], coeffs)
+    rc, outs = run_emu(emu, variant, k, 0, 1, nx, ny, [tabs[0].ctypes.data, tabs[1].ctypes.data],
+                       [tabs[2].ctypes.data, tabs[3].ctypes.data], ops, coeffs, rows, [True] * k)
+    assert rc == 0
+    for l in range(k):
+        assert np.array_equal(outs[l], want[l].ravel()), "level %d" % (l + 1)
+
+
+def deep_halo(field, i0, j0, nx, ny, g, g2):
+    """[S | N | W | E] deep halo of the block [j0, j0+ny) x [i0, i0+nx) of a periodic global field
+    (layout of b200_deep_halo_exchange: S/N g rows x nx; W/E (ny+2g) rows x g2, corners inside W/E)."""
+    NY, NX = field.shape
+    rows = lambda a, b: np.arange(a, b) % NY
+    cols = lambda a, b: np.arange(a, b) % NX
+    S = field[np.ix_(rows(j0 - g, j0), cols(i0, i0 + nx))]
+    N = field[np.ix_(rows(j0 + ny, j0 + ny + g), cols(i0, i0 + nx))]
+    W = field[np.ix_(rows(j0 - g, j0 + ny + g), cols(i0 - g2, i0))]
+    E = field[np.ix_(rows(j0 - g, j0 + ny + g), cols(i0 + nx, i0 + nx + g2))]
+    return np.ascontiguousarray(np.concatenate([S.ravel(), N.ravel(), W.ravel(), E.ravel()]))
+
+
+@pytest.mark.parametrize("block", [(0, 0), (1, 1)], ids=["block00", "block11"])
+@pytest.mark.parametrize("k", [2, 4, 5])
+@pytest.mark.parametrize("variant", [0, 1], ids=["march", "quad"])
+def test_chain_kernels_halo_flavour_bit_exact(emu, block, k, variant):
+    """A 2 x 2 block decomposition of a periodic field: every block, fed with deep halos and the
+    coefficient tables extended by the global periodic index, must reproduce the global result."""
+    nx, ny, g, g2, M, rows = 132, 20, 6, 6, 16, 6
+    if k > 4:
+        g2 = 8  # the quad kernel needs 4 * ceil(K/4) deep-halo columns
+    NX, NY = 2 * nx, 2 * ny
+    rng = np.random.default_rng(100 + k)
+    T = [rng.random(NX) + 0.5, rng.random(NX) + 0.5, rng.random(NY) + 0.5, rng.random(NY) + 0.5]
+    G = [rng.standard_normal((NY, NX)) for _ in range(4)]
+    coeffs = coeffs_for(k)
+    want = chain_np(*T, *G, coeffs)
+    bi, bj = block
+    i0, j0 = bi * nx, bj * ny
+    ext_x = [np.ascontiguousarray(t[np.arange(i0 - M, i0 + nx + M) % NX]) for t in T[:2]]
+    ext_y = [np.ascontiguousarray(t[np.arange(j0 - M, j0 + ny + M) % NY]) for t in T[2:]]
+    cx = [t.ctypes.data + 8 * M for t in ext_x]
+    cy = [t.ctypes.data + 8 * M for t in ext_y]
+    ops = [np.ascontiguousarray(f[j0:j0 + ny, i0:i0 + nx].ravel()) for f in G]
+    halos = [deep_halo(f, i0, j0, nx, ny, g, g2) for f in G]
+    for lazy in (0, 1):
+        rc, outs = run_emu(emu, variant, k, 0, lazy, nx, ny, cx, cy, ops, coeffs, rows, [True] * k, halos, g, g2)
+        assert rc == 0
+        for l in range(k):
+            assert np.array_equal(outs[l], want[l][j0:j0 + ny, i0:i0 + nx].ravel()), "level %d" % (l + 1)
+
+
+def test_fma_flavour_consistent_between_kernels_and_close_to_exact(emu):
+    nx, ny, rows, k = 256, 20, 8, 4
+    rng = np.random.default_rng(77)
+    tabs = [rng.random(nx) + 0.5, rng.random(nx) + 0.5, rng.random(ny) + 0.5, rng.random(ny) + 0.5]
+    ops = [np.ascontiguousarray(rng.standard_normal(nx * ny)) for _ in range(4)]
+    coeffs = coeffs_for(k)
+    cx = [tabs[0].ctypes.data, tabs[1].ctypes.data]
+    cy = [tabs[2].ctypes.data, tabs[3].ctypes.data]
+    want = chain_np(*tabs, *[o.reshape(ny, nx) for o in ops], coeffs)
+    _, m = run_emu(emu, 0, k, 1, 0, nx, ny, cx, cy, ops, coeffs, rows, [True] * k)
+    _, q = run_emu(emu, 1, k, 1, 0, nx, ny, cx, cy, ops, coeffs, rows, [True] * k)
+    for l in range(k):
+        assert np.array_equal(m[l], q[l])
+        rel = np.linalg.norm(m[l] - want[l].ravel()) / np.linalg.norm(want[l])
+        assert 0 < rel < 1e-13  # contracted arithmetic differs, by rounding only
+
+
+def test_quad_kernel_rejects_unsupported_shapes(emu):
+    rng = np.random.default_rng(1)
+    nx, ny = 130, 16  # nx % 4 != 0
+    tabs = [rng.random(nx), rng.random(nx), rng.random(ny), rng.random(ny)]
+    ops = [rng.standard_normal(nx * ny) for _ in range(4)]
+    rc, _ = run_emu(emu, 1, 4, 0, 0, nx, ny, [tabs[0].ctypes.data, tabs[1].ctypes.data],
+                    [tabs[2].ctypes.data, tabs[3].ctypes.data], ops, coeffs_for(4), 8, [True] * 4)
+    assert rc == -1
