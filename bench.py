@@ -37,6 +37,7 @@ sys.path.insert(0, ROOT)
 
 ALG_BYTES_PER_UPDATE = 40.0
 H_FIXED = 1.0e-4
+DEFAULT_ARITH = "exact"
 XL, XU0, YL, YU0 = -3.141592653589793, 3.141592653589793, -6.0, 6.0
 
 
@@ -198,6 +199,11 @@ def main():
     ap.add_argument("--method", default="rkc")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--chain", type=int, default=0, help="temporal-blocking depth (0 = library default)")
+    ap.add_argument("--chain-variant", type=int, default=-1, help="0 = k_chain_march, 1 = k_chain_quad (default)")
+    ap.add_argument("--arith", default=DEFAULT_ARITH, choices=["exact", "fma"],
+                    help="exact = bit-identical to the reference's baseline x86-64 build; fma = contracted multiply-adds")
+    ap.add_argument("--e2e-mode", default="pipelined", choices=["pipelined", "sequential"])
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -230,7 +236,11 @@ def main():
 
     npx, npy = dims_create(world)
     n = args.local_n
-    wargs = workload_args(n, npx, npy, method=args.method, base_n=n)
+    wargs = workload_args(n, npx, npy, method=args.method, base_n=n) + ["--arith", args.arith]
+    if args.chain > 0:
+        wargs += ["--chain", str(args.chain)]
+    if args.chain_variant >= 0:
+        wargs += ["--chain-variant", str(args.chain_variant)]
     prob = b200.Diffusion2D(wargs, rank=rank, nranks=world, nccl_id=nccl_id, device=local_rank)
     ncell_global = (n * npx) * (n * npy)
     ncell_local = n * n
@@ -269,21 +279,34 @@ def main():
     value = evals * ncell_global / (ms_max * 1e-3)
 
     # ---- e2e: host buffers, H2D + step + D2H every step ---------------------------------------
+    # Every timed step starts from a state in pinned HOST memory and ends with its result back in
+    # pinned host memory, through the problem layer's public calls.
+    #   pipelined (default): the steps are independent batches (b200_d2d_run_batches): the upload of
+    #     batch i+1 and the download of batch i-1 run on copy streams while batch i is integrated;
+    #     every batch's 2 x 8 B x cells cross PCIe inside the timed region.
+    #   sequential: one dependent chain, set_state -> step -> get_state, nothing overlaps.
     e2e = None
     if not args.no_e2e:
-        h_in = torch.empty(ncell_local, dtype=torch.float64, pin_memory=True)
-        h_out = torch.empty(ncell_local, dtype=torch.float64, pin_memory=True)
-        prob.get_state(h_in)
+        hin = [torch.empty(ncell_local, dtype=torch.float64, pin_memory=True) for _ in range(2)]
+        hout = [torch.empty(ncell_local, dtype=torch.float64, pin_memory=True) for _ in range(2)]
+        prob.get_state(hin[0])
+        hin[1].copy_(hin[0])
+        t_cur = prob.stats()["t"]
+        if args.e2e_mode == "pipelined":
+            prob.run_batches([hin[0], hin[1]], [hout[0], hout[1]], t_cur, 1)  # warm-up: staging buffers, streams
         e_s0 = prob.stats()
-        t_cur = e_s0["t"]
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            prob.set_state(h_in, t_cur)  # H2D + ARKodeReset
-            prob.step(1)
-            prob.get_state(h_out)  # D2H (synchronises)
-            h_in, h_out = h_out, h_in
-            t_cur += H_FIXED
+        if args.e2e_mode == "pipelined":
+            prob.run_batches([hin[i % 2] for i in range(args.steps)], [hout[i % 2] for i in range(args.steps)], t_cur, 1)
+        else:
+            h_in, h_out = hin[0], hout[0]
+            for _ in range(args.steps):
+                prob.set_state(h_in, t_cur)  # H2D + ARKodeReset
+                prob.step(1)
+                prob.get_state(h_out)  # D2H (synchronises)
+                h_in, h_out = h_out, h_in
+                t_cur += H_FIXED
         barrier()
         dt = time.perf_counter() - t0
         e_s1 = prob.stats()
@@ -293,8 +316,10 @@ def main():
         e_evals = e_s1["rhs_evals"] - e_s0["rhs_evals"]
         e2e = {"value": e_evals * ncell_global / float(tt.item()), "unit": "cell-updates/s",
                "h2d_bytes_per_step": 8 * ncell_local * world, "d2h_bytes_per_step": 8 * ncell_local * world,
-               "ms_per_step": 1e3 * float(tt.item()) / args.steps}
-        del h_in, h_out
+               "ms_per_step": 1e3 * float(tt.item()) / args.steps, "mode": args.e2e_mode,
+               "note": ("independent batches, double-buffered: copies of batches i-1 / i+1 overlap the integration of batch i"
+                        if args.e2e_mode == "pipelined" else "dependent steps: upload, step, download, nothing overlaps")}
+        del hin, hout
 
     stats_final = prob.stats()
     prob.close()
@@ -313,6 +338,8 @@ def main():
     # The SURVEY 8(d) basis of 40 B per cell-update (one HBM pass per stage) is reported beside it:
     # on that basis temporal blocking exceeds the one-pass-per-stage ceiling.
     peak, peak_src = measured_peak()
+    klib.b200_last_chain_kernel.restype = ctypes.c_char_p
+    chain_kernel = (klib.b200_last_chain_kernel() or b"").decode() or "k_chain_march"
     chain_l = s1["chain_launches"] - s0["chain_launches"]
     chain_s = s1["chain_stages"] - s0["chain_stages"]
     depth = (chain_s / chain_l) if chain_l else 1.0
@@ -328,7 +355,7 @@ def main():
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src,
-                "kernel": ("k_chain_march<K=%d> (temporally blocked STS stages)" % round(depth)) if chain_l
+                "kernel": ("%s<K=%d> (temporally blocked STS stages)" % (chain_kernel, round(depth))) if chain_l
                           else "k_stage_march<5,PAT5(S,V,V,C,V)>",
                 "modelled_bytes_timed": int(alg_bytes), "bytes_per_cell_update": alg_bytes / max(evals * ncell_local, 1),
                 "stages_per_launch": depth, "chain_launches_timed": chain_l, "rhs_evals_timed": evals,
@@ -364,7 +391,10 @@ def main():
                    "global_grid": [n * npx, n * npy], "parallelism": "%dx%d blocks, NCCL halo exchange" % (npx, npy),
                    "l2_note": "per-stage working set %.1f GiB >> 126 MB L2 (inputs larger than L2, no flush needed)"
                               % (5 * 8 * ncell_local / 2**30),
-                   "rhs_evals_timed": evals},
+                   "rhs_evals_timed": evals,
+                   "arith": ("exact: every multiply / add rounded separately, bit-identical to the reference's baseline build"
+                             if args.arith == "exact" else
+                             "fma: multiply-adds of the chained stages contracted (agrees with the reference to rounding, <= 1e-10 bar)")},
         "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
         "clocks": sampler.summary(),
         "stage_chain_depth": depth,

@@ -305,6 +305,16 @@ class Diffusion2D:
         if self._lib.b200_d2d_set_state(self.handle, _ptr(host), ctypes.c_double(t)) != 0:
             raise RuntimeError("b200_d2d_set_state failed")
 
+    def run_batches(self, host_ins, host_outs, t=0.0, nsteps=1):
+        """b200_d2d_run_batches: independent states host_ins[i] (pinned) -> nsteps steps from time t ->
+        host_outs[i] (pinned), uploads / downloads of neighbouring batches overlapping the integration."""
+        n = len(host_ins)
+        assert len(host_outs) == n
+        ins = (ctypes.c_void_p * n)(*[_ptr(h) for h in host_ins])
+        outs = (ctypes.c_void_p * n)(*[_ptr(h) for h in host_outs])
+        if self._lib.b200_d2d_run_batches(self.handle, n, ins, outs, ctypes.c_double(t), int(nsteps)) != 0:
+            raise RuntimeError("b200_d2d_run_batches failed: %s" % kernel_lib().b200_last_error().decode())
+
     def stats(self):
         s = D2DStats()
         self._lib.b200_d2d_get_stats(self.handle, ctypes.byref(s))

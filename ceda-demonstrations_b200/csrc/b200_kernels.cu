@@ -193,6 +193,117 @@ extern "C" int b200_d2h(b200_ctx* c, double* dst, const double* src, int64_t n)
   return 0;
 }
 
+// ------------------------------------------------- pipelined host <-> device staging
+// A stream of independent states (ensemble members, parameter sweeps, bench.py's end-to-end leg):
+// the upload of state i+1 and the download of result i-1 run on their own copy streams while
+// state i is integrated on the compute stream.  Two input and two output staging buffers in HBM;
+// the hand-over to / from the integrator's vectors is a device-to-device copy on the compute
+// stream, so pooled vector buffers are never touched from a copy stream.
+struct b200_pipe
+{
+  b200_ctx* ctx;
+  int64_t n;
+  double* in[2];
+  double* out[2];
+  cudaStream_t h2d, d2h;
+  cudaEvent_t in_ready[2], in_free[2], out_ready[2], out_free[2];
+};
+
+extern "C" int b200_pipe_destroy(b200_pipe* p)
+{
+  if (!p) return 0;
+  cudaSetDevice(p->ctx->device);
+  if (p->h2d) cudaStreamSynchronize(p->h2d);
+  if (p->d2h) cudaStreamSynchronize(p->d2h);
+  cudaStreamSynchronize(p->ctx->stream);
+  for (int s = 0; s < 2; s++)
+  {
+    if (p->in[s]) cudaFree(p->in[s]);
+    if (p->out[s]) cudaFree(p->out[s]);
+    if (p->in_ready[s]) cudaEventDestroy(p->in_ready[s]);
+    if (p->in_free[s]) cudaEventDestroy(p->in_free[s]);
+    if (p->out_ready[s]) cudaEventDestroy(p->out_ready[s]);
+    if (p->out_free[s]) cudaEventDestroy(p->out_free[s]);
+  }
+  if (p->h2d) cudaStreamDestroy(p->h2d);
+  if (p->d2h) cudaStreamDestroy(p->d2h);
+  delete p;
+  return 0;
+}
+
+static int pipe_init(b200_pipe* p)
+{
+  CU_TRY(cudaSetDevice(p->ctx->device));
+  CU_TRY(cudaStreamCreateWithFlags(&p->h2d, cudaStreamNonBlocking));
+  CU_TRY(cudaStreamCreateWithFlags(&p->d2h, cudaStreamNonBlocking));
+  for (int s = 0; s < 2; s++)
+  {
+    CU_TRY(cudaMalloc(&p->in[s], sizeof(double) * (size_t)p->n));
+    CU_TRY(cudaMalloc(&p->out[s], sizeof(double) * (size_t)p->n));
+    CU_TRY(cudaEventCreateWithFlags(&p->in_ready[s], cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&p->in_free[s], cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&p->out_ready[s], cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&p->out_free[s], cudaEventDisableTiming));
+  }
+  return 0;
+}
+
+extern "C" int b200_pipe_create(b200_ctx* c, int64_t n, b200_pipe** out)
+{
+  if (!c || n <= 0 || !out) return fail("b200_pipe_create: bad argument");
+  b200_pipe* p = new b200_pipe();
+  memset(p, 0, sizeof(*p));
+  p->ctx = c;
+  p->n   = n;
+  int rc = pipe_init(p);
+  if (rc)
+  {
+    b200_pipe_destroy(p);
+    return rc;
+  }
+  *out = p;
+  return 0;
+}
+
+// A wait on an event that was never recorded is a no-op, which is what the first use of a slot needs.
+extern "C" int b200_pipe_upload(b200_pipe* p, int64_t seq, const double* host_src)
+{
+  const int s = (int)(seq & 1);
+  CU_TRY(cudaStreamWaitEvent(p->h2d, p->in_free[s], 0));
+  CU_TRY(cudaMemcpyAsync(p->in[s], host_src, sizeof(double) * (size_t)p->n, cudaMemcpyHostToDevice, p->h2d));
+  CU_TRY(cudaEventRecord(p->in_ready[s], p->h2d));
+  return 0;
+}
+
+extern "C" int b200_pipe_take(b200_pipe* p, int64_t seq, double* dst_dev)
+{
+  const int s = (int)(seq & 1);
+  CU_TRY(cudaStreamWaitEvent(p->ctx->stream, p->in_ready[s], 0));
+  CU_TRY(cudaMemcpyAsync(dst_dev, p->in[s], sizeof(double) * (size_t)p->n, cudaMemcpyDeviceToDevice, p->ctx->stream));
+  CU_TRY(cudaEventRecord(p->in_free[s], p->ctx->stream));
+  return 0;
+}
+
+extern "C" int b200_pipe_put(b200_pipe* p, int64_t seq, const double* src_dev, double* host_dst)
+{
+  const int s = (int)(seq & 1);
+  CU_TRY(cudaStreamWaitEvent(p->ctx->stream, p->out_free[s], 0));
+  CU_TRY(cudaMemcpyAsync(p->out[s], src_dev, sizeof(double) * (size_t)p->n, cudaMemcpyDeviceToDevice, p->ctx->stream));
+  CU_TRY(cudaEventRecord(p->out_ready[s], p->ctx->stream));
+  CU_TRY(cudaStreamWaitEvent(p->d2h, p->out_ready[s], 0));
+  CU_TRY(cudaMemcpyAsync(host_dst, p->out[s], sizeof(double) * (size_t)p->n, cudaMemcpyDeviceToHost, p->d2h));
+  CU_TRY(cudaEventRecord(p->out_free[s], p->d2h));
+  return 0;
+}
+
+extern "C" int b200_pipe_drain(b200_pipe* p)
+{
+  CU_TRY(cudaStreamSynchronize(p->h2d));
+  CU_TRY(cudaStreamSynchronize(p->ctx->stream));
+  CU_TRY(cudaStreamSynchronize(p->d2h));
+  return 0;
+}
+
 // ------------------------------------------------------------ device helpers
 #include "kernel_prims.cuh"
 
@@ -1060,6 +1171,8 @@ static int launch_quad(const ChainArgs& a, dim3 grid, cudaStream_t st)
 }
 
 static int g_chain_rows = 64;
+static const char* g_last_chain_kernel = "";
+extern "C" const char* b200_last_chain_kernel(void) { return g_last_chain_kernel; }
 // 1: four cells per thread (k_chain_quad) wherever its shape requirements hold, else k_chain_march;
 // 0: always k_chain_march.  B200_CHAIN_VARIANT overrides the initial value.
 static int g_chain_variant = -1;
@@ -1132,6 +1245,7 @@ static int stencil_chain_common(b200_ctx* c, const b200_stencil_geom* g, int nst
   if (b200_get_chain_variant() == 1 && chain_quad_supported(a.nx, a.ny, nstages, halos ? hg2 : -1))
   {
     dim3 grid = chain_quad_grid(a.nx, a.ny, nstages, &a.rows);
+    g_last_chain_kernel = "k_chain_quad";
     switch (nstages)
     {
     case 2: rc = launch_quad<2, kQuadPF>(a, grid, c->stream); break;
@@ -1144,6 +1258,7 @@ static int stencil_chain_common(b200_ctx* c, const b200_stencil_geom* g, int nst
   else
   {
     dim3 grid = chain_march_grid(a.nx, a.ny, nstages, &a.rows);
+    g_last_chain_kernel = "k_chain_march";
     switch (nstages)
     {
     case 2: rc = launch_chain<2, 4>(a, grid, c->stream); break;

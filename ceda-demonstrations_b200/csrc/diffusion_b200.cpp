@@ -405,6 +405,8 @@ struct UserOptions
   bool no_overlap = false, no_fusion = false;
   int rows_per_block = 0;
   int chain = 0; // temporal-blocking depth (0 = default / B200_CHAIN, 1 = off)
+  int chain_variant = -1; // -1 = library default (B200_CHAIN_VARIANT), 0 = two cells / thread, 1 = four
+  std::string arith;      // "" = B200_ARITH or exact; "exact" | "fma" (b200_set_contract)
   bool force_halo = false;
 };
 
@@ -441,7 +443,7 @@ int parse_args(std::vector<std::string> args, UserData& ud, UserOptions& uo, boo
     ARG_B("--noprec", uo.preconditioning, false) ARG_B("--internaleig", uo.internaleig, true)
     ARG_I("--output", uo.output) ARG_I("--nout", uo.nout)
     ARG_B("--no-overlap", uo.no_overlap, true) ARG_B("--no-fusion", uo.no_fusion, true)
-    ARG_I("--rows-per-block", uo.rows_per_block) ARG_I("--chain", uo.chain) ARG_B("--force-halo", uo.force_halo, true)
+    ARG_I("--rows-per-block", uo.rows_per_block) ARG_I("--chain", uo.chain) ARG_I("--chain-variant", uo.chain_variant) ARG_S("--arith", uo.arith) ARG_B("--force-halo", uo.force_halo, true)
     if (outproc) fprintf(stderr, "ERROR: Unknown inputs: %s\n", a.c_str());
     return -1;
   }
@@ -473,6 +475,7 @@ struct b200_d2d
   FILE* uout = nullptr;
   B200VecStats vs0{};          // process-wide counters at creation (stats are reported per session)
   uint64_t launches0 = 0;
+  b200_pipe* pipe    = nullptr; // staging for b200_d2d_run_batches (created on first use)
 };
 
 #define CHK(call, name)                                                       \
@@ -666,6 +669,21 @@ extern "C" int b200_d2d_create(int argc, const char* const* argv, int rank, int 
     N_VSetStageChain_B200(depth);
   }
   if (p->uo.rows_per_block > 0) b200_set_rows_per_block(p->uo.rows_per_block);
+  if (p->uo.chain_variant >= 0 && b200_set_chain_variant(p->uo.chain_variant))
+  {
+    fprintf(stderr, "ERROR: --chain-variant must be 0 or 1\n");
+    return -1;
+  }
+  {
+    std::string ar = p->uo.arith;
+    if (ar.empty()) { const char* e = getenv("B200_ARITH"); ar = e ? e : "exact"; }
+    if (ar != "exact" && ar != "fma")
+    {
+      fprintf(stderr, "ERROR: --arith must be exact or fma\n");
+      return -1;
+    }
+    b200_set_contract(ar == "fma");
+  }
   N_VSetLazyFusion_B200(p->uo.no_fusion ? 0 : 1);
   if (p->ud.upload_tables()) return -1;
   if (SUNContext_Create(SUN_COMM_NULL, &p->sunctx)) return -1;
@@ -678,6 +696,7 @@ extern "C" int b200_d2d_destroy(b200_d2d* p)
 {
   if (!p) return 0;
   if (p->uout) fclose(p->uout);
+  if (p->pipe) b200_pipe_destroy(p->pipe);
   if (p->Ctrl) SUNAdaptController_Destroy(p->Ctrl);
   if (p->arkode_mem) ARKodeFree(&p->arkode_mem);
   if (p->arkref_mem) ARKodeFree(&p->arkref_mem);
@@ -729,6 +748,31 @@ extern "C" int b200_d2d_set_state(b200_d2d* p, const double* host, double t)
   CHK(ARKodeReset(p->arkode_mem, t, p->u), "ARKodeReset");
   p->t = t;
   return 0;
+}
+
+extern "C" int b200_d2d_run_batches(b200_d2d* p, int nbatch, const double* const* host_in,
+                                    double* const* host_out, double t, int nsteps)
+{
+  if (nbatch <= 0) return 0;
+  if (!p->pipe && b200_pipe_create(p->ctx, p->ud.nx_loc * p->ud.ny_loc, &p->pipe))
+  {
+    fprintf(stderr, "b200_d2d_run_batches: %s\n", b200_last_error());
+    return -1;
+  }
+  b200_pipe* pp = p->pipe;
+  if (b200_pipe_upload(pp, 0, host_in[0])) return -1;
+  if (nbatch > 1 && b200_pipe_upload(pp, 1, host_in[1])) return -1;
+  for (int i = 0; i < nbatch; i++)
+  {
+    if (b200_pipe_take(pp, i, N_VGetDeviceArrayPointerForWrite_B200(p->u))) return -1;
+    // slot i%2 is free again once the take above has run: the upload after next may start
+    if (i + 2 < nbatch && b200_pipe_upload(pp, i + 2, host_in[i + 2])) return -1;
+    CHK(ARKodeReset(p->arkode_mem, t, p->u), "ARKodeReset");
+    p->t = t;
+    if (b200_d2d_step(p, nsteps)) return -1;
+    if (b200_pipe_put(pp, i, N_VGetDeviceArrayPointer_B200(p->u), host_out[i])) return -1;
+  }
+  return b200_pipe_drain(pp);
 }
 
 extern "C" int b200_d2d_get_stats(b200_d2d* p, b200_d2d_stats* s)

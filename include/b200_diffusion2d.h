@@ -60,6 +60,13 @@ int b200_d2d_step(b200_d2d* p, int nsteps);
 int b200_d2d_get_state(b200_d2d* p, double* host);
 /* overwrite the state from host memory and ARKodeReset to time t */
 int b200_d2d_set_state(b200_d2d* p, const double* host, double t);
+/* A stream of `nbatch` independent states through the same integrator: for each i, the state is
+   overwritten from host_in[i] (pinned), ARKodeReset to time t, `nsteps` steps are taken and the
+   result goes to host_out[i] (pinned).  Uploads and downloads are double-buffered on their own copy
+   streams (b200_pipe_*), so the copies of neighbouring batches overlap the integration; results are
+   identical to set_state / step / get_state per batch.  Returns after all results have landed. */
+int b200_d2d_run_batches(b200_d2d* p, int nbatch, const double* const* host_in, double* const* host_out,
+                         double t, int nsteps);
 /* COLLECTIVE when nranks > 1 (urms is an all-reduced dot product): call on every rank. */
 int b200_d2d_get_stats(b200_d2d* p, b200_d2d_stats* s);
 /* print ARKodePrintAllStats exactly as the reference main.cpp:486 does */

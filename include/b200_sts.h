@@ -56,6 +56,23 @@ int b200_host_free(double* hptr);
 int b200_h2d(b200_ctx* ctx, double* dst_dev, const double* src_host, int64_t n);
 int b200_d2h(b200_ctx* ctx, double* dst_host, const double* src_dev, int64_t n);
 
+/* ----------------------------------------- pipelined host <-> device staging */
+/* For a stream of INDEPENDENT states (ensemble members, sweeps, bench.py's end-to-end leg): the
+   upload of state seq+1 and the download of result seq-1 overlap the integration of state seq.
+   Two input and two output staging buffers of n doubles in HBM, one H2D and one D2H copy stream;
+   slot = seq % 2.  Host buffers must be pinned (b200_host_alloc) for the copies to be asynchronous.
+   Call order per state: upload(seq) [may run ahead by two], take(seq, vec), ...work on the
+   context's stream..., put(seq, vec, host); b200_pipe_drain before reading the host results.
+   (The reference keeps its state in host memory, diffusion_2D/main.cpp:176-190: this replaces the
+   plain b200_h2d / b200_d2h round trip when there is more than one state to process.) */
+typedef struct b200_pipe b200_pipe;
+int b200_pipe_create(b200_ctx* ctx, int64_t n_doubles, b200_pipe** out);
+int b200_pipe_destroy(b200_pipe* p);
+int b200_pipe_upload(b200_pipe* p, int64_t seq, const double* host_src);
+int b200_pipe_take(b200_pipe* p, int64_t seq, double* dst_dev);
+int b200_pipe_put(b200_pipe* p, int64_t seq, const double* src_dev, double* host_dst);
+int b200_pipe_drain(b200_pipe* p);
+
 /* ------------------------------------------------- elementwise vector kernels */
 /* z = sum_k c[k]*v[k] evaluated left to right:  acc = c0*v0; acc = acc + ck*vk.
    This is SUNDIALS' generic N_VLinearCombination fallback
@@ -186,6 +203,23 @@ int b200_deep_halo_exchange(b200_ctx* ctx, const int peers[4], int x_split, int 
                             const double* const* fields, double* const* halos);
 /* rows of output each thread block of the chain kernel marches over (default 64) */
 int b200_set_chain_rows(int rows);
+/* Which kernel runs a chain: 1 (default) = k_chain_quad, four cells per thread, wherever its shape
+   requirements hold (nx % 4 == 0; halo flavour: halo_cols >= 4*ceil(nstages/4)), else
+   k_chain_march; 0 = always k_chain_march (two cells per thread).  Results are bit-identical
+   either way.  The environment variable B200_CHAIN_VARIANT sets the initial value. */
+int b200_set_chain_variant(int variant);
+int b200_get_chain_variant(void);
+/* name of the kernel the most recent chain launch used ("k_chain_quad" / "k_chain_march", "" if none) */
+const char* b200_last_chain_kernel(void);
+/* Arithmetic of the chain kernels.  0 (default) = the arithmetic contract stated at the top of this
+   header: every multiply and add rounded separately, bit-identical to the reference's baseline
+   x86-64 build.  1 = each c + a*b of diffusion.cpp:48-53 / sundials_nvector.c:557-565 is contracted
+   to one fused multiply-add, i.e. what gcc's default -ffp-contract=fast makes of the reference on an
+   FMA-baseline ISA (aarch64, ppc64le, x86-64-v3): results then agree with the baseline build to
+   rounding (~1e-15 relative per stage; the parity bar of 1e-10 on the final state holds), not bit
+   for bit, and the FP64 pipe has 22 instead of 38 instructions per two cell-updates to issue. */
+int b200_set_contract(int on);
+int b200_get_contract(void);
 
 /* Tuning knob: rows of the sub-domain each thread block of the fused kernel marches over
    (default 8).  Results do not depend on it. */

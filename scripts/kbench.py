@@ -27,8 +27,12 @@ def main():
     ap.add_argument("--ny", type=int, default=0)
     ap.add_argument("--rows", default="32")
     ap.add_argument("--iters", type=int, default=20)
-    ap.add_argument("--pattern", default="stage")
+    ap.add_argument("--pattern", default="stage", help="stage | rhs | final | chainK; comma list = sweep in one process")
+    ap.add_argument("--variant", default="1", help="chain kernel: 0 = two cells / thread, 1 = four (comma list)")
+    ap.add_argument("--arith", default="exact", help="exact | fma (comma list)")
     args = ap.parse_args()
+    combos = [(p_, int(v_), a_) for p_ in args.pattern.split(",") for v_ in args.variant.split(",")
+              for a_ in args.arith.split(",")]
     nx = args.n
     ny = args.ny or args.n
     ctx = b200.Context(0)
@@ -41,7 +45,12 @@ def main():
     g = b200.StencilGeom(nx, ny, cx[0].data_ptr(), cx[1].data_ptr(), cy[0].data_ptr(), cy[1].data_ptr(), None, None, None, None)
     coeffs = [1e-7, -0.3, 0.2, 1.1, -2e-8]
     out = {}
-    for rows in [int(r) for r in args.rows.split(",")]:
+    for pattern, variant, arith, rows in [(p_, v_, a_, int(r)) for (p_, v_, a_) in combos for r in args.rows.split(",")]:
+        if not pattern.startswith("chain") and (variant, arith) != (combos[0][1], combos[0][2]):
+            continue  # variant / arith only concern the chain kernels
+        args.pattern, args.variant, args.arith = pattern, variant, arith
+        lib.b200_set_chain_variant(variant)
+        lib.b200_set_contract(1 if arith == "fma" else 0)
         lib.b200_set_rows_per_block(rows)
         if args.pattern.startswith("chain"):
             lib.b200_set_chain_rows(rows)
@@ -79,9 +88,10 @@ def main():
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.iters
         gbs = bpc * N / (ms * 1e-3) / 1e9
-        out[rows] = {"ms": ms, "GBs": gbs}
-        print("n=%dx%d pattern=%s rows=%d: %.3f ms/launch  %.1f GB/s (%.0f B/cell basis)  %.3e cell-updates/s"
-              % (nx, ny, args.pattern, rows, ms, gbs, bpc, N / (ms * 1e-3)))
+        out[(pattern, variant, arith, rows)] = {"ms": ms, "GBs": gbs}
+        kk = int(args.pattern[5:]) if args.pattern.startswith("chain") else 1
+        print("n=%dx%d pattern=%s variant=%d arith=%s rows=%d: %.3f ms/launch  %.1f GB/s (%.0f B/cell basis)  %.3e cell-updates/s"
+              % (nx, ny, args.pattern, args.variant, args.arith, rows, ms, gbs, bpc, kk * N / (ms * 1e-3)))
     return out
 
 

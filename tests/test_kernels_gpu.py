@@ -368,7 +368,8 @@ def test_full_size_shift_equivariance_and_conservation(ctx, b200, n):
 @pytest.mark.parametrize("size", [(128, 16), (192, 70), (1024, 96), (2050, 33)], ids=lambda s: "%dx%d" % s)
 @pytest.mark.parametrize("k", [2, 3, 4, 5, 6])
 @pytest.mark.parametrize("rows", [64, 5])
-def test_stencil_chain_equals_single_stage_launches(ctx, b200, size, k, rows):
+@pytest.mark.parametrize("variant", [1, 0], ids=["quad", "march"])
+def test_stencil_chain_equals_single_stage_launches(ctx, b200, size, k, rows, variant):
     """b200_stencil_chain (K stages in one pass) must be bit-identical to K b200_stencil_lincomb launches
     (which are themselves pinned against the oracle above), including periodic wrap in x and y, partial
     windows (nx not a multiple of 60/56) and partial row blocks."""
@@ -377,6 +378,8 @@ def test_stencil_chain_equals_single_stage_launches(ctx, b200, size, k, rows):
     rng = np.random.default_rng(nx * 7 + ny + k)
     lib = b200.kernel_lib()
     lib.b200_set_chain_rows(rows)
+    lib.b200_set_chain_variant(variant)
+    lib.b200_set_contract(0)
     cx = [dev(rng.random(nx) + 0.5) for _ in range(2)]
     cy = [dev(rng.random(ny) + 0.5) for _ in range(2)]
     g = b200.StencilGeom(nx, ny, cx[0].data_ptr(), cx[1].data_ptr(), cy[0].data_ptr(), cy[1].data_ptr(), None, None, None, None)
@@ -403,4 +406,38 @@ def test_stencil_chain_equals_single_stage_launches(ctx, b200, size, k, rows):
     ctx.stencil_chain(g, x, p2, yn, fn, coeffs, outs2)
     ctx.sync()
     assert np.array_equal(host(outs2[k - 1]), host(zs[k - 1])) and np.array_equal(host(outs2[k - 2]), host(zs[k - 2]))
+    lib.b200_last_chain_kernel.restype = ctypes.c_char_p
+    assert lib.b200_last_chain_kernel() == (b"k_chain_quad" if (variant == 1 and nx % 4 == 0) else b"k_chain_march")
     lib.b200_set_chain_rows(64)
+    lib.b200_set_chain_variant(1)
+
+
+@pytest.mark.parametrize("size", [(256, 40), (1024, 96)], ids=lambda s: "%dx%d" % s)
+@pytest.mark.parametrize("k", [2, 4, 6])
+def test_stencil_chain_fma_flavour(ctx, b200, size, k):
+    """b200_set_contract(1): the chained stages' multiply-adds become FMAs.  Both chain kernels contract the
+    same operations, so they agree bit for bit with each other, and with the exact flavour to rounding."""
+    nx, ny = size
+    n = nx * ny
+    rng = np.random.default_rng(nx + ny + k)
+    lib = b200.kernel_lib()
+    cx = [dev(rng.random(nx) + 0.5) for _ in range(2)]
+    cy = [dev(rng.random(ny) + 0.5) for _ in range(2)]
+    g = b200.StencilGeom(nx, ny, cx[0].data_ptr(), cx[1].data_ptr(), cy[0].data_ptr(), cy[1].data_ptr(), None, None, None, None)
+    x, p2, yn, fn = (dev(rng.standard_normal(n)) for _ in range(4))
+    coeffs = [[1e-3 * (l + 1), -0.3 + 0.1 * l, 0.2, 1.1 - 0.05 * l, -2e-4] for l in range(k)]
+    res = {}
+    for contract, variant in ((0, 1), (1, 1), (1, 0)):
+        lib.b200_set_contract(contract)
+        lib.b200_set_chain_variant(variant)
+        outs = [torch.full((n,), np.nan, dtype=torch.float64, device="cuda") for _ in range(k)]
+        ctx.stencil_chain(g, x, p2, yn, fn, coeffs, outs)
+        ctx.sync()
+        res[(contract, variant)] = [host(o) for o in outs]
+    lib.b200_set_contract(0)
+    lib.b200_set_chain_variant(1)
+    for l in range(k):
+        assert np.array_equal(res[(1, 1)][l], res[(1, 0)][l]), l
+        e, f = res[(0, 1)][l], res[(1, 1)][l]
+        rel = np.linalg.norm(e - f) / np.linalg.norm(e)
+        assert 0.0 < rel < 1e-13, (l, rel)
