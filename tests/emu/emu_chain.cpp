@@ -36,7 +36,7 @@ void run_quad_k(const ChainArgs& a, dim3 grid, bool halo, bool fma)
 // variant: 0 = k_chain_march (2 cells / thread), 1 = k_chain_quad (4 cells / thread)
 // halos: NULL (periodic wrap) or the four deep-halo buffers {x, prev2, yn, fn} (g rows, g2 columns)
 // lazy_cp_async: see cuda_emu.h.  Returns 0, or -1 for an unsupported combination.
-extern "C" int emu_stencil_chain(int variant, int K, int fma, int lazy_cp_async, int64_t nx, int64_t ny,
+extern "C" __attribute__((visibility("default"))) int emu_stencil_chain(int variant, int K, int fma, int lazy_cp_async, int64_t nx, int64_t ny,
                                  const double* cxw, const double* cxe, const double* cys, const double* cyn,
                                  const double* x, const double* prev2, const double* yn, const double* fn,
                                  const double* coeffs, double* const* out, int rows,
