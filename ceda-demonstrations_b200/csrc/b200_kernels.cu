@@ -24,6 +24,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "b200_sts.h"
 
@@ -76,6 +77,7 @@ extern "C" uint64_t b200_algorithmic_bytes(void) { return g_alg_bytes.load(); }
 
 // -------------------------------------------------------------------- context
 static const int kMaxPartials = 1 << 18;
+static const int kSmallMax    = 64; // doubles read back through mapped host memory instead of a DMA copy
 static ncclResult_t (*g_nccl_destroy)(ncclComm_t) = nullptr; // set once NCCL is bound
 
 struct b200_ctx
@@ -91,7 +93,8 @@ struct b200_ctx
   double* partials    = nullptr; // [kMaxPartials] block partials
   unsigned* ticket    = nullptr; // last-block-done counter
   double* dev_result  = nullptr; // [8] device scalars
-  double* host_result = nullptr; // [8] pinned mirror
+  double* host_result = nullptr; // [kSmallMax] pinned, MAPPED: kernels write results straight into it
+  double* host_result_dev = nullptr; // device alias of host_result
   ncclComm_t comm     = nullptr;
   int rank = 0, nranks = 1;
   double* strips      = nullptr; // W/E send staging of b200_deep_halo_exchange
@@ -120,7 +123,8 @@ extern "C" int b200_ctx_create(int device, void* stream, b200_ctx** out)
   CU_TRY(cudaMalloc(&c->ticket, sizeof(unsigned) * 4));
   CU_TRY(cudaMemset(c->ticket, 0, sizeof(unsigned) * 4));
   CU_TRY(cudaMalloc(&c->dev_result, sizeof(double) * 8));
-  CU_TRY(cudaMallocHost(&c->host_result, sizeof(double) * 8));
+  CU_TRY(cudaHostAlloc(&c->host_result, sizeof(double) * kSmallMax, cudaHostAllocMapped));
+  CU_TRY(cudaHostGetDevicePointer(&c->host_result_dev, c->host_result, 0));
   *out = c;
   return 0;
 }
@@ -186,8 +190,27 @@ extern "C" int b200_h2d(b200_ctx* c, double* dst, const double* src, int64_t n)
   return 0;
 }
 
+// Scalars and other tiny read-backs (reduction results, fused WRMS slots) do not go through the copy
+// engine: a 1-block kernel stores them into mapped pinned host memory and the host waits for the
+// stream.  A DMA copy would queue behind whatever bulk transfer is in flight on the same engine
+// (b200_pipe_*: a 2 GiB download delays every reduction of the next batch by ~40 ms).
+__global__ void k_publish_small(double* __restrict__ host_mapped, const double* __restrict__ src, int n)
+{
+  for (int i = threadIdx.x; i < n; i += blockDim.x) host_mapped[i] = src[i];
+}
+static int read_small(b200_ctx* c, double* dst, const double* src, int n)
+{
+  k_publish_small<<<1, 32, 0, c->stream>>>(c->host_result_dev, src, n);
+  CU_TRY(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  memcpy(dst, c->host_result, sizeof(double) * (size_t)n);
+  return 0;
+}
+
 extern "C" int b200_d2h(b200_ctx* c, double* dst, const double* src, int64_t n)
 {
+  if (n <= kSmallMax) return read_small(c, dst, src, (int)n);
   CU_TRY(cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
   CU_TRY(cudaStreamSynchronize(c->stream));
   return 0;
@@ -207,7 +230,25 @@ struct b200_pipe
   double* out[2];
   cudaStream_t h2d, d2h;
   cudaEvent_t in_ready[2], in_free[2], out_ready[2], out_free[2];
+  // B200_PIPE_TRACE=1: timing events around every transfer, printed by b200_pipe_drain
+  bool trace;
+  struct Span { const char* what; int64_t seq; cudaEvent_t a, b; };
+  std::vector<Span>* spans;
 };
+
+static void pipe_mark(b200_pipe* p, const char* what, int64_t seq, cudaStream_t st, bool begin)
+{
+  if (!p->trace) return;
+  if (begin)
+  {
+    b200_pipe::Span sp{what, seq, nullptr, nullptr};
+    cudaEventCreate(&sp.a);
+    cudaEventCreate(&sp.b);
+    cudaEventRecord(sp.a, st);
+    p->spans->push_back(sp);
+  }
+  else cudaEventRecord(p->spans->back().b, st);
+}
 
 extern "C" int b200_pipe_destroy(b200_pipe* p)
 {
@@ -227,6 +268,11 @@ extern "C" int b200_pipe_destroy(b200_pipe* p)
   }
   if (p->h2d) cudaStreamDestroy(p->h2d);
   if (p->d2h) cudaStreamDestroy(p->d2h);
+  if (p->spans)
+  {
+    for (auto& sp : *p->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    delete p->spans;
+  }
   delete p;
   return 0;
 }
@@ -255,6 +301,8 @@ extern "C" int b200_pipe_create(b200_ctx* c, int64_t n, b200_pipe** out)
   memset(p, 0, sizeof(*p));
   p->ctx = c;
   p->n   = n;
+  p->trace = getenv("B200_PIPE_TRACE") != nullptr;
+  p->spans = new std::vector<b200_pipe::Span>();
   int rc = pipe_init(p);
   if (rc)
   {
@@ -270,7 +318,9 @@ extern "C" int b200_pipe_upload(b200_pipe* p, int64_t seq, const double* host_sr
 {
   const int s = (int)(seq & 1);
   CU_TRY(cudaStreamWaitEvent(p->h2d, p->in_free[s], 0));
+  pipe_mark(p, "h2d", seq, p->h2d, true);
   CU_TRY(cudaMemcpyAsync(p->in[s], host_src, sizeof(double) * (size_t)p->n, cudaMemcpyHostToDevice, p->h2d));
+  pipe_mark(p, "h2d", seq, p->h2d, false);
   CU_TRY(cudaEventRecord(p->in_ready[s], p->h2d));
   return 0;
 }
@@ -279,7 +329,9 @@ extern "C" int b200_pipe_take(b200_pipe* p, int64_t seq, double* dst_dev)
 {
   const int s = (int)(seq & 1);
   CU_TRY(cudaStreamWaitEvent(p->ctx->stream, p->in_ready[s], 0));
+  pipe_mark(p, "take", seq, p->ctx->stream, true);
   CU_TRY(cudaMemcpyAsync(dst_dev, p->in[s], sizeof(double) * (size_t)p->n, cudaMemcpyDeviceToDevice, p->ctx->stream));
+  pipe_mark(p, "take", seq, p->ctx->stream, false);
   CU_TRY(cudaEventRecord(p->in_free[s], p->ctx->stream));
   return 0;
 }
@@ -288,10 +340,14 @@ extern "C" int b200_pipe_put(b200_pipe* p, int64_t seq, const double* src_dev, d
 {
   const int s = (int)(seq & 1);
   CU_TRY(cudaStreamWaitEvent(p->ctx->stream, p->out_free[s], 0));
+  pipe_mark(p, "put", seq, p->ctx->stream, true);
   CU_TRY(cudaMemcpyAsync(p->out[s], src_dev, sizeof(double) * (size_t)p->n, cudaMemcpyDeviceToDevice, p->ctx->stream));
+  pipe_mark(p, "put", seq, p->ctx->stream, false);
   CU_TRY(cudaEventRecord(p->out_ready[s], p->ctx->stream));
   CU_TRY(cudaStreamWaitEvent(p->d2h, p->out_ready[s], 0));
+  pipe_mark(p, "d2h", seq, p->d2h, true);
   CU_TRY(cudaMemcpyAsync(host_dst, p->out[s], sizeof(double) * (size_t)p->n, cudaMemcpyDeviceToHost, p->d2h));
+  pipe_mark(p, "d2h", seq, p->d2h, false);
   CU_TRY(cudaEventRecord(p->out_free[s], p->d2h));
   return 0;
 }
@@ -301,6 +357,19 @@ extern "C" int b200_pipe_drain(b200_pipe* p)
   CU_TRY(cudaStreamSynchronize(p->h2d));
   CU_TRY(cudaStreamSynchronize(p->ctx->stream));
   CU_TRY(cudaStreamSynchronize(p->d2h));
+  if (p->trace && !p->spans->empty())
+  {
+    cudaEvent_t base = p->spans->front().a;
+    for (auto& sp : *p->spans)
+    {
+      float t0 = 0.f, t1 = 0.f;
+      cudaEventElapsedTime(&t0, base, sp.a);
+      cudaEventElapsedTime(&t1, base, sp.b);
+      fprintf(stderr, "[b200_pipe] %-4s seq %2lld  %9.3f -> %9.3f ms  (%.3f ms)\n", sp.what, (long long)sp.seq, t0, t1, t1 - t0);
+    }
+    for (auto& sp : *p->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    p->spans->clear();
+  }
   return 0;
 }
 
@@ -669,10 +738,7 @@ static int run_reduce(b200_ctx* c, const double* x, const double* y, int64_t n, 
     int rc = nccl_allreduce_inplace(c, c->dev_result, 1, ROP);
     if (rc) return rc;
   }
-  CU_TRY(cudaMemcpyAsync(c->host_result, c->dev_result, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CU_TRY(cudaStreamSynchronize(c->stream));
-  *result = c->host_result[0];
-  return 0;
+  return read_small(c, result, c->dev_result, 1);
 }
 
 extern "C" int b200_dot(b200_ctx* c, const double* x, const double* y, int64_t n, double* r)
@@ -1149,32 +1215,32 @@ static int launch_chain(const ChainArgs& a, dim3 grid, cudaStream_t st)
   return a.hx ? launch_chain_k<K, PF, true, false>(a, grid, st) : launch_chain_k<K, PF, false, false>(a, grid, st);
 }
 
-template <int K, int PF, bool HALO, bool FMA>
+template <int K, int PF, bool HALO, bool FMA, int MINB>
 static int launch_quad_k(const ChainArgs& a, dim3 grid, cudaStream_t st)
 {
   const size_t smem = chain_quad_smem(K, PF, a.rows);
   static size_t configured = 0;
   if (smem > configured)
   {
-    CU_TRY(cudaFuncSetAttribute(k_chain_quad<K, PF, HALO, FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_TRY(cudaFuncSetAttribute(k_chain_quad<K, PF, HALO, FMA, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  k_chain_quad<K, PF, HALO, FMA><<<grid, kQuadThreads, smem, st>>>(a);
+  k_chain_quad<K, PF, HALO, FMA, MINB><<<grid, kQuadThreads, smem, st>>>(a);
   return 0;
 }
-template <int K, int PF>
+template <int K, int PF, int MINB>
 static int launch_quad(const ChainArgs& a, dim3 grid, cudaStream_t st)
 {
   if (g_contract)
-    return a.hx ? launch_quad_k<K, PF, true, true>(a, grid, st) : launch_quad_k<K, PF, false, true>(a, grid, st);
-  return a.hx ? launch_quad_k<K, PF, true, false>(a, grid, st) : launch_quad_k<K, PF, false, false>(a, grid, st);
+    return a.hx ? launch_quad_k<K, PF, true, true, MINB>(a, grid, st) : launch_quad_k<K, PF, false, true, MINB>(a, grid, st);
+  return a.hx ? launch_quad_k<K, PF, true, false, MINB>(a, grid, st) : launch_quad_k<K, PF, false, false, MINB>(a, grid, st);
 }
 
 static int g_chain_rows = 64;
 static const char* g_last_chain_kernel = "";
 extern "C" const char* b200_last_chain_kernel(void) { return g_last_chain_kernel; }
-// 1: four cells per thread (k_chain_quad) wherever its shape requirements hold, else k_chain_march;
-// 0: always k_chain_march.  B200_CHAIN_VARIANT overrides the initial value.
+// 0 (default): k_chain_march, two cells per thread; 1: k_chain_quad, four cells per thread.
+// B200_CHAIN_VARIANT overrides the initial value.
 static int g_chain_variant = -1;
 
 extern "C" int b200_set_chain_variant(int v)
@@ -1188,7 +1254,7 @@ extern "C" int b200_get_chain_variant(void)
   if (g_chain_variant < 0)
   {
     const char* e   = getenv("B200_CHAIN_VARIANT");
-    g_chain_variant = (e && e[0] == '0') ? 0 : 1;
+    g_chain_variant = (e && e[0] == '1') ? 1 : 0;
   }
   return g_chain_variant;
 }
@@ -1242,17 +1308,18 @@ static int stencil_chain_common(b200_ctx* c, const b200_stencil_geom* g, int nst
   if (!any || !a.out[nstages - 1]) return fail("b200_stencil_chain: the last stage must be stored");
   a.rows        = g_chain_rows;
   int rc = 0;
-  if (b200_get_chain_variant() == 1 && chain_quad_supported(a.nx, a.ny, nstages, halos ? hg2 : -1))
+  const int variant = b200_get_chain_variant();
+  if (variant == 1 && chain_quad_supported(a.nx, a.ny, nstages, halos ? hg2 : -1))
   {
     dim3 grid = chain_quad_grid(a.nx, a.ny, nstages, &a.rows);
     g_last_chain_kernel = "k_chain_quad";
     switch (nstages)
     {
-    case 2: rc = launch_quad<2, kQuadPF>(a, grid, c->stream); break;
-    case 3: rc = launch_quad<3, kQuadPF>(a, grid, c->stream); break;
-    case 4: rc = launch_quad<4, kQuadPF>(a, grid, c->stream); break;
-    case 5: rc = launch_quad<5, kQuadPF>(a, grid, c->stream); break;
-    default: rc = launch_quad<6, kQuadPF>(a, grid, c->stream); break;
+    case 2: rc = launch_quad<2, kQuadPF, 2>(a, grid, c->stream); break;
+    case 3: rc = launch_quad<3, kQuadPF, 2>(a, grid, c->stream); break;
+    case 4: rc = launch_quad<4, kQuadPF, 2>(a, grid, c->stream); break;
+    case 5: rc = launch_quad<5, kQuadPF, 2>(a, grid, c->stream); break;
+    default: rc = launch_quad<6, kQuadPF, 2>(a, grid, c->stream); break;
     }
   }
   else

@@ -1,38 +1,60 @@
 // chain_quad.cuh -- k_chain_quad: K temporally blocked STS stages per launch, FOUR cells per thread.
 //
 // Same computation, tiling idea and bit-for-bit arithmetic as k_chain_march (chain_march.cuh); what
-// changes is the width of a thread.  k_chain_march (two cells per thread) is bound by the FP64 pipe
-// AND the issue slots at the same time: per level and thread it issues 38 FP64 instructions next to
-// ~20 integer / shuffle / shared-memory instructions, and 8 of a warp's 64 cells are halo.  Here a
-// lane owns four adjacent cells of a 128-cell warp window:
-//   * the per-row and per-level bookkeeping (ring slots, pointers, coefficient loads, shuffles) is
-//     amortised over twice the cells: the shuffles per level stay 2 (west of cell 0, east of cell 3);
-//   * for K <= 4 one halo lane per side is enough (level l is valid on cells [l, 127-l]):
-//     120 of 128 cells are stored instead of 56 of 64 (K = 5, 6: two lanes per side, 112 of 128);
-//   * a warp carries four independent dependency chains per level, so the FP64 pipe stays fed with
-//     8 warps per SM (2 blocks x 128 threads; the thread-private cp.async ring is what limits
-//     residency: (2(PF+1) + 2(PF+K)) x 32 B per thread).
-// Requirements beyond k_chain_march's: nx % 4 == 0 (every lane's four cells wrap together and all
-// 16-byte accesses stay aligned) and, in halo mode, deep-halo columns g2 >= 4 * ceil(K/4).
+// changes is the width of a thread.  A warp owns a 128-cell window made of two 64-cell halves; lane i
+// owns cells {2i, 2i+1} of the left half ("a") and cells {64+2i, 64+2i+1} of the right half ("b"):
+//   * every global access is, per half, exactly k_chain_march's: 16 bytes per lane, 512 contiguous
+//     bytes per warp instruction (a first version gave each lane four ADJACENT cells: its two 16-byte
+//     accesses then touched half of each 32-byte sector and doubled the L2 tag requests -- ncu:
+//     lts__t_tag_requests at 66 % with DRAM at 52 %; profiles/r01_quad_v1_*);
+//   * the halo is only at the two ends of the 128-cell window: 2*ceil(K/2) cells per side, so for
+//     K = 4, 120 of 128 cells are stored instead of 56 of 64;
+//   * the per-row and per-level bookkeeping (ring slots, row pointers, y-coefficient loads, store
+//     addresses, loop control) is paid once for four cells instead of two;
+//   * the two halves are independent dependency chains, which doubles the FP64 work in flight per
+//     warp (8 warps per SM: 2 blocks x 128 threads; the thread-private cp.async ring limits residency).
+// West/east neighbours come from rotating warp shuffles; the seam between the halves (lane 31 of
+// "a" <-> lane 0 of "b") is one select per side.  Shape requirements are k_chain_march's: nx even,
+// nx >= 128, ny >= 16; halo flavour: g2 even >= 2*ceil(K/2).
 #pragma once
 #include "chain_march.cuh"
 
 static const int kQuadThreads = 128;
 static const int kQuadPF      = 3;
 
-struct QuadState
+// per-half source state: where this lane's two cells of a row come from
+struct QuadHalf
 {
-  int64_t soff;                    // r1*nx + ic (unwrapped row; valid whenever a store can happen)
   const double *px, *pp, *py, *pf; // next group: x at row ir+1 ; prev2 / yn / fn at row ir
-  int64_t pstep;                   // row stride of this lane's source (nx, or g2 in a W/E halo strip)
-  int ir;                          // unwrapped row of the next group
-  int sx_issue, sy_issue, sx_use, sy_use; // ring slots
-  int trow;                        // index of row r1 in the y-coefficient table
-  bool we;                         // halo mode: this lane reads the W/E halo strips
-  int64_t lane_col;                // column (halo mode: strip offset + column) of this lane's first cell
+  int64_t pstep;                   // row stride of the source (nx, or g2 in a W/E halo strip)
+  int64_t lane_col;                // column (halo mode: strip offset + column) of the first cell
+  int64_t soff;                    // r1*nx + column (unwrapped row; valid whenever a store can happen)
+  bool we;                         // halo mode: this half of the lane reads the W/E halo strips
 };
 
-// ring addressing: slot s, half h (cells 0-1 / 2-3) of this thread = base[(2*s + h) * kQuadThreads]
+struct QuadState
+{
+  QuadHalf h[2];
+  int ir;                                 // unwrapped row of the next group
+  int sx_issue, sy_issue, sx_use, sy_use; // ring slots
+  int trow;                               // index of row r1 in the y-coefficient table
+};
+
+template <bool HALO>
+__device__ __forceinline__ void quad_half_advance(const ChainArgs& a, QuadHalf& q, int r, int64_t nx, int ny)
+{
+  if (r == 0 || r == ny)
+  {
+    q.pp = row_ptr<HALO>(a.prev2, a.hp, r, q.we, q.lane_col, nx, ny, a.g, a.g2);
+    q.py = row_ptr<HALO>(a.yn, a.hy, r, q.we, q.lane_col, nx, ny, a.g, a.g2);
+    q.pf = row_ptr<HALO>(a.fn, a.hf, r, q.we, q.lane_col, nx, ny, a.g, a.g2);
+  }
+  else { q.pp += q.pstep; q.py += q.pstep; q.pf += q.pstep; }
+  if (r + 1 == 0 || r + 1 == ny) q.px = row_ptr<HALO>(a.x, a.hx, r + 1, q.we, q.lane_col, nx, ny, a.g, a.g2);
+  else q.px += q.pstep;
+}
+
+// ring addressing: slot s, half h of this thread = base[(2*s + h) * kQuadThreads]
 template <int K, int PF, bool HALO>
 __device__ __forceinline__ void quad_issue(const ChainArgs& a, QuadState& st, double2* rx, double2* rp,
                                            double2* ry, double2* rf, int64_t nx, int ny, bool issue)
@@ -44,24 +66,17 @@ __device__ __forceinline__ void quad_issue(const ChainArgs& a, QuadState& st, do
     double2* sp = rp + 2 * st.sx_issue * kQuadThreads;
     double2* sy = ry + 2 * st.sy_issue * kQuadThreads;
     double2* sf = rf + 2 * st.sy_issue * kQuadThreads;
-    cp_async16(sx, st.px);                cp_async16(sx + kQuadThreads, st.px + 2);
-    cp_async16(sp, st.pp);                cp_async16(sp + kQuadThreads, st.pp + 2);
-    cp_async16(sy, st.py);                cp_async16(sy + kQuadThreads, st.py + 2);
-    cp_async16(sf, st.pf);                cp_async16(sf + kQuadThreads, st.pf + 2);
+    cp_async16(sx, st.h[0].px);           cp_async16(sx + kQuadThreads, st.h[1].px);
+    cp_async16(sp, st.h[0].pp);           cp_async16(sp + kQuadThreads, st.h[1].pp);
+    cp_async16(sy, st.h[0].py);           cp_async16(sy + kQuadThreads, st.h[1].py);
+    cp_async16(sf, st.h[0].pf);           cp_async16(sf + kQuadThreads, st.h[1].pf);
   }
   cp_async_commit();
   st.sx_issue = (st.sx_issue + 1 == DX) ? 0 : st.sx_issue + 1;
   st.sy_issue = (st.sy_issue + 1 == DY) ? 0 : st.sy_issue + 1;
   const int r = ++st.ir;
-  if (r == 0 || r == ny)
-  {
-    st.pp = row_ptr<HALO>(a.prev2, a.hp, r, st.we, st.lane_col, nx, ny, a.g, a.g2);
-    st.py = row_ptr<HALO>(a.yn, a.hy, r, st.we, st.lane_col, nx, ny, a.g, a.g2);
-    st.pf = row_ptr<HALO>(a.fn, a.hf, r, st.we, st.lane_col, nx, ny, a.g, a.g2);
-  }
-  else { st.pp += st.pstep; st.py += st.pstep; st.pf += st.pstep; }
-  if (r + 1 == 0 || r + 1 == ny) st.px = row_ptr<HALO>(a.x, a.hx, r + 1, st.we, st.lane_col, nx, ny, a.g, a.g2);
-  else st.px += st.pstep;
+  quad_half_advance<HALO>(a, st.h[0], r, nx, ny);
+  quad_half_advance<HALO>(a, st.h[1], r, nx, ny);
 }
 
 // x-direction face coefficients of this lane's four columns and their sums (diffusion.cpp:48)
@@ -95,7 +110,8 @@ template <int K, int PF, int PH, bool CHECK, bool HALO, bool FMA>
 __device__ __forceinline__ void quad_row(const ChainArgs& a, QuadState& st, double2 (&Wa)[K][3], double2 (&Wb)[K][3],
                                          double2* rx, double2* rp, double2* ry, double2* rf,
                                          const double2* ytab, const double* stab, int64_t nx, int ny,
-                                         const QuadXCoef& xc, unsigned smask, int r1, int j0, int j1, bool issue)
+                                         const QuadXCoef& xc, unsigned smask_a, unsigned smask_b, int lane,
+                                         int r1, int j0, int j1, bool issue)
 {
   constexpr int DX = PF + 1, DY = PF + K;
   constexpr int IO = PH % 3, IM = (PH + 1) % 3, IC = (PH + 2) % 3; // oldest (overwritten), then um, uc ; up = IO
@@ -106,7 +122,8 @@ __device__ __forceinline__ void quad_row(const ChainArgs& a, QuadState& st, doub
   Wb[0][IO]        = rx[(2 * st.sx_use + 1) * kQuadThreads];
   const double2 Pa = rp[(2 * st.sx_use) * kQuadThreads];
   const double2 Pb = rp[(2 * st.sx_use + 1) * kQuadThreads];
-  int64_t so       = st.soff;
+  int64_t soa = st.h[0].soff, sob = st.h[1].soff;
+  const int lw = (lane + 31) & 31, le = (lane + 1) & 31;
 #pragma unroll
   for (int l = 1; l <= K; l++)
   {
@@ -114,8 +131,15 @@ __device__ __forceinline__ void quad_row(const ChainArgs& a, QuadState& st, doub
     const double sy  = stab[st.trow - (l - 1)]; // Dy_s + Dy_n
     const double2 uma = Wa[l - 1][IM], uca = Wa[l - 1][IC], upa = Wa[l - 1][IO];
     const double2 umb = Wb[l - 1][IM], ucb = Wb[l - 1][IC], upb = Wb[l - 1][IO];
-    const double uw = __shfl_up_sync(0xffffffffu, ucb.y, 1);   // west of cell 0: the lane to the left, cell 3
-    const double ue = __shfl_down_sync(0xffffffffu, uca.x, 1); // east of cell 3: the lane to the right, cell 0
+    // rotating shuffles; the seam: west of half b's lane 0 is half a's lane 31, east of half a's
+    // lane 31 is half b's lane 0.  (West of a's lane 0 / east of b's lane 31 lie outside the
+    // window: whatever arrives there only reaches halo cells.)
+    const double wa = __shfl_sync(0xffffffffu, uca.y, lw);
+    const double wb = __shfl_sync(0xffffffffu, ucb.y, lw);
+    const double ea = __shfl_sync(0xffffffffu, uca.x, le);
+    const double eb = __shfl_sync(0xffffffffu, ucb.x, le);
+    const double uw_a = wa, uw_b = (lane == 0) ? wa : wb;
+    const double ue_a = (lane == 31) ? eb : ea, ue_b = eb;
     // z_{l-2} at this row: prev2 for the first stage, else the oldest row of level l-2's window
     const double2 p2a = (l == 1) ? Pa : Wa[(l >= 2) ? l - 2 : 0][IM];
     const double2 p2b = (l == 1) ? Pb : Wb[(l >= 2) ? l - 2 : 0][IM];
@@ -125,36 +149,79 @@ __device__ __forceinline__ void quad_row(const ChainArgs& a, QuadState& st, doub
     const double2 fva = rf[(2 * sl) * kQuadThreads], fvb = rf[(2 * sl + 1) * kQuadThreads];
     const double* cf = a.c[l - 1];
     double2 za, zb;
-    za.x = quad_cell<FMA>(xc.sxa.x, sy, xc.cwa.x, xc.cea.x, dy.x, dy.y, uca.x, uw, uca.y, uma.x, upa.x, cf, p2a.x, yva.x, fva.x);
-    za.y = quad_cell<FMA>(xc.sxa.y, sy, xc.cwa.y, xc.cea.y, dy.x, dy.y, uca.y, uca.x, ucb.x, uma.y, upa.y, cf, p2a.y, yva.y, fva.y);
-    zb.x = quad_cell<FMA>(xc.sxb.x, sy, xc.cwb.x, xc.ceb.x, dy.x, dy.y, ucb.x, uca.y, ucb.y, umb.x, upb.x, cf, p2b.x, yvb.x, fvb.x);
-    zb.y = quad_cell<FMA>(xc.sxb.y, sy, xc.cwb.y, xc.ceb.y, dy.x, dy.y, ucb.y, ucb.x, ue, umb.y, upb.y, cf, p2b.y, yvb.y, fvb.y);
-    bool doit = (smask >> (l - 1)) & 1u;
+    za.x = quad_cell<FMA>(xc.sxa.x, sy, xc.cwa.x, xc.cea.x, dy.x, dy.y, uca.x, uw_a, uca.y, uma.x, upa.x, cf, p2a.x, yva.x, fva.x);
+    za.y = quad_cell<FMA>(xc.sxa.y, sy, xc.cwa.y, xc.cea.y, dy.x, dy.y, uca.y, uca.x, ue_a, uma.y, upa.y, cf, p2a.y, yva.y, fva.y);
+    zb.x = quad_cell<FMA>(xc.sxb.x, sy, xc.cwb.x, xc.ceb.x, dy.x, dy.y, ucb.x, uw_b, ucb.y, umb.x, upb.x, cf, p2b.x, yvb.x, fvb.x);
+    zb.y = quad_cell<FMA>(xc.sxb.y, sy, xc.cwb.y, xc.ceb.y, dy.x, dy.y, ucb.y, ucb.x, ue_b, umb.y, upb.y, cf, p2b.y, yvb.y, fvb.y);
+    bool row_ok = true;
     if (CHECK)
     {
       const int rl = r1 - (l - 1);
-      doit         = doit && rl >= j0 && rl < j1;
+      row_ok       = rl >= j0 && rl < j1;
     }
-    if (doit)
-    {
-      double2* o = reinterpret_cast<double2*>(a.out[l - 1] + so);
-      o[0]       = za;
-      o[1]       = zb;
-    }
-    so -= nx;
+    if (row_ok && ((smask_a >> (l - 1)) & 1u)) *reinterpret_cast<double2*>(a.out[l - 1] + soa) = za;
+    if (row_ok && ((smask_b >> (l - 1)) & 1u)) *reinterpret_cast<double2*>(a.out[l - 1] + sob) = zb;
+    soa -= nx;
+    sob -= nx;
     if (l < K) { Wa[l][IO] = za; Wb[l][IO] = zb; } // newest row of level l replaces its oldest
   }
-  st.soff += nx;
+  st.h[0].soff += nx;
+  st.h[1].soff += nx;
   st.trow += 1;
   st.sx_use = (st.sx_use + 1 == DX) ? 0 : st.sx_use + 1;
   st.sy_use = (st.sy_use + 1 == DY) ? 0 : st.sy_use + 1;
 }
 
-template <int K, int PF, bool HALO, bool FMA>
-__global__ void __launch_bounds__(kQuadThreads, 2) k_chain_quad(const ChainArgs a)
+// where one half of a lane reads and stores: col_u = unwrapped column of its first cell
+template <bool HALO>
+__device__ __forceinline__ void quad_half_setup(const ChainArgs& a, QuadHalf& q, int64_t col_u, int64_t nx, int ny,
+                                                int rstart, int64_t* xi)
 {
-  constexpr int HL   = (K + 3) / 4;   // halo lanes per side (4 cells each): 4*HL >= K
-  constexpr int WUSE = 128 - 8 * HL;  // cells a warp stores per row
+  int64_t ic = col_u; // column used for stores and (wrap mode) loads
+  *xi        = col_u; // column index into the x-direction coefficient tables
+  q.we       = false;
+  q.pstep    = nx;
+  if (HALO)
+  { // columns outside [0, nx) come from the W / E halo strips; beyond the strips: clamp (never used)
+    const int64_t strip = (int64_t)(ny + 2 * a.g) * a.g2;
+    if (col_u < 0)
+    {
+      int64_t c = col_u + a.g2;
+      if (c < 0) { c = 0; *xi = -(int64_t)a.g2; }
+      q.we       = true;
+      q.lane_col = 2 * a.g * nx + c;
+    }
+    else if (col_u >= nx)
+    {
+      int64_t c = col_u - nx;
+      if (c > a.g2 - 2) { c = a.g2 - 2; *xi = nx + c; }
+      q.we       = true;
+      q.lane_col = 2 * a.g * nx + strip + c;
+    }
+    else q.lane_col = col_u;
+    if (q.we) q.pstep = a.g2;
+  }
+  else
+  {
+    if (ic < 0) ic += nx;
+    else if (ic >= nx) ic -= nx;
+    *xi        = ic;
+    q.lane_col = ic;
+  }
+  q.soff = (int64_t)rstart * nx + ic;
+  q.px   = row_ptr<HALO>(a.x, a.hx, rstart + 1, q.we, q.lane_col, nx, ny, a.g, a.g2);
+  q.pp   = row_ptr<HALO>(a.prev2, a.hp, rstart, q.we, q.lane_col, nx, ny, a.g, a.g2);
+  q.py   = row_ptr<HALO>(a.yn, a.hy, rstart, q.we, q.lane_col, nx, ny, a.g, a.g2);
+  q.pf   = row_ptr<HALO>(a.fn, a.hf, rstart, q.we, q.lane_col, nx, ny, a.g, a.g2);
+}
+
+// MINB = resident blocks per SM the register allocation is held to.  (Holding K <= 4 to 3 blocks,
+// 168 registers and PF = 2, was measured: no faster, small spills -- 8 warps per SM are enough.)
+template <int K, int PF, bool HALO, bool FMA, int MINB = 2>
+__global__ void __launch_bounds__(kQuadThreads, MINB) k_chain_quad(const ChainArgs a)
+{
+  constexpr int HC   = (K + 1) / 2;   // halo lanes at each end of the window (2 cells each): 2*HC >= K
+  constexpr int WUSE = 128 - 4 * HC;  // cells a warp stores per row
   constexpr int DX   = PF + 1;        // ring depth of x and prev2
   constexpr int DY   = PF + K;        // ring depth of yn and fn
   B200_DYN_SMEM(double2, ring);
@@ -185,78 +252,49 @@ __global__ void __launch_bounds__(kQuadThreads, 2) k_chain_quad(const ChainArgs 
 
   const int64_t wg = (int64_t)blockIdx.x * (kQuadThreads / 32) + (threadIdx.x >> 5);
   if (wg * WUSE >= nx) return; // window entirely outside the field (no block-level sync below)
-  const int64_t col_u = wg * WUSE - 4 * HL + 4 * lane; // unwrapped column of my first cell
-  const bool store_ok = (lane >= HL) && (lane < 32 - HL) && (col_u < nx);
-  unsigned smask      = 0;
+  const int64_t col_a = wg * WUSE - 2 * HC + 2 * lane; // unwrapped column of my first cell, left half
+  const int64_t col_b = col_a + 64;                    // right half
+  const bool ok_a     = (lane >= HC) && (col_a < nx);
+  const bool ok_b     = (lane < 32 - HC) && (col_b < nx);
+  unsigned smask_a = 0, smask_b = 0;
 #pragma unroll
   for (int l = 0; l < K; l++)
-    if (store_ok && a.out[l]) smask |= 1u << l;
+    if (a.out[l])
+    {
+      if (ok_a) smask_a |= 1u << l;
+      if (ok_b) smask_b |= 1u << l;
+    }
 
   QuadState st;
-  int64_t ic = col_u; // column used for stores and (wrap mode) loads
-  int64_t xi = col_u; // column index into the x-direction coefficient tables
-  st.we      = false;
-  st.pstep   = nx;
-  if (HALO)
-  { // columns outside [0, nx) come from the W / E halo strips; beyond the strips: clamp (never used)
-    const int64_t strip = (int64_t)(ny + 2 * a.g) * a.g2;
-    if (col_u < 0)
-    {
-      int64_t c = col_u + a.g2;
-      if (c < 0) { c = 0; xi = -(int64_t)a.g2; }
-      st.we       = true;
-      st.lane_col = 2 * a.g * nx + c;
-    }
-    else if (col_u >= nx)
-    {
-      int64_t c = col_u - nx;
-      if (c > a.g2 - 4) { c = a.g2 - 4; xi = nx + c; }
-      st.we       = true;
-      st.lane_col = 2 * a.g * nx + strip + c;
-    }
-    else st.lane_col = col_u;
-    if (st.we) st.pstep = a.g2;
-  }
-  else
-  {
-    if (ic < 0) ic += nx;
-    else if (ic >= nx) ic -= nx;
-    xi          = ic;
-    st.lane_col = ic;
-  }
+  int64_t xia, xib;
+  quad_half_setup<HALO>(a, st.h[0], col_a, nx, ny, rstart, &xia);
+  quad_half_setup<HALO>(a, st.h[1], col_b, nx, ny, rstart, &xib);
   QuadXCoef xc;
-  xc.cwa = ld_keep2(a.cxw + xi); xc.cwb = ld_keep2(a.cxw + xi + 2);
-  xc.cea = ld_keep2(a.cxe + xi); xc.ceb = ld_keep2(a.cxe + xi + 2);
+  xc.cwa = ld_keep2(a.cxw + xia); xc.cwb = ld_keep2(a.cxw + xib);
+  xc.cea = ld_keep2(a.cxe + xia); xc.ceb = ld_keep2(a.cxe + xib);
   xc.sxa = make_double2(DADD(xc.cwa.x, xc.cea.x), DADD(xc.cwa.y, xc.cea.y));
   xc.sxb = make_double2(DADD(xc.cwb.x, xc.ceb.x), DADD(xc.cwb.y, xc.ceb.y));
 
-  st.soff     = (int64_t)rstart * nx + ic;
   st.sx_issue = st.sy_issue = st.sx_use = st.sy_use = 0;
   st.trow     = K - 1;
   st.ir       = rstart;
-  st.px = row_ptr<HALO>(a.x, a.hx, rstart + 1, st.we, st.lane_col, nx, ny, a.g, a.g2);
-  st.pp = row_ptr<HALO>(a.prev2, a.hp, rstart, st.we, st.lane_col, nx, ny, a.g, a.g2);
-  st.py = row_ptr<HALO>(a.yn, a.hy, rstart, st.we, st.lane_col, nx, ny, a.g, a.g2);
-  st.pf = row_ptr<HALO>(a.fn, a.hf, rstart, st.we, st.lane_col, nx, ny, a.g, a.g2);
 
   double2 Wa[K][3], Wb[K][3];
 #pragma unroll
   for (int l = 0; l < K; l++)
     Wa[l][0] = Wa[l][1] = Wa[l][2] = Wb[l][0] = Wb[l][1] = Wb[l][2] = make_double2(0.0, 0.0);
   // canonical layout at phase 0: index 0 oldest (about to be overwritten), 1 = um, 2 = uc
-  {
-    const double* q1 = row_ptr<HALO>(a.x, a.hx, rstart - 1, st.we, st.lane_col, nx, ny, a.g, a.g2);
-    const double* q2 = row_ptr<HALO>(a.x, a.hx, rstart, st.we, st.lane_col, nx, ny, a.g, a.g2);
-    Wa[0][1] = ld_keep2(q1); Wb[0][1] = ld_keep2(q1 + 2);
-    Wa[0][2] = ld_keep2(q2); Wb[0][2] = ld_keep2(q2 + 2);
-  }
+  Wa[0][1] = ld_keep2(row_ptr<HALO>(a.x, a.hx, rstart - 1, st.h[0].we, st.h[0].lane_col, nx, ny, a.g, a.g2));
+  Wa[0][2] = ld_keep2(row_ptr<HALO>(a.x, a.hx, rstart, st.h[0].we, st.h[0].lane_col, nx, ny, a.g, a.g2));
+  Wb[0][1] = ld_keep2(row_ptr<HALO>(a.x, a.hx, rstart - 1, st.h[1].we, st.h[1].lane_col, nx, ny, a.g, a.g2));
+  Wb[0][2] = ld_keep2(row_ptr<HALO>(a.x, a.hx, rstart, st.h[1].we, st.h[1].lane_col, nx, ny, a.g, a.g2));
 
   // prologue of the pipeline: groups rstart .. rstart+PF-1
 #pragma unroll
   for (int q = 0; q < PF; q++) quad_issue<K, PF, HALO>(a, st, rx, rp, ry, rf, nx, ny, true);
 
 #define QROW(PH, CHECK, R1) \
-  quad_row<K, PF, PH, CHECK, HALO, FMA>(a, st, Wa, Wb, rx, rp, ry, rf, ytab, stab, nx, ny, xc, smask, R1, j0, j1, (R1) + PF < rend)
+  quad_row<K, PF, PH, CHECK, HALO, FMA>(a, st, Wa, Wb, rx, rp, ry, rf, ytab, stab, nx, ny, xc, smask_a, smask_b, lane, R1, j0, j1, (R1) + PF < rend)
 
   // phases as in k_chain_march: checked warm-up in whole triples, unchecked steady state, checked
   // drain; the trip count is rounded up to a multiple of 3 (the extra rows compute values that are
@@ -303,14 +341,14 @@ static inline size_t chain_quad_smem(int K, int PF, int rows)
 static inline bool chain_quad_supported(int64_t nx, int64_t ny, int K, int halo_cols)
 {
   if (K < 2 || K > B200_MAX_CHAIN) return false;
-  if ((nx & 3) || nx < 128 || ny < 16) return false;
-  if (halo_cols >= 0 && halo_cols < 4 * ((K + 3) / 4)) return false;
+  if ((nx & 1) || nx < 128 || ny < 16) return false;
+  if (halo_cols >= 0 && ((halo_cols & 1) || halo_cols < 2 * ((K + 1) / 2))) return false;
   return true;
 }
 static inline dim3 chain_quad_grid(int64_t nx, int64_t ny, int K, int* rows)
 {
-  const int hl  = (K + 3) / 4;
-  const int use = 128 - 8 * hl;
+  const int hc  = (K + 1) / 2;
+  const int use = 128 - 4 * hc;
   int64_t warps = (nx + use - 1) / use;
   int64_t gx    = (warps + kQuadThreads / 32 - 1) / (kQuadThreads / 32);
   int64_t gy    = (ny + *rows - 1) / *rows;

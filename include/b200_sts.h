@@ -54,6 +54,8 @@ int b200_free(b200_ctx* ctx, double* dptr);
 int b200_host_alloc(int64_t n_doubles, double** hptr);
 int b200_host_free(double* hptr);
 int b200_h2d(b200_ctx* ctx, double* dst_dev, const double* src_host, int64_t n);
+/* n <= 64: read back through mapped pinned memory written by a 1-block kernel (no DMA copy, so a
+   scalar never queues behind a bulk transfer on the copy engine); larger n: cudaMemcpyAsync + sync */
 int b200_d2h(b200_ctx* ctx, double* dst_host, const double* src_dev, int64_t n);
 
 /* ----------------------------------------- pipelined host <-> device staging */
@@ -203,10 +205,11 @@ int b200_deep_halo_exchange(b200_ctx* ctx, const int peers[4], int x_split, int 
                             const double* const* fields, double* const* halos);
 /* rows of output each thread block of the chain kernel marches over (default 64) */
 int b200_set_chain_rows(int rows);
-/* Which kernel runs a chain: 1 (default) = k_chain_quad, four cells per thread, wherever its shape
-   requirements hold (nx % 4 == 0; halo flavour: halo_cols >= 4*ceil(nstages/4)), else
-   k_chain_march; 0 = always k_chain_march (two cells per thread).  Results are bit-identical
-   either way.  The environment variable B200_CHAIN_VARIANT sets the initial value. */
+/* Which kernel runs a chain: 0 (default) = k_chain_march, two cells per thread; 1 = k_chain_quad,
+   four cells per thread (two 64-cell halves per warp window, 120 of 128 cells useful at depth 4).
+   Same shape requirements, bit-identical results; at depth 4 on 16384^2 both sit at 85-90 % of the
+   measured HBM copy bandwidth on the chain's own 48 B per cell (profiles/).  The environment
+   variable B200_CHAIN_VARIANT sets the initial value. */
 int b200_set_chain_variant(int variant);
 int b200_get_chain_variant(void);
 /* name of the kernel the most recent chain launch used ("k_chain_quad" / "k_chain_march", "" if none) */

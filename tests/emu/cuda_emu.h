@@ -104,6 +104,7 @@ static inline double emu_shfl(double v, int src_lane)
 static inline double __shfl_up_sync(unsigned, double v, int d) { return emu_shfl(v, emu::ts.lane - d); }
 static inline double __shfl_down_sync(unsigned, double v, int d) { return emu_shfl(v, emu::ts.lane + d); }
 static inline double __shfl_xor_sync(unsigned, double v, int m) { return emu_shfl(v, emu::ts.lane ^ m); }
+static inline double __shfl_sync(unsigned, double v, int src) { return emu_shfl(v, src & 31); }
 
 static inline double2 ld_stream2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 static inline double2 ld_keep2(const double* p) { return *reinterpret_cast<const double2*>(p); }

@@ -89,6 +89,7 @@ CASES = [  # (nx, ny, rows)
     (128, 16, 64),   # smallest supported field: a second warp window that wraps in x
     (132, 21, 5),    # partial last window, partial row blocks, short blocks (warm-up and drain only)
     (376, 26, 8),    # > 1 block in x for the quad kernel (4 warps x 120 cells), steady-state rows
+    (190, 17, 9),    # nx % 4 == 2: the halves of a lane wrap at different lanes
 ]
 
 
@@ -195,7 +196,7 @@ def test_fma_flavour_consistent_between_kernels_and_close_to_exact(emu):
 
 def test_quad_kernel_rejects_unsupported_shapes(emu):
     rng = np.random.default_rng(1)
-    nx, ny = 130, 16  # nx % 4 != 0
+    nx, ny = 131, 16  # odd nx: no 16-byte row alignment
     tabs = [rng.random(nx), rng.random(nx), rng.random(ny), rng.random(ny)]
     ops = [rng.standard_normal(nx * ny) for _ in range(4)]
     rc, _ = run_emu(emu, 1, 4, 0, 0, nx, ny, [tabs[0].ctypes.data, tabs[1].ctypes.data],
