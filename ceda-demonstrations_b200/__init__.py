@@ -41,6 +41,8 @@ class StencilGeom(ctypes.Structure):
         ("cys", ctypes.c_void_p), ("cyn", ctypes.c_void_p),
         ("halo_w", ctypes.c_void_p), ("halo_e", ctypes.c_void_p),
         ("halo_s", ctypes.c_void_p), ("halo_n", ctypes.c_void_p),
+        ("uniform", ctypes.c_int),
+        ("u_cxw", ctypes.c_double), ("u_cxe", ctypes.c_double), ("u_cys", ctypes.c_double), ("u_cyn", ctypes.c_double),
     ]
 
 

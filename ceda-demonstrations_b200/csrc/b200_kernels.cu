@@ -1182,17 +1182,17 @@ extern "C" int b200_stencil_lincomb(b200_ctx* c, const b200_stencil_geom* g, con
 #include "chain_march.cuh"
 #include "chain_quad.cuh"
 
-template <int K, int PF, bool HALO, bool FMA>
+template <int K, int PF, bool HALO, bool FMA, bool UNI>
 static int launch_chain_k(const ChainArgs& a, dim3 grid, cudaStream_t st)
 {
   const size_t smem = chain_march_smem(K, PF, a.rows);
   static size_t configured = 0;
   if (smem > configured)
   {
-    CU_TRY(cudaFuncSetAttribute(k_chain_march<K, PF, HALO, FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_TRY(cudaFuncSetAttribute(k_chain_march<K, PF, HALO, FMA, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  k_chain_march<K, PF, HALO, FMA><<<grid, kChainThreads, smem, st>>>(a);
+  k_chain_march<K, PF, HALO, FMA, UNI><<<grid, kChainThreads, smem, st>>>(a);
   return 0;
 }
 
@@ -1207,12 +1207,17 @@ extern "C" int b200_set_contract(int on)
 }
 extern "C" int b200_get_contract(void) { return g_contract; }
 
+template <int K, int PF, bool HALO, bool FMA>
+static int launch_chain_u(const ChainArgs& a, dim3 grid, cudaStream_t st, bool uni)
+{
+  return uni ? launch_chain_k<K, PF, HALO, FMA, true>(a, grid, st) : launch_chain_k<K, PF, HALO, FMA, false>(a, grid, st);
+}
 template <int K, int PF>
-static int launch_chain(const ChainArgs& a, dim3 grid, cudaStream_t st)
+static int launch_chain(const ChainArgs& a, dim3 grid, cudaStream_t st, bool uni)
 {
   if (g_contract)
-    return a.hx ? launch_chain_k<K, PF, true, true>(a, grid, st) : launch_chain_k<K, PF, false, true>(a, grid, st);
-  return a.hx ? launch_chain_k<K, PF, true, false>(a, grid, st) : launch_chain_k<K, PF, false, false>(a, grid, st);
+    return a.hx ? launch_chain_u<K, PF, true, true>(a, grid, st, uni) : launch_chain_u<K, PF, false, true>(a, grid, st, uni);
+  return a.hx ? launch_chain_u<K, PF, true, false>(a, grid, st, uni) : launch_chain_u<K, PF, false, false>(a, grid, st, uni);
 }
 
 template <int K, int PF, bool HALO, bool FMA, int MINB>
@@ -1237,6 +1242,12 @@ static int launch_quad(const ChainArgs& a, dim3 grid, cudaStream_t st)
 }
 
 static int g_chain_rows = 64;
+static int g_chain_uniform = 1; // honour b200_stencil_geom.uniform (0: always load the tables; for A/B tests)
+extern "C" int b200_set_chain_uniform(int on)
+{
+  g_chain_uniform = on ? 1 : 0;
+  return 0;
+}
 static const char* g_last_chain_kernel = "";
 extern "C" const char* b200_last_chain_kernel(void) { return g_last_chain_kernel; }
 // 0 (default): k_chain_march, two cells per thread; 1: k_chain_quad, four cells per thread.
@@ -1281,6 +1292,14 @@ static int stencil_chain_common(b200_ctx* c, const b200_stencil_geom* g, int nst
   a.nx = g->nx; a.ny = g->ny;
   a.cxw = g->cxw; a.cxe = g->cxe; a.cys = g->cys; a.cyn = g->cyn;
   a.x = x; a.prev2 = prev2; a.yn = yn; a.fn = fn;
+  const bool uni = g->uniform != 0 && g_chain_uniform;
+  if (uni)
+  { // centre coefficient in the reference's association, diffusion.cpp:48 (host IEEE adds = device DADD)
+    a.u_cxw = g->u_cxw; a.u_cxe = g->u_cxe; a.u_cys = g->u_cys; a.u_cyn = g->u_cyn;
+    volatile double sx = g->u_cxw + g->u_cxe, sy = g->u_cys + g->u_cyn;
+    volatile double sc = sx + sy;
+    a.u_ndc = -sc;
+  }
   if (!aligned16(x) || !aligned16(prev2) || !aligned16(yn) || !aligned16(fn) || !aligned16(a.cxw) || !aligned16(a.cxe))
     return fail("b200_stencil_chain: operand not 16-byte aligned");
   if (halos)
@@ -1328,11 +1347,11 @@ static int stencil_chain_common(b200_ctx* c, const b200_stencil_geom* g, int nst
     g_last_chain_kernel = "k_chain_march";
     switch (nstages)
     {
-    case 2: rc = launch_chain<2, 4>(a, grid, c->stream); break;
-    case 3: rc = launch_chain<3, 4>(a, grid, c->stream); break;
-    case 4: rc = launch_chain<4, 3>(a, grid, c->stream); break;
-    case 5: rc = launch_chain<5, 3>(a, grid, c->stream); break;
-    default: rc = launch_chain<6, 3>(a, grid, c->stream); break;
+    case 2: rc = launch_chain<2, 4>(a, grid, c->stream, uni); break;
+    case 3: rc = launch_chain<3, 4>(a, grid, c->stream, uni); break;
+    case 4: rc = launch_chain<4, 3>(a, grid, c->stream, uni); break;
+    case 5: rc = launch_chain<5, 3>(a, grid, c->stream, uni); break;
+    default: rc = launch_chain<6, 3>(a, grid, c->stream, uni); break;
     }
   }
   if (rc) return rc;

@@ -35,6 +35,9 @@ struct ChainArgs
   // multi-rank (HALO = true): per-operand deep-halo buffers, layout of b200_deep_halo_exchange
   const double *hx, *hp, *hy, *hf;
   int g, g2; // halo depth in rows / in columns (g >= K, g2 even >= 2*ceil(K/2))
+  // uniform coefficients (b200_stencil_geom.uniform): the four face coefficients and
+  // u_ndc = -((cxw + cxe) + (cys + cyn)), summed on the host in the reference's order (IEEE add)
+  double u_cxw, u_cxe, u_cys, u_cyn, u_ndc;
 };
 
 static const int kChainThreads = 256;
@@ -114,7 +117,7 @@ __device__ __forceinline__ void chain_issue(const ChainArgs& a, ChainState& st, 
   else st.px += st.pstep;
 }
 
-template <int K, int PF, int PH, bool CHECK, bool HALO, bool FMA>
+template <int K, int PF, int PH, bool CHECK, bool HALO, bool FMA, bool UNI>
 __device__ __forceinline__ void chain_row(const ChainArgs& a, ChainState& st, double2 (&W)[K][3],
                                           double2* rx, double2* rp, double2* ry, double2* rf,
                                           const double2* ytab, const double* stab, int64_t nx, int ny,
@@ -132,14 +135,16 @@ __device__ __forceinline__ void chain_row(const ChainArgs& a, ChainState& st, do
 #pragma unroll
   for (int l = 1; l <= K; l++)
   {
-    const double2 dy = ytab[st.trow - (l - 1)]; // (Dy_s, Dy_n) of row r1-(l-1)
-    const double sy  = stab[st.trow - (l - 1)]; // Dy_s + Dy_n, summed once per block when the table is filled
+    // UNI: the coefficients are kernel parameters (constant bank): no table loads, and the centre
+    // coefficient -((Dxw+Dxe)+(Dys+Dyn)) is one number for the whole field
+    const double2 dy = UNI ? make_double2(a.u_cys, a.u_cyn) : ytab[st.trow - (l - 1)]; // (Dy_s, Dy_n) of row r1-(l-1)
+    const double sy  = UNI ? 0.0 : stab[st.trow - (l - 1)]; // Dy_s + Dy_n, summed once per block when the table is filled
     const double2 um = W[l - 1][IM], uc = W[l - 1][IC], up = W[l - 1][IO];
     const double uw0 = __shfl_up_sync(0xffffffffu, uc.y, 1);
     const double ue1 = __shfl_down_sync(0xffffffffu, uc.x, 1);
     // diffusion.cpp:48-53, same association as k_stage_march
-    double L0 = DMUL(-DADD(sx0, sy), uc.x);
-    double L1 = DMUL(-DADD(sx1, sy), uc.y);
+    double L0 = DMUL(UNI ? a.u_ndc : -DADD(sx0, sy), uc.x);
+    double L1 = DMUL(UNI ? a.u_ndc : -DADD(sx1, sy), uc.y);
     L0 = mad<FMA>(cw.x, uw0, L0);  L1 = mad<FMA>(cw.y, uc.x, L1);
     L0 = mad<FMA>(ce.x, uc.y, L0); L1 = mad<FMA>(ce.y, ue1, L1);
     L0 = mad<FMA>(dy.x, um.x, L0); L1 = mad<FMA>(dy.x, um.y, L1);
@@ -176,7 +181,7 @@ __device__ __forceinline__ void chain_row(const ChainArgs& a, ChainState& st, do
   st.sy_use = (st.sy_use + 1 == DY) ? 0 : st.sy_use + 1;
 }
 
-template <int K, int PF, bool HALO, bool FMA>
+template <int K, int PF, bool HALO, bool FMA, bool UNI = false>
 __global__ void __launch_bounds__(kChainThreads, 2) k_chain_march(const ChainArgs a)
 {
   constexpr int HL   = (K + 1) / 2;  // halo lanes per side (2 cells each): 2*HL >= K
@@ -200,14 +205,17 @@ __global__ void __launch_bounds__(kChainThreads, 2) k_chain_march(const ChainArg
   const int rstart = j0 - (K - 1), rend = j1 + (K - 1); // level-1 rows [rstart, rend)
 #define WROW(r) ((r) < 0 ? (r) + ny : ((r) >= ny ? (r) - ny : (r)))
   // y-direction face coefficients of rows rstart-(K-1) .. rend+1 (table index 0 = row rstart-(K-1))
-  for (int t = threadIdx.x; t < (rend - rstart) + (K - 1) + 2; t += kChainThreads)
-  { // HALO: the tables are extended by the caller (global periodic index), negative rows are valid
-    const int rw = HALO ? (rstart - (K - 1) + t) : WROW(rstart - (K - 1) + t);
-    const double ds = a.cys[rw], dn = a.cyn[rw];
-    ytab[t]         = make_double2(ds, dn);
-    stab[t]         = DADD(ds, dn); // diffusion.cpp:48: (Dys + Dyn)
+  if (!UNI)
+  {
+    for (int t = threadIdx.x; t < (rend - rstart) + (K - 1) + 2; t += kChainThreads)
+    { // HALO: the tables are extended by the caller (global periodic index), negative rows are valid
+      const int rw = HALO ? (rstart - (K - 1) + t) : WROW(rstart - (K - 1) + t);
+      const double ds = a.cys[rw], dn = a.cyn[rw];
+      ytab[t]         = make_double2(ds, dn);
+      stab[t]         = DADD(ds, dn); // diffusion.cpp:48: (Dys + Dyn)
+    }
+    __syncthreads();
   }
-  __syncthreads();
 
   const int64_t wg = (int64_t)blockIdx.x * (kChainThreads / 32) + (threadIdx.x >> 5);
   if (wg * WUSE >= nx) return; // window entirely outside the field (no block-level sync below)
@@ -244,7 +252,8 @@ __global__ void __launch_bounds__(kChainThreads, 2) k_chain_march(const ChainArg
     xc          = ic;
     st.lane_col = ic;
   }
-  const double2 cw = ld_keep2(a.cxw + xc), ce = ld_keep2(a.cxe + xc);
+  const double2 cw = UNI ? make_double2(a.u_cxw, a.u_cxw) : ld_keep2(a.cxw + xc);
+  const double2 ce = UNI ? make_double2(a.u_cxe, a.u_cxe) : ld_keep2(a.cxe + xc);
   const double sx0 = DADD(cw.x, ce.x), sx1 = DADD(cw.y, ce.y);
 
   st.soff     = (int64_t)rstart * nx + ic;
@@ -268,7 +277,7 @@ __global__ void __launch_bounds__(kChainThreads, 2) k_chain_march(const ChainArg
   for (int q = 0; q < PF; q++) chain_issue<K, PF, HALO>(a, st, rx, rp, ry, rf, nx, ny, true);
 
 #define ROW(PH, CHECK, R1) \
-  chain_row<K, PF, PH, CHECK, HALO, FMA>(a, st, W, rx, rp, ry, rf, ytab, stab, nx, ny, cw, ce, sx0, sx1, smask, R1, j0, j1, (R1) + PF < rend)
+  chain_row<K, PF, PH, CHECK, HALO, FMA, UNI>(a, st, W, rx, rp, ry, rf, ytab, stab, nx, ny, cw, ce, sx0, sx1, smask, R1, j0, j1, (R1) + PF < rend)
 
   // phases: [rstart, s0) checked warm-up in whole triples, [s0, s1) unchecked steady state in
   // triples, [s1, rend3) checked drain; rend3 rounds the trip count up to a multiple of 3 (the

@@ -133,6 +133,12 @@ typedef struct b200_stencil_geom
   const double* halo_e;    /* [ny] or NULL */
   const double* halo_s;    /* [nx] or NULL */
   const double* halo_n;    /* [nx] or NULL */
+  /* Optional promise (0 = none): every entry of cxw / cxe / cys / cyn (margins of the halo flavour
+     included) is bitwise equal to u_cxw / u_cxe / u_cys / u_cyn -- the homogeneous problem,
+     Diffusion_Coeff_X/Y = kx / ky (diffusion_2D.cpp:887-897).  b200_stencil_chain[_halo] then takes the
+     coefficients from kernel parameters instead of loading tables; results are bit-identical. */
+  int uniform;
+  double u_cxw, u_cxe, u_cys, u_cyn;
 } b200_stencil_geom;
 
 /* term sources for b200_stencil_lincomb */
@@ -212,6 +218,8 @@ int b200_set_chain_rows(int rows);
    variable B200_CHAIN_VARIANT sets the initial value. */
 int b200_set_chain_variant(int variant);
 int b200_get_chain_variant(void);
+/* 1 (default): honour b200_stencil_geom.uniform; 0: always load the coefficient tables (A/B tests) */
+int b200_set_chain_uniform(int on);
 /* name of the kernel the most recent chain launch used ("k_chain_quad" / "k_chain_march", "" if none) */
 const char* b200_last_chain_kernel(void);
 /* Arithmetic of the chain kernels.  0 (default) = the arithmetic contract stated at the top of this

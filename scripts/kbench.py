@@ -30,9 +30,10 @@ def main():
     ap.add_argument("--pattern", default="stage", help="stage | rhs | final | chainK; comma list = sweep in one process")
     ap.add_argument("--variant", default="1", help="chain kernel: 0 = two cells / thread, 1 = four (comma list)")
     ap.add_argument("--arith", default="exact", help="exact | fma (comma list)")
+    ap.add_argument("--uniform", default="0", help="0 = random coefficient tables, 1 = uniform coefficients flagged in the geometry (comma list)")
     args = ap.parse_args()
-    combos = [(p_, int(v_), a_) for p_ in args.pattern.split(",") for v_ in args.variant.split(",")
-              for a_ in args.arith.split(",")]
+    combos = [(p_, int(v_), a_, int(u_)) for p_ in args.pattern.split(",") for v_ in args.variant.split(",")
+              for a_ in args.arith.split(",") for u_ in args.uniform.split(",")]
     nx = args.n
     ny = args.ny or args.n
     ctx = b200.Context(0)
@@ -42,13 +43,18 @@ def main():
     bufs = [torch.rand(N, dtype=torch.float64, device=dev) for _ in range(6)]
     cx = [torch.rand(nx, dtype=torch.float64, device=dev) + 1.0 for _ in range(2)]
     cy = [torch.rand(ny, dtype=torch.float64, device=dev) + 1.0 for _ in range(2)]
-    g = b200.StencilGeom(nx, ny, cx[0].data_ptr(), cx[1].data_ptr(), cy[0].data_ptr(), cy[1].data_ptr(), None, None, None, None)
+    g_rand = b200.StencilGeom(nx, ny, cx[0].data_ptr(), cx[1].data_ptr(), cy[0].data_ptr(), cy[1].data_ptr(), None, None, None, None)
+    ux = [torch.full((nx,), 1.25, dtype=torch.float64, device=dev) for _ in range(2)]
+    uy = [torch.full((ny,), 1.75, dtype=torch.float64, device=dev) for _ in range(2)]
+    g_uni = b200.StencilGeom(nx, ny, ux[0].data_ptr(), ux[1].data_ptr(), uy[0].data_ptr(), uy[1].data_ptr(), None, None, None, None,
+                             1, 1.25, 1.25, 1.75, 1.75)
     coeffs = [1e-7, -0.3, 0.2, 1.1, -2e-8]
     out = {}
-    for pattern, variant, arith, rows in [(p_, v_, a_, int(r)) for (p_, v_, a_) in combos for r in args.rows.split(",")]:
-        if not pattern.startswith("chain") and (variant, arith) != (combos[0][1], combos[0][2]):
-            continue  # variant / arith only concern the chain kernels
+    for pattern, variant, arith, uniform, rows in [(p_, v_, a_, u_, int(r)) for (p_, v_, a_, u_) in combos for r in args.rows.split(",")]:
+        if not pattern.startswith("chain") and (variant, arith, uniform) != combos[0][1:]:
+            continue  # variant / arith / uniform only concern the chain kernels
         args.pattern, args.variant, args.arith = pattern, variant, arith
+        g = g_uni if uniform else g_rand
         lib.b200_set_chain_variant(variant)
         lib.b200_set_contract(1 if arith == "fma" else 0)
         lib.b200_set_rows_per_block(rows)
@@ -88,10 +94,10 @@ def main():
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.iters
         gbs = bpc * N / (ms * 1e-3) / 1e9
-        out[(pattern, variant, arith, rows)] = {"ms": ms, "GBs": gbs}
+        out[(pattern, variant, arith, uniform, rows)] = {"ms": ms, "GBs": gbs}
         kk = int(args.pattern[5:]) if args.pattern.startswith("chain") else 1
-        print("n=%dx%d pattern=%s variant=%d arith=%s rows=%d: %.3f ms/launch  %.1f GB/s (%.0f B/cell basis)  %.3e cell-updates/s"
-              % (nx, ny, args.pattern, args.variant, args.arith, rows, ms, gbs, bpc, kk * N / (ms * 1e-3)))
+        print("n=%dx%d pattern=%s variant=%d arith=%s uniform=%d rows=%d: %.3f ms/launch  %.1f GB/s (%.0f B/cell basis)  %.3e cell-updates/s"
+              % (nx, ny, args.pattern, args.variant, args.arith, uniform, rows, ms, gbs, bpc, kk * N / (ms * 1e-3)))
     return out
 
 

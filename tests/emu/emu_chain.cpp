@@ -9,15 +9,16 @@
 namespace
 {
 template <int K, int PF, bool HALO, bool FMA>
-void run_march(const ChainArgs& a, dim3 grid)
+void run_march(const ChainArgs& a, dim3 grid, bool uni)
 {
-  emu::launch(k_chain_march<K, PF, HALO, FMA>, grid, kChainThreads, chain_march_smem(K, PF, a.rows), a);
+  if (uni) emu::launch(k_chain_march<K, PF, HALO, FMA, true>, grid, kChainThreads, chain_march_smem(K, PF, a.rows), a);
+  else emu::launch(k_chain_march<K, PF, HALO, FMA, false>, grid, kChainThreads, chain_march_smem(K, PF, a.rows), a);
 }
 template <int K, int PF>
-void run_march_k(const ChainArgs& a, dim3 grid, bool halo, bool fma)
+void run_march_k(const ChainArgs& a, dim3 grid, bool halo, bool fma, bool uni)
 {
-  if (halo) fma ? run_march<K, PF, true, true>(a, grid) : run_march<K, PF, true, false>(a, grid);
-  else fma ? run_march<K, PF, false, true>(a, grid) : run_march<K, PF, false, false>(a, grid);
+  if (halo) fma ? run_march<K, PF, true, true>(a, grid, uni) : run_march<K, PF, true, false>(a, grid, uni);
+  else fma ? run_march<K, PF, false, true>(a, grid, uni) : run_march<K, PF, false, false>(a, grid, uni);
 }
 
 template <int K, int PF, bool HALO, bool FMA>
@@ -35,12 +36,13 @@ void run_quad_k(const ChainArgs& a, dim3 grid, bool halo, bool fma)
 
 // variant: 0 = k_chain_march (2 cells / thread), 1 = k_chain_quad (4 cells / thread)
 // halos: NULL (periodic wrap) or the four deep-halo buffers {x, prev2, yn, fn} (g rows, g2 columns)
-// lazy_cp_async: see cuda_emu.h.  Returns 0, or -1 for an unsupported combination.
+// lazy_cp_async: see cuda_emu.h.  uniform4: NULL, or {cxw, cxe, cys, cyn} = the uniform-coefficient
+// flavour of k_chain_march (the tables are then not read).  Returns 0, or -1 if unsupported.
 extern "C" __attribute__((visibility("default"))) int emu_stencil_chain(int variant, int K, int fma, int lazy_cp_async, int64_t nx, int64_t ny,
                                  const double* cxw, const double* cxe, const double* cys, const double* cyn,
                                  const double* x, const double* prev2, const double* yn, const double* fn,
                                  const double* coeffs, double* const* out, int rows,
-                                 const double* const* halos, int g, int g2)
+                                 const double* const* halos, int g, int g2, const double* uniform4)
 {
   ChainArgs a;
   memset(&a, 0, sizeof(a));
@@ -54,6 +56,12 @@ extern "C" __attribute__((visibility("default"))) int emu_stencil_chain(int vari
   }
   a.rows = rows;
   if (halos) { a.hx = halos[0]; a.hp = halos[1]; a.hy = halos[2]; a.hf = halos[3]; a.g = g; a.g2 = g2; }
+  const bool uni = uniform4 != nullptr;
+  if (uni)
+  {
+    a.u_cxw = uniform4[0]; a.u_cxe = uniform4[1]; a.u_cys = uniform4[2]; a.u_cyn = uniform4[3];
+    a.u_ndc = -((uniform4[0] + uniform4[1]) + (uniform4[2] + uniform4[3]));
+  }
   emu::cp_async_lazy = lazy_cp_async != 0;
   const bool h = halos != nullptr, f = fma != 0;
   if (variant == 0)
@@ -61,17 +69,18 @@ extern "C" __attribute__((visibility("default"))) int emu_stencil_chain(int vari
     dim3 grid = chain_march_grid(nx, ny, K, &a.rows);
     switch (K)
     {
-    case 2: run_march_k<2, 4>(a, grid, h, f); break;
-    case 3: run_march_k<3, 4>(a, grid, h, f); break;
-    case 4: run_march_k<4, 3>(a, grid, h, f); break;
-    case 5: run_march_k<5, 3>(a, grid, h, f); break;
-    case 6: run_march_k<6, 3>(a, grid, h, f); break;
+    case 2: run_march_k<2, 4>(a, grid, h, f, uni); break;
+    case 3: run_march_k<3, 4>(a, grid, h, f, uni); break;
+    case 4: run_march_k<4, 3>(a, grid, h, f, uni); break;
+    case 5: run_march_k<5, 3>(a, grid, h, f, uni); break;
+    case 6: run_march_k<6, 3>(a, grid, h, f, uni); break;
     default: return -1;
     }
     return 0;
   }
   if (variant == 1)
   {
+    if (uni) return -1;
     if (!chain_quad_supported(nx, ny, K, h ? g2 : -1)) return -1;
     dim3 grid = chain_quad_grid(nx, ny, K, &a.rows);
     switch (K)

@@ -168,8 +168,21 @@ def test_oracle_laplacian_halo_equals_periodic_wrap(orc):
     assert np.array_equal(f1, f2)
 
 
-def test_python_and_header_struct_sizes_agree(b200):
-    """ctypes mirrors must match the C structs (sizes are checked against known layouts)."""
-    assert ctypes.sizeof(b200.StencilGeom) == 2 * 8 + 8 * 8
-    assert ctypes.sizeof(b200.StageExtras) == 7 * 8
-    assert ctypes.sizeof(b200.AdrParams) == 2 * 8 + 9 * 8
+def test_python_and_header_struct_sizes_agree(b200, tmp_path):
+    """ctypes mirrors must match the C structs: sizes and the offsets of the last fields as gcc lays the
+    headers out."""
+    import subprocess
+
+    src = tmp_path / "sz.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "b200_sts.h"\n'
+        'int main(void){printf("%zu %zu %zu %zu %zu\\n", sizeof(b200_stencil_geom), offsetof(b200_stencil_geom, uniform),'
+        ' offsetof(b200_stencil_geom, u_cyn), sizeof(b200_stage_extras), sizeof(b200_adr_params));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    geom, off_uniform, off_ucyn, extras, adr = (int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True,
+                                                                                check=True).stdout.split())
+    assert ctypes.sizeof(b200.StencilGeom) == geom
+    assert b200.StencilGeom.uniform.offset == off_uniform and b200.StencilGeom.u_cyn.offset == off_ucyn
+    assert ctypes.sizeof(b200.StageExtras) == extras
+    assert ctypes.sizeof(b200.AdrParams) == adr

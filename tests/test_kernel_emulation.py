@@ -57,7 +57,7 @@ def coeffs_for(k):
     return [[1e-3 * (l + 1), -0.3 + 0.1 * l, 0.2, 1.1 - 0.05 * l, -2e-4] for l in range(k)]
 
 
-def run_emu(emu, variant, k, fma, lazy, nx, ny, cx, cy, ops, coeffs, rows, store, halos=None, g=0, g2=0):
+def run_emu(emu, variant, k, fma, lazy, nx, ny, cx, cy, ops, coeffs, rows, store, halos=None, g=0, g2=0, uniform=None):
     n = nx * ny
     outs = [np.full(n, np.nan) if store[l] else None for l in range(k)]
     optr = (ctypes.c_void_p * k)(*[o.ctypes.data if o is not None else None for o in outs])
@@ -67,7 +67,8 @@ def run_emu(emu, variant, k, fma, lazy, nx, ny, cx, cy, ops, coeffs, rows, store
         hptr = (ctypes.c_void_p * 4)(*[h.ctypes.data for h in halos])
     rc = emu.emu_stencil_chain(variant, k, int(fma), int(lazy), ctypes.c_int64(nx), ctypes.c_int64(ny),
                                ctypes.c_void_p(cx[0]), ctypes.c_void_p(cx[1]), ctypes.c_void_p(cy[0]), ctypes.c_void_p(cy[1]),
-                               P(ops[0]), P(ops[1]), P(ops[2]), P(ops[3]), P(cf), optr, rows, hptr, g, g2)
+                               P(ops[0]), P(ops[1]), P(ops[2]), P(ops[3]), P(cf), optr, rows, hptr, g, g2,
+                               None if uniform is None else P(np.ascontiguousarray(np.array(uniform, dtype=np.float64))))
     return rc, outs
 
 
@@ -192,6 +193,42 @@ def test_fma_flavour_consistent_between_kernels_and_close_to_exact(emu):
         assert np.array_equal(m[l], q[l])
         rel = np.linalg.norm(m[l] - want[l].ravel()) / np.linalg.norm(want[l])
         assert 0 < rel < 1e-13  # contracted arithmetic differs, by rounding only
+
+
+@pytest.mark.parametrize("k", [3, 4])
+@pytest.mark.parametrize("halo", [False, True], ids=["wrap", "halo"])
+def test_uniform_coefficient_flavour_bit_exact(emu, k, halo):
+    """b200_stencil_geom.uniform: coefficients from kernel parameters, centre coefficient summed on the
+    host.  Must equal both the numpy restatement and the table-driven flavour bit for bit."""
+    nx, ny, rows, g, g2, M = 132, 20, 6, 6, 6, 16
+    u4 = [1.7, 1.7, 0.45, 0.45]
+    rng = np.random.default_rng(9 + k)
+    coeffs = coeffs_for(k)
+    if not halo:
+        tabs = [np.full(nx, u4[0]), np.full(nx, u4[1]), np.full(ny, u4[2]), np.full(ny, u4[3])]
+        ops = [np.ascontiguousarray(rng.standard_normal(nx * ny)) for _ in range(4)]
+        want = [w.ravel() for w in chain_np(*tabs, *[o.reshape(ny, nx) for o in ops], coeffs)]
+        cx = [tabs[0].ctypes.data, tabs[1].ctypes.data]
+        cy = [tabs[2].ctypes.data, tabs[3].ctypes.data]
+        halos = None
+    else:
+        NX, NY = 2 * nx, 2 * ny
+        T = [np.full(NX, u4[0]), np.full(NX, u4[1]), np.full(NY, u4[2]), np.full(NY, u4[3])]
+        G = [rng.standard_normal((NY, NX)) for _ in range(4)]
+        i0, j0 = nx, 0
+        want = [w[j0:j0 + ny, i0:i0 + nx].ravel() for w in chain_np(*T, *G, coeffs)]
+        ext = [np.full(nx + 2 * M, u4[0]), np.full(nx + 2 * M, u4[1]), np.full(ny + 2 * M, u4[2]), np.full(ny + 2 * M, u4[3])]
+        cx = [ext[0].ctypes.data + 8 * M, ext[1].ctypes.data + 8 * M]
+        cy = [ext[2].ctypes.data + 8 * M, ext[3].ctypes.data + 8 * M]
+        ops = [np.ascontiguousarray(f[j0:j0 + ny, i0:i0 + nx].ravel()) for f in G]
+        halos = [deep_halo(f, i0, j0, nx, ny, g, g2) for f in G]
+    rc, tab = run_emu(emu, 0, k, 0, 0, nx, ny, cx, cy, ops, coeffs, rows, [True] * k, halos, g, g2)
+    assert rc == 0
+    rc, uni = run_emu(emu, 0, k, 0, 1, nx, ny, cx, cy, ops, coeffs, rows, [True] * k, halos, g, g2, uniform=u4)
+    assert rc == 0
+    for l in range(k):
+        assert np.array_equal(uni[l], want[l]), "level %d" % (l + 1)
+        assert np.array_equal(uni[l], tab[l]), "level %d" % (l + 1)
 
 
 def test_quad_kernel_rejects_unsupported_shapes(emu):

@@ -442,3 +442,34 @@ def test_stencil_chain_fma_flavour(ctx, b200, size, k):
         e, f = res[(0, 1)][l], res[(1, 1)][l]
         rel = np.linalg.norm(e - f) / np.linalg.norm(e)
         assert 0.0 < rel < 1e-13, (l, rel)
+
+
+@pytest.mark.parametrize("size", [(256, 40), (1030, 70)], ids=lambda s: "%dx%d" % s)
+@pytest.mark.parametrize("k", [2, 3, 4, 5, 6])
+def test_stencil_chain_uniform_coefficient_flavour(ctx, b200, size, k):
+    """b200_stencil_geom.uniform (homogeneous problem): coefficients from kernel parameters instead of
+    tables; bit-identical to the table-driven launch, in both arithmetic flavours."""
+    nx, ny = size
+    n = nx * ny
+    rng = np.random.default_rng(nx + 3 * ny + k)
+    lib = b200.kernel_lib()
+    u4 = [0.8125, 0.8125, 2.3, 2.3]
+    cx = [torch.full((nx,), u4[0], dtype=torch.float64, device="cuda"), torch.full((nx,), u4[1], dtype=torch.float64, device="cuda")]
+    cy = [torch.full((ny,), u4[2], dtype=torch.float64, device="cuda"), torch.full((ny,), u4[3], dtype=torch.float64, device="cuda")]
+    base = (nx, ny, cx[0].data_ptr(), cx[1].data_ptr(), cy[0].data_ptr(), cy[1].data_ptr(), None, None, None, None)
+    g_tab = b200.StencilGeom(*base)
+    g_uni = b200.StencilGeom(*base, 1, *u4)
+    x, p2, yn, fn = (dev(rng.standard_normal(n)) for _ in range(4))
+    coeffs = [[1e-3 * (l + 1), -0.3 + 0.1 * l, 0.2, 1.1 - 0.05 * l, -2e-4] for l in range(k)]
+    lib.b200_set_chain_variant(0)
+    for contract in (0, 1):
+        lib.b200_set_contract(contract)
+        res = []
+        for g in (g_tab, g_uni):
+            outs = [torch.full((n,), np.nan, dtype=torch.float64, device="cuda") for _ in range(k)]
+            ctx.stencil_chain(g, x, p2, yn, fn, coeffs, outs)
+            ctx.sync()
+            res.append([host(o) for o in outs])
+        for l in range(k):
+            assert np.array_equal(res[0][l], res[1][l]), (contract, l)
+    lib.b200_set_contract(0)
