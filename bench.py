@@ -138,6 +138,15 @@ def run_reference_sample(nsteps, sample_n, cores, base_n=16384):
     return evals * sample_n * sample_n / t, t, evals
 
 
+def cpu_sample_plan(ranks, target_s=10.0):
+    """(sample_n, nsteps) so that the reference's CPU path works for about target_s seconds:
+    ~7.5e7 cell-updates/s per core was measured for it on this pool's hosts (profiles/)."""
+    sample_n = 4096 if ranks >= 8 else 2048
+    per_step = 93.0 * sample_n * sample_n
+    nsteps = int(round(target_s * 7.5e7 * ranks / per_step))
+    return sample_n, max(1, min(nsteps, 40))
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -372,11 +381,12 @@ def main():
         while ranks * 2 <= min(cores, 64):
             ranks *= 2
         try:
-            sample_n = 2048
-            v, t, ev = run_reference_sample(1, sample_n, ranks)
+            sample_n, sample_steps = cpu_sample_plan(ranks)
+            v, t, ev = run_reference_sample(sample_steps, sample_n, ranks)
             cpu_baseline = {"value": v, "unit": "cell-updates/s", "cores": ranks, "kind": "reference",
-                            "sample": "%d^2 block of the workload (same dx, dy, h => 92 RKC stages), 1 step = %d RHS evals, "
-                                      "%d shared-memory MPI ranks, %.1f s" % (sample_n, ev, ranks, t)}
+                            "sample": "%d^2 block of the workload (same dx, dy, h => 92 RKC stages), %d steps = %d RHS evals, "
+                                      "%d shared-memory MPI ranks of the unmodified reference build, %.1f s"
+                                      % (sample_n, sample_steps, ev, ranks, t)}
         except Exception as exc:  # the reference binary is test infrastructure; report, do not hide
             cpu_baseline = {"value": None, "unit": "cell-updates/s", "cores": 0, "kind": "reference",
                             "sample": "unavailable: %s" % exc}
