@@ -57,6 +57,32 @@ D2D_CASES = {
 }
 
 
+# A sample of the reference's own evaluation matrix, diffusion_2D/runtests-diffusion2d.py:72-104
+# (solvers x grids x kx x rtol, and the fixed-step series), with exactly its common flags :76-83.
+SWEEP_COMMON = ["--inhomogeneous", "--atol", "1.e-11", "--controller", "2", "--error", "--nonlinear", "--msbp", "1",
+                "--maxsteps", "100000", "--internaleig"]
+SWEEP_SOLVERS = {"rkc": ["--integrator", "rkc"], "rkl": ["--integrator", "rkl"],
+                 "erk2": ["--integrator", "erk", "--order", "-2"], "erk3": ["--integrator", "erk", "--order", "-3"],
+                 "erk4": ["--integrator", "erk", "--order", "-4"],
+                 "dirk2": ["--integrator", "dirk", "--order", "2"], "dirk3": ["--integrator", "dirk", "--order", "3"]}
+SWEEP_SAMPLE = [  # (solver, grid, kx, rtol, fixed h or 0)
+    ("rkc", 32, 0.1, 1e-2, 0.0), ("rkc", 64, 1.0, 1e-4, 0.0), ("rkc", 128, 10.0, 1e-6, 0.0), ("rkc", 256, 1.0, 1e-3, 0.0),
+    ("rkl", 32, 10.0, 1e-3, 0.0), ("rkl", 64, 0.1, 1e-5, 0.0), ("rkl", 128, 1.0, 1e-2, 0.0), ("rkl", 256, 10.0, 1e-4, 0.0),
+    ("erk2", 64, 1.0, 1e-3, 0.0), ("erk3", 32, 10.0, 1e-4, 0.0), ("erk4", 64, 0.1, 1e-5, 0.0),
+    ("dirk2", 64, 1.0, 1e-4, 0.0), ("dirk3", 128, 0.1, 1e-3, 0.0),
+    ("rkc", 64, 1.0, 1e-9, 1e-2 / 8), ("erk4", 32, 0.1, 1e-9, 1e-2 / 64), ("dirk3", 32, 1.0, 1e-9, 1e-2 / 4),
+    # not sampled: the matrix's fixed-step RKL rows at 128^2 (kx = 10, h = 1e-2/32) and 256^2 (kx = 1,
+    # h = 1e-2/2) -- the reference itself returns NaN there (h rho exceeds what 200 stages cover)
+]
+for _solver, _grid, _kx, _rtol, _h in SWEEP_SAMPLE:
+    _name = "sweep_%s_%d_kx%g_%s" % (_solver, _grid, _kx, ("h%g" % _h) if _h > 0 else ("rtol%g" % _rtol))
+    _args = ["--nx", str(_grid), "--ny", str(_grid), "--rtol", "%e" % _rtol, "--kx", "%e" % _kx, "--ky", "%e" % 0.0]
+    _args += SWEEP_SOLVERS[_solver] + SWEEP_COMMON
+    if _h > 0:
+        _args += ["--fixedstep", "%e" % _h]
+    D2D_CASES[_name] = _args
+
+
 # adr 2-D (oracle/_ref/adr2d_ref): name -> reference command line (all --nout 1 --output 1)
 ADR_CASES = {
     "strang_rkc_64": ["--nx", "64", "--ny", "64", "--integrator", "3", "--sts_method", "0", "--fixed_h", "0.01", "--tf", "0.1"],
@@ -116,7 +142,7 @@ def parse_lsrk_log(path):
     return steps
 
 
-def main():
+def main(only_missing=False):
     out = {"source": "deps/sundials/test/unit_tests/logging/test_logging_arkode_lsrkstep_lvl5_{0..3}.out",
            "problem": "prv.hpp: y' = L(t)(y - atan t) + 1/(1+t^2), L(t) = -1000 - 10 cos((10-t)/10 pi); dom_eig = L(t)",
            "rtol": 1e-6, "atol": 1e-10, "methods": {}}
@@ -127,12 +153,17 @@ def main():
     print("lsrk_logging_golden.json:", {k: len(v) for k, v in out["methods"].items()})
 
     for name, args in D2D_CASES.items():
+        if only_missing and os.path.exists(os.path.join(HERE, "d2d_%s.json" % name)):
+            continue
         full = args + ["--nout", "1", "--output", "2"]
         nx, ny = int(cr.get_arg(full, "--nx", 64)), int(cr.get_arg(full, "--ny", 64))
         wd, text = cr.run(cr.REF_BIN, full, 1)
         t, u = cr.read_solution(wd, nx, ny)
         stats = cr.parse_stats(text)
         stats.pop("sim_time", None)
+        m = re.search(r"Maximum relative error = ([-+0-9.eE]+)", text)
+        if m:
+            stats["max_rel_error"] = float(m.group(1))
         wd4, text4 = cr.run(cr.REF_BIN, full, 4)
         t4, u4 = cr.read_solution(wd4, nx, ny)
         spread = float(np.linalg.norm(u - u4) / np.linalg.norm(u))
@@ -162,6 +193,8 @@ def main_adr():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "adr":
         main_adr()
+    elif len(sys.argv) > 1 and sys.argv[1] == "missing":
+        main(only_missing=True)
     else:
         main()
         main_adr()
