@@ -213,6 +213,7 @@ def main():
     ap.add_argument("--arith", default=DEFAULT_ARITH, choices=["exact", "fma"],
                     help="exact = bit-identical to the reference's baseline x86-64 build; fma = contracted multiply-adds")
     ap.add_argument("--e2e-mode", default="pipelined", choices=["pipelined", "sequential"])
+    ap.add_argument("--chain-rows", type=int, default=0, help="rows per block of the chain kernel (0 = library default)")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -251,6 +252,8 @@ def main():
     if args.chain_variant >= 0:
         wargs += ["--chain-variant", str(args.chain_variant)]
     prob = b200.Diffusion2D(wargs, rank=rank, nranks=world, nccl_id=nccl_id, device=local_rank)
+    if args.chain_rows > 0:
+        b200.kernel_lib().b200_set_chain_rows(args.chain_rows)
     ncell_global = (n * npx) * (n * npy)
     ncell_local = n * n
 
