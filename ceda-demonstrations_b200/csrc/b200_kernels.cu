@@ -1241,7 +1241,22 @@ static int launch_quad(const ChainArgs& a, dim3 grid, cudaStream_t st)
   return a.hx ? launch_quad_k<K, PF, true, false, MINB>(a, grid, st) : launch_quad_k<K, PF, false, false, MINB>(a, grid, st);
 }
 
-static int g_chain_rows = 64;
+static int g_chain_rows = 0; // 0 = automatic (chain_rows_auto), else what b200_set_chain_rows asked for
+// Rows each block marches over: more rows = less redundant work (a block starts K-1 rows early and the
+// K-1 rows around it are recomputed: (rows + 2(K-1)) / rows) but fewer blocks.  128 rows where that still
+// leaves >= 4 waves of blocks (2 resident blocks on each SM), else 64, else 32.  Measured at 16384^2,
+// K = 4: 62.4 / 57.5 / 54.4 ms per step for 32 / 64 / 128 rows (profiles/r01_bench_chain_rows.log).
+static int chain_rows_auto(const b200_ctx* c, int64_t nx, int64_t ny, int nstages, bool quad)
+{
+  const int use       = quad ? 128 - 4 * ((nstages + 1) / 2) : 64 - 4 * ((nstages + 1) / 2);
+  const int wpb       = quad ? kQuadThreads / 32 : kChainThreads / 32;
+  const int64_t gx    = ((nx + use - 1) / use + wpb - 1) / wpb;
+  const int64_t waves = 4 * 2 * (int64_t)(c->sm_count > 0 ? c->sm_count : 148);
+  const int cand[3]   = {128, 64, 32};
+  for (int r : cand)
+    if (gx * ((ny + r - 1) / r) >= waves) return r;
+  return 32;
+}
 static int g_chain_uniform = 1; // honour b200_stencil_geom.uniform (0: always load the tables; for A/B tests)
 extern "C" int b200_set_chain_uniform(int on)
 {
@@ -1272,7 +1287,7 @@ extern "C" int b200_get_chain_variant(void)
 
 extern "C" int b200_set_chain_rows(int r)
 {
-  if (r < 1) return -1;
+  if (r < 0) return -1; // 0 = back to automatic
   g_chain_rows = r;
   return 0;
 }
@@ -1325,10 +1340,10 @@ static int stencil_chain_common(b200_ctx* c, const b200_stencil_geom* g, int nst
     }
   }
   if (!any || !a.out[nstages - 1]) return fail("b200_stencil_chain: the last stage must be stored");
-  a.rows        = g_chain_rows;
+  const bool use_quad = b200_get_chain_variant() == 1 && chain_quad_supported(a.nx, a.ny, nstages, halos ? hg2 : -1);
+  a.rows              = g_chain_rows > 0 ? g_chain_rows : chain_rows_auto(c, a.nx, a.ny, nstages, use_quad);
   int rc = 0;
-  const int variant = b200_get_chain_variant();
-  if (variant == 1 && chain_quad_supported(a.nx, a.ny, nstages, halos ? hg2 : -1))
+  if (use_quad)
   {
     dim3 grid = chain_quad_grid(a.nx, a.ny, nstages, &a.rows);
     g_last_chain_kernel = "k_chain_quad";

@@ -209,7 +209,8 @@ int64_t b200_deep_halo_doubles(int64_t nx, int64_t ny, int rows, int cols);
 int b200_deep_halo_exchange(b200_ctx* ctx, const int peers[4], int x_split, int y_split,
                             int64_t nx, int64_t ny, int rows, int cols, int nfields,
                             const double* const* fields, double* const* halos);
-/* rows of output each thread block of the chain kernel marches over (default 64) */
+/* rows of output each thread block of the chain kernel marches over; 0 (default) = automatic: 128
+   where that leaves at least 4 waves of blocks, else 64, else 32.  Results do not depend on it. */
 int b200_set_chain_rows(int rows);
 /* Which kernel runs a chain: 0 (default) = k_chain_march, two cells per thread; 1 = k_chain_quad,
    four cells per thread (two 64-cell halves per warp window, 120 of 128 cells useful at depth 4).

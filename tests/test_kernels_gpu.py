@@ -409,7 +409,7 @@ def test_stencil_chain_equals_single_stage_launches(ctx, b200, size, k, rows, va
     assert np.array_equal(host(outs2[k - 1]), host(zs[k - 1])) and np.array_equal(host(outs2[k - 2]), host(zs[k - 2]))
     lib.b200_last_chain_kernel.restype = ctypes.c_char_p
     assert lib.b200_last_chain_kernel() == (b"k_chain_quad" if variant == 1 else b"k_chain_march")
-    lib.b200_set_chain_rows(64)
+    lib.b200_set_chain_rows(0)
     lib.b200_set_chain_variant(0)
 
 
