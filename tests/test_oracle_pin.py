@@ -4,7 +4,10 @@
     (tests/golden/lsrk_logging_golden.json, extracted from
     deps/sundials/test/unit_tests/logging/test_logging_arkode_lsrkstep_lvl5_{0..3}.out);
 (b) final states written by the unmodified reference driver (tests/golden/d2d_*.npy);
-(c) when the reference binary is present (build container), a live run of it.
+(c) when the reference binary is present (build container), a live run of it;
+(e) SUNDIALS' known answers for the power iteration
+    (deps/sundials/test/answers/.../test_sundomeigest_power_{1000,10000,100000}_100_0_0.out:
+    eigenvalue estimate, iteration count and residual).
 """
 import ctypes
 import json
@@ -157,3 +160,46 @@ def test_reference_multirank_shim_matches_single_rank():
     for np_ranks in (2, 3, 4, 6):
         _, up = cr.read_solution(cr.run(cr.REF_BIN, args, np_ranks)[0], 50, 34)
         assert np.array_equal(u1, up), np_ranks
+
+
+# ---- (e) SUNDIALS' known answers for the power iteration ---------------------------------------
+# test/unit_tests/sundomeigest/Power/test_sundomeigest_power.c: A = diag(-100*[3..N]) plus a 2x2 block
+# [[-30000, -10000], [-10000, -30000]] on the last two rows, initial guess q_i = rand()/RAND_MAX (glibc, default
+# seed), rel_tol 0.01, no warm-ups; answers in test/answers/linux-ubuntu20.04-x86_64/gcc-9.4.0/double/
+# test_sundomeigest_power_<N>_100_0_0.out (printed with 15 significant digits).
+POWER_GOLDEN = {1000: (-93929.2359849011, 8, 0.00959956382300218),
+                10000: (-936780.175307443, 8, 0.00966387730674346),
+                100000: (-9374195.86189535, 8, 0.00950100649833683)}
+
+
+@pytest.mark.parametrize("n", sorted(POWER_GOLDEN))
+def test_oracle_power_iteration_matches_sundials_known_answers(orc, n):
+    from conftest import ATIMES_FN
+
+    libc = ctypes.CDLL("libc.so.6")
+    libc.srand(1)  # the C default seed
+    rand_max = 2147483647
+    q = np.array([libc.rand() / rand_max for _ in range(n)])
+    diag = -100.0 * (np.arange(n - 2) + 3.0)
+    lambdas = []
+
+    def atimes(user, v, z):
+        va = np.ctypeslib.as_array(v, shape=(n,))
+        za = np.ctypeslib.as_array(z, shape=(n,))
+        za[:n - 2] = diag * va[:n - 2]
+        za[n - 2] = va[n - 2] * -30000.0 + va[n - 1] * -10000.0
+        za[n - 1] = va[n - 1] * -30000.0 + va[n - 2] * -10000.0
+        lambdas.append(float(np.dot(va, za)))
+        return 0
+
+    V = q / math.sqrt(orc.orc_dot(P(q), P(q), ctypes.c_int64(n)))  # SUNDomEigEstimator_Initialize_Power :181-186
+    V = np.ascontiguousarray(V)
+    work = np.zeros(n)
+    lam, iters = ctypes.c_double(), ctypes.c_int()
+    rc = orc.orc_power_iteration(ATIMES_FN(atimes), None, P(V), P(work), ctypes.c_int64(n), 0, 100,
+                                 ctypes.c_double(0.01), ctypes.byref(lam), ctypes.byref(iters))
+    want_lam, want_iters, want_res = POWER_GOLDEN[n]
+    assert rc == 0 and iters.value == want_iters
+    assert lam.value == pytest.approx(want_lam, rel=2e-14)
+    res = abs(lambdas[-1] - lambdas[-2]) / abs(lambdas[-1])
+    assert res == pytest.approx(want_res, rel=1e-10)
