@@ -2,7 +2,8 @@
 // just large enough to run the stage kernels of ceda-demonstrations_b200/csrc/*.cuh on CPU threads.
 //
 // One OS thread per CUDA thread of a block, blocks one after the other.  What is emulated:
-//   threadIdx / blockIdx / blockDim / gridDim, dynamic shared memory, __syncthreads (block barrier),
+//   threadIdx / blockIdx / blockDim / gridDim, dynamic and static shared memory, __syncthreads (block
+//   barrier), atomicAdd(unsigned) / __threadfence (the last-block ticket of the reductions),
 //   __shfl_{up,down,xor}_sync on doubles (per-warp exchange + barrier), exactly rounded FP64
 //   (__dmul_rn ... compile with -ffp-contract=off; DFMA = std::fma), and cp.async groups.
 // cp.async has two modes (emu::cp_async_lazy): eager = the copy happens at issue time; lazy = the
@@ -78,6 +79,7 @@ inline thread_local emu_uint3 threadIdx, blockIdx;
 inline thread_local dim3 blockDim, gridDim;
 
 #define __global__
+#define __shared__ static /* blocks run one after the other, so a function-level static is block-shared */
 #define __device__
 #define __host__
 #define __forceinline__ inline
@@ -105,6 +107,17 @@ static inline double __shfl_up_sync(unsigned, double v, int d) { return emu_shfl
 static inline double __shfl_down_sync(unsigned, double v, int d) { return emu_shfl(v, emu::ts.lane + d); }
 static inline double __shfl_xor_sync(unsigned, double v, int m) { return emu_shfl(v, emu::ts.lane ^ m); }
 static inline double __shfl_sync(unsigned, double v, int src) { return emu_shfl(v, src & 31); }
+
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline double __longlong_as_double(long long v)
+{
+  double d;
+  memcpy(&d, &v, sizeof(d));
+  return d;
+}
+using std::fmax;
+using std::fmin;
 
 static inline double2 ld_stream2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 static inline double2 ld_keep2(const double* p) { return *reinterpret_cast<const double2*>(p); }

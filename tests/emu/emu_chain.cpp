@@ -5,9 +5,20 @@
 #include "b200_sts.h"
 #include "chain_march.cuh"
 #include "chain_quad.cuh"
+#include "stage_kernels.cuh"
+
+#include <vector>
 
 namespace
 {
+template <int NT, uint32_t PAT>
+void run_stage(const StageArgs& a, dim3 grid)
+{
+  if (a.region == 2) emu::launch(k_stage_march<NT, PAT, 2, false>, grid, kThreads, 0, a);
+  else if (a.rw) emu::launch(k_stage_march<NT, PAT, 0, true>, grid, kThreads, 0, a);
+  else emu::launch(k_stage_march<NT, PAT, 0, false>, grid, kThreads, 0, a);
+}
+
 template <int K, int PF, bool HALO, bool FMA>
 void run_march(const ChainArgs& a, dim3 grid, bool uni)
 {
@@ -95,4 +106,62 @@ extern "C" __attribute__((visibility("default"))) int emu_stencil_chain(int vari
     return 0;
   }
   return -1;
+}
+
+
+// b200_stencil_lincomb on the emulator: the same kernel choice as the launcher in b200_kernels.cu
+// (region 1 -> k_stage_ring; even nx -> k_stage_march with the compiled pattern for the LSRKStep
+// sequences, else the runtime pattern; odd nx or force_generic -> k_stage_generic).
+// wrms_w / wrms_result: fused sum((z*w)^2) or NULL.  Returns 0, or -1 for a bad argument.
+extern "C" __attribute__((visibility("default"))) int emu_stencil_lincomb(
+  int64_t nx, int64_t ny, const double* cxw, const double* cxe, const double* cys, const double* cyn,
+  const double* hw, const double* he, const double* hs, const double* hn, const double* x, int nterms,
+  const double* cf, const int* src, const double* const* v, double* z, double* f_out, double* send_w,
+  double* send_e, double* send_s, double* send_n, const double* wrms_w, double* wrms_result, int rows,
+  int region, int force_generic)
+{
+  if (nterms < 1 || nterms > B200_MAX_TERMS) return -1;
+  StageArgs a;
+  memset(&a, 0, sizeof(a));
+  a.nx = nx; a.ny = ny;
+  a.cxw = cxw; a.cxe = cxe; a.cys = cys; a.cyn = cyn;
+  a.hw = hw; a.he = he; a.hs = hs; a.hn = hn;
+  a.x = x; a.z = z;
+  a.t.n = nterms;
+  for (int k = 0; k < nterms; k++)
+  {
+    a.t.c[k]   = cf[k];
+    a.t.src[k] = src[k];
+    a.t.v[k]   = (src[k] == B200_SRC_VECTOR) ? v[k] : nullptr;
+  }
+  a.f_out = f_out;
+  a.send_w = send_w; a.send_e = send_e; a.send_s = send_s; a.send_n = send_n;
+  a.rw = wrms_w; a.result = wrms_result;
+  a.region = region;
+  std::vector<double> partials(1 << 16);
+  unsigned ticket = 0;
+  a.partials = partials.data();
+  a.ticket   = &ticket;
+  if (region == 1)
+  {
+    const int64_t cells = 2 * nx + 2 * (ny - 2);
+    emu::launch(k_stage_ring, dim3((unsigned)((cells + kThreads - 1) / kThreads)), kThreads, 0, a);
+    return 0;
+  }
+  if ((nx % 2 == 0) && !force_generic)
+  {
+    a.rows = rows;
+    dim3 grid((unsigned)((nx / 2 + kThreads - 1) / kThreads), (unsigned)((ny + rows - 1) / rows));
+    uint32_t pat = 0;
+    for (int k = 0; k < nterms; k++) pat |= (uint32_t)src[k] << (2 * k);
+    const int V = B200_SRC_VECTOR, C = B200_SRC_CENTRE, S = B200_SRC_STENCIL;
+    if (nterms == 1 && pat == PAT1(S)) run_stage<1, PAT1(S)>(a, grid);
+    else if (nterms == 2 && pat == PAT2(C, S)) run_stage<2, PAT2(C, S)>(a, grid);
+    else if (nterms == 4 && pat == PAT4(V, C, V, S)) run_stage<4, PAT4(V, C, V, S)>(a, grid);
+    else if (nterms == 5 && pat == PAT5(S, V, V, C, V)) run_stage<5, PAT5(S, V, V, C, V)>(a, grid);
+    else run_stage<B200_MAX_TERMS, PAT_RUNTIME>(a, grid);
+    return 0;
+  }
+  emu::launch(k_stage_generic, dim3((unsigned)((nx + kThreads - 1) / kThreads), (unsigned)ny), kThreads, 0, a);
+  return 0;
 }

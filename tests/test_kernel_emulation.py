@@ -1,5 +1,6 @@
-"""CPU tests of the temporally blocked stage kernels' SOURCE (csrc/chain_march.cuh, chain_quad.cuh)
-run through the host emulation harness tests/emu (one OS thread per CUDA thread, warp shuffles,
+"""CPU tests of the stage kernels' SOURCE (csrc/chain_march.cuh, chain_quad.cuh: K temporally blocked
+stages per launch; csrc/stage_kernels.cuh + reduce_prims.cuh: the fused one-stage kernels with halo pack and
+fused WRMS reduction) run through the host emulation harness tests/emu (one OS thread per CUDA thread, warp shuffles,
 cp.async groups in eager and lazy completion order).  They check the tiling / ring / halo / wrap
 indexing and the arithmetic order against a numpy restatement of the stage recurrence
 (diffusion_2D/diffusion.cpp:34-55 + arkode_lsrkstep.c:706-717), which is itself checked against the
@@ -239,3 +240,97 @@ def test_quad_kernel_rejects_unsupported_shapes(emu):
     rc, _ = run_emu(emu, 1, 4, 0, 0, nx, ny, [tabs[0].ctypes.data, tabs[1].ctypes.data],
                     [tabs[2].ctypes.data, tabs[3].ctypes.data], ops, coeffs_for(4), 8, [True] * 4)
     assert rc == -1
+
+
+# ------------------------------------------------------------------ the fused one-stage kernels
+# (csrc/stage_kernels.cuh: k_stage_march / k_stage_generic / k_stage_ring), against the oracle's
+# orc_laplacian + orc_linear_combination + orc_wsqrsum -- the CPU twin of
+# test_kernels_gpu.py::test_stencil_lincomb_bit_exact / test_fused_wrms_matches_separate_norm.
+STAGE_PATTERNS = {
+    "rhs": [2], "ssp_stage": [1, 2], "sts_embed": [0, 1, 0, 2], "sts_stage": [2, 0, 0, 1, 0],
+    "general3": [0, 2, 0],  # not a compiled pattern -> runtime-pattern instantiation
+}
+
+
+def emu_stage(emu, nx, ny, tabs, halos, x, coeffs, srcs, vecs, region=0, rows=8, wrms_w=None, force_generic=0,
+              z=None, f=None):
+    n = nx * ny
+    z = np.full(n, np.nan) if z is None else z
+    f = np.full(n, np.nan) if f is None else f
+    send = [np.zeros(ny), np.zeros(ny), np.zeros(nx), np.zeros(nx)]
+    res = np.zeros(1)
+    nt = len(srcs)
+    varr = (ctypes.c_void_p * nt)(*[v.ctypes.data if v is not None else None for v in vecs])
+    hp = [P(h) if h is not None else None for h in (halos or [None] * 4)]
+    emu.emu_stencil_lincomb.restype = ctypes.c_int
+    rc = emu.emu_stencil_lincomb(
+        ctypes.c_int64(nx), ctypes.c_int64(ny), P(tabs[0]), P(tabs[1]), P(tabs[2]), P(tabs[3]), *hp, P(x), nt,
+        (ctypes.c_double * nt)(*coeffs), (ctypes.c_int * nt)(*srcs), varr, P(z), P(f),
+        *([P(s) for s in send] if region == 0 else [None] * 4),
+        P(wrms_w) if wrms_w is not None else None, P(res) if wrms_w is not None else None, rows, region, force_generic)
+    assert rc == 0
+    return z, f, send, float(res[0])
+
+
+def oracle_stage(orc, g, x, coeffs, srcs, vecs, halos):
+    n = x.size
+    L = np.zeros(n)
+    hp = [P(h) if h is not None else None for h in (halos or [None] * 4)]
+    orc.orc_laplacian(ctypes.byref(g), P(x), P(L), *hp)
+    terms = [L if s == 2 else (x if s == 1 else v) for s, v in zip(srcs, vecs)]
+    z = np.zeros(n)
+    arr = (ctypes.c_void_p * len(terms))(*[t.ctypes.data for t in terms])
+    orc.orc_linear_combination(len(terms), (ctypes.c_double * len(terms))(*coeffs), arr, P(z), ctypes.c_int64(n))
+    return z, L
+
+
+@pytest.mark.parametrize("size", [(64, 20), (514, 9), (4, 5), (75, 11)], ids=lambda s: "%dx%d" % s)
+@pytest.mark.parametrize("pat", sorted(STAGE_PATTERNS))
+@pytest.mark.parametrize("halo_mode", ["wrap", "all"])
+def test_stage_kernels_bit_exact(emu, orc, size, pat, halo_mode):
+    nx, ny = size
+    srcs = STAGE_PATTERNS[pat]
+    rng = np.random.default_rng(nx * 131 + ny + len(srcs))
+    x = rng.standard_normal(nx * ny)
+    vecs = [rng.standard_normal(nx * ny) if s == 0 else None for s in srcs]
+    coeffs = list(rng.standard_normal(len(srcs)))
+    halos = None
+    if halo_mode == "all":
+        halos = [rng.standard_normal(ny), rng.standard_normal(ny), rng.standard_normal(nx), rng.standard_normal(nx)]
+    g = make_grid(nx, ny, kx=1.0, ky=0.5, inhom=True)
+    tabs = [np.zeros(nx), np.zeros(nx), np.zeros(ny), np.zeros(ny)]
+    orc.orc_coeff_tables(ctypes.byref(g), *[P(t) for t in tabs])
+    want_z, want_L = oracle_stage(orc, g, x, coeffs, srcs, vecs, halos)
+    z, f, send, _ = emu_stage(emu, nx, ny, tabs, halos, x, coeffs, srcs, vecs)
+    assert np.array_equal(z, want_z) and np.array_equal(f, want_L)
+    Z = want_z.reshape(ny, nx)
+    assert np.array_equal(send[0], Z[:, 0]) and np.array_equal(send[1], Z[:, -1])  # buffers.cpp:20-43
+    assert np.array_equal(send[2], Z[0, :]) and np.array_equal(send[3], Z[-1, :])
+    if nx % 2 == 0:  # the any-width kernel must agree with the fast path
+        zg, fg, _, _ = emu_stage(emu, nx, ny, tabs, halos, x, coeffs, srcs, vecs, force_generic=1)
+        assert np.array_equal(zg, want_z) and np.array_equal(fg, want_L)
+    if nx >= 4 and ny >= 4:  # interior (region 2) + ring (region 1) tile the sub-domain exactly
+        z2, f2, _, _ = emu_stage(emu, nx, ny, tabs, halos, x, coeffs, srcs, vecs, region=2)
+        inter = z2.reshape(ny, nx)
+        assert np.all(np.isnan(inter[0, :])) and np.all(np.isnan(inter[:, 0])) and np.all(np.isnan(inter[-1, :])) \
+            and np.all(np.isnan(inter[:, -1]))
+        emu_stage(emu, nx, ny, tabs, halos, x, coeffs, srcs, vecs, region=1, z=z2, f=f2)
+        assert np.array_equal(z2, want_z) and np.array_equal(f2, want_L)
+
+
+@pytest.mark.parametrize("size", [(64, 20), (1024, 12), (75, 11)], ids=lambda s: "%dx%d" % s)
+def test_stage_kernel_fused_wrms(emu, orc, size):
+    """Fused sum((z*w)^2): deterministic block tree + last-ticket finish (grid_finish) on the emulator."""
+    nx, ny = size
+    rng = np.random.default_rng(99)
+    x = rng.standard_normal(nx * ny)
+    yn, fn, w = rng.standard_normal(nx * ny), rng.standard_normal(nx * ny), rng.random(nx * ny) + 0.1
+    srcs, coeffs = [0, 1, 0, 2], [0.8, -0.8, 0.4e-3, 0.4e-3]
+    g = make_grid(nx, ny)
+    tabs = [np.zeros(nx), np.zeros(nx), np.zeros(ny), np.zeros(ny)]
+    orc.orc_coeff_tables(ctypes.byref(g), *[P(t) for t in tabs])
+    want_z, _ = oracle_stage(orc, g, x, coeffs, srcs, [yn, None, fn, None], None)
+    z, _, _, res = emu_stage(emu, nx, ny, tabs, None, x, coeffs, srcs, [yn, None, fn, None], wrms_w=w, rows=4)
+    assert np.array_equal(z, want_z)
+    want = orc.orc_wsqrsum(P(want_z), P(w), ctypes.c_int64(nx * ny))
+    assert res == pytest.approx(want, rel=1e-13)
