@@ -65,6 +65,7 @@ oracle:
 	@$(MAKE) -s -C oracle all
 ifneq ($(HAVE_REF),)
 	@$(MAKE) -s -C oracle ref
+	@$(MAKE) -s -C oracle nvsuite
 endif
 
 clean:
