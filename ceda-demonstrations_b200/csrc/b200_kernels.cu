@@ -379,111 +379,7 @@ extern "C" int b200_pipe_drain(b200_pipe* p)
 #include "reduce_prims.cuh"
 
 // ------------------------------------------------------ elementwise kernels
-enum EwOp
-{
-  EW_LINCOMB = 0,
-  EW_SCALESUM,
-  EW_SCALEDIFF,
-  EW_CONST,
-  EW_PROD,
-  EW_DIV,
-  EW_ABS,
-  EW_INV,
-  EW_ADDCONST,
-  EW_EWT
-};
-
-struct EwArgs
-{
-  LinTerms t;   // LINCOMB
-  const double* x;
-  const double* y;
-  double a, b;
-  double* z;
-  int64_t n;
-};
-
-template <int OP>
-__device__ __forceinline__ double ew_apply(const EwArgs& a, int64_t i)
-{
-  if (OP == EW_LINCOMB)
-  {
-    double acc = DMUL(a.t.c[0], a.t.v[0][i]);
-#pragma unroll
-    for (int k = 1; k < B200_MAX_TERMS; k++)
-      if (k < a.t.n) acc = DADD(acc, DMUL(a.t.c[k], a.t.v[k][i]));
-    return acc;
-  }
-  if (OP == EW_SCALESUM) return DMUL(a.a, DADD(a.x[i], a.y[i]));
-  if (OP == EW_SCALEDIFF) return DMUL(a.a, DSUB(a.x[i], a.y[i]));
-  if (OP == EW_CONST) return a.a;
-  if (OP == EW_PROD) return DMUL(a.x[i], a.y[i]);
-  if (OP == EW_DIV) return __ddiv_rn(a.x[i], a.y[i]);
-  if (OP == EW_ABS) return fabs(a.x[i]);
-  if (OP == EW_INV) return __ddiv_rn(1.0, a.x[i]);
-  if (OP == EW_ADDCONST) return DADD(a.x[i], a.b);
-  // EW_EWT: N_VAbs, N_VScale(rtol), N_VAddConst(atol), N_VInv
-  return __ddiv_rn(1.0, DADD(DMUL(a.a, fabs(a.x[i])), a.b));
-}
-
-template <int OP>
-__device__ __forceinline__ double2 ew_apply2(const EwArgs& a, int64_t i)
-{
-  double2 r;
-  if (OP == EW_LINCOMB)
-  {
-    double2 v = ld_keep2(a.t.v[0] + i);
-    r.x = DMUL(a.t.c[0], v.x);
-    r.y = DMUL(a.t.c[0], v.y);
-#pragma unroll
-    for (int k = 1; k < B200_MAX_TERMS; k++)
-      if (k < a.t.n)
-      {
-        v   = ld_keep2(a.t.v[k] + i);
-        r.x = DADD(r.x, DMUL(a.t.c[k], v.x));
-        r.y = DADD(r.y, DMUL(a.t.c[k], v.y));
-      }
-    return r;
-  }
-  if (OP == EW_CONST) { r.x = a.a; r.y = a.a; return r; }
-  double2 x = ld_keep2(a.x + i);
-  if (OP == EW_SCALESUM || OP == EW_SCALEDIFF || OP == EW_PROD || OP == EW_DIV)
-  {
-    double2 y = ld_keep2(a.y + i);
-    if (OP == EW_SCALESUM) { r.x = DMUL(a.a, DADD(x.x, y.x)); r.y = DMUL(a.a, DADD(x.y, y.y)); }
-    if (OP == EW_SCALEDIFF) { r.x = DMUL(a.a, DSUB(x.x, y.x)); r.y = DMUL(a.a, DSUB(x.y, y.y)); }
-    if (OP == EW_PROD) { r.x = DMUL(x.x, y.x); r.y = DMUL(x.y, y.y); }
-    if (OP == EW_DIV) { r.x = __ddiv_rn(x.x, y.x); r.y = __ddiv_rn(x.y, y.y); }
-    return r;
-  }
-  if (OP == EW_ABS) { r.x = fabs(x.x); r.y = fabs(x.y); }
-  if (OP == EW_INV) { r.x = __ddiv_rn(1.0, x.x); r.y = __ddiv_rn(1.0, x.y); }
-  if (OP == EW_ADDCONST) { r.x = DADD(x.x, a.b); r.y = DADD(x.y, a.b); }
-  if (OP == EW_EWT)
-  {
-    r.x = __ddiv_rn(1.0, DADD(DMUL(a.a, fabs(x.x)), a.b));
-    r.y = __ddiv_rn(1.0, DADD(DMUL(a.a, fabs(x.y)), a.b));
-  }
-  return r;
-}
-
-// grid-stride, 2 x double2 per thread per trip (4 independent 16-byte loads / vector)
-template <int OP>
-__global__ void __launch_bounds__(kThreads) k_elementwise(const EwArgs a)
-{
-  const int64_t n2     = a.n >> 1; // number of double2
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  int64_t p            = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  for (; p + stride < n2; p += 2 * stride)
-  {
-    double2 r0 = ew_apply2<OP>(a, 2 * p);
-    double2 r1 = ew_apply2<OP>(a, 2 * (p + stride));
-    *reinterpret_cast<double2*>(a.z + 2 * p)            = r0;
-    *reinterpret_cast<double2*>(a.z + 2 * (p + stride)) = r1;
-  }
-  if (p < n2) { *reinterpret_cast<double2*>(a.z + 2 * p) = ew_apply2<OP>(a, 2 * p); }
-  if ((a.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) a.z[a.n - 1] = ew_apply<OP>(a, a.n - 1);
-}
+#include "vector_kernels.cuh"
 
 template <int OP>
 static int launch_ew(b200_ctx* c, const EwArgs& a)
@@ -585,41 +481,6 @@ extern "C" int b200_ewt_ss(b200_ctx* c, const double* y, double rtol, double ato
 }
 
 // ---------------------------------------------------------------- reductions
-enum RdKind { RD_DOT = 0, RD_WSQR, RD_MAXNORM, RD_MIN, RD_L1 };
-
-template <int KIND>
-__device__ __forceinline__ double rd_term(double x, double y)
-{
-  if (KIND == RD_DOT) return DMUL(x, y);
-  if (KIND == RD_WSQR) { double p = DMUL(x, y); return DMUL(p, p); }
-  if (KIND == RD_MAXNORM) return fabs(x);
-  if (KIND == RD_MIN) return x;
-  return fabs(x);
-}
-
-template <int KIND, int ROP>
-__global__ void __launch_bounds__(kThreads)
-  k_reduce(const double* __restrict__ x, const double* __restrict__ y, int64_t n,
-           double* partials, unsigned* ticket, double* result)
-{
-  __shared__ double smem[32];
-  const bool two       = (KIND == RD_DOT || KIND == RD_WSQR);
-  const int64_t n2     = n >> 1;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  double acc0 = red_identity<ROP>(), acc1 = red_identity<ROP>();
-  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n2; p += stride)
-  {
-    double2 a = ld_keep2(x + 2 * p);
-    double2 b = two ? ld_keep2(y + 2 * p) : make_double2(0.0, 0.0);
-    acc0      = red_combine<ROP>(acc0, rd_term<KIND>(a.x, b.x));
-    acc1      = red_combine<ROP>(acc1, rd_term<KIND>(a.y, b.y));
-  }
-  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0)
-    acc0 = red_combine<ROP>(acc0, rd_term<KIND>(x[n - 1], two ? y[n - 1] : 0.0));
-  double v = block_reduce<ROP>(red_combine<ROP>(acc0, acc1), smem);
-  grid_finish<ROP>(v, gridDim.x, blockIdx.x, partials, ticket, result, smem);
-}
-
 static int nccl_allreduce_inplace(b200_ctx* c, double* buf, int n, int op);
 
 template <int KIND, int ROP>
@@ -1018,25 +879,7 @@ extern "C" int b200_stencil_chain_halo(b200_ctx* c, const b200_stencil_geom* g, 
 }
 
 // ------------------------------------------------------------ deep halo exchange
-// W / E strips of one field: columns [0, g2) and [nx-g2, nx) over rows -g..ny+g-1, the rows
-// outside the field taken from the S / N halo (so corners travel with the second phase).
-__global__ void __launch_bounds__(kThreads)
-  k_pack_strips(const double* __restrict__ field, const double* __restrict__ halo, int64_t nx, int64_t ny,
-                int g, int g2, double* __restrict__ wstrip, double* __restrict__ estrip)
-{
-  const int64_t t     = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t nrows = ny + 2 * g;
-  if (t >= nrows * g2) return;
-  const int64_t rr = t / g2; // 0 .. ny+2g-1  <->  row rr - g
-  const int cc     = (int)(t - rr * g2);
-  const int64_t r  = rr - g;
-  const double* row;
-  if (r < 0) row = halo + (r + g) * nx;
-  else if (r >= ny) row = halo + (g + (r - ny)) * nx;
-  else row = field + r * nx;
-  wstrip[t] = row[cc];
-  estrip[t] = row[nx - g2 + cc];
-}
+#include "halo_kernels.cuh"
 
 extern "C" int64_t b200_deep_halo_doubles(int64_t nx, int64_t ny, int g, int g2)
 {
@@ -1120,23 +963,6 @@ extern "C" int b200_deep_halo_exchange(b200_ctx* c, const int peers[4], int x_sp
 }
 
 // ------------------------------------------------------------------ halo pack
-__global__ void __launch_bounds__(kThreads)
-  k_pack(const double* __restrict__ u, int64_t nx, int64_t ny, double* sw, double* se,
-         double* ss, double* sn)
-{
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < ny)
-  {
-    if (sw) sw[t] = u[t * nx];
-    if (se) se[t] = u[t * nx + nx - 1];
-  }
-  if (t < nx)
-  {
-    if (ss) ss[t] = u[t];
-    if (sn) sn[t] = u[(ny - 1) * nx + t];
-  }
-}
-
 extern "C" int b200_pack_halo(b200_ctx* c, const double* u, int64_t nx, int64_t ny,
                               double* sw, double* se, double* ss, double* sn)
 {
@@ -1147,18 +973,6 @@ extern "C" int b200_pack_halo(b200_ctx* c, const double* u, int64_t nx, int64_t 
 }
 
 // --------------------------------------------------------------- Jacobi setup
-__global__ void __launch_bounds__(kThreads)
-  k_jacobi(int64_t nx, int64_t ny, const double* __restrict__ pxw, const double* __restrict__ pxe,
-           const double* __restrict__ pys, const double* __restrict__ pyn, double gamma, double* diag)
-{
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t j = blockIdx.y;
-  if (i >= nx) return;
-  // preconditioner_jacobi.cpp:41-42: diag = -((Dx_w+Dx_e)+(Dy_s+Dy_n)); 1/(1 - gamma*diag)
-  const double d   = -DADD(DADD(pxw[i], pxe[i]), DADD(pys[j], pyn[j]));
-  diag[j * nx + i] = __ddiv_rn(1.0, DSUB(1.0, DMUL(gamma, d)));
-}
-
 extern "C" int b200_jacobi_setup(b200_ctx* c, int64_t nx, int64_t ny, const double* pxw,
                                  const double* pxe, const double* pys, const double* pyn,
                                  double gamma, double* diag)
@@ -1172,158 +986,7 @@ extern "C" int b200_jacobi_setup(b200_ctx* c, int64_t nx, int64_t ny, const doub
 }
 
 // -------------------------------------------------------------- adr kernels
-// Scalar factors of the three operators, computed ONCE on the host with the reference's own
-// expressions (IEEE division, so the bits are those of the reference's per-call scalars):
-//   advection  ...2d.cpp:1417-1420: c = ONE*cu/(TWO*dx)
-//   diffusion  ...2d.cpp:1461-1462: d*dxinv2 with dxinv2 = ONE/(dx*dx)
-//   reaction   ...2d.cpp:1515:      (B + 1)
-struct AdrConsts
-{
-  double cux, cuy, cvx, cvy;
-  double kx, ky;
-  double A, B, Bp1;
-};
-
-static AdrConsts adr_consts(const b200_adr_params& p)
-{
-  AdrConsts k;
-  k.cux = (1.0 * p.cux) / (2.0 * p.dx);
-  k.cuy = (1.0 * p.cuy) / (2.0 * p.dy);
-  k.cvx = (1.0 * p.cvx) / (2.0 * p.dx);
-  k.cvy = (1.0 * p.cvy) / (2.0 * p.dy);
-  k.kx  = p.d * (1.0 / (p.dx * p.dx));
-  k.ky  = p.d * (1.0 / (p.dy * p.dy));
-  k.A   = p.A;
-  k.B   = p.B;
-  k.Bp1 = p.B + 1.0;
-  return k;
-}
-
-struct AdrArgs
-{
-  int64_t nx, ny;
-  AdrConsts k;
-  const double* y;
-  double* f;  // plain RHS output (b200_adr_rhs) or f_out
-  LinTerms t; // fused combination (b200_adr_lincomb); t.n == 0: plain RHS
-  double* z;
-  int rows;   // rows marched per block
-};
-
-// One grid point, both species: c = centre, l/r = west/east, b/t = south/north.  Composite callbacks add in
-// the order advection, diffusion, reaction (f_adv_react ...2d.cpp:1602-1619, f_adv_diff_react :1622-1646,
-// f_diff_react, f_adv_diff; the N_VLinearSum(1,f,1,temp,f) there is Vaxpy: f += temp).
-template <int MODE>
-__device__ __forceinline__ double2 adr_point(const AdrConsts& k, double2 c, double2 l, double2 r, double2 b, double2 t)
-{
-  double2 res = make_double2(0, 0);
-  if (MODE & 1)
-  { // ...2d.cpp:1440-1441: f = cx*(r-l) + cy*(t-b)
-    res.x = DADD(DMUL(k.cux, DSUB(r.x, l.x)), DMUL(k.cuy, DSUB(t.x, b.x)));
-    res.y = DADD(DMUL(k.cvx, DSUB(r.y, l.y)), DMUL(k.cvy, DSUB(t.y, b.y)));
-  }
-  if (MODE & 2)
-  { // ...2d.cpp:1483-1486: d*dxinv2*(l + r - 2c) + d*dyinv2*(b + t - 2c)
-    const double c2x = DMUL(2.0, c.x), c2y = DMUL(2.0, c.y);
-    double2 fd;
-    fd.x = DADD(DMUL(k.kx, DSUB(DADD(l.x, r.x), c2x)), DMUL(k.ky, DSUB(DADD(b.x, t.x), c2x)));
-    fd.y = DADD(DMUL(k.kx, DSUB(DADD(l.y, r.y), c2y)), DMUL(k.ky, DSUB(DADD(b.y, t.y), c2y)));
-    res  = (MODE & 1) ? make_double2(DADD(res.x, fd.x), DADD(res.y, fd.y)) : fd;
-  }
-  if (MODE & 4)
-  { // ...2d.cpp:1515-1516: A + u*u*v - (B+1)*u ; B*u - u*u*v
-    const double uuv = DMUL(DMUL(c.x, c.x), c.y);
-    double2 fr;
-    fr.x = DSUB(DADD(k.A, uuv), DMUL(k.Bp1, c.x));
-    fr.y = DSUB(DMUL(k.B, c.x), uuv);
-    res  = (MODE & 3) ? make_double2(DADD(res.x, fr.x), DADD(res.y, fr.y)) : fr;
-  }
-  return res;
-}
-
-// Marching kernel: a thread owns one grid point (both species = one 16-byte access) of a 256-point strip and
-// marches down `rows` rows with the three live rows of y in registers, so a row of y is fetched once per
-// block; west/east neighbours come from warp shuffles (lanes 0 / 31 and the strip ends issue one extra
-// load; the domain is periodic, the reference wraps indices the same way, ...2d.cpp:1425-1433).  With
-// t.n > 0 the operator value is consumed in registers by z = sum_k c[k]*T_k, T_k in {vector, y, F(y)}
-// (left to right like SUNDIALS' N_VLinearCombination fallback) and optionally stored as well.
-template <int MODE>
-__global__ void __launch_bounds__(kThreads) k_adr_march(const AdrArgs a)
-{
-  constexpr bool NB = (MODE & 3) != 0; // the reaction alone is pointwise
-  const int64_t nx  = a.nx;
-  const int ny      = (int)a.ny;
-  const int lane    = threadIdx.x & 31;
-  const int64_t i0  = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  const bool active = i0 < nx;
-  const int64_t i   = active ? i0 : 0;
-  const int j0      = (int)blockIdx.y * a.rows;
-  int j1            = j0 + a.rows;
-  if (j1 > ny) j1 = ny;
-  const bool wload = NB && active && (lane == 0 || i == 0);
-  const bool eload = NB && active && (lane == 31 || i == nx - 1);
-  const int64_t iw = (i > 0) ? i - 1 : nx - 1, ie = (i < nx - 1) ? i + 1 : 0;
-  const double* yb = a.y;
-  int64_t off      = 2 * ((int64_t)j0 * nx + i);
-  double2 ym = make_double2(0, 0), yc = make_double2(0, 0);
-  if (active && j0 < j1)
-  {
-    yc = ld_keep2(yb + off);
-    if (NB) ym = ld_keep2(yb + 2 * ((int64_t)(j0 > 0 ? j0 - 1 : ny - 1) * nx + i));
-  }
-  const int nt = a.t.n;
-#pragma unroll 1
-  for (int j = j0; j < j1; j++)
-  {
-    double2 yp = make_double2(0, 0), wv = make_double2(0, 0), ev = make_double2(0, 0);
-    double2 tv[B200_MAX_TERMS];
-    if (active)
-    {
-      if (NB) yp = ld_keep2(yb + 2 * ((int64_t)(j < ny - 1 ? j + 1 : 0) * nx + i));
-      else if (j + 1 < j1) yp = ld_keep2(yb + off + 2 * nx);
-      if (wload) wv = ld_keep2(yb + 2 * ((int64_t)j * nx + iw));
-      if (eload) ev = ld_keep2(yb + 2 * ((int64_t)j * nx + ie));
-#pragma unroll
-      for (int k = 0; k < B200_MAX_TERMS; k++)
-        if (k < nt && a.t.src[k] == B200_SRC_VECTOR) tv[k] = ld_stream2(a.t.v[k] + off);
-    }
-    double2 l = make_double2(0, 0), r = make_double2(0, 0);
-    if (NB)
-    {
-      l.x = __shfl_up_sync(0xffffffffu, yc.x, 1);
-      l.y = __shfl_up_sync(0xffffffffu, yc.y, 1);
-      r.x = __shfl_down_sync(0xffffffffu, yc.x, 1);
-      r.y = __shfl_down_sync(0xffffffffu, yc.y, 1);
-      if (wload) l = wv;
-      if (eload) r = ev;
-    }
-    if (active)
-    {
-      const double2 F = adr_point<MODE>(a.k, yc, l, r, ym, yp);
-      if (nt > 0)
-      {
-        double2 acc = make_double2(0, 0);
-#pragma unroll
-        for (int k = 0; k < B200_MAX_TERMS; k++)
-          if (k < nt)
-          {
-            double2 v;
-            if (a.t.src[k] == B200_SRC_STENCIL) v = F;
-            else if (a.t.src[k] == B200_SRC_CENTRE) v = yc;
-            else v = tv[k];
-            const double p0 = DMUL(a.t.c[k], v.x), p1 = DMUL(a.t.c[k], v.y);
-            acc.x = (k == 0) ? p0 : DADD(acc.x, p0);
-            acc.y = (k == 0) ? p1 : DADD(acc.y, p1);
-          }
-        *reinterpret_cast<double2*>(a.z + off) = acc;
-      }
-      if (a.f) *reinterpret_cast<double2*>(a.f + off) = F;
-    }
-    ym = yc;
-    yc = yp;
-    off += 2 * nx;
-  }
-}
+#include "adr_kernels.cuh"
 
 static int launch_adr(b200_ctx* c, AdrArgs& a, int mode)
 {

@@ -90,6 +90,7 @@ inline thread_local dim3 blockDim, gridDim;
 #define DADD(a, b) ((double)(a) + (double)(b))
 #define DSUB(a, b) ((double)(a) - (double)(b))
 #define DFMA(a, b, c) std::fma((double)(a), (double)(b), (double)(c))
+static inline double __ddiv_rn(double a, double b) { return a / b; }
 #define B200_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::ts.blk->smem)
 
 static inline void __syncthreads() { emu::ts.blk->bar->arrive_and_wait(); }

@@ -1,6 +1,7 @@
 """CPU tests of the stage kernels' SOURCE (csrc/chain_march.cuh, chain_quad.cuh: K temporally blocked
 stages per launch; csrc/stage_kernels.cuh + reduce_prims.cuh: the fused one-stage kernels with halo pack and
-fused WRMS reduction) run through the host emulation harness tests/emu (one OS thread per CUDA thread, warp shuffles,
+fused WRMS reduction; csrc/vector_kernels.cuh, halo_kernels.cuh, adr_kernels.cuh: elementwise ops, reductions,
+halo packing, Jacobi diagonal, adr Brusselator kernels) run through the host emulation harness tests/emu (one OS thread per CUDA thread, warp shuffles,
 cp.async groups in eager and lazy completion order).  They check the tiling / ring / halo / wrap
 indexing and the arithmetic order against a numpy restatement of the stage recurrence
 (diffusion_2D/diffusion.cpp:34-55 + arkode_lsrkstep.c:706-717), which is itself checked against the
@@ -334,3 +335,136 @@ def test_stage_kernel_fused_wrms(emu, orc, size):
     assert np.array_equal(z, want_z)
     want = orc.orc_wsqrsum(P(want_z), P(w), ctypes.c_int64(nx * ny))
     assert res == pytest.approx(want, rel=1e-13)
+
+
+# ------------------------------------------------- the vector / halo / Jacobi / adr kernels on the emulator
+# (csrc/vector_kernels.cuh, halo_kernels.cuh, adr_kernels.cuh; entry points tests/emu/emu_kernels.cpp)
+def _aligned(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    assert a.ctypes.data % 16 == 0
+    return a
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 1025, 4099])
+def test_elementwise_kernels_bit_exact(emu, orc, n):
+    rng = np.random.default_rng(n)
+    x, y = _aligned(rng.standard_normal(n)), _aligned(rng.standard_normal(n) + 3.0)
+    N = ctypes.c_int64(n)
+
+    def run(op, a=0.0, b=0.0, terms=None):
+        z = _aligned(np.full(n, np.nan))
+        nt, cf, vv = 0, None, None
+        if terms:
+            nt = len(terms)
+            cf = (ctypes.c_double * nt)(*[t[0] for t in terms])
+            vv = (ctypes.c_void_p * nt)(*[t[1].ctypes.data for t in terms])
+        assert emu.emu_elementwise(op, N, P(x), P(y), ctypes.c_double(a), ctypes.c_double(b), nt, cf, vv, P(z), 3) == 0
+        return z
+
+    want = np.zeros(n)
+    vs = [_aligned(rng.standard_normal(n)) for _ in range(5)]
+    cs = list(rng.standard_normal(5))
+    arr = (ctypes.c_void_p * 5)(*[v.ctypes.data for v in vs])
+    orc.orc_linear_combination(5, (ctypes.c_double * 5)(*cs), arr, P(want), N)
+    assert np.array_equal(run(0, terms=list(zip(cs, vs))), want)
+    assert np.array_equal(run(1, a=0.75), 0.75 * (x + y)) and np.array_equal(run(2, a=-1.5), -1.5 * (x - y))
+    assert np.array_equal(run(3, a=2.5), np.full(n, 2.5))
+    for op, fn in ((4, orc.orc_prod), (5, orc.orc_div)):
+        fn(P(x), P(y), P(want), N)
+        assert np.array_equal(run(op), want)
+    for op, fn in ((6, orc.orc_abs), (7, orc.orc_inv)):
+        fn(P(x), P(want), N)
+        assert np.array_equal(run(op), want)
+    orc.orc_addconst(P(x), ctypes.c_double(0.3), P(want), N)
+    assert np.array_equal(run(8, b=0.3), want)
+    tmp = np.zeros(n)
+    orc.orc_ewt_ss(P(x), ctypes.c_double(1e-5), ctypes.c_double(1e-10), P(tmp), P(want), N)  # arkode.c:2932-2944
+    assert np.array_equal(run(9, a=1e-5, b=1e-10), want)
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 10001])
+@pytest.mark.parametrize("blocks", [1, 5])
+def test_reduction_kernels(emu, orc, n, blocks):
+    """Deterministic tree reductions: equal to the oracle's sequential sums to 1e-13 (summation order), max / min
+    exactly; the same input reduced twice gives the same bits."""
+    rng = np.random.default_rng(n + blocks)
+    x, w = _aligned(rng.standard_normal(n)), _aligned(rng.random(n) + 0.1)
+    emu.emu_reduce.restype = ctypes.c_double
+    N = ctypes.c_int64(n)
+    got = [emu.emu_reduce(k, N, P(x), P(w), blocks) for k in range(5)]
+    assert got[0] == pytest.approx(orc.orc_dot(P(x), P(w), N), rel=1e-13, abs=1e-15)
+    assert got[1] == pytest.approx(orc.orc_wsqrsum(P(x), P(w), N), rel=1e-13)
+    assert got[2] == orc.orc_maxnorm(P(x), N)
+    assert got[3] == orc.orc_min(P(x), N)
+    assert got[4] == pytest.approx(orc.orc_l1norm(P(x), N), rel=1e-13)
+    assert got == [emu.emu_reduce(k, N, P(x), P(w), blocks) for k in range(5)]
+
+
+def test_pack_jacobi_and_strip_kernels(emu, orc):
+    nx, ny, g, g2 = 70, 37, 6, 6
+    rng = np.random.default_rng(4)
+    u = _aligned(rng.standard_normal(nx * ny))
+    grid = make_grid(nx, ny)
+    want = [np.zeros(ny), np.zeros(ny), np.zeros(nx), np.zeros(nx)]
+    orc.orc_pack(ctypes.byref(grid), P(u), *[P(w) for w in want])  # buffers.cpp:20-43
+    got = [np.full(ny, np.nan), np.full(ny, np.nan), np.full(nx, np.nan), np.full(nx, np.nan)]
+    emu.emu_pack(P(u), ctypes.c_int64(nx), ctypes.c_int64(ny), *[P(b) for b in got])
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+    # Jacobi diagonal, preconditioner_jacobi.cpp:41-46, from given face tables
+    t = [rng.random(nx) + 0.5, rng.random(nx) + 0.5, rng.random(ny) + 0.5, rng.random(ny) + 0.5]
+    gamma = 0.0123
+    diag = np.full(nx * ny, np.nan)
+    emu.emu_jacobi(ctypes.c_int64(nx), ctypes.c_int64(ny), *[P(a) for a in t], ctypes.c_double(gamma), P(diag))
+    d = -((t[0] + t[1])[None, :] + (t[2] + t[3])[:, None])
+    assert np.array_equal(diag.reshape(ny, nx), 1.0 / (1.0 - gamma * d))
+    # W / E strips of the deep halo: columns [0, g2) and [nx-g2, nx) of rows -g .. ny+g-1, the rows outside the
+    # field taken from the S / N halo blocks (corners travel with the second exchange phase)
+    F = u.reshape(ny, nx)
+    S, Nn = rng.standard_normal((g, nx)), rng.standard_normal((g, nx))
+    halo = _aligned(np.concatenate([S.ravel(), Nn.ravel()]))
+    ws, es = np.full((ny + 2 * g) * g2, np.nan), np.full((ny + 2 * g) * g2, np.nan)
+    emu.emu_pack_strips(P(u), P(halo), ctypes.c_int64(nx), ctypes.c_int64(ny), g, g2, P(ws), P(es))
+    tall = np.vstack([S, F, Nn])
+    assert np.array_equal(ws.reshape(ny + 2 * g, g2), tall[:, :g2])
+    assert np.array_equal(es.reshape(ny + 2 * g, g2), tall[:, nx - g2:])
+
+
+@pytest.mark.parametrize("size", [(16, 12), (300, 9), (101, 33)], ids=lambda s: "%dx%d" % s)
+@pytest.mark.parametrize("mode", [1, 2, 3, 4, 5, 6, 7])
+def test_adr_kernel_every_composite_bit_exact(emu, orc, size, mode):
+    """k_adr_march<MODE>: z = c0*v0 + c1*y + c2*F_mode(y) + c3*v3 in one pass vs the oracle's callbacks summed in
+    the reference's order (adr/advection_diffusion_reaction_2d.cpp:1406-1520, :1602-1619), and the plain RHS."""
+    from conftest import OrcAdr
+
+    class AdrParams(ctypes.Structure):  # b200_adr_params, include/b200_sts.h
+        _fields_ = OrcAdr._fields_
+
+    nx, ny = size
+    vals = (nx, ny, 1.0 / nx, 1.0 / ny, -0.5, 1.0, 0.4, 0.7, 1e-2, 1.3, 1.0)
+    p, bp = OrcAdr(*vals), AdrParams(*vals)
+    n = 2 * nx * ny
+    y = _aligned(np.zeros(n))
+    orc.orc_adr_ic(ctypes.byref(p), ctypes.c_double(0.0), ctypes.c_double(0.0), P(y))
+    y += 0.01 * np.random.default_rng(mode).standard_normal(n)
+    parts = {}
+    for bit, fn in ((1, orc.orc_adr_advection), (2, orc.orc_adr_diffusion), (4, orc.orc_adr_reaction)):
+        parts[bit] = np.zeros(n)
+        fn(ctypes.byref(p), P(y), P(parts[bit]))
+    F = None
+    for bit in (1, 2, 4):
+        if mode & bit:
+            F = parts[bit].copy() if F is None else F + parts[bit]
+    rng = np.random.default_rng(100 + mode)
+    v0, v3 = _aligned(rng.standard_normal(n)), _aligned(rng.standard_normal(n))
+    c = [0.7, -0.25, 3e-3, 1.5]
+    want = ((c[0] * v0 + c[1] * y) + c[2] * F) + c[3] * v3
+    z, f = _aligned(np.full(n, np.nan)), _aligned(np.full(n, np.nan))
+    vv = (ctypes.c_void_p * 4)(v0.ctypes.data, None, None, v3.ctypes.data)
+    rc = emu.emu_adr(ctypes.byref(bp), mode, P(y), 4, (ctypes.c_double * 4)(*c), (ctypes.c_int * 4)(0, 1, 2, 0), vv,
+                     P(z), P(f), 8)
+    assert rc == 0
+    assert np.array_equal(z, want) and np.array_equal(f, F)
+    f2 = _aligned(np.full(n, np.nan))
+    assert emu.emu_adr(ctypes.byref(bp), mode, P(y), 0, None, None, None, None, P(f2), 5) == 0
+    assert np.array_equal(f2, F)
