@@ -298,9 +298,26 @@ def main():
     #     every batch's 2 x 8 B x cells cross PCIe inside the timed region.
     #   sequential: one dependent chain, set_state -> step -> get_state, nothing overlaps.
     e2e = None
+    hin = hout = None
     if not args.no_e2e:
-        hin = [torch.empty(ncell_local, dtype=torch.float64, pin_memory=True) for _ in range(2)]
-        hout = [torch.empty(ncell_local, dtype=torch.float64, pin_memory=True) for _ in range(2)]
+        # the pinned staging buffers (4 x 8 B x cells per rank) are the only host allocation of size; whether they
+        # could be had is decided collectively so that no rank waits in a halo exchange for one that gave up
+        hin = hout = None
+        try:
+            hin = [torch.empty(ncell_local, dtype=torch.float64, pin_memory=True) for _ in range(2)]
+            hout = [torch.empty(ncell_local, dtype=torch.float64, pin_memory=True) for _ in range(2)]
+            have = 1
+        except Exception as exc:  # noqa: BLE001 -- reported in the JSON line
+            have = 0
+            sys.stderr.write("bench.py: pinned host allocation failed on rank %d: %s\n" % (rank, exc))
+        flag = torch.tensor([have], dtype=torch.int32, device="cuda")
+        if dist is not None:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            e2e = {"value": None, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                   "error": "pinned host memory for the staging buffers could not be allocated on every rank"}
+            hin = hout = None
+    if hin is not None:
         prob.get_state(hin[0])
         hin[1].copy_(hin[0])
         t_cur = prob.stats()["t"]
