@@ -163,6 +163,8 @@ def reference_arm(args):
     while ranks * 2 <= min(cores, 64):
         ranks *= 2
     sample_n = 4096 if ranks >= 8 else 2048
+    if os.environ.get("B200_BENCH_REF_SAMPLE_N"):  # tests/test_bench_contract.py: a seconds-long sample
+        sample_n = int(os.environ["B200_BENCH_REF_SAMPLE_N"])
     if args.warmup > 0:
         run_reference_sample(1, sample_n, ranks)
     t0 = time.time()
