@@ -89,6 +89,7 @@ struct AdrOptions
   bool linear = false, calc_error = false, write_solution = false;
   int output = 1, nout = 1;
   bool no_fusion = false; // B200 extra
+  int sts_chain  = 1;     // B200 extra: temporal-blocking depth of the STS diffusion stages (1 = off)
 };
 
 int adr_fused(void* self, b200_ctx* ctx, const double* y, int nterms, const double* c, const int* src,
@@ -101,6 +102,18 @@ int adr_fused(void* self, b200_ctx* ctx, const double* y, int nterms, const doub
   m->ud->rhs_calls++;
   const b200_adr_params p = m->ud->params();
   return b200_adr_lincomb(ctx, &p, m->mode, y, nterms, c, src, v, z, f_out);
+}
+
+// K consecutive STS stages of the diffusion partition in one pass (B200RhsOp::chain; one periodic rank)
+int adr_chain_cb(void* self, b200_ctx* ctx, int nstages, const double* x, const double* prev2, const double* yn,
+                 const double* fn, const double* coeffs, double* const* z_out, double* const* halos,
+                 const int* halo_valid)
+{
+  (void)halos; (void)halo_valid;
+  ModeOp* m = static_cast<ModeOp*>(self);
+  m->ud->rhs_calls += nstages;
+  const b200_adr_params p = m->ud->params();
+  return b200_adr_chain(ctx, &p, nstages, x, prev2, yn, fn, coeffs, z_out);
 }
 
 int defer(int mode, N_Vector y, N_Vector f, void* user_data)
@@ -220,7 +233,7 @@ int read_inputs(const std::vector<std::string>& args, AdrData& ud, AdrOptions& u
     ARG_B("--linear", uo.linear, true) ARG_B("--calc_error", uo.calc_error, true)
     ARG_B("--write_solution", uo.write_solution, true)
     ARG_I("--output", uo.output) ARG_I("--nout", uo.nout)
-    ARG_B("--no-fusion", uo.no_fusion, true)
+    ARG_B("--no-fusion", uo.no_fusion, true) ARG_I("--sts_chain", uo.sts_chain)
     fprintf(stderr, "ERROR: Unknown input: %s\n", a.c_str());
     return -1;
   }
@@ -547,6 +560,16 @@ extern "C" int b200_adr_create(int argc, const char* const* argv, int device, vo
     p->ud.ops[m].mode     = m;
     p->ud.ops[m].op.self  = &p->ud.ops[m];
     p->ud.ops[m].op.fused = adr_fused;
+    p->ud.ops[m].op.chain        = nullptr;
+    p->ud.ops[m].op.chain_max    = 0;
+    p->ud.ops[m].op.halo_doubles = 0;
+  }
+  if (p->uo.sts_chain >= 2 && p->ud.nx >= 64 && p->ud.ny >= 16)
+  { // opt-in: the pure diffusion operator (Strang's STS partition) may be chained
+    const int depth              = p->uo.sts_chain > B200_MAX_CHAIN ? B200_MAX_CHAIN : p->uo.sts_chain;
+    p->ud.ops[2].op.chain        = adr_chain_cb;
+    p->ud.ops[2].op.chain_max    = depth;
+    N_VSetStageChain_B200(depth);
   }
   N_VSetLazyFusion_B200(p->uo.no_fusion ? 0 : 1);
   if (SUNContext_Create(SUN_COMM_NULL, &p->sunctx)) return -1;

@@ -1065,6 +1065,70 @@ extern "C" int b200_adr_diffusion_lincomb(b200_ctx* c, const b200_adr_params* p,
   return b200_adr_lincomb(c, p, 2, y, nterms, cf, src, v, z, f_out);
 }
 
+// ----------------------------------------- adr: temporally blocked diffusion stages
+#include "adr_chain.cuh"
+
+template <int K>
+static int launch_adr_chain_k(const AdrChainArgs& a, dim3 grid, cudaStream_t st)
+{
+  const size_t smem = adr_chain_smem(K, kAdrChainPF);
+  static bool configured = false;
+  if (!configured)
+  {
+    CU_TRY(cudaFuncSetAttribute(k_adr_chain<K, kAdrChainPF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  k_adr_chain<K, kAdrChainPF><<<grid, kAdrChainThreads, smem, st>>>(a);
+  return 0;
+}
+
+extern "C" int b200_adr_chain(b200_ctx* c, const b200_adr_params* p, int nstages, const double* x,
+                              const double* prev2, const double* yn, const double* fn, const double* coeffs,
+                              double* const* z_out)
+{
+  if (!adr_chain_supported(p->nx, p->ny, nstages)) return fail("b200_adr_chain: needs 2 <= nstages <= B200_MAX_CHAIN, nx >= 64, ny >= 16");
+  if (p->ny >= (int64_t)1 << 30) return fail("b200_adr_chain: ny too large");
+  if (!aligned16(x) || !aligned16(prev2) || !aligned16(yn) || !aligned16(fn)) return fail("b200_adr_chain: operand not 16-byte aligned");
+  AdrChainArgs a;
+  memset(&a, 0, sizeof(a));
+  a.nx = p->nx; a.ny = p->ny; a.k = adr_consts(*p);
+  a.x = x; a.prev2 = prev2; a.yn = yn; a.fn = fn;
+  int stored = 0;
+  for (int l = 0; l < nstages; l++)
+  {
+    for (int q = 0; q < 5; q++) a.c[l][q] = coeffs[5 * l + q];
+    a.out[l] = z_out[l];
+    if (a.out[l])
+    {
+      stored++;
+      if (!aligned16(a.out[l])) return fail("b200_adr_chain: output not 16-byte aligned");
+      if (a.out[l] == x || a.out[l] == prev2 || a.out[l] == yn || a.out[l] == fn) return fail("b200_adr_chain: an output aliases an input");
+    }
+  }
+  if (!a.out[nstages - 1]) return fail("b200_adr_chain: the last stage must be stored");
+  // rows per block: the largest of 128 / 64 / 32 / 16 that leaves >= 2 waves of blocks (2 per SM)
+  const int64_t gx    = adr_chain_grid(a.nx, a.ny, nstages, 16).x;
+  const int64_t waves = 2 * 2 * (int64_t)(c->sm_count > 0 ? c->sm_count : 148);
+  a.rows              = 16;
+  for (int r : {128, 64, 32})
+    if (gx * ((a.ny + r - 1) / r) >= waves) { a.rows = r; break; }
+  if ((a.ny + a.rows - 1) / a.rows > 65535) a.rows = (int)((a.ny + 65534) / 65535);
+  dim3 grid = adr_chain_grid(a.nx, a.ny, nstages, a.rows);
+  int rc    = 0;
+  switch (nstages)
+  {
+  case 2: rc = launch_adr_chain_k<2>(a, grid, c->stream); break;
+  case 3: rc = launch_adr_chain_k<3>(a, grid, c->stream); break;
+  case 4: rc = launch_adr_chain_k<4>(a, grid, c->stream); break;
+  case 5: rc = launch_adr_chain_k<5>(a, grid, c->stream); break;
+  default: rc = launch_adr_chain_k<6>(a, grid, c->stream); break;
+  }
+  if (rc) return rc;
+  LAUNCH_CHECK();
+  ALG_BYTES(4 + stored, 2 * p->nx * p->ny);
+  return 0;
+}
+
 // --------------------------------------------------------------------- NCCL
 // NCCL is resolved at first use with dlopen("libnccl.so.2") instead of being a link-time
 // dependency: inside a Python process torch has usually loaded its own bundled NCCL

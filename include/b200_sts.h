@@ -280,6 +280,17 @@ int b200_adr_diffusion_lincomb(b200_ctx* ctx, const b200_adr_params* p,
                                const int* src, const double* const* v, double* z,
                                double* f_out);
 
+/* Temporal blocking of the adr diffusion partition: `nstages` (2..B200_MAX_CHAIN) consecutive RKC / RKL
+   stages  z_l = c[l][0] F(z_{l-1}) + c[l][1] z_{l-2} + c[l][2] yn + c[l][3] z_{l-1} + c[l][4] fn  with
+   F = f_diffusion (adr/advection_diffusion_reaction_2d.cpp:1448-1491), z_0 = x, z_{-1} = prev2, in one
+   pass; bit-identical to nstages b200_adr_lincomb launches (mode 2, sources {2,0,0,1,0}).  coeffs is
+   [nstages][5]; z_out[l] may be NULL for a stage nobody reads (the last one must be stored).
+   nx >= 64, ny >= 16.  (k_adr_chain, csrc/adr_chain.cuh; verified on the host emulator, opt-in in the
+   adr driver through --sts_chain K until measured on the GPU.) */
+int b200_adr_chain(b200_ctx* ctx, const b200_adr_params* p, int nstages, const double* x,
+                   const double* prev2, const double* yn, const double* fn, const double* coeffs,
+                   double* const* z_out);
+
 /* --------------------------------------------------- multi-GPU (NCCL, NVLink) */
 /* One process per GPU.  rank 0 calls b200_comm_unique_id and distributes the 128
    bytes out of band (torch.distributed / a file); every rank then calls

@@ -125,3 +125,43 @@ EMU_API int emu_adr(const b200_adr_params* p, int mode, const double* y, int nte
   }
   return 0;
 }
+
+// b200_adr_chain on the emulator: K temporally blocked stages of the adr diffusion partition
+#include "adr_chain.cuh"
+
+namespace
+{
+template <int K>
+void run_adr_chain(const AdrChainArgs& a)
+{
+  emu::launch(k_adr_chain<K, kAdrChainPF>, adr_chain_grid(a.nx, a.ny, K, a.rows), kAdrChainThreads,
+              adr_chain_smem(K, kAdrChainPF), a);
+}
+} // namespace
+
+EMU_API int emu_adr_chain(const b200_adr_params* p, int K, const double* x, const double* prev2, const double* yn,
+                          const double* fn, const double* coeffs, double* const* out, int rows, int lazy_cp_async)
+{
+  if (!adr_chain_supported(p->nx, p->ny, K)) return -1;
+  AdrChainArgs a;
+  memset(&a, 0, sizeof(a));
+  a.nx = p->nx; a.ny = p->ny; a.k = adr_consts(*p);
+  a.x = x; a.prev2 = prev2; a.yn = yn; a.fn = fn;
+  for (int l = 0; l < K; l++)
+  {
+    for (int q = 0; q < 5; q++) a.c[l][q] = coeffs[5 * l + q];
+    a.out[l] = out[l];
+  }
+  a.rows             = rows;
+  emu::cp_async_lazy = lazy_cp_async != 0;
+  switch (K)
+  {
+  case 2: run_adr_chain<2>(a); break;
+  case 3: run_adr_chain<3>(a); break;
+  case 4: run_adr_chain<4>(a); break;
+  case 5: run_adr_chain<5>(a); break;
+  case 6: run_adr_chain<6>(a); break;
+  default: return -1;
+  }
+  return 0;
+}

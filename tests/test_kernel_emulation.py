@@ -468,3 +468,39 @@ def test_adr_kernel_every_composite_bit_exact(emu, orc, size, mode):
     f2 = _aligned(np.full(n, np.nan))
     assert emu.emu_adr(ctypes.byref(bp), mode, P(y), 0, None, None, None, None, P(f2), 5) == 0
     assert np.array_equal(f2, F)
+
+
+@pytest.mark.parametrize("size", [(64, 16, 64), (100, 21, 5), (250, 26, 8)], ids=lambda s: "%dx%d_rows%d" % s)
+@pytest.mark.parametrize("k", [2, 3, 4, 6])
+def test_adr_chain_kernel_equals_single_stage_launches(emu, orc, size, k):
+    """k_adr_chain (csrc/adr_chain.cuh): K stages of the adr diffusion partition in one pass must be bit-identical
+    to K launches of k_adr_march<2> with the LSRKStep stage pattern [F(y), z_{j-2}, yn, y, fn] (which is pinned
+    against the oracle above), including the periodic wrap in both directions and partial windows / row blocks."""
+    from conftest import OrcAdr
+
+    class AdrParams(ctypes.Structure):
+        _fields_ = OrcAdr._fields_
+
+    nx, ny, rows = size
+    bp = AdrParams(nx, ny, 1.0 / nx, 1.0 / ny, -0.5, 1.0, 0.4, 0.7, 2e-2, 1.3, 1.0)
+    n = 2 * nx * ny
+    rng = np.random.default_rng(nx + 7 * ny + k)
+    x, p2, yn, fn = (_aligned(rng.standard_normal(n)) for _ in range(4))
+    coeffs = [[1e-4 * (l + 1), -0.3 + 0.1 * l, 0.2, 1.1 - 0.05 * l, -2e-4] for l in range(k)]
+    # reference: one fused launch per stage
+    want, prev, cur = [], p2, x
+    for l in range(k):
+        z = _aligned(np.full(n, np.nan))
+        vv = (ctypes.c_void_p * 5)(None, prev.ctypes.data, yn.ctypes.data, None, fn.ctypes.data)
+        assert emu.emu_adr(ctypes.byref(bp), 2, P(cur), 5, (ctypes.c_double * 5)(*coeffs[l]),
+                           (ctypes.c_int * 5)(2, 0, 0, 1, 0), vv, P(z), None, 8) == 0
+        want.append(z)
+        prev, cur = cur, z
+    cf = np.ascontiguousarray(np.array(coeffs).ravel())
+    for lazy, store in ((0, [True] * k), (1, [l >= k - 2 for l in range(k)])):
+        outs = [_aligned(np.full(n, np.nan)) if s else None for s in store]
+        optr = (ctypes.c_void_p * k)(*[o.ctypes.data if o is not None else None for o in outs])
+        assert emu.emu_adr_chain(ctypes.byref(bp), k, P(x), P(p2), P(yn), P(fn), P(cf), optr, rows, lazy) == 0
+        for l in range(k):
+            if store[l]:
+                assert np.array_equal(outs[l], want[l]), "level %d (lazy=%d)" % (l + 1, lazy)
