@@ -73,3 +73,33 @@ def test_cpu_sample_plan_is_bounded():
         n, steps = b.cpu_sample_plan(ranks)
         assert n in (2048, 4096) and 1 <= steps <= 40
         assert 5.0 <= 93.0 * n * n * steps / (7.5e7 * ranks) <= 30.0  # ~10 s of CPU work by the measured rate
+
+
+@pytest.mark.parametrize("fail_pin", ["0", "1"], ids=["pinned_ok", "pinned_alloc_fails"])
+def test_measured_arm_control_flow_and_contract_keys(fail_pin):
+    """bench.py's measured arm needs a B200; its host-side control flow does not.  tests/mock_bench_main.py runs
+    main() with torch.cuda and the package mocked: the line must carry every key of the contract, and a failing
+    pinned allocation must turn into an e2e error entry, not into an exception or a rank that stops taking part."""
+    env = dict(os.environ, MOCK_FAIL_PIN=fail_pin)
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "mock_bench_main.py"), "--steps", "3", "--warmup", "3"],
+                         capture_output=True, text=True, timeout=300, env=env, cwd="/tmp")
+    assert res.returncode == 0, res.stderr[-3000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
+        assert key in d, key
+    assert d["scaling"] == "weak" and d["dtype"] == "f64" and d["vs_baseline"] is None and d["data"] == "synthetic"
+    assert "workload" in d["config"] and "model" not in d["config"] and "arith" in d["config"]
+    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic", "kernel"):
+        assert key in d["roofline"], key
+    assert d["roofline"]["bound"] == "hbm" and d["roofline"]["unit"] == "GB/s"
+    for key in ("value", "unit", "cores", "kind", "sample"):
+        assert key in d["cpu_baseline"], key
+    for key in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert key in d["e2e"], key
+    if fail_pin == "1":
+        assert d["e2e"]["value"] is None and "error" in d["e2e"]
+    else:
+        assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 8 * 16384 * 16384
