@@ -1,7 +1,8 @@
 // cuda_emu.h -- TEST INFRASTRUCTURE ONLY: a minimal host emulation of the CUDA execution model,
 // just large enough to run the stage kernels of ceda-demonstrations_b200/csrc/*.cuh on CPU threads.
 //
-// One OS thread per CUDA thread of a block, blocks one after the other.  What is emulated:
+// One fiber per CUDA thread, a block on one OS thread, blocks one after the other: deterministic and
+// fast (a context switch costs a fraction of a microsecond).  What is emulated:
 //   threadIdx / blockIdx / blockDim / gridDim, dynamic and static shared memory, __syncthreads (block
 //   barrier), atomicAdd(unsigned) / __threadfence (the last-block ticket of the reductions),
 //   __shfl_{up,down,xor}_sync on doubles (per-warp exchange + barrier), exactly rounded FP64
@@ -14,15 +15,14 @@
 // Nothing in the product includes this file: kernel_prims.cuh pulls it in only under
 // B200_HOST_EMU, which only tests/emu/Makefile defines.
 #pragma once
-#include <barrier>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <functional>
 #include <memory>
-#include <thread>
 #include <vector>
 
 struct alignas(16) double2
@@ -43,17 +43,10 @@ struct dim3
 
 namespace emu
 {
-struct Warp
-{
-  std::unique_ptr<std::barrier<>> bar;
-  double xch[32];
-};
-struct Block
-{
-  std::unique_ptr<std::barrier<>> bar;
-  std::vector<Warp> warps;
-  char* smem = nullptr;
-};
+// One CUDA thread = one fiber; a block runs on ONE OS thread, blocks one after the other.  Fibers
+// are resumed warp by warp, lane by lane, and give the processor back only at barriers (a shuffle is two warp
+// barriers), so execution is deterministic and a context switch costs a fraction of a microsecond.
+struct Block;
 struct PendingCopy
 {
   void* dst;
@@ -66,8 +59,112 @@ struct ThreadState
   std::deque<std::vector<PendingCopy>> groups; // committed cp.async groups, oldest first
   std::vector<PendingCopy> open;               // copies issued since the last commit
 };
-inline thread_local ThreadState ts;
+// Context switch: callee-saved registers + stack pointer, no signal mask (glibc's swapcontext makes two
+// system calls per switch, which dominated the run time).  x86-64 System V only; defined once, in the
+// translation unit that sets EMU_DEFINE_SWITCH before including this header.
+#if !defined(__x86_64__)
+#error "tests/emu: the fiber switch is written for x86-64"
+#endif
+extern "C" void emu_switch(void** save_sp, void* load_sp);
+#ifdef EMU_DEFINE_SWITCH
+asm(R"(
+.text
+.globl emu_switch
+.hidden emu_switch
+.type emu_switch,@function
+emu_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size emu_switch,.-emu_switch
+)");
+#endif
+
+struct Fiber
+{
+  void* sp = nullptr; // saved stack pointer while the fiber is not running
+  char* stack = nullptr; // from stack_pool(): uninitialised, kept across launches (pages are touched on demand)
+  ThreadState st;
+  unsigned tid = 0;
+  bool done    = false;
+};
+struct Warp
+{
+  double xch[32];
+  int arrived = 0, alive = 32;
+  unsigned gen = 0;
+};
+struct Block
+{
+  std::vector<Warp> warps;
+  std::vector<Fiber> fibers;
+  int arrived = 0, alive = 0;
+  unsigned gen = 0;
+  unsigned long progress = 0; // barrier arrivals + finished threads: a scheduler pass without any is a deadlock
+  char* smem   = nullptr;
+  void* sched_sp = nullptr; // the scheduler's saved stack pointer
+  Fiber* cur     = nullptr;
+  std::function<void()> body; // kernel(args)
+};
+constexpr size_t kStackBytes = 256 * 1024;
+inline std::vector<std::unique_ptr<char[]>>& stack_pool()
+{
+  static thread_local std::vector<std::unique_ptr<char[]>> pool;
+  return pool;
+}
+inline thread_local Block* cur_block = nullptr;
+inline ThreadState& cur() { return cur_block->cur->st; }
 inline bool cp_async_lazy = false;
+
+inline void yield_to_scheduler()
+{
+  Block* b = cur_block;
+  emu_switch(&b->cur->sp, b->sched_sp);
+}
+inline void warp_barrier()
+{
+  Warp& w          = cur_block->warps[cur().warp];
+  const unsigned g = w.gen;
+  cur_block->progress++;
+  if (++w.arrived == w.alive) { w.arrived = 0; w.gen++; }
+  else
+    while (w.gen == g) yield_to_scheduler();
+}
+inline void block_barrier()
+{
+  Block* b         = cur_block;
+  const unsigned g = b->gen;
+  b->progress++;
+  if (++b->arrived == b->alive) { b->arrived = 0; b->gen++; }
+  else
+    while (b->gen == g) yield_to_scheduler();
+}
+inline void fiber_main()
+{
+  Block* b = cur_block;
+  Fiber* f = b->cur;
+  b->body();
+  // an exited thread no longer takes part in barriers (CUDA semantics): release whoever waits for it
+  f->done = true;
+  b->progress++;
+  Warp& w = b->warps[f->st.warp];
+  if (--w.alive > 0 && w.arrived == w.alive) { w.arrived = 0; w.gen++; }
+  if (--b->alive > 0 && b->arrived == b->alive) { b->arrived = 0; b->gen++; }
+  emu_switch(&f->sp, b->sched_sp); // never resumed
+  abort();
+}
 
 inline void run_copies(const std::vector<PendingCopy>& g)
 {
@@ -91,22 +188,23 @@ inline thread_local dim3 blockDim, gridDim;
 #define DSUB(a, b) ((double)(a) - (double)(b))
 #define DFMA(a, b, c) std::fma((double)(a), (double)(b), (double)(c))
 static inline double __ddiv_rn(double a, double b) { return a / b; }
-#define B200_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::ts.blk->smem)
+#define B200_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::cur().blk->smem)
 
-static inline void __syncthreads() { emu::ts.blk->bar->arrive_and_wait(); }
+static inline void __syncthreads() { emu::block_barrier(); }
 
 static inline double emu_shfl(double v, int src_lane)
 {
-  emu::Warp& w       = emu::ts.blk->warps[emu::ts.warp];
-  w.xch[emu::ts.lane] = v;
-  w.bar->arrive_and_wait();
+  emu::ThreadState& t = emu::cur();
+  emu::Warp& w        = t.blk->warps[t.warp];
+  w.xch[t.lane]       = v;
+  emu::warp_barrier();
   const double r = (src_lane >= 0 && src_lane < 32) ? w.xch[src_lane] : v;
-  w.bar->arrive_and_wait();
+  emu::warp_barrier();
   return r;
 }
-static inline double __shfl_up_sync(unsigned, double v, int d) { return emu_shfl(v, emu::ts.lane - d); }
-static inline double __shfl_down_sync(unsigned, double v, int d) { return emu_shfl(v, emu::ts.lane + d); }
-static inline double __shfl_xor_sync(unsigned, double v, int m) { return emu_shfl(v, emu::ts.lane ^ m); }
+static inline double __shfl_up_sync(unsigned, double v, int d) { return emu_shfl(v, emu::cur().lane - d); }
+static inline double __shfl_down_sync(unsigned, double v, int d) { return emu_shfl(v, emu::cur().lane + d); }
+static inline double __shfl_xor_sync(unsigned, double v, int m) { return emu_shfl(v, emu::cur().lane ^ m); }
 static inline double __shfl_sync(unsigned, double v, int src) { return emu_shfl(v, src & 31); }
 
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
@@ -126,31 +224,33 @@ static inline double2 ld_keep2(const double* p) { return *reinterpret_cast<const
 static inline void cp_async16(void* smem, const void* gmem)
 {
   if (((uintptr_t)smem & 15) || ((uintptr_t)gmem & 15)) abort(); // cp.async 16 needs 16-byte alignment
-  if (emu::cp_async_lazy) emu::ts.open.push_back({smem, gmem});
+  if (emu::cp_async_lazy) emu::cur().open.push_back({smem, gmem});
   else memcpy(smem, gmem, 16);
 }
 static inline void cp_async_commit()
 {
-  emu::ts.groups.push_back(std::move(emu::ts.open));
-  emu::ts.open.clear();
+  emu::cur().groups.push_back(std::move(emu::cur().open));
+  emu::cur().open.clear();
 }
 template <int N>
 static inline void cp_async_wait()
 {
-  while ((int)emu::ts.groups.size() > N)
+  while ((int)emu::cur().groups.size() > N)
   {
-    emu::run_copies(emu::ts.groups.front());
-    emu::ts.groups.pop_front();
+    emu::run_copies(emu::cur().groups.front());
+    emu::cur().groups.pop_front();
   }
 }
 
 namespace emu
 {
-// launch<<<grid, block, smem>>>: blocks sequentially, one OS thread per CUDA thread
+// launch<<<grid, block, smem>>>: blocks one after the other, each on the calling OS thread
 template <class Kernel, class Args>
 void launch(Kernel kernel, dim3 grid, unsigned nthreads, size_t smem_bytes, const Args& args)
 {
   if (nthreads % 32) abort();
+  auto& pool = stack_pool();
+  while (pool.size() < nthreads) pool.emplace_back(new char[kStackBytes]);
   std::vector<char> smem_store(smem_bytes + 64);
   char* smem = smem_store.data();
   smem += (64 - ((uintptr_t)smem & 63)) & 63;
@@ -160,29 +260,49 @@ void launch(Kernel kernel, dim3 grid, unsigned nthreads, size_t smem_bytes, cons
       Block blk;
       blk.smem = smem;
       memset(smem, 0xff, smem_bytes); // NaN-poison: a slot read before it was filled shows up
-      blk.bar = std::make_unique<std::barrier<>>((std::ptrdiff_t)nthreads);
       blk.warps.resize(nthreads / 32);
-      for (Warp& w : blk.warps) w.bar = std::make_unique<std::barrier<>>(32);
-      std::vector<std::thread> threads;
-      threads.reserve(nthreads);
+      blk.fibers.resize(nthreads);
+      blk.alive = (int)nthreads;
+      blk.body  = [&]() { kernel(args); };
+      cur_block = &blk;
       for (unsigned t = 0; t < nthreads; t++)
-        threads.emplace_back(
-          [&, t]()
-          {
-            threadIdx = {t, 0, 0};
-            blockIdx  = {bx, by, 0};
-            blockDim  = dim3(nthreads);
-            gridDim   = grid;
-            ts        = ThreadState();
-            ts.blk    = &blk;
-            ts.lane   = (int)(t & 31);
-            ts.warp   = (int)(t >> 5);
-            kernel(args);
-            // an exited thread no longer takes part in barriers (CUDA semantics)
-            blk.warps[ts.warp].bar->arrive_and_drop();
-            blk.bar->arrive_and_drop();
-          });
-      for (std::thread& th : threads) th.join();
+      {
+        Fiber& f  = blk.fibers[t];
+        f.tid     = t;
+        f.st.blk  = &blk;
+        f.st.lane = (int)(t & 31);
+        f.st.warp = (int)(t >> 5);
+        f.stack = pool[t].get();
+        // initial frame: six callee-saved registers, then the entry point as the return address; after the
+        // `ret` the stack pointer must be 8 modulo 16, as it is right after a call instruction
+        uintptr_t top = ((uintptr_t)(f.stack + kStackBytes) & ~(uintptr_t)15) - 8;
+        void** frame  = reinterpret_cast<void**>(top) - 7;
+        for (int q = 0; q < 6; q++) frame[q] = nullptr;
+        frame[6] = reinterpret_cast<void*>(&fiber_main);
+        f.sp     = frame;
+      }
+      blockIdx = {bx, by, 0};
+      blockDim = dim3(nthreads);
+      gridDim  = grid;
+      int remaining = (int)nthreads;
+      while (remaining > 0)
+      {
+        const unsigned long before = blk.progress;
+        for (Fiber& f : blk.fibers)
+        {
+          if (f.done) continue;
+          blk.cur   = &f;
+          threadIdx = {f.tid, 0, 0};
+          emu_switch(&blk.sched_sp, f.sp);
+          if (f.done) remaining--;
+        }
+        if (remaining > 0 && blk.progress == before)
+        {
+          fprintf(stderr, "cuda_emu: deadlock in block (%u, %u): %d threads wait at a barrier the others never reach\n", bx, by, remaining);
+          abort();
+        }
+      }
+      cur_block = nullptr;
     }
 }
 } // namespace emu

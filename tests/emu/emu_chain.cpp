@@ -2,6 +2,7 @@
 // (csrc/chain_march.cuh, csrc/chain_quad.cuh) on CPU threads through cuda_emu.h and exposes one
 // C entry point for the pytest side (tests/test_kernel_emulation.py).  Built by tests/emu/Makefile
 // with -DB200_HOST_EMU; the product never links this.
+#define EMU_DEFINE_SWITCH
 #include "b200_sts.h"
 #include "chain_march.cuh"
 #include "chain_quad.cuh"
