@@ -504,3 +504,89 @@ def test_adr_chain_kernel_equals_single_stage_launches(emu, orc, size, k):
         for l in range(k):
             if store[l]:
                 assert np.array_equal(outs[l], want[l]), "level %d (lazy=%d)" % (l + 1, lazy)
+
+
+def _random_shapes(count, seed):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(count):
+        nx = int(rng.integers(64, 350)) * 2
+        ny = int(rng.integers(16, 90))
+        rows = int(rng.integers(1, 48))
+        k = int(rng.integers(2, 7))
+        out.append((nx, ny, rows, k, int(rng.integers(0, 2)), int(rng.integers(0, 2))))
+    return out
+
+
+@pytest.mark.parametrize("shape", _random_shapes(40, 2026), ids=lambda s: "%dx%d_rows%d_k%d_v%d_l%d" % s)
+def test_chain_kernels_random_shapes_bit_exact(emu, shape):
+    """Seeded random widths (even, 128..698), heights, rows per block (1..47, mostly not dividing ny), depths,
+    both kernels, both cp.async completion orders: every level against the numpy restatement."""
+    nx, ny, rows, k, variant, lazy = shape
+    rng = np.random.default_rng(nx * 1009 + ny * 31 + rows + k)
+    tabs = [rng.random(nx) + 0.5, rng.random(nx) + 0.5, rng.random(ny) + 0.5, rng.random(ny) + 0.5]
+    ops = [np.ascontiguousarray(rng.standard_normal(nx * ny)) for _ in range(4)]
+    coeffs = coeffs_for(k)
+    want = chain_np(*tabs, *[o.reshape(ny, nx) for o in ops], coeffs)
+    store = [bool(rng.integers(0, 2)) or l == k - 1 for l in range(k)]
+    rc, outs = run_emu(emu, variant, k, 0, lazy, nx, ny, [tabs[0].ctypes.data, tabs[1].ctypes.data],
+                       [tabs[2].ctypes.data, tabs[3].ctypes.data], ops, coeffs, rows, store)
+    assert rc == 0
+    for l in range(k):
+        if store[l]:
+            assert np.array_equal(outs[l], want[l].ravel()), "level %d" % (l + 1)
+
+
+@pytest.mark.parametrize("shape", _random_shapes(16, 777), ids=lambda s: "%dx%d_rows%d_k%d_v%d_l%d" % s)
+def test_chain_kernels_random_decompositions_bit_exact(emu, shape):
+    """The halo flavour on a random block of a random 2 x 2 / 3 x 2 decomposition of a periodic field."""
+    nx, ny, rows, k, variant, lazy = shape
+    g, g2, M = 6, 6, 16
+    rng = np.random.default_rng(nx + ny + rows + k)
+    npx, npy = int(rng.integers(2, 4)), 2
+    bi, bj = int(rng.integers(0, npx)), int(rng.integers(0, npy))
+    NX, NY = npx * nx, npy * ny
+    T = [rng.random(NX) + 0.5, rng.random(NX) + 0.5, rng.random(NY) + 0.5, rng.random(NY) + 0.5]
+    G = [rng.standard_normal((NY, NX)) for _ in range(4)]
+    coeffs = coeffs_for(k)
+    want = chain_np(*T, *G, coeffs)
+    i0, j0 = bi * nx, bj * ny
+    ext_x = [np.ascontiguousarray(t[np.arange(i0 - M, i0 + nx + M) % NX]) for t in T[:2]]
+    ext_y = [np.ascontiguousarray(t[np.arange(j0 - M, j0 + ny + M) % NY]) for t in T[2:]]
+    ops = [np.ascontiguousarray(f[j0:j0 + ny, i0:i0 + nx].ravel()) for f in G]
+    halos = [deep_halo(f, i0, j0, nx, ny, g, g2) for f in G]
+    rc, outs = run_emu(emu, variant, k, 0, lazy, nx, ny, [t.ctypes.data + 8 * M for t in ext_x],
+                       [t.ctypes.data + 8 * M for t in ext_y], ops, coeffs, rows, [True] * k, halos, g, g2)
+    assert rc == 0
+    for l in range(k):
+        assert np.array_equal(outs[l], want[l][j0:j0 + ny, i0:i0 + nx].ravel()), "level %d" % (l + 1)
+
+
+@pytest.mark.parametrize("shape", _random_shapes(12, 4242), ids=lambda s: "%dx%d_rows%d_k%d_v%d_l%d" % s)
+def test_adr_chain_random_shapes_bit_exact(emu, shape):
+    from conftest import OrcAdr
+
+    class AdrParams(ctypes.Structure):
+        _fields_ = OrcAdr._fields_
+
+    nx, ny, rows, k, _, lazy = shape
+    nx //= 2  # grid points (each is two doubles); 64..349, odd widths included
+    bp = AdrParams(nx, ny, 1.0 / nx, 1.0 / ny, -0.5, 1.0, 0.4, 0.7, 3e-2, 1.3, 1.0)
+    n = 2 * nx * ny
+    rng = np.random.default_rng(nx * 17 + ny + k)
+    x, p2, yn, fn = (_aligned(rng.standard_normal(n)) for _ in range(4))
+    coeffs = [[1e-4 * (l + 1), -0.3 + 0.1 * l, 0.2, 1.1 - 0.05 * l, -2e-4] for l in range(k)]
+    want, prev, cur = [], p2, x
+    for l in range(k):
+        z = _aligned(np.full(n, np.nan))
+        vv = (ctypes.c_void_p * 5)(None, prev.ctypes.data, yn.ctypes.data, None, fn.ctypes.data)
+        assert emu.emu_adr(ctypes.byref(bp), 2, P(cur), 5, (ctypes.c_double * 5)(*coeffs[l]),
+                           (ctypes.c_int * 5)(2, 0, 0, 1, 0), vv, P(z), None, 8) == 0
+        want.append(z)
+        prev, cur = cur, z
+    outs = [_aligned(np.full(n, np.nan)) for _ in range(k)]
+    optr = (ctypes.c_void_p * k)(*[o.ctypes.data for o in outs])
+    cf = np.ascontiguousarray(np.array(coeffs).ravel())
+    assert emu.emu_adr_chain(ctypes.byref(bp), k, P(x), P(p2), P(yn), P(fn), P(cf), optr, rows, lazy) == 0
+    for l in range(k):
+        assert np.array_equal(outs[l], want[l]), "level %d" % (l + 1)
