@@ -15,6 +15,7 @@
  * multiply-add, and the reference's own association order, so that elementwise
  * results are bit-identical to the reference's CPU build (gcc -O2, baseline
  * x86-64).  Reductions are deterministic (fixed tree) but not sequential.
+ * The one opt-in exception is b200_set_contract(1) (chain kernels only, see there).
  */
 #ifndef B200_STS_H
 #define B200_STS_H
