@@ -590,3 +590,23 @@ def test_adr_chain_random_shapes_bit_exact(emu, shape):
     assert emu.emu_adr_chain(ctypes.byref(bp), k, P(x), P(p2), P(yn), P(fn), P(cf), optr, rows, lazy) == 0
     for l in range(k):
         assert np.array_equal(outs[l], want[l]), "level %d" % (l + 1)
+
+
+@pytest.mark.parametrize("k", [2, 4, 6])
+def test_uniform_flavour_with_fma_arithmetic(emu, k):
+    """The <FMA, UNI> instantiations: uniform coefficients from kernel parameters with contracted multiply-adds
+    must equal the table-driven FMA launch bit for bit (same operations, same operands)."""
+    nx, ny, rows = 196, 23, 7
+    u4 = [0.9, 0.9, 1.6, 1.6]
+    rng = np.random.default_rng(50 + k)
+    tabs = [np.full(nx, u4[0]), np.full(nx, u4[1]), np.full(ny, u4[2]), np.full(ny, u4[3])]
+    ops = [np.ascontiguousarray(rng.standard_normal(nx * ny)) for _ in range(4)]
+    coeffs = coeffs_for(k)
+    cx = [tabs[0].ctypes.data, tabs[1].ctypes.data]
+    cy = [tabs[2].ctypes.data, tabs[3].ctypes.data]
+    rc, tab = run_emu(emu, 0, k, 1, 0, nx, ny, cx, cy, ops, coeffs, rows, [True] * k)
+    assert rc == 0
+    rc, uni = run_emu(emu, 0, k, 1, 1, nx, ny, cx, cy, ops, coeffs, rows, [True] * k, uniform=u4)
+    assert rc == 0
+    for l in range(k):
+        assert np.array_equal(uni[l], tab[l]), "level %d" % (l + 1)
