@@ -15,9 +15,15 @@
 //   Jacobi setup       diffusion_2D/preconditioner_jacobi.cpp:9-46
 //   adr callbacks      adr/advection_diffusion_reaction_2d.cpp:1406-1520
 
+#ifdef B200_HOST_EMU
+// tests/emu only: the same translation unit compiled with g++ against a host emulation of the CUDA runtime and
+// execution model, so that the host stack above the C-ABI can be tested without a GPU.  Never part of the product.
+#include "cuda_runtime_emu.h"
+#else
 #include <cuda_runtime.h>
-#include <dlfcn.h>
 #include <nccl.h> // types only: the library is bound with dlopen (see nccl_api below)
+#endif
+#include <dlfcn.h>
 
 #include <atomic>
 #include <cstdint>
@@ -26,7 +32,26 @@
 #include <cstring>
 #include <vector>
 
+#ifdef B200_HOST_EMU
+#pragma GCC visibility push(default) // the emulated build hides everything but the C-ABI
+#endif
 #include "b200_sts.h"
+#ifdef B200_HOST_EMU
+#pragma GCC visibility pop
+#endif
+#include "kernel_prims.cuh"
+
+// every kernel launch of the library goes through here
+template <class... KArgs, class... Args>
+static inline void klaunch(void (*kern)(KArgs...), dim3 grid, unsigned block, size_t smem, cudaStream_t st, Args&&... args)
+{
+#ifdef B200_HOST_EMU
+  (void)st;
+  emu::launch_body(grid, block, smem, [&]() { kern(args...); });
+#else
+  kern<<<grid, block, smem, st>>>(args...);
+#endif
+}
 
 // --------------------------------------------------------------------- errors
 static thread_local char g_err[512] = "";
@@ -200,7 +225,7 @@ __global__ void k_publish_small(double* __restrict__ host_mapped, const double* 
 }
 static int read_small(b200_ctx* c, double* dst, const double* src, int n)
 {
-  k_publish_small<<<1, 32, 0, c->stream>>>(c->host_result_dev, src, n);
+  klaunch(k_publish_small, 1, 32, 0, c->stream, c->host_result_dev, src, n);
   CU_TRY(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
   CU_TRY(cudaStreamSynchronize(c->stream));
@@ -390,7 +415,7 @@ static int launch_ew(b200_ctx* c, const EwArgs& a)
   int64_t cap    = (int64_t)c->sm_count * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  k_elementwise<OP><<<(unsigned)blocks, kThreads, 0, c->stream>>>(a);
+  klaunch(k_elementwise<OP>, (unsigned)blocks, kThreads, 0, c->stream, a);
   LAUNCH_CHECK();
   const int reads = (OP == EW_LINCOMB) ? a.t.n
                     : (OP == EW_CONST) ? 0
@@ -492,7 +517,7 @@ static int run_reduce(b200_ctx* c, const double* x, const double* y, int64_t n, 
   int64_t cap    = (int64_t)c->sm_count * 4;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  k_reduce<KIND, ROP><<<(unsigned)blocks, kThreads, 0, c->stream>>>(x, y, n, c->partials, c->ticket, c->dev_result);
+  klaunch(k_reduce<KIND, ROP>, (unsigned)blocks, kThreads, 0, c->stream, x, y, n, c->partials, c->ticket, c->dev_result);
   LAUNCH_CHECK();
   ALG_BYTES((KIND == RD_DOT || KIND == RD_WSQR) ? 2 : 1, n);
   if (c->comm && c->nranks > 1)
@@ -530,9 +555,9 @@ extern "C" int b200_l1norm(b200_ctx* c, const double* x, int64_t n, double* r)
 template <int NT, uint32_t PAT>
 static void launch_march(const StageArgs& a, dim3 grid, cudaStream_t st)
 {
-  if (a.region == 2) k_stage_march<NT, PAT, 2, false><<<grid, kThreads, 0, st>>>(a);
-  else if (a.rw) k_stage_march<NT, PAT, 0, true><<<grid, kThreads, 0, st>>>(a);
-  else k_stage_march<NT, PAT, 0, false><<<grid, kThreads, 0, st>>>(a);
+  if (a.region == 2) klaunch(k_stage_march<NT, PAT, 2, false>, grid, kThreads, 0, st, a);
+  else if (a.rw) klaunch(k_stage_march<NT, PAT, 0, true>, grid, kThreads, 0, st, a);
+  else klaunch(k_stage_march<NT, PAT, 0, false>, grid, kThreads, 0, st, a);
 }
 
 // pick the compiled pattern for the term sequence, else the general kernel
@@ -616,7 +641,7 @@ extern "C" int b200_stencil_lincomb(b200_ctx* c, const b200_stencil_geom* g, con
   {
     int64_t cells  = 2 * a.nx + 2 * (a.ny - 2);
     unsigned blocks = (unsigned)((cells + kThreads - 1) / kThreads);
-    k_stage_ring<<<blocks, kThreads, 0, c->stream>>>(a);
+    klaunch(k_stage_ring, blocks, kThreads, 0, c->stream, a);
     LAUNCH_CHECK();
     return 0;
   }
@@ -650,7 +675,7 @@ extern "C" int b200_stencil_lincomb(b200_ctx* c, const b200_stencil_geom* g, con
     if (a.ny > 65535) return fail("b200_stencil_lincomb: generic path supports ny <= 65535");
     if (a.rw && gx * a.ny > kMaxPartials) return fail("b200_stencil_lincomb: too many blocks for fused WRMS");
     dim3 grid((unsigned)gx, (unsigned)a.ny);
-    k_stage_generic<<<grid, kThreads, 0, c->stream>>>(a);
+    klaunch(k_stage_generic, grid, kThreads, 0, c->stream, a);
     LAUNCH_CHECK();
   }
   {
@@ -675,7 +700,7 @@ static int launch_chain_k(const ChainArgs& a, dim3 grid, cudaStream_t st)
     CU_TRY(cudaFuncSetAttribute(k_chain_march<K, PF, HALO, FMA, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  k_chain_march<K, PF, HALO, FMA, UNI><<<grid, kChainThreads, smem, st>>>(a);
+  klaunch(k_chain_march<K, PF, HALO, FMA, UNI>, grid, kChainThreads, smem, st, a);
   return 0;
 }
 
@@ -713,7 +738,7 @@ static int launch_quad_k(const ChainArgs& a, dim3 grid, cudaStream_t st)
     CU_TRY(cudaFuncSetAttribute(k_chain_quad<K, PF, HALO, FMA, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  k_chain_quad<K, PF, HALO, FMA, MINB><<<grid, kQuadThreads, smem, st>>>(a);
+  klaunch(k_chain_quad<K, PF, HALO, FMA, MINB>, grid, kQuadThreads, smem, st, a);
   return 0;
 }
 template <int K, int PF, int MINB>
@@ -939,7 +964,7 @@ extern "C" int b200_deep_halo_exchange(b200_ctx* c, const int peers[4], int x_sp
     {
       double* ws = c->strips + (size_t)(2 * f) * strip;
       double* es = ws + strip;
-      k_pack_strips<<<blocks, kThreads, 0, c->stream>>>(fields[f], halos[f], nx, ny, g, g2, ws, es);
+      klaunch(k_pack_strips, blocks, kThreads, 0, c->stream, fields[f], halos[f], nx, ny, g, g2, ws, es);
       LAUNCH_CHECK();
       lo[f]  = ws;                              // my west columns -> W neighbour's E halo
       hi[f]  = es;                              // my east columns -> E neighbour's W halo
@@ -954,7 +979,7 @@ extern "C" int b200_deep_halo_exchange(b200_ctx* c, const int peers[4], int x_sp
   {
     for (int f = 0; f < nfields; f++)
     { // one rank in x: my own east columns are my W halo and vice versa
-      k_pack_strips<<<blocks, kThreads, 0, c->stream>>>(fields[f], halos[f], nx, ny, g, g2,
+      klaunch(k_pack_strips, blocks, kThreads, 0, c->stream, fields[f], halos[f], nx, ny, g, g2,
                                                         halos[f] + 2 * srow + strip, halos[f] + 2 * srow);
       LAUNCH_CHECK();
     }
@@ -967,7 +992,7 @@ extern "C" int b200_pack_halo(b200_ctx* c, const double* u, int64_t nx, int64_t 
                               double* sw, double* se, double* ss, double* sn)
 {
   int64_t m = nx > ny ? nx : ny;
-  k_pack<<<(unsigned)((m + kThreads - 1) / kThreads), kThreads, 0, c->stream>>>(u, nx, ny, sw, se, ss, sn);
+  klaunch(k_pack, (unsigned)((m + kThreads - 1) / kThreads), kThreads, 0, c->stream, u, nx, ny, sw, se, ss, sn);
   LAUNCH_CHECK();
   return 0;
 }
@@ -979,7 +1004,7 @@ extern "C" int b200_jacobi_setup(b200_ctx* c, int64_t nx, int64_t ny, const doub
 {
   if (ny > 65535) return fail("b200_jacobi_setup: ny <= 65535");
   dim3 grid((unsigned)((nx + kThreads - 1) / kThreads), (unsigned)ny);
-  k_jacobi<<<grid, kThreads, 0, c->stream>>>(nx, ny, pxw, pxe, pys, pyn, gamma, diag);
+  klaunch(k_jacobi, grid, kThreads, 0, c->stream, nx, ny, pxw, pxe, pys, pyn, gamma, diag);
   LAUNCH_CHECK();
   ALG_BYTES(1, nx * ny);
   return 0;
@@ -1002,13 +1027,13 @@ static int launch_adr(b200_ctx* c, AdrArgs& a, int mode)
   dim3 grid((unsigned)gx, (unsigned)gy);
   switch (mode)
   {
-  case 1: k_adr_march<1><<<grid, kThreads, 0, c->stream>>>(a); break;
-  case 2: k_adr_march<2><<<grid, kThreads, 0, c->stream>>>(a); break;
-  case 3: k_adr_march<3><<<grid, kThreads, 0, c->stream>>>(a); break;
-  case 4: k_adr_march<4><<<grid, kThreads, 0, c->stream>>>(a); break;
-  case 5: k_adr_march<5><<<grid, kThreads, 0, c->stream>>>(a); break;
-  case 6: k_adr_march<6><<<grid, kThreads, 0, c->stream>>>(a); break;
-  default: k_adr_march<7><<<grid, kThreads, 0, c->stream>>>(a); break;
+  case 1: klaunch(k_adr_march<1>, grid, kThreads, 0, c->stream, a); break;
+  case 2: klaunch(k_adr_march<2>, grid, kThreads, 0, c->stream, a); break;
+  case 3: klaunch(k_adr_march<3>, grid, kThreads, 0, c->stream, a); break;
+  case 4: klaunch(k_adr_march<4>, grid, kThreads, 0, c->stream, a); break;
+  case 5: klaunch(k_adr_march<5>, grid, kThreads, 0, c->stream, a); break;
+  case 6: klaunch(k_adr_march<6>, grid, kThreads, 0, c->stream, a); break;
+  default: klaunch(k_adr_march<7>, grid, kThreads, 0, c->stream, a); break;
   }
   LAUNCH_CHECK();
   return 0;
@@ -1078,7 +1103,7 @@ static int launch_adr_chain_k(const AdrChainArgs& a, dim3 grid, cudaStream_t st)
     CU_TRY(cudaFuncSetAttribute(k_adr_chain<K, kAdrChainPF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  k_adr_chain<K, kAdrChainPF><<<grid, kAdrChainThreads, smem, st>>>(a);
+  klaunch(k_adr_chain<K, kAdrChainPF>, grid, kAdrChainThreads, smem, st, a);
   return 0;
 }
 

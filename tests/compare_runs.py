@@ -4,7 +4,8 @@ line and compare integrator statistics and the final state.
 
 usage: python scripts/compare_runs.py [--np P] -- <diffusion_2D args...>
 
-Used by the GPU parity tests (tests/test_parity_gpu.py) and by hand.
+Test infrastructure (it executes oracle/_ref): used by the GPU parity tests
+(tests/test_parity_gpu.py) and by hand.
 """
 import os
 import re
@@ -74,6 +75,66 @@ def read_solution(workdir, nx, ny):
         i0, i1, j0, j1 = int(hdr["is"]), int(hdr["ie"]), int(hdr["js"]), int(hdr["je"])
         u[j0 : j1 + 1, i0 : i1 + 1] = vals[1:].reshape(j1 - j0 + 1, i1 - i0 + 1)
     return t_final, u
+
+
+_text_lib = None
+
+
+def text_lib():
+    """oracle/liboracle_sts.so's text helpers (oracle/ref_text.c): the reference's only state output is
+    16-digit text, one line per output time; at 10^7..10^8 values numpy parsing takes minutes."""
+    global _text_lib
+    if _text_lib is None:
+        import ctypes
+
+        lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "liboracle_sts.so"))
+        lib.orc_text_last_line.restype = ctypes.c_long
+        lib.orc_text_last_line.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p]
+        lib.orc_text_print_mismatches.restype = ctypes.c_long
+        lib.orc_text_print_mismatches.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long]
+        _text_lib = lib
+    return _text_lib
+
+
+def read_solution_fast(workdir, nx, ny):
+    """read_solution for large grids: header lines in Python, the last data line of every rank file in C."""
+    import ctypes
+
+    lib = text_lib()
+    u = np.full((ny, nx), np.nan)
+    t_final = None
+    for name in sorted(os.listdir(workdir)):
+        if not name.startswith("diffusion_2d_solution."):
+            continue
+        path = os.path.join(workdir, name)
+        hdr = {}
+        with open(path) as f:
+            while True:
+                line = f.readline(256)
+                if not line.startswith("#"):
+                    break
+                parts = line[1:].split()
+                if len(parts) >= 2:
+                    hdr[parts[0]] = parts[1]
+        i0, i1, j0, j1 = int(hdr["is"]), int(hdr["ie"]), int(hdr["js"]), int(hdr["je"])
+        n = (j1 - j0 + 1) * (i1 - i0 + 1)
+        vals = np.empty(n)
+        t = ctypes.c_double()
+        got = lib.orc_text_last_line(path.encode(), vals.ctypes.data, n, ctypes.byref(t))
+        if got != n:
+            raise RuntimeError("%s: expected %d values in the last line, found %d" % (path, n, got))
+        t_final = t.value
+        u[j0 : j1 + 1, i0 : i1 + 1] = vals.reshape(j1 - j0 + 1, i1 - i0 + 1)
+    return t_final, u
+
+
+def print_mismatches(ours, ref):
+    """How many values of `ours` do not print ("%.15e", diffusion_2D.cpp:819-824) to the characters the reference
+    printed (`ref` = its output parsed back)."""
+    a = np.ascontiguousarray(ours, dtype=np.float64).ravel()
+    b = np.ascontiguousarray(ref, dtype=np.float64).ravel()
+    assert a.size == b.size
+    return int(text_lib().orc_text_print_mismatches(a.ctypes.data, b.ctypes.data, a.size))
 
 
 def run(binary, args, np_ranks=1, env_extra=None, timeout=600):

@@ -244,9 +244,9 @@ static inline void cp_async_wait()
 
 namespace emu
 {
-// launch<<<grid, block, smem>>>: blocks one after the other, each on the calling OS thread
-template <class Kernel, class Args>
-void launch(Kernel kernel, dim3 grid, unsigned nthreads, size_t smem_bytes, const Args& args)
+// launch<<<grid, block, smem>>>: blocks one after the other, each on the calling OS thread; `body` is what every
+// CUDA thread executes (the kernel bound to its arguments)
+inline void launch_body(dim3 grid, unsigned nthreads, size_t smem_bytes, const std::function<void()>& body)
 {
   if (nthreads % 32) abort();
   auto& pool = stack_pool();
@@ -263,7 +263,7 @@ void launch(Kernel kernel, dim3 grid, unsigned nthreads, size_t smem_bytes, cons
       blk.warps.resize(nthreads / 32);
       blk.fibers.resize(nthreads);
       blk.alive = (int)nthreads;
-      blk.body  = [&]() { kernel(args); };
+      blk.body  = body;
       cur_block = &blk;
       for (unsigned t = 0; t < nthreads; t++)
       {
@@ -304,5 +304,10 @@ void launch(Kernel kernel, dim3 grid, unsigned nthreads, size_t smem_bytes, cons
       }
       cur_block = nullptr;
     }
+}
+template <class Kernel, class Args>
+void launch(Kernel kernel, dim3 grid, unsigned nthreads, size_t smem_bytes, const Args& args)
+{
+  launch_body(grid, nthreads, smem_bytes, [&]() { kernel(args); });
 }
 } // namespace emu

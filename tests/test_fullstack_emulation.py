@@ -1,0 +1,193 @@
+"""The whole product stack on a CPU (no GPU needed): unchanged ARKODE -> N_Vector_B200 (lazy stage fusion, pending-stage
+chains, fused WRMS) -> problem layers (diffusion_2D / adr callbacks) -> the C-ABI of csrc/b200_kernels.cu -> the
+kernel SOURCES executed by the host emulator (tests/emu: one fiber per CUDA thread, emulated CUDA runtime).
+
+This is test infrastructure (tests/emu/Makefile `fullstack`; built lazily here): it exists so that the host logic
+above the C-ABI -- which only ever runs against a device in the product -- is covered by the `-m "not gpu"` suite
+against the SAME reference fixtures the GPU suite uses (tests/golden, written by the unmodified reference build),
+with the same bars: equal integrator statistics, fixed-step states equal to every printed digit, adaptive states
+within 1e-10 relative L2 (or the reference's own np=1 / np=4 spread).  The emulated library has its own file name,
+binds -Bsymbolic and is loaded RTLD_LOCAL only by this module; the product never sees it.
+"""
+import ctypes
+import importlib
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+from conftest import GOLDEN, ROOT, fmt16, load_golden
+
+EMU_DIR = os.path.join(ROOT, "tests", "emu")
+EMU_LIB = os.path.join(EMU_DIR, "_build", "libb200_fullstack_emu.so")
+REL_L2_TOL = 1e-10
+
+STAT_MAP = {"steps": "steps", "attempts": "step_attempts", "err_fails": "err_test_fails", "rhs_evals": "rhs_evals",
+            "rhs_evals_e": "rhs_evals", "rhs_evals_i": "rhs_evals", "dom_eig_updates": "dom_eig_updates",
+            "max_stages": "max_stages", "dee_evals": "dee_rhs_evals", "lin_iters": "lin_iters",
+            "nls_iters": "nonlin_iters", "prec_solves": "prec_solves"}
+
+
+@pytest.fixture(scope="module")
+def emu(b200):
+    """The package's ctypes classes bound to the emulated library for the duration of this module."""
+    if not os.path.exists(os.path.join(ROOT, "ceda-demonstrations_b200", "_sundials", "lib", "libsundials_host.so")):
+        pytest.skip("SUNDIALS host library not built")
+    subprocess.run(["make", "-s", "-C", EMU_DIR, "fullstack"], check=True)
+    lib = ctypes.CDLL(EMU_LIB)  # RTLD_LOCAL
+    lib.b200_last_error.restype = ctypes.c_char_p
+    lib.b200_launch_count.restype = ctypes.c_uint64
+    lib.b200_last_chain_kernel.restype = ctypes.c_char_p
+    saved = (b200._kernel_lib, b200._sundials_lib)
+    b200._kernel_lib = b200._sundials_lib = lib
+    yield b200
+    b200._kernel_lib, b200._sundials_lib = saved
+
+
+def run_d2d(b200, args):
+    args = [str(a) for a in args] + ["--nout", "1", "--output", "0"]
+    prob = b200.Diffusion2D(args, device=0, stream=None)
+    tf = float(args[args.index("--tf") + 1]) if "--tf" in args else 1.0
+    prob.evolve(tf)
+    st = prob.stats()
+    u = np.empty(st["nx_loc"] * st["ny_loc"])
+    prob.get_state(u)
+    prob.close()
+    return st, u.reshape(st["ny_loc"], st["nx_loc"])
+
+
+def check_stats(meta, st, implicit):
+    np4 = meta.get("stats_np4", {})
+    for k, v in meta["stats"].items():
+        if k not in STAT_MAP or (k == "rhs_evals_e" and implicit) or (k == "rhs_evals_i" and not implicit):
+            continue
+        v4 = np4.get(k, v)
+        d = abs(v4 - v)
+        assert min(v, v4) - d <= st[STAT_MAP[k]] <= max(v, v4) + d, (k, st[STAT_MAP[k]], v, v4)
+
+
+D2D_CASES = ["c1_rkc_128", "rkc_fixed_aniso_inhom_96x64", "rkl_fixed_aniso_inhom_96x64", "rkl_adaptive_inhom_64",
+             "rkl_internaleig_64", "rkc_odd_75x51", "ssp2_fixed_64", "ssp3_fixed_64", "ssp104_fixed_64",
+             "ssp104_adaptive_64", "erk3_adaptive_64", "dirk3_pcg_64", "dirk2_pcg_inhom_noprec_48"]
+
+
+@pytest.mark.parametrize("name", D2D_CASES)
+def test_diffusion_fixture_parity_through_the_emulated_stack(emu, name):
+    meta, ref = load_golden(name)
+    st, u = run_d2d(emu, meta["args"])
+    check_stats(meta, st, "dirk" in meta["args"])
+    assert st["t"] == meta["t_final"]
+    rel = float(np.linalg.norm(u - ref) / np.linalg.norm(ref))
+    if "--fixedstep" in meta["args"]:
+        assert np.array_equal(fmt16(u), fmt16(ref)), rel
+    else:
+        assert rel <= max(REL_L2_TOL, 3.0 * meta["ref_np1_vs_np4_rel_l2"]), rel
+    assert st["kernel_launches"] > 0
+    if any(m in meta["args"] for m in ("rkc", "rkl")):
+        assert st["fused_launches"] >= 0.9 * (st["rhs_evals"] - 4)
+
+
+# minutes on the emulator (thousands of steps); they stay in the GPU suite
+SWEEP_SLOW = ("sweep_erk4_32_kx0.1_h0.00015625", "sweep_dirk3_32_kx1_h0.0025", "sweep_dirk2_64_kx1_rtol0.0001",
+              "sweep_rkc_64_kx1_h0.00125")
+SWEEP_SMALL = sorted(n for n in (os.path.basename(p)[4:-5] for p in __import__("glob").glob(os.path.join(GOLDEN, "d2d_sweep_*.json")))
+                     if "_256_" not in n and "_128_" not in n and n not in SWEEP_SLOW)
+
+
+@pytest.mark.parametrize("name", SWEEP_SMALL)
+def test_reference_sweep_sample_through_the_emulated_stack(emu, name):
+    """The 32^2 / 64^2 rows of the sample of the reference's evaluation matrix (runtests-diffusion2d.py)."""
+    meta, ref = load_golden(name)
+    st, u = run_d2d(emu, meta["args"])
+    check_stats(meta, st, "dirk" in meta["args"])
+    rel = float(np.linalg.norm(u - ref) / np.linalg.norm(ref))
+    assert rel <= max(REL_L2_TOL, 3.0 * meta["ref_np1_vs_np4_rel_l2"]), rel
+
+
+CHAIN_ARGS = [
+    ["--nx", 128, "--ny", 48, "--kx", "1.0", "--ky", "0.5", "--inhomogeneous", "--integrator", "rkc",
+     "--fixedstep", "0.0009765625", "--tf", "0.001953125"],
+    ["--nx", 130, "--ny", 40, "--integrator", "rkl", "--fixedstep", "0.001953125", "--tf", "0.00390625"],
+    ["--nx", 128, "--ny", 64, "--integrator", "rkc", "--tf", "0.05"],
+]
+
+
+@pytest.mark.parametrize("args", CHAIN_ARGS, ids=["rkc_fixed_inhom_128x48", "rkl_fixed_uniform_130x40", "rkc_adaptive_128x64"])
+def test_temporal_blocking_and_deep_halo_paths_do_not_change_a_bit(emu, args):
+    """--chain K (pending-stage chains -> k_chain_march), the k_chain_quad variant and the deep-halo flavour
+    (--force-halo: halo buffers, extended tables, local-copy exchange) against one launch per stage."""
+    st1, u1 = run_d2d(emu, args + ["--chain", "1"])
+    assert st1["chain_launches"] == 0
+    for extra in (["--chain", "2"], ["--chain", "4"], ["--chain", "6"], ["--chain", "4", "--force-halo"],
+                  ["--chain", "3", "--chain-variant", "1"]):
+        st, u = run_d2d(emu, args + extra)
+        assert st["chain_launches"] > 0, extra
+        for k in ("steps", "step_attempts", "err_test_fails", "rhs_evals", "max_stages"):
+            assert st[k] == st1[k], (extra, k)
+        assert np.array_equal(u, u1), extra
+        if "--force-halo" not in extra:  # (the local-copy halo exchange adds pack / copy launches)
+            assert st["kernel_launches"] < st1["kernel_launches"]
+    emu.kernel_lib().b200_set_chain_variant(0)
+    emu.sundials_lib().N_VSetStageChain_B200(4)
+
+
+def test_lazy_fusion_off_is_the_same_bits(emu):
+    args = ["--nx", 96, "--ny", 64, "--kx", "1.0", "--ky", "0.5", "--inhomogeneous", "--integrator", "rkc",
+            "--fixedstep", "0.0009765625", "--tf", "0.00390625"]
+    st1, u1 = run_d2d(emu, args)
+    st0, u0 = run_d2d(emu, args + ["--no-fusion"])
+    emu.sundials_lib().N_VSetLazyFusion_B200(1)
+    assert np.array_equal(u0, u1) and st0["rhs_evals"] == st1["rhs_evals"]
+    assert st0["fused_launches"] == 0 and st1["fused_launches"] > 0
+
+
+def test_pipelined_batches_equal_sequential_round_trips(emu):
+    args = ["--nx", 128, "--ny", 32, "--integrator", "rkc", "--fixedstep", "0.000244140625", "--tf", "1.0",
+            "--nout", "1", "--output", "0"]
+    prob = emu.Diffusion2D([str(a) for a in args], device=0, stream=None)
+    n, nb = 128 * 32, 3
+    rng = np.random.default_rng(3)
+    ins = [rng.random(n) for _ in range(nb)]
+    want = []
+    for i in range(nb):
+        prob.set_state(ins[i], 0.125)
+        prob.step(2)
+        w = np.empty(n)
+        prob.get_state(w)
+        want.append(w)
+    outs = [np.full(n, np.nan) for _ in range(nb)]
+    prob.run_batches(ins, outs, 0.125, 2)
+    prob.close()
+    for i in range(nb):
+        assert np.array_equal(outs[i], want[i]), i
+
+
+# ------------------------------------------------------------------------------------------------ adr
+ADR_CASES = ["strang_rkc_64", "strang_rkl_96x48_d", "strang_rkc_noadv_64", "extsts_ars_rkc_64",
+             "extsts_ralston_rkl_fixed_48", "extsts_heun_rkc_fixed_64x48", "erk3_fixed_64x32"]
+
+
+def fmt15(a):
+    return np.array(["%.15g" % v for v in np.asarray(a).ravel()])
+
+
+@pytest.mark.parametrize("name", ADR_CASES)
+def test_adr_fixture_parity_through_the_emulated_stack(emu, name):
+    with open(os.path.join(GOLDEN, "adr_%s.json" % name)) as f:
+        meta = json.load(f)
+    ref = np.load(os.path.join(GOLDEN, "adr_%s.npy" % name))
+    args = [str(a) for a in meta["args"]]
+    tf = float(args[args.index("--tf") + 1]) if "--tf" in args else 1.0
+    prob = emu.Adr2D(args + ["--nout", "1", "--output", "0"], device=0, stream=None)
+    prob.evolve(tf)
+    st = prob.stats()
+    y = np.empty(st["neq"])
+    prob.get_state(y)
+    prob.close()
+    assert st["steps"] == meta["stats"]["outer.steps"]
+    if "lsrk.rhs_evals" in meta["stats"]:
+        assert st["lsrk_rhs_evals"] == meta["stats"]["lsrk.rhs_evals"]
+        assert st["lsrk_max_stages"] == meta["stats"]["lsrk.max_stages"]
+    assert st["fused_launches"] > 0
+    assert np.array_equal(fmt15(y), fmt15(ref))
