@@ -80,18 +80,21 @@ def test_product_does_not_reference_the_oracle():
 
 def test_product_is_never_built_with_the_host_emulator(b200):
     """tests/emu compiles the kernel headers with -DB200_HOST_EMU to run them on CPU threads (test
-    infrastructure).  The product must not: the define appears in no product build recipe, the only place
-    that reacts to it is the guarded include in kernel_prims.cuh, and the shipped libraries carry neither the
-    emulator's entry points nor its runtime."""
+    infrastructure).  The product must not: the define appears in no product build recipe, the only places
+    that react to it are the guarded include in kernel_prims.cuh and the launch / runtime switch at the top of
+    b200_kernels.cu (klaunch, cuda_runtime_emu.h), and the shipped libraries carry neither the emulator's entry
+    points nor its runtime."""
     for recipe in ("Makefile", "__graft_entry__.py", os.path.join("scripts", "sundials_host.mk")):
         assert "B200_HOST_EMU" not in open(os.path.join(ROOT, recipe)).read(), recipe
     csrc = os.path.join(ROOT, "ceda-demonstrations_b200", "csrc")
     users = sorted(fn for fn in os.listdir(csrc) if "#ifdef B200_HOST_EMU" in open(os.path.join(csrc, fn)).read())
-    assert users == ["kernel_prims.cuh"], users
+    assert users == ["b200_kernels.cu", "kernel_prims.cuh"], users
     for lib in (b200.KERNEL_LIB, b200.SUNDIALS_LIB):
         if os.path.exists(lib):
             syms = subprocess.run(["nm", "-D", "--defined-only", lib], capture_output=True, text=True).stdout
-            assert "emu_" not in syms and "cuda_emu" not in syms, lib
+            assert "emu_" not in syms and "cuda_emu" not in syms and "_ZN3emu" not in syms, lib
+            allsyms = subprocess.run(["nm", "-D", lib], capture_output=True, text=True).stdout
+            assert "_ZN3emu" not in allsyms and "emu_switch" not in allsyms, lib
 
 
 # ---- decomposition: diffusion_2D.cpp:243-317 ----------------------------------------------------
