@@ -509,7 +509,7 @@ extern "C" int b200_ewt_ss(b200_ctx* c, const double* y, double rtol, double ato
 static int nccl_allreduce_inplace(b200_ctx* c, double* buf, int n, int op);
 
 template <int KIND, int ROP>
-static int run_reduce(b200_ctx* c, const double* x, const double* y, int64_t n, double* result)
+static int run_reduce(b200_ctx* c, const double* x, const double* y, int64_t n, double* result, double ys = 0.0)
 {
   if (!aligned16(x) || (y && !aligned16(y))) return fail("b200 reduce: pointer not 16-byte aligned");
   int64_t n2     = (n + 1) >> 1;
@@ -517,7 +517,7 @@ static int run_reduce(b200_ctx* c, const double* x, const double* y, int64_t n, 
   int64_t cap    = (int64_t)c->sm_count * 4;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  klaunch(k_reduce<KIND, ROP>, (unsigned)blocks, kThreads, 0, c->stream, x, y, n, c->partials, c->ticket, c->dev_result);
+  klaunch(k_reduce<KIND, ROP>, (unsigned)blocks, kThreads, 0, c->stream, x, y, ys, n, c->partials, c->ticket, c->dev_result);
   LAUNCH_CHECK();
   ALG_BYTES((KIND == RD_DOT || KIND == RD_WSQR) ? 2 : 1, n);
   if (c->comm && c->nranks > 1)
@@ -535,6 +535,10 @@ extern "C" int b200_dot(b200_ctx* c, const double* x, const double* y, int64_t n
 extern "C" int b200_wsqrsum(b200_ctx* c, const double* x, const double* w, int64_t n, double* r)
 {
   return run_reduce<RD_WSQR, RED_SUM>(c, x, w, n, r);
+}
+extern "C" int b200_wsqrsum_scalar(b200_ctx* c, const double* x, double w, int64_t n, double* r)
+{
+  return run_reduce<RD_WSQRC, RED_SUM>(c, x, nullptr, n, r, w);
 }
 extern "C" int b200_maxnorm(b200_ctx* c, const double* x, int64_t n, double* r)
 {

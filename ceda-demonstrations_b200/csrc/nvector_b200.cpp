@@ -82,6 +82,8 @@ struct Value
   const B200RhsOp* op; // deferred: value = op(src)
   Value* src;
   StageRec* st;        // pending stage (d == nullptr, op == nullptr)
+  bool is_const;       // every entry equals cval (N_VConst); the buffer is only filled if somebody needs one
+  double cval;
   double* halo;        // deep halo of this value (multi-rank temporal blocking), filled on demand
   bool halo_valid;
   // fused WRMS partial: sum (this_i * w_i)^2 already sits in slot
@@ -152,6 +154,8 @@ Value* value_new(Shared* sh, bool with_buffer)
   v->op        = nullptr;
   v->src       = nullptr;
   v->st        = nullptr;
+  v->is_const  = false;
+  v->cval      = 0.0;
   v->halo      = nullptr;
   v->halo_valid = false;
   v->wrms_w    = nullptr;
@@ -342,6 +346,12 @@ void materialise(Shared* sh, Value* v)
 {
   if (v->d) return;
   if (v->st) { launch_chain(sh, v); return; }
+  if (v->is_const)
+  { // a constant that somebody wants to read element by element after all
+    v->d = pool_get(sh);
+    DEV(b200_const(sh->ctx, v->cval, v->d, sh->nloc));
+    return;
+  }
   if (!v->op) die("materialise: value has neither data nor operator", -1);
   // f = 1 * L(src), stored through the f_out path so v itself becomes plain
   const double one = 1.0;
@@ -520,10 +530,13 @@ void op_linearsum(sunrealtype a, N_Vector x, sunrealtype b, N_Vector y, N_Vector
 }
 
 void op_const(sunrealtype c, N_Vector z)
-{
-  Content* zc = C(z);
-  Value* out  = value_new(zc->sh, true);
-  DEV(b200_const(zc->sh->ctx, c, out->d, zc->sh->nloc));
+{ // nothing is written: the value is the number itself until an operation needs an array (materialise).  Fixed-step
+  // explicit runs set ewt = N_VConst(SUN_SMALL_REAL) every step (arkode.c:2985-2990) and only ever take a norm with it.
+  Content* zc   = C(z);
+  Value* out    = value_new(zc->sh, !g_lazy);
+  out->is_const = true;
+  out->cval     = c;
+  if (out->d) DEV(b200_const(zc->sh->ctx, c, out->d, zc->sh->nloc));
   assign(zc, out);
 }
 
@@ -600,9 +613,11 @@ sunrealtype wsqrsum(N_Vector x, N_Vector w)
   Content* xc      = C(x);
   Shared* sh       = xc->sh;
   const double* xd = mat(x);
-  const double* wd = mat(w);
-  Value* xv        = xc->val;
+  sync_from_host(C(w));
   Value* wv        = C(w)->val;
+  const bool wc    = wv->is_const && !wv->d; // constant weight that was never stored: pass the number
+  const double* wd = wc ? nullptr : mat(w);
+  Value* xv        = xc->val;
   double r         = 0.0;
   if (xv->wrms_w == wv && xv->wrms_slot >= 0)
   { // the fused kernel that produced x already reduced sum (x*w)^2
@@ -612,6 +627,7 @@ sunrealtype wsqrsum(N_Vector x, N_Vector w)
     xv->wrms_slot = -1; // the all-reduce is in place: do not reuse
     g_stats.wrms_fused++;
   }
+  else if (wc) { DEV(b200_wsqrsum_scalar(sh->ctx, xd, wv->cval, sh->nloc, &r)); }
   else { DEV(b200_wsqrsum(sh->ctx, xd, wd, sh->nloc, &r)); }
   // learn: x came out of a fused launch issued while w was already the most recent
   // norm weight, i.e. fusing the norm into that launch would have hit -> do so next time
@@ -802,7 +818,11 @@ int N_VSetDeferredRhs_B200(N_Vector f, const B200RhsOp* op, N_Vector y)
   return 0;
 }
 
-int N_VIsDeferred_B200(N_Vector v) { return (C(v)->val && !C(v)->val->d) ? 1 : 0; }
+int N_VIsDeferred_B200(N_Vector v)
+{
+  const Value* val = C(v)->val;
+  return (val && !val->d && (val->op || val->st)) ? 1 : 0;
+}
 void N_VSetLazyFusion_B200(int on) { g_lazy = (on != 0); }
 void N_VSetStageChain_B200(int depth)
 {

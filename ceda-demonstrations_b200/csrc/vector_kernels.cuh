@@ -111,13 +111,15 @@ __global__ void __launch_bounds__(kThreads) k_elementwise(const EwArgs a)
 }
 
 
-enum RdKind { RD_DOT = 0, RD_WSQR, RD_MAXNORM, RD_MIN, RD_L1 };
+// RD_WSQRC: sum (x_i * w)^2 with ONE weight for every entry (a constant-valued weight vector is never stored;
+// fixed-step LSRKStep sets ewt = N_VConst(SUN_SMALL_REAL) every step, arkode.c:2985-2990)
+enum RdKind { RD_DOT = 0, RD_WSQR, RD_MAXNORM, RD_MIN, RD_L1, RD_WSQRC };
 
 template <int KIND>
 __device__ __forceinline__ double rd_term(double x, double y)
 {
   if (KIND == RD_DOT) return DMUL(x, y);
-  if (KIND == RD_WSQR) { double p = DMUL(x, y); return DMUL(p, p); }
+  if (KIND == RD_WSQR || KIND == RD_WSQRC) { double p = DMUL(x, y); return DMUL(p, p); }
   if (KIND == RD_MAXNORM) return fabs(x);
   if (KIND == RD_MIN) return x;
   return fabs(x);
@@ -125,7 +127,7 @@ __device__ __forceinline__ double rd_term(double x, double y)
 
 template <int KIND, int ROP>
 __global__ void __launch_bounds__(kThreads)
-  k_reduce(const double* __restrict__ x, const double* __restrict__ y, int64_t n,
+  k_reduce(const double* __restrict__ x, const double* __restrict__ y, double ys, int64_t n,
            double* partials, unsigned* ticket, double* result)
 {
   __shared__ double smem[32];
@@ -136,12 +138,12 @@ __global__ void __launch_bounds__(kThreads)
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n2; p += stride)
   {
     double2 a = ld_keep2(x + 2 * p);
-    double2 b = two ? ld_keep2(y + 2 * p) : make_double2(0.0, 0.0);
+    double2 b = two ? ld_keep2(y + 2 * p) : make_double2(ys, ys);
     acc0      = red_combine<ROP>(acc0, rd_term<KIND>(a.x, b.x));
     acc1      = red_combine<ROP>(acc1, rd_term<KIND>(a.y, b.y));
   }
   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0)
-    acc0 = red_combine<ROP>(acc0, rd_term<KIND>(x[n - 1], two ? y[n - 1] : 0.0));
+    acc0 = red_combine<ROP>(acc0, rd_term<KIND>(x[n - 1], two ? y[n - 1] : ys));
   double v = block_reduce<ROP>(red_combine<ROP>(acc0, acc1), smem);
   grid_finish<ROP>(v, gridDim.x, blockIdx.x, partials, ticket, result, smem);
 }

@@ -107,6 +107,9 @@ int b200_ewt_ss(b200_ctx* ctx, const double* y, double rtol, double atol,
    nvector_parallel.c:658-730. */
 int b200_dot(b200_ctx* ctx, const double* x, const double* y, int64_t n, double* result);      /* N_VDotProd :658 */
 int b200_wsqrsum(b200_ctx* ctx, const double* x, const double* w, int64_t n, double* result);  /* N_VWSqrSumLocal :700 + Allreduce :728 */
+/* the same with ONE weight w for every entry (a constant-valued weight vector, e.g. the ewt = N_VConst(SUN_SMALL_REAL)
+   of fixed-step explicit runs, SUN/src/arkode/arkode.c:2985-2990): w is never read from memory */
+int b200_wsqrsum_scalar(b200_ctx* ctx, const double* x, double w, int64_t n, double* result);
 int b200_maxnorm(b200_ctx* ctx, const double* x, int64_t n, double* result);                   /* N_VMaxNorm :689 */
 int b200_min(b200_ctx* ctx, const double* x, int64_t n, double* result);                       /* N_VMin :780 */
 int b200_l1norm(b200_ctx* ctx, const double* x, int64_t n, double* result);                    /* N_VL1Norm :815 */

@@ -26,12 +26,12 @@ void run_ew(const EwArgs& a, unsigned blocks)
 }
 
 template <int KIND, int ROP>
-double run_reduce(const double* x, const double* y, int64_t n, unsigned blocks)
+double run_reduce(const double* x, const double* y, int64_t n, unsigned blocks, double ys = 0.0)
 {
   std::vector<double> partials(blocks + 8);
   unsigned ticket = 0;
   double result   = 0.0;
-  launch_fn([&]() { k_reduce<KIND, ROP>(x, y, n, partials.data(), &ticket, &result); }, dim3(blocks));
+  launch_fn([&]() { k_reduce<KIND, ROP>(x, y, ys, n, partials.data(), &ticket, &result); }, dim3(blocks));
   return result;
 }
 } // namespace
@@ -63,11 +63,12 @@ EMU_API int emu_elementwise(int op, int64_t n, const double* x, const double* y,
   return 0;
 }
 
-// kind: RdKind (0 dot, 1 sum((x*w)^2), 2 max|x|, 3 min, 4 sum|x|)
+// kind: RdKind (0 dot, 1 sum((x*w)^2), 2 max|x|, 3 min, 4 sum|x|, 5 sum((x*ys)^2) with the scalar weight y[0])
 EMU_API double emu_reduce(int kind, int64_t n, const double* x, const double* y, int blocks)
 {
   switch (kind)
   {
+  case RD_WSQRC: return run_reduce<RD_WSQRC, RED_SUM>(x, nullptr, n, blocks, y[0]);
   case RD_DOT: return run_reduce<RD_DOT, RED_SUM>(x, y, n, blocks);
   case RD_WSQR: return run_reduce<RD_WSQR, RED_SUM>(x, y, n, blocks);
   case RD_MAXNORM: return run_reduce<RD_MAXNORM, RED_MAX>(x, nullptr, n, blocks);
