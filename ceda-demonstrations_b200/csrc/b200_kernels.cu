@@ -991,6 +991,7 @@ extern "C" int b200_deep_halo_exchange(b200_ctx* c, const int peers[4], int x_sp
   return 0;
 }
 
+
 // ------------------------------------------------------------------ halo pack
 extern "C" int b200_pack_halo(b200_ctx* c, const double* u, int64_t nx, int64_t ny,
                               double* sw, double* se, double* ss, double* sn)
@@ -1172,6 +1173,7 @@ struct NcclApi
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
   ncclResult_t (*GroupStart)();
   ncclResult_t (*GroupEnd)();
   bool ok = false;
@@ -1194,6 +1196,7 @@ static int nccl_load()
   NCCL_SYM(AllReduce, "ncclAllReduce")
   NCCL_SYM(Send, "ncclSend")
   NCCL_SYM(Recv, "ncclRecv")
+  NCCL_SYM(AllGather, "ncclAllGather")
   NCCL_SYM(GroupStart, "ncclGroupStart")
   NCCL_SYM(GroupEnd, "ncclGroupEnd")
 #undef NCCL_SYM
@@ -1207,6 +1210,7 @@ static int nccl_load()
 #define ncclAllReduce g_nccl.AllReduce
 #define ncclSend g_nccl.Send
 #define ncclRecv g_nccl.Recv
+#define ncclAllGather g_nccl.AllGather
 #define ncclGroupStart g_nccl.GroupStart
 #define ncclGroupEnd g_nccl.GroupEnd
 extern "C" int b200_comm_unique_id(unsigned char id[128])
@@ -1306,5 +1310,184 @@ extern "C" int b200_halo_wait(b200_ctx* c)
     CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
     c->comm_pending = false;
   }
+  return 0;
+}
+
+// ------------------------------------------------------- peer-mapped deep-halo exchange
+// The deep halos of temporally blocked launches without NCCL: a ring of halo slots per rank, mapped into the
+// neighbours' address spaces (CUDA IPC, one process per GPU), filled by the NEIGHBOURS' k_peer_exchange kernels with
+// plain stores over NVLink.  Slot numbers are chosen by a deterministic allocator that every rank runs in lockstep
+// (all ranks issue the same sequence of vector operations), so "slot s" names the same logical halo everywhere.
+struct b200_peer_halo
+{
+  b200_ctx* ctx = nullptr;
+  int64_t nx = 0, ny = 0, ny_s = 0, ny_n = 0; // my block, and the heights of the blocks south / north of me
+  int g = 0, g2 = 0, nslots = 0;
+  int64_t slot_doubles = 0;      // doubles per slot, sized for the tallest block of the decomposition
+  int64_t ny_max = 0;
+  double* base = nullptr;        // [nslots * slot_doubles doubles | 8 arrival counters | ticket]
+  size_t bytes = 0;
+  double* nbr_base[8] = {};      // the same region of each neighbour, in my address space
+  void* opened[8] = {};          // IPC mappings to close (distinct, non-self neighbours)
+  int nbr_rank[8] = {};
+  unsigned long long epoch = 0;  // exchanges enqueued so far
+  std::vector<unsigned long long> avail; // slot s may be handed out for an exchange with epoch >= avail[s]; ~0 = in use
+  int* host_err = nullptr;       // mapped
+  int* host_err_dev = nullptr;
+  uint64_t exchanges = 0, doubles_pushed = 0;
+};
+
+static unsigned long long* ph_flags(const b200_peer_halo* ph, double* base)
+{
+  return reinterpret_cast<unsigned long long*>(base + (size_t)ph->nslots * ph->slot_doubles);
+}
+
+extern "C" int b200_peer_halo_destroy(b200_peer_halo* ph)
+{
+  if (!ph) return 0;
+  cudaSetDevice(ph->ctx->device);
+  cudaStreamSynchronize(ph->ctx->stream);
+#ifndef B200_HOST_EMU
+  for (int d = 0; d < 8; d++)
+    if (ph->opened[d]) cudaIpcCloseMemHandle(ph->opened[d]);
+#endif
+  if (ph->base) cudaFree(ph->base);
+  if (ph->host_err) cudaFreeHost(ph->host_err);
+  delete ph;
+  return 0;
+}
+
+static int peer_halo_init(b200_peer_halo* ph, const int nbr[8])
+{
+  b200_ctx* c = ph->ctx;
+  CU_TRY(cudaSetDevice(c->device));
+  ph->slot_doubles = (b200_deep_halo_doubles(ph->nx, ph->ny_max, ph->g, ph->g2) + 31) & ~(int64_t)31;
+  ph->bytes        = sizeof(double) * (size_t)ph->nslots * ph->slot_doubles + 256;
+  CU_TRY(cudaMalloc(&ph->base, ph->bytes));
+  CU_TRY(cudaMemset(ph->base, 0, ph->bytes));
+  CU_TRY(cudaHostAlloc(&ph->host_err, sizeof(int) * 4, cudaHostAllocMapped));
+  ph->host_err[0] = 0;
+  CU_TRY(cudaHostGetDevicePointer(&ph->host_err_dev, ph->host_err, 0));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  ph->avail.assign((size_t)ph->nslots, 0ull);
+  bool remote = false;
+  for (int d = 0; d < 8; d++)
+  {
+    ph->nbr_rank[d] = nbr[d];
+    if (nbr[d] == c->rank || c->nranks <= 1) ph->nbr_base[d] = ph->base;
+    else remote = true;
+  }
+  if (!remote) return 0;
+#ifdef B200_HOST_EMU
+  return fail("b200_peer_halo_create: the emulated build is single-rank");
+#else
+  if (!c->comm) return fail("b200_peer_halo_create: communicator not initialised");
+  // every rank publishes the IPC handle of its region; all-gather over the communicator
+  cudaIpcMemHandle_t mine;
+  CU_TRY(cudaIpcGetMemHandle(&mine, ph->base));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  char *dsend = nullptr, *drecv = nullptr;
+  CU_TRY(cudaMalloc(&dsend, 64));
+  CU_TRY(cudaMalloc(&drecv, 64 * (size_t)c->nranks));
+  CU_TRY(cudaMemcpyAsync(dsend, &mine, 64, cudaMemcpyHostToDevice, c->stream));
+  NCCL_TRY(ncclAllGather(dsend, drecv, 64, ncclChar, c->comm, c->stream));
+  std::vector<cudaIpcMemHandle_t> all((size_t)c->nranks);
+  CU_TRY(cudaMemcpyAsync(all.data(), drecv, 64 * (size_t)c->nranks, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  CU_TRY(cudaFree(dsend));
+  CU_TRY(cudaFree(drecv));
+  for (int d = 0; d < 8; d++)
+  {
+    if (ph->nbr_base[d]) continue;
+    for (int e = 0; e < d; e++) // the same rank in two directions (2 x 1, 2 x 2 layouts): map it once
+      if (nbr[e] == nbr[d] && ph->nbr_base[e]) { ph->nbr_base[d] = ph->nbr_base[e]; break; }
+    if (ph->nbr_base[d]) continue;
+    void* p = nullptr;
+    CU_TRY(cudaIpcOpenMemHandle(&p, all[(size_t)nbr[d]], cudaIpcMemLazyEnablePeerAccess));
+    ph->opened[d]   = p;
+    ph->nbr_base[d] = static_cast<double*>(p);
+  }
+  // nobody may push before everybody has mapped (and zeroed) everything: one barrier
+  NCCL_TRY(ncclAllReduce(c->dev_result, c->dev_result, 1, ncclDouble, ncclSum, c->comm, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  return 0;
+#endif
+}
+
+extern "C" int b200_peer_halo_create(b200_ctx* c, const int nbr[8], int64_t nx, int64_t ny, int64_t ny_south,
+                                     int64_t ny_north, int64_t ny_max, int g, int g2, int nslots, b200_peer_halo** out)
+{
+  if (!c || !out || nslots < 8 || g < 1 || g2 < 2 || (g2 & 1) || g > ny || g2 > nx) return fail("b200_peer_halo_create: bad argument");
+  b200_peer_halo* ph = new b200_peer_halo();
+  ph->ctx = c; ph->nx = nx; ph->ny = ny; ph->ny_s = ny_south; ph->ny_n = ny_north; ph->ny_max = ny_max;
+  ph->g = g; ph->g2 = g2; ph->nslots = nslots;
+  int rc = peer_halo_init(ph, nbr);
+  if (rc) { b200_peer_halo_destroy(ph); return rc; }
+  *out = ph;
+  return 0;
+}
+
+// Slot allocator.  A slot released while `epoch` exchanges have been enqueued may still be read by this rank's
+// launch that follows exchange `epoch`; a neighbour can write into it from exchange epoch + 2 on at the earliest
+// (it starts that exchange only after it has seen this rank's flag of exchange epoch + 1, raised after that launch).
+extern "C" double* b200_peer_halo_slot_alloc(b200_peer_halo* ph)
+{
+  const unsigned long long next = ph->epoch + 1;
+  for (int s = 0; s < ph->nslots; s++)
+    if (ph->avail[(size_t)s] <= next)
+    {
+      ph->avail[(size_t)s] = ~0ull;
+      return ph->base + (size_t)s * ph->slot_doubles;
+    }
+  fail("b200_peer_halo_slot_alloc: all halo slots are in use");
+  return nullptr;
+}
+
+extern "C" int b200_peer_halo_slot_free(b200_peer_halo* ph, double* slot)
+{
+  const int64_t s = (slot - ph->base) / ph->slot_doubles;
+  if (s < 0 || s >= ph->nslots || ph->avail[(size_t)s] != ~0ull) return fail("b200_peer_halo_slot_free: not an allocated slot");
+  ph->avail[(size_t)s] = ph->epoch + 2;
+  return 0;
+}
+
+extern "C" int b200_peer_halo_stats(const b200_peer_halo* ph, uint64_t* exchanges, uint64_t* doubles_pushed)
+{
+  *exchanges      = ph->exchanges;
+  *doubles_pushed = ph->doubles_pushed;
+  return 0;
+}
+
+extern "C" int b200_peer_halo_exchange(b200_peer_halo* ph, int nfields, const double* const* fields, double* const* slots)
+{
+  if (nfields < 1 || nfields > 4) return fail("b200_peer_halo_exchange: 1..4 fields");
+  b200_ctx* c = ph->ctx;
+  if (ph->host_err[0]) return fail("b200_peer_halo_exchange: a neighbour did not arrive in an earlier exchange (time limit)");
+  PeerXArgs a;
+  memset(&a, 0, sizeof(a));
+  a.nf = nfields; a.nx = ph->nx; a.ny = ph->ny; a.g = ph->g; a.g2 = ph->g2;
+  a.epoch = ++ph->epoch;
+  for (int f = 0; f < nfields; f++)
+  {
+    const int64_t off = slots[f] - ph->base; // the same offset in every rank's region (lockstep allocator)
+    if (off < 0 || off % ph->slot_doubles || off / ph->slot_doubles >= ph->nslots) return fail("b200_peer_halo_exchange: not a slot");
+    if (!aligned16(fields[f])) return fail("b200_peer_halo_exchange: field not 16-byte aligned");
+    a.field[f] = fields[f];
+    double* nbr_slot[8];
+    for (int d = 0; d < 8; d++) nbr_slot[d] = ph->nbr_base[d] + off;
+    peer_dst_pointers(nbr_slot, ph->nx, ph->ny, ph->ny_s, ph->ny_n, ph->g, ph->g2, a.dst[f]);
+  }
+  for (int d = 0; d < 8; d++) a.peer_flag[d] = ph_flags(ph, ph->nbr_base[d]) + kPeerOpposite[d];
+  a.my_flag    = ph_flags(ph, ph->base);
+  a.ticket     = reinterpret_cast<unsigned*>(ph_flags(ph, ph->base) + 8);
+  a.err        = ph->host_err_dev;
+  a.timeout_ns = 20ull * 1000000000ull;
+  const int64_t total = 2 * (int64_t)ph->g * ph->nx + 2 * ph->ny * ph->g2 + 4 * (int64_t)ph->g * ph->g2;
+  int64_t blocks      = (total + kThreads - 1) / kThreads;
+  if (blocks > 2 * (int64_t)c->sm_count) blocks = 2 * (int64_t)c->sm_count;
+  klaunch(k_peer_exchange, dim3((unsigned)blocks, (unsigned)nfields), kThreads, 0, c->stream, a);
+  LAUNCH_CHECK();
+  ph->exchanges++;
+  ph->doubles_pushed += (uint64_t)total * (uint64_t)nfields;
   return 0;
 }

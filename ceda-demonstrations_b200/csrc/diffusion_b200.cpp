@@ -74,6 +74,9 @@ struct UserData
   double *cxw_ext = nullptr, *cxe_ext = nullptr, *cys_ext = nullptr, *cyn_ext = nullptr;
   double *ext_base[4] = {nullptr, nullptr, nullptr, nullptr};
   bool force_halo = false; // use the deep-halo path even on one rank (tests)
+  // deep halos of temporally blocked launches: peer-mapped slot ring written by the neighbours over NVLink
+  // (default), or -- peer_halo == nullptr -- two NCCL phases per exchange (--halo-nccl / B200_HALO_NCCL=1)
+  b200_peer_halo* peer_halo = nullptr;
   B200RhsOp rhs_op{};
   bool overlap = true; // interior kernel overlaps the NCCL exchange
   long rhs_calls = 0;
@@ -336,12 +339,24 @@ int rhs_chain(void* self, b200_ctx* ctx, int nstages, const double* x, const dou
     if (!halo_valid[q]) { xf[nf] = fields[q]; xh[nf] = halos[q]; nf++; }
   if (nf > 0)
   {
-    const int peers[4] = {ud->ipW, ud->ipE, ud->ipS, ud->ipN};
-    int rc = b200_deep_halo_exchange(ctx, peers, ud->npx > 1, ud->npy > 1, g.nx, g.ny, kHaloRows, kHaloCols, nf, xf, xh);
+    int rc;
+    if (ud->peer_halo) rc = b200_peer_halo_exchange(ud->peer_halo, nf, xf, xh);
+    else
+    {
+      const int peers[4] = {ud->ipW, ud->ipE, ud->ipS, ud->ipN};
+      rc = b200_deep_halo_exchange(ctx, peers, ud->npx > 1, ud->npy > 1, g.nx, g.ny, kHaloRows, kHaloCols, nf, xf, xh);
+    }
     if (rc) return rc;
   }
   g.cxw = ud->cxw_ext; g.cxe = ud->cxe_ext; g.cys = ud->cys_ext; g.cyn = ud->cyn_ext;
   return b200_stencil_chain_halo(ctx, &g, nstages, x, prev2, yn, fn, coeffs, z_out, halos, kHaloRows, kHaloCols);
+}
+
+double* halo_slot_alloc(void* self) { return b200_peer_halo_slot_alloc(static_cast<UserData*>(self)->peer_halo); }
+void halo_slot_free(void* self, double* h)
+{
+  UserData* ud = static_cast<UserData*>(self);
+  if (ud->peer_halo) b200_peer_halo_slot_free(ud->peer_halo, h);
 }
 
 } // namespace
@@ -427,6 +442,7 @@ struct UserOptions
   int chain_variant = -1; // -1 = library default (B200_CHAIN_VARIANT), 0 = two cells / thread, 1 = four
   std::string arith;      // "" = B200_ARITH or exact; "exact" | "fma" (b200_set_contract)
   bool force_halo = false;
+  bool halo_nccl  = false; // deep halos through NCCL send / recv instead of peer-mapped stores
 };
 
 // One pass over argv; unknown flags are an error like main.cpp:116-132.
@@ -462,7 +478,7 @@ int parse_args(std::vector<std::string> args, UserData& ud, UserOptions& uo, boo
     ARG_B("--noprec", uo.preconditioning, false) ARG_B("--internaleig", uo.internaleig, true)
     ARG_I("--output", uo.output) ARG_I("--nout", uo.nout)
     ARG_B("--no-overlap", uo.no_overlap, true) ARG_B("--no-fusion", uo.no_fusion, true)
-    ARG_I("--rows-per-block", uo.rows_per_block) ARG_I("--chain", uo.chain) ARG_I("--chain-variant", uo.chain_variant) ARG_S("--arith", uo.arith) ARG_B("--force-halo", uo.force_halo, true)
+    ARG_I("--rows-per-block", uo.rows_per_block) ARG_I("--chain", uo.chain) ARG_I("--chain-variant", uo.chain_variant) ARG_S("--arith", uo.arith) ARG_B("--force-halo", uo.force_halo, true) ARG_B("--halo-nccl", uo.halo_nccl, true)
     if (outproc) fprintf(stderr, "ERROR: Unknown inputs: %s\n", a.c_str());
     return -1;
   }
@@ -680,7 +696,31 @@ extern "C" int b200_d2d_create(int argc, const char* const* argv, int rank, int 
     p->ud.rhs_op.chain     = rhs_chain;
     p->ud.rhs_op.chain_max = B200_MAX_CHAIN;
     if (nranks > 1 || p->ud.force_halo)
+    {
       p->ud.rhs_op.halo_doubles = b200_deep_halo_doubles(p->ud.nx_loc, p->ud.ny_loc, kHaloRows, kHaloCols);
+      if (!(p->uo.halo_nccl || getenv("B200_HALO_NCCL")))
+      { // the eight neighbours of this block in the periodic process grid, and the heights of the rows of blocks
+        // below / above it (remainder rows go to the low coordinates, diffusion_2D.cpp:286-317)
+        UserData& u = p->ud;
+        auto height = [&](int cy) {
+          cy = ((cy % u.npy) + u.npy) % u.npy;
+          return u.ny / u.npy + (cy < u.ny % u.npy ? 1 : 0);
+        };
+        const int nbr[8] = {cart_rank(u.idx - 1, u.idy, u.npx, u.npy),     cart_rank(u.idx + 1, u.idy, u.npx, u.npy),
+                            cart_rank(u.idx, u.idy - 1, u.npx, u.npy),     cart_rank(u.idx, u.idy + 1, u.npx, u.npy),
+                            cart_rank(u.idx - 1, u.idy - 1, u.npx, u.npy), cart_rank(u.idx + 1, u.idy - 1, u.npx, u.npy),
+                            cart_rank(u.idx - 1, u.idy + 1, u.npx, u.npy), cart_rank(u.idx + 1, u.idy + 1, u.npx, u.npy)};
+        const int64_t ny_max = u.ny / u.npy + (u.ny % u.npy ? 1 : 0);
+        if (b200_peer_halo_create(p->ctx, nbr, u.nx_loc, u.ny_loc, height(u.idy - 1), height(u.idy + 1), ny_max, kHaloRows,
+                                  kHaloCols, 16, &u.peer_halo))
+        {
+          fprintf(stderr, "b200_d2d_create: %s\n", b200_last_error());
+          return -1;
+        }
+        u.rhs_op.halo_alloc = halo_slot_alloc;
+        u.rhs_op.halo_free  = halo_slot_free;
+      }
+    }
   }
   {
     int depth = p->uo.chain;
@@ -726,6 +766,7 @@ extern "C" int b200_d2d_destroy(b200_d2d* p)
   if (p->uerr) N_VDestroy(p->uerr);
   if (p->u) N_VDestroy(p->u);
   p->ud.free_device();
+  if (p->ud.peer_halo) { b200_peer_halo_destroy(p->ud.peer_halo); p->ud.peer_halo = nullptr; }
   if (p->sunctx) SUNContext_Free(&p->sunctx);
   if (p->ctx) b200_ctx_destroy(p->ctx);
   delete p;

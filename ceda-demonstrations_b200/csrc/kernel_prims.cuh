@@ -39,6 +39,27 @@ __device__ __forceinline__ void cp_async_wait()
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+
+// system-scope flag traffic of the peer-mapped halo exchange (flags live in another GPU's memory, reached over NVLink)
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v)
+{
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p)
+{
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_sys() { __threadfence_system(); }
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void nap_ns(unsigned ns) { __nanosleep(ns); }
+
 #endif // B200_HOST_EMU
 
 // c + a*b: two roundings (the reference's baseline x86-64 build) or one (FMA-contracted arithmetic,

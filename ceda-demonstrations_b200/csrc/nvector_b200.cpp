@@ -86,6 +86,7 @@ struct Value
   double cval;
   double* halo;        // deep halo of this value (multi-rank temporal blocking), filled on demand
   bool halo_valid;
+  const B200RhsOp* halo_op; // who handed out `halo` (halo_alloc / halo_free); nullptr = this vector's pool
   // fused WRMS partial: sum (this_i * w_i)^2 already sits in slot
   Value* wrms_w;
   int wrms_slot;
@@ -129,7 +130,11 @@ void value_release(Shared* sh, Value* v)
   {
     if (--v->refs > 0) return;
     if (v->d) sh->free_bufs.push_back(v->d);
-    if (v->halo) sh->free_halos.push_back(v->halo);
+    if (v->halo)
+    {
+      if (v->halo_op) v->halo_op->halo_free(v->halo_op->self, v->halo);
+      else sh->free_halos.push_back(v->halo);
+    }
     if (v->wrms_w) value_release(sh, v->wrms_w);
     Value* next = v->src; // a deferred value owns a reference on its source
     if (v->st)
@@ -158,6 +163,7 @@ Value* value_new(Shared* sh, bool with_buffer)
   v->cval      = 0.0;
   v->halo      = nullptr;
   v->halo_valid = false;
+  v->halo_op   = nullptr;
   v->wrms_w    = nullptr;
   v->wrms_slot = -1;
   v->sig       = 0;
@@ -305,7 +311,13 @@ void launch_chain(Shared* sh, Value* top)
       {
         if (!opv[q]->halo)
         {
-          if (!sh->free_halos.empty()) { opv[q]->halo = sh->free_halos.back(); sh->free_halos.pop_back(); }
+          if (first->op->halo_alloc)
+          {
+            opv[q]->halo    = first->op->halo_alloc(first->op->self);
+            opv[q]->halo_op = first->op;
+            if (!opv[q]->halo) die("halo_alloc", -1);
+          }
+          else if (!sh->free_halos.empty()) { opv[q]->halo = sh->free_halos.back(); sh->free_halos.pop_back(); }
           else DEV(b200_malloc(sh->ctx, sh->halo_doubles, &opv[q]->halo));
           opv[q]->halo_valid = false;
         }

@@ -213,6 +213,25 @@ int64_t b200_deep_halo_doubles(int64_t nx, int64_t ny, int rows, int cols);
 int b200_deep_halo_exchange(b200_ctx* ctx, const int peers[4], int x_split, int y_split,
                             int64_t nx, int64_t ny, int rows, int cols, int nfields,
                             const double* const* fields, double* const* halos);
+/* ---- the same halos WITHOUT NCCL: peer-mapped slots written by the neighbours over NVLink --------------------
+   b200_peer_halo_create allocates a ring of `nslots` deep-halo slots (each sized for a block nx x ny_max) on this
+   rank, publishes it to the other ranks (CUDA IPC handles all-gathered over the communicator of b200_comm_init) and
+   maps the rings of the eight neighbours nbr[] = { W, E, S, N, SW, SE, NW, NE } (a rank may appear several times, and
+   may be this rank itself: periodic wrap with one rank in a direction).  ny_south / ny_north are the heights of the
+   blocks below / above this one (the strips of the diagonal neighbours are laid out for THEIR height).
+   b200_peer_halo_exchange(fields, slots): ONE kernel per rank -- it stores the edge bands and corners of each field
+   into slot slots[f] of the neighbours (same slot number on every rank: ranks call the allocator in lockstep), raises
+   one flag per neighbour and waits for the neighbours' flags; after it, slots[f] on this rank holds the deep halo of
+   fields[f] in the layout above.  It replaces b200_deep_halo_exchange (two dependent NCCL groups plus pack kernels)
+   and with it MPI_Isend / Irecv / Waitall of diffusion_2D.cpp:400-584 for temporally blocked launches. */
+typedef struct b200_peer_halo b200_peer_halo;
+int b200_peer_halo_create(b200_ctx* ctx, const int nbr[8], int64_t nx, int64_t ny, int64_t ny_south, int64_t ny_north,
+                          int64_t ny_max, int rows, int cols, int nslots, b200_peer_halo** out);
+int b200_peer_halo_destroy(b200_peer_halo* ph);
+double* b200_peer_halo_slot_alloc(b200_peer_halo* ph);            /* NULL when the ring is exhausted */
+int b200_peer_halo_slot_free(b200_peer_halo* ph, double* slot);
+int b200_peer_halo_exchange(b200_peer_halo* ph, int nfields, const double* const* fields, double* const* slots);
+int b200_peer_halo_stats(const b200_peer_halo* ph, uint64_t* exchanges, uint64_t* doubles_pushed);
 /* rows of output each thread block of the chain kernel marches over; 0 (default) = automatic: 128
    where that leaves at least 4 waves of blocks, else 64, else 32.  Results do not depend on it. */
 int b200_set_chain_rows(int rows);

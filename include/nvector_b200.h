@@ -54,6 +54,11 @@ typedef struct B200RhsOp
      buffers per value; `chain` receives halos[4] and halo_valid[4] and must fill (exchange)
      the stale ones before launching.  0: halos == NULL. */
   int64_t halo_doubles;
+  /* Optional (NULL = the vector allocates halo_doubles per value from its own pool): where a value's deep-halo
+     buffer comes from and goes back to -- e.g. the slots of a peer-mapped ring that the neighbouring ranks write
+     into (b200_peer_halo_*).  Every rank must see the same sequence of calls. */
+  double* (*halo_alloc)(void* self);
+  void (*halo_free)(void* self, double* halo);
 } B200RhsOp;
 
 /* Create a vector: local_length entries on this rank's GPU, global_length overall

@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <deque>
 #include <functional>
 #include <memory>
@@ -217,6 +218,22 @@ static inline double __longlong_as_double(long long v)
 }
 using std::fmax;
 using std::fmin;
+
+// system-scope flag traffic of the peer-mapped halo exchange: one process, one "device" here
+static inline void st_release_sys_u64(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+static inline unsigned long long ld_acquire_sys_u64(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+static inline void fence_sys() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline unsigned long long global_timer_ns()
+{
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (unsigned long long)ts.tv_sec * 1000000000ull + (unsigned long long)ts.tv_nsec;
+}
+static inline void nap_ns(unsigned)
+{ // a spinning thread lets the other fibers of its block run (they may be the ones that raise the flag)
+  emu::cur_block->progress++;
+  emu::yield_to_scheduler();
+}
 
 static inline double2 ld_stream2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 static inline double2 ld_keep2(const double* p) { return *reinterpret_cast<const double2*>(p); }

@@ -166,3 +166,38 @@ EMU_API int emu_adr_chain(const b200_adr_params* p, int K, const double* x, cons
   }
   return 0;
 }
+
+// A periodic npx x npy process grid simulated in one process: every "rank" pushes the edge bands and corners of its
+// block into its neighbours' deep-halo slots with k_peer_exchange, addressed by peer_dst_pointers exactly as
+// b200_peer_halo_exchange does.  Ranks run one after the other here, so the arrival flags are raised beforehand.
+// blocks[r] / slots[r]: rank r's nx_loc x ny_loc[r] block and its [S | N | W | E] deep halo; rank = idx * npy + idy
+// (diffusion_2D.cpp:243-317), all blocks nx_loc wide, heights ny_loc[idy].
+EMU_API int emu_peer_exchange_grid(int npx, int npy, int64_t nx_loc, const int64_t* ny_loc, int g, int g2,
+                                   const double* const* blocks, double* const* slots)
+{
+  const int np = npx * npy;
+  std::vector<unsigned long long> flags((size_t)np * 8, 1ull), sink(8);
+  std::vector<unsigned> ticket((size_t)np, 0u);
+  int err = 0;
+  auto rank_of = [&](int cx, int cy) { return ((cx % npx + npx) % npx) * npy + ((cy % npy + npy) % npy); };
+  for (int r = 0; r < np; r++)
+  {
+    const int cx = r / npy, cy = r % npy;
+    const int nbr[8] = {rank_of(cx - 1, cy),     rank_of(cx + 1, cy),     rank_of(cx, cy - 1),     rank_of(cx, cy + 1),
+                        rank_of(cx - 1, cy - 1), rank_of(cx + 1, cy - 1), rank_of(cx - 1, cy + 1), rank_of(cx + 1, cy + 1)};
+    PeerXArgs a;
+    memset(&a, 0, sizeof(a));
+    a.nf = 1; a.nx = nx_loc; a.ny = ny_loc[cy]; a.g = g; a.g2 = g2; a.epoch = 1;
+    a.field[0] = blocks[r];
+    double* nbr_slot[8];
+    for (int d = 0; d < 8; d++) nbr_slot[d] = slots[nbr[d]];
+    peer_dst_pointers(nbr_slot, nx_loc, ny_loc[cy], ny_loc[((cy - 1) % npy + npy) % npy], ny_loc[(cy + 1) % npy], g, g2, a.dst[0]);
+    for (int d = 0; d < 8; d++) a.peer_flag[d] = &sink[(size_t)d];
+    a.my_flag    = &flags[(size_t)r * 8];
+    a.ticket     = &ticket[(size_t)r];
+    a.err        = &err;
+    a.timeout_ns = 1000000000ull;
+    emu::launch(k_peer_exchange, dim3(3, 1), kThreads, 0, a);
+  }
+  return err;
+}

@@ -610,3 +610,40 @@ def test_uniform_flavour_with_fma_arithmetic(emu, k):
     assert rc == 0
     for l in range(k):
         assert np.array_equal(uni[l], tab[l]), "level %d" % (l + 1)
+
+
+# ---- peer-mapped deep-halo exchange (k_peer_exchange + peer_dst_pointers) on a simulated process grid ----------
+@pytest.mark.parametrize("npx,npy,nx_loc,ny_glob", [(1, 1, 16, 12), (2, 1, 8, 9), (1, 2, 16, 17), (2, 2, 10, 21), (4, 2, 8, 19), (3, 3, 6, 31)])
+@pytest.mark.parametrize("g,g2", [(2, 2), (6, 6), (3, 4)])
+def test_peer_exchange_fills_every_deep_halo_of_a_process_grid(emu, npx, npy, nx_loc, ny_glob, g, g2):
+    """Every rank of a periodic npx x npy grid (uneven block heights: remainder rows to the low coordinates,
+    diffusion_2D.cpp:286-317) pushes its edges and corners; afterwards every rank's slot must hold the deep halo
+    [S | N | W | E] of its block, i.e. the periodic continuation of the global field, corners included."""
+    nx_glob = nx_loc * npx
+    rng = np.random.default_rng(npx * 100 + npy * 10 + g)
+    U = rng.standard_normal((ny_glob, nx_glob))
+    q, r = divmod(ny_glob, npy)
+    ny_loc = [q + (1 if c < r else 0) for c in range(npy)]
+    js = [sum(ny_loc[:c]) for c in range(npy)]
+    if min(ny_loc) < g:
+        pytest.skip("block lower than the halo")
+    blocks, slots = [], []
+    for rank in range(npx * npy):
+        cx, cy = rank // npy, rank % npy
+        blocks.append(np.ascontiguousarray(U[js[cy]:js[cy] + ny_loc[cy], cx * nx_loc:(cx + 1) * nx_loc]))
+        slots.append(np.full(2 * g * nx_loc + 2 * (ny_loc[cy] + 2 * g) * g2, np.nan))
+    bp = (ctypes.c_void_p * len(blocks))(*[b.ctypes.data for b in blocks])
+    sp = (ctypes.c_void_p * len(slots))(*[s.ctypes.data for s in slots])
+    nyl = (ctypes.c_int64 * npy)(*ny_loc)
+    assert emu.emu_peer_exchange_grid(npx, npy, ctypes.c_int64(nx_loc), nyl, g, g2, bp, sp) == 0
+    for rank in range(npx * npy):
+        cx, cy = rank // npy, rank % npy
+        i0, j0, ny = cx * nx_loc, js[cy], ny_loc[cy]
+        rows = lambda a, b: np.arange(j0 + a, j0 + b) % ny_glob  # noqa: E731
+        cols = lambda a, b: np.arange(i0 + a, i0 + b) % nx_glob  # noqa: E731
+        want = np.concatenate([
+            U[np.ix_(rows(-g, 0), cols(0, nx_loc))].ravel(),
+            U[np.ix_(rows(ny, ny + g), cols(0, nx_loc))].ravel(),
+            U[np.ix_(rows(-g, ny + g), cols(-g2, 0))].ravel(),
+            U[np.ix_(rows(-g, ny + g), cols(nx_loc, nx_loc + g2))].ravel()])
+        assert np.array_equal(slots[rank], want), rank
