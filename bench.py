@@ -147,6 +147,61 @@ def cpu_sample_plan(ranks, target_s=10.0):
     return sample_n, max(1, min(nsteps, 40))
 
 
+# ------------------------------------------------------------------------ host placement (N > 1)
+def gpu_numa_node(index):
+    """NUMA node the GPU's PCIe root hangs off (sysfs), or None."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        if bus.count(":") == 2 and len(bus.split(":")[0]) == 8:  # 00000000:1B:00.0 -> 0000:1b:00.0
+            bus = bus[4:]
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        return node if node >= 0 else None
+    except Exception:
+        return None
+
+
+def node_cpus(node):
+    try:
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            txt = f.read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        return cpus
+    except Exception:
+        return set()
+
+
+def bind_to_gpu_numa_node(index):
+    """Run this rank on the CPUs of its GPU's NUMA node, so that the pinned staging buffers it allocates afterwards
+    are first-touched there (Linux's default local allocation) and its copies do not cross the socket link.
+    Returns what was done (reported in the JSON line)."""
+    node = gpu_numa_node(index)
+    if node is None:
+        return {"node": None, "why": "GPU NUMA node unknown"}
+    allowed = os.sched_getaffinity(0)
+    cpus = node_cpus(node) & allowed
+    if not cpus:
+        return {"node": node, "why": "no allowed CPU on that node (affinity mask %d CPUs)" % len(allowed)}
+    os.sched_setaffinity(0, cpus)
+    return {"node": node, "cpus": len(cpus)}
+
+
+def pages_numa_node(tensor):
+    """NUMA node of the first page of a host tensor (move_pages query), or None."""
+    try:
+        libc = ctypes.CDLL(None, use_errno=True)
+        page = ctypes.c_void_p(tensor.data_ptr() & ~4095)
+        status = ctypes.c_int(-1)
+        rc = libc.syscall(279, 0, ctypes.c_ulong(1), ctypes.byref(page), None, ctypes.byref(status), 0)  # move_pages
+        return status.value if rc == 0 and status.value >= 0 else None
+    except Exception:
+        return None
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -234,6 +289,10 @@ def main():
     if world != args.gpus and world > 1:
         raise SystemExit("--gpus %d does not match WORLD_SIZE %d" % (args.gpus, world))
     torch.cuda.set_device(local_rank)
+    # one rank per GPU: keep the rank (and the pinned staging buffers it first-touches) on its GPU's NUMA node
+    placement = {"gpu_numa": gpu_numa_node(local_rank), "bound": None}
+    if os.environ.get("B200_BENCH_NO_BIND") is None:
+        placement["bound"] = bind_to_gpu_numa_node(local_rank)
     dist = None
     nccl_id = None
     if world > 1:
@@ -320,6 +379,7 @@ def main():
                    "error": "pinned host memory for the staging buffers could not be allocated on every rank"}
             hin = hout = None
     if hin is not None:
+        placement["pinned_pages_numa"] = pages_numa_node(hin[0])
         prob.get_state(hin[0])
         hin[1].copy_(hin[0])
         t_cur = prob.stats()["t"]
@@ -348,6 +408,8 @@ def main():
         e2e = {"value": e_evals * ncell_global / float(tt.item()), "unit": "cell-updates/s",
                "h2d_bytes_per_step": 8 * ncell_local * world, "d2h_bytes_per_step": 8 * ncell_local * world,
                "ms_per_step": 1e3 * float(tt.item()) / args.steps, "mode": args.e2e_mode,
+               "host_placement_rank0": placement,
+               "pcie_gbs_per_gpu_per_direction": 8 * ncell_local / 1e9 / (float(tt.item()) / args.steps),
                "note": ("independent batches, double-buffered: copies of batches i-1 / i+1 overlap the integration of batch i"
                         if args.e2e_mode == "pipelined" else "dependent steps: upload, step, download, nothing overlaps")}
         del hin, hout
