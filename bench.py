@@ -241,6 +241,212 @@ def reference_arm(args):
     emit(line)
 
 
+# ------------------------------------------------------------------ the other BASELINE configs (--config)
+# c3 (default) is the headline line above.  c2 / c4 / c5 are BASELINE.json configs[1] / [3] / [4] with the same line
+# shape: `value` = state resident in HBM, CUDA events on the launching stream; `e2e` = every batch starts and ends in
+# pinned host memory; `roofline` = modelled bytes of every launch in the timed region (b200_algorithmic_bytes: 8 B x
+# entries x full vectors read + written) / device time against the measured HBM copy peak; `cpu_baseline` = the
+# unmodified reference build on the host cores on a bounded sample of the same workload.
+CONFIGS = {
+    "c2": {
+        "kind": "d2d", "steps": 25, "e2e_batch_steps": 5, "cells": 4096 * 4096,
+        "args": ["--nx", "4096", "--ny", "4096", "--integrator", "rkl", "--kx", "1", "--ky", "0.1", "--inhomogeneous",
+                 "--internaleig", "--tf", "1.0", "--nout", "1", "--output", "0"],
+        "metric": "cell-updates/s ((RHS + DEE evals) x cells / s), diffusion_2D 4096^2 RKL2 anisotropic inhomogeneous, power-iteration eigenvalue",
+        "workload": "diffusion_2D 4096x4096 FP64, kx=1 ky=0.1 inhomogeneous, LSRKStep RKL2 adaptive (rtol 1e-5), --internaleig "
+                    "(power iteration every 25 steps: one falls into the default 25 timed steps)",
+        "kernel": "k_chain_march<4> (table-driven coefficients) + k_dq_march (power-iteration difference quotients)",
+        "ref": {"bin": "diffusion_2D_ref", "args": ["--nx", "4096", "--ny", "4096", "--integrator", "rkl", "--kx", "1", "--ky", "0.1",
+                                                     "--inhomogeneous", "--internaleig", "--tf", "0.001", "--nout", "1", "--output", "0"],
+                "cells": 4096 * 4096, "sample": "the full 4096^2 problem to tf = 1e-3 (19 steps)"},
+    },
+    "c4": {
+        "kind": "adr", "steps": 5, "cells": 2048 * 2048,
+        "args": ["--nx", "2048", "--ny", "2048", "--integrator", "3", "--sts_method", "0", "--fixed_h", "0.001", "--tf", "10.0",
+                 "--nout", "1", "--output", "0"],
+        "metric": "grid-point-updates/s (RHS evals x grid points / s, 2 species per point), adr 2D Brusselator 2048^2, Strang + RKC",
+        "workload": "adr 2D advection-diffusion-reaction (Brusselator) 2048x2048 x 2 species, Strang splitting: RKC diffusion "
+                    "half steps (17 stages) + explicit advection-reaction, fixed h = 1e-3",
+        "kernel": "k_adr_march<2> / k_adr_chain (diffusion stages) + k_adr_march<5> (advection-reaction)",
+        # --output 1: the reference prints its statistics and "Total solve time" (2 significant digits) only then
+        "ref": {"bin": "adr2d_ref", "args": ["--nx", "2048", "--ny", "2048", "--integrator", "3", "--sts_method", "0", "--fixed_h", "0.001",
+                                              "--nout", "1", "--output", "1"],
+                "cells": 2048 * 2048, "sample": "the full 2048^2 problem, %d Strang steps (the reference adr driver is serial: 1 core)"},
+    },
+    "c5": {
+        "kind": "d2d", "steps": 5, "e2e_batch_steps": 3, "cells": 8192 * 8192,
+        "args": ["--nx", "8192", "--ny", "8192", "--integrator", "dirk", "--order", "3", "--tf", "1.0", "--nout", "1", "--output", "0"],
+        "metric": "cell-updates/s ((implicit RHS + linear-solver RHS evals) x cells / s), diffusion_2D 8192^2 DIRK3 + PCG + Jacobi",
+        "workload": "diffusion_2D 8192x8192 FP64, ARKStep DIRK order 3 adaptive (rtol 1e-5), matrix-free PCG (<= 20 iterations) "
+                    "with Jacobi preconditioner",
+        "kernel": "k_dq_march (A*p = p - gamma*J p by difference quotient, fused with <Ap,p>) + k_lin2_wsqr / k_prod_dot (PCG vector work)",
+        "ref": {"bin": "diffusion_2D_ref", "args": ["--nx", "8192", "--ny", "1024", "--integrator", "dirk", "--order", "3", "--tf", "0.0008",
+                                                     "--nout", "1", "--output", "0"],
+                "cells": 8192 * 1024, "sample": "an 8192 x 1024 block (same dx, hence the same stiffness) to tf = 8e-4 (8 steps)"},
+    },
+}
+
+
+def config_evals(kind, st):
+    if kind == "adr":
+        return st["lsrk_rhs_evals"] + st["ark_rhs_evals"] + st["rhs_evals_explicit"]
+    return st["rhs_evals"] + st["dee_rhs_evals"] + st["lin_rhs_evals"]
+
+
+def reference_config_sample(cfg, ranks, reps=1):
+    """(value, seconds, evals) of the unmodified reference build on the host cores for this config's sample."""
+    ref = cfg["ref"]
+    binary = os.path.join(ROOT, "oracle", "_ref", ref["bin"])
+    if not os.path.exists(binary):
+        raise RuntimeError("oracle/_ref/%s missing (built by __graft_entry__.build())" % ref["bin"])
+    rargs = list(ref["args"])
+    if cfg["kind"] == "adr":
+        rargs += ["--tf", repr(0.001 * max(reps, 1))]
+        ranks = 1
+    env = dict(os.environ, MPISHIM_NP=str(ranks))
+    import tempfile
+
+    t0 = time.time()
+    out = subprocess.run([binary] + rargs, env=env, capture_output=True, text=True, timeout=3000, cwd=tempfile.mkdtemp(prefix="ref_")).stdout
+    wall = time.time() - t0
+    if cfg["kind"] == "adr":
+        m = re.search(r"Total solve time\s*=\s*([-+0-9.eE]+)", out)
+        t = float(m.group(1)) if m else wall
+        evals = sum(int(v) for v in re.findall(r"RHS fn evals\s*=\s*(\d+)", out))
+    else:
+        t = float(re.search(r"Total simulation time\s*=\s*([-+0-9.eE]+)", out).group(1))
+        evals = sum(int(v) for v in re.findall(r"(?:^|\n)\s*(?:RHS fn evals|Implicit RHS fn evals|LS RHS fn evals|Number of fe calls for DEE)\s*=\s*(\d+)", out))
+    return evals * ref["cells"] / t, t, evals, ranks
+
+
+def config_bench(args, cfgname):
+    cfg = CONFIGS[cfgname]
+    rank = int(os.environ.get("RANK", "0"))
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 or args.gpus > 1:
+        # these configurations are single-GPU measurements (the adr driver is serial in the reference; c2 is quoted on 1 B200);
+        # c5's 8-GPU leg is the weak-scaling line of the default workload's process grid and is not built here
+        if rank == 0:
+            emit({"metric": cfg["metric"], "config": {"workload": cfg["workload"]}, "n_gpus": args.gpus,
+                  "unavailable": "--config %s is measured on one GPU" % cfgname})
+        return
+    cores = host_cores()
+    ranks = 1
+    while ranks * 2 <= min(cores, 64):
+        ranks *= 2
+    steps = args.steps if args.steps_given else cfg["steps"]
+    warmup = max(args.warmup, 3)
+    base = {"metric": cfg["metric"], "unit": "cell-updates/s" if cfg["kind"] == "d2d" else "grid-point-updates/s", "n_gpus": 1,
+            "steps": steps, "warmup": warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": cfg["workload"], "name": cfgname}}
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        v, t, ev, used = reference_config_sample(cfg, ranks, reps=max(steps, 1))
+        sample = (cfg["ref"]["sample"] % max(steps, 1)) if "%d" in cfg["ref"]["sample"] else cfg["ref"]["sample"]
+        emit(dict(base, impl="reference", value=v, ms_per_step=1e3 * t / max(steps, 1), gpu_launches=0,
+                  cpu_baseline={"value": v, "unit": base["unit"], "cores": used, "kind": "reference", "sample": sample + ", %d RHS evals, %.1f s" % (ev, t)},
+                  e2e={"value": v, "unit": base["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}))
+        return
+
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
+    b200 = importlib.import_module("ceda-demonstrations_b200")
+    torch.cuda.set_device(0)
+    placement = {"gpu_numa": gpu_numa_node(0), "bound": bind_to_gpu_numa_node(0) if os.environ.get("B200_BENCH_NO_BIND") is None else None}
+    klib = b200.kernel_lib()
+    klib.b200_algorithmic_bytes.restype = ctypes.c_uint64
+    extra = list(args.config_args or [])
+    prob = (b200.Adr2D if cfg["kind"] == "adr" else b200.Diffusion2D)(cfg["args"] + extra, device=0)
+    nvals = cfg["cells"] * (2 if cfg["kind"] == "adr" else 1)
+
+    prob.step(warmup)
+    torch.cuda.synchronize()
+    s0 = prob.stats()
+    ab0 = klib.b200_algorithmic_bytes()
+    sampler = ClockSampler(0)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    prob.step(steps)
+    ev1.record()
+    torch.cuda.synchronize()
+    sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    s1 = prob.stats()
+    alg_bytes = klib.b200_algorithmic_bytes() - ab0
+    evals = config_evals(cfg["kind"], s1) - config_evals(cfg["kind"], s0)
+    launches = s1["kernel_launches"] - s0["kernel_launches"]
+    value = evals * cfg["cells"] / (ms * 1e-3)
+
+    # ---- e2e: every batch starts from a state in pinned host memory and ends with its result there
+    e2e = None
+    if not args.no_e2e:
+        hin = [torch.empty(nvals, dtype=torch.float64, pin_memory=True) for _ in range(2)]
+        hout = [torch.empty(nvals, dtype=torch.float64, pin_memory=True) for _ in range(2)]
+        placement["pinned_pages_numa"] = pages_numa_node(hin[0])
+        prob.get_state(hin[0])
+        hin[1].copy_(hin[0])
+        t_cur = prob.stats()["t"]
+        bsteps = cfg.get("e2e_batch_steps", 1)
+        nb = max(2, steps // bsteps) if cfg["kind"] == "d2d" else max(2, steps)
+        if cfg["kind"] == "d2d":
+            prob.run_batches([hin[0], hin[1]], [hout[0], hout[1]], t_cur, 1)  # staging buffers, copy streams
+            e0 = prob.stats()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            prob.run_batches([hin[i % 2] for i in range(nb)], [hout[i % 2] for i in range(nb)], t_cur, bsteps)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            mode = "pipelined: independent batches of %d steps, uploads / downloads of neighbouring batches overlap the integration" % bsteps
+        else:
+            bsteps = 1
+            prob.set_state(hin[0], t_cur)
+            e0 = prob.stats()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(nb):
+                prob.set_state(hin[i % 2], t_cur)  # H2D + ARKodeReset
+                prob.step(1)
+                prob.get_state(hout[i % 2])  # D2H (synchronises)
+            dt = time.perf_counter() - t0
+            mode = "sequential: upload, one Strang step, download (the adr session has no batch pipeline)"
+        e1 = prob.stats()
+        e_evals = config_evals(cfg["kind"], e1) - config_evals(cfg["kind"], e0)
+        e2e = {"value": e_evals * cfg["cells"] / dt, "unit": base["unit"], "h2d_bytes_per_step": 8 * nvals, "d2h_bytes_per_step": 8 * nvals,
+               "ms_per_step": 1e3 * dt / (nb * bsteps), "batches": nb, "steps_per_batch": bsteps, "mode": mode, "host_placement": placement}
+        del hin, hout
+    stats_final = prob.stats()
+    prob.close()
+
+    peak, peak_src = measured_peak()
+    achieved = alg_bytes / (ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "kernel": cfg["kernel"], "modelled_bytes_timed": int(alg_bytes),
+                "bytes_per_update": alg_bytes / max(evals * cfg["cells"], 1), "rhs_evals_timed": evals,
+                "one_pass_per_stage_basis": {"bytes_per_update": ALG_BYTES_PER_UPDATE * (2 if cfg["kind"] == "adr" else 1),
+                                             "achieved": ALG_BYTES_PER_UPDATE * (2 if cfg["kind"] == "adr" else 1) * evals * cfg["cells"] / (ms * 1e-3) / 1e9}}
+    roofline["one_pass_per_stage_basis"]["frac"] = roofline["one_pass_per_stage_basis"]["achieved"] / peak
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        try:
+            reps = 3 if cfg["kind"] == "adr" else 1
+            v, t, ev, used = reference_config_sample(cfg, ranks, reps=reps)
+            sample = (cfg["ref"]["sample"] % reps) if "%d" in cfg["ref"]["sample"] else cfg["ref"]["sample"]
+            cpu_baseline = {"value": v, "unit": base["unit"], "cores": used, "kind": "reference",
+                            "sample": sample + ", %d RHS evals, %.1f s" % (ev, t)}
+        except Exception as exc:
+            cpu_baseline = {"value": None, "unit": base["unit"], "cores": 0, "kind": "reference", "sample": "unavailable: %s" % exc}
+    keep = ("steps", "step_attempts", "err_test_fails", "rhs_evals", "dee_rhs_evals", "lin_iters", "lin_rhs_evals", "max_stages",
+            "lsrk_rhs_evals", "lsrk_max_stages", "ark_rhs_evals", "dq_fused", "ew_fused", "chain_launches", "chain_stages")
+    emit(dict(base, value=value, ms_per_step=ms / steps, e2e=e2e, gpu_launches=int(launches), roofline=roofline,
+              cpu_baseline=cpu_baseline, clocks=sampler.summary(),
+              integrator_stats={k: stats_final[k] for k in keep if k in stats_final},
+              launches_per_rhs_eval=launches / max(evals, 1)))
+
+
 # ------------------------------------------------------------------------------------ our arm
 def emit(line):
     """The contract is ONE JSON line on stdout: libraries (NCCL prints its version banner to stdout)
@@ -258,7 +464,7 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--local-n", type=int, default=16384, help="per-GPU block edge (default: the headline 16384)")
@@ -271,7 +477,16 @@ def main():
                     help="exact = bit-identical to the reference's baseline x86-64 build; fma = contracted multiply-adds")
     ap.add_argument("--e2e-mode", default="pipelined", choices=["pipelined", "sequential"])
     ap.add_argument("--chain-rows", type=int, default=0, help="rows per block of the chain kernel (0 = library default)")
+    ap.add_argument("--config", default="c3", choices=["c3", "c2", "c4", "c5"],
+                    help="c3 (default) = the headline 16384^2 RKC line; c2 / c4 / c5 = BASELINE configs[1] / [3] / [4]")
+    ap.add_argument("--config-args", nargs=argparse.REMAINDER, help="extra driver flags for --config c2/c4/c5 (e.g. --sts_chain 6)")
     args = ap.parse_args()
+    args.steps_given = args.steps is not None
+    if args.steps is None:
+        args.steps = 5
+    if args.config != "c3":
+        config_bench(args, args.config)
+        return
 
     if args.impl == "reference":
         reference_arm(args)

@@ -88,6 +88,7 @@ class D2DStats(ctypes.Structure):
         ("ny_loc", ctypes.c_int64), ("is_", ctypes.c_int64), ("js", ctypes.c_int64),
         ("npx", ctypes.c_int), ("npy", ctypes.c_int), ("rank", ctypes.c_int), ("nranks", ctypes.c_int),
         ("chain_launches", ctypes.c_long), ("chain_stages", ctypes.c_long),
+        ("dq_fused", ctypes.c_long), ("ew_fused", ctypes.c_long),
     ]
 
     def as_dict(self):

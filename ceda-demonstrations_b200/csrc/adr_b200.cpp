@@ -565,6 +565,7 @@ extern "C" int b200_adr_create(int argc, const char* const* argv, int device, vo
     p->ud.ops[m].op.halo_doubles = 0;
     p->ud.ops[m].op.halo_alloc   = nullptr;
     p->ud.ops[m].op.halo_free    = nullptr;
+    p->ud.ops[m].op.dq           = nullptr;
   }
   if (p->uo.sts_chain >= 2 && p->ud.nx >= 64 && p->ud.ny >= 16)
   { // opt-in: the pure diffusion operator (Strang's STS partition) may be chained

@@ -30,6 +30,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <vector>
 
 #ifdef B200_HOST_EMU
@@ -42,16 +43,66 @@
 #include "kernel_prims.cuh"
 
 // every kernel launch of the library goes through here
+// B200_TRACE_LAUNCHES=1: every launch is bracketed by stream synchronisations and its wall time (launch latency +
+// execution) is accumulated per kernel, as is the host time that passes BETWEEN launches; b200_trace_report() prints
+// the table (also called when a context is destroyed).  A diagnostic: it serialises host and device.
+struct LaunchTrace
+{
+  struct Row { const char* name; const void* key; uint64_t n; double ms; unsigned gx, gy, block; size_t smem; };
+  std::vector<Row> rows;
+  double gap_ms = 0.0, last_end = 0.0;
+  int on = -1;
+};
+static LaunchTrace g_trace;
+static double trace_now_ms()
+{
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return 1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec;
+}
+static bool trace_on()
+{
+  if (g_trace.on < 0) g_trace.on = getenv("B200_TRACE_LAUNCHES") ? 1 : 0;
+  return g_trace.on == 1;
+}
+extern "C" void b200_trace_report(void)
+{
+  if (!trace_on() || g_trace.rows.empty()) return;
+  double total = 0.0;
+  uint64_t n   = 0;
+  for (auto& r : g_trace.rows) { total += r.ms; n += r.n; }
+  fprintf(stderr, "[b200 trace] %llu launches, %.3f ms in kernels (launch + execution), %.3f ms of host time between launches\n",
+          (unsigned long long)n, total, g_trace.gap_ms);
+  for (auto& r : g_trace.rows)
+    fprintf(stderr, "[b200 trace]   %-46s grid %5u x %5u x %3u smem %6zu  n=%6llu  total %10.3f ms  avg %9.1f us\n", r.name, r.gx, r.gy,
+            r.block, r.smem, (unsigned long long)r.n, r.ms, 1e3 * r.ms / (double)r.n);
+  g_trace.rows.clear();
+  g_trace.gap_ms = 0.0;
+  g_trace.last_end = 0.0;
+}
+
 template <class... KArgs, class... Args>
-static inline void klaunch(void (*kern)(KArgs...), dim3 grid, unsigned block, size_t smem, cudaStream_t st, Args&&... args)
+static inline void klaunch_named(const char* name, void (*kern)(KArgs...), dim3 grid, unsigned block, size_t smem, cudaStream_t st, Args&&... args)
 {
 #ifdef B200_HOST_EMU
-  (void)st;
+  (void)st; (void)name;
   emu::launch_body(grid, block, smem, [&]() { kern(args...); });
 #else
+  if (!trace_on()) { kern<<<grid, block, smem, st>>>(args...); return; }
+  cudaStreamSynchronize(st);
+  const double t0 = trace_now_ms();
+  if (g_trace.last_end > 0.0) g_trace.gap_ms += t0 - g_trace.last_end;
   kern<<<grid, block, smem, st>>>(args...);
+  cudaStreamSynchronize(st);
+  const double t1 = trace_now_ms();
+  g_trace.last_end = t1;
+  const void* key = reinterpret_cast<const void*>(kern); // one row per instantiation (the label is the call site's spelling)
+  for (auto& r : g_trace.rows)
+    if (r.key == key) { r.n++; r.ms += t1 - t0; return; }
+  g_trace.rows.push_back({name, key, 1, t1 - t0, grid.x, grid.y, block, smem});
 #endif
 }
+#define klaunch(kern, ...) klaunch_named(#kern, kern, __VA_ARGS__)
 
 // --------------------------------------------------------------------- errors
 static thread_local char g_err[512] = "";
@@ -157,6 +208,7 @@ extern "C" int b200_ctx_create(int device, void* stream, b200_ctx** out)
 extern "C" int b200_ctx_destroy(b200_ctx* c)
 {
   if (!c) return 0;
+  b200_trace_report();
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   cudaStreamSynchronize(c->comm_stream);
@@ -415,7 +467,7 @@ static int launch_ew(b200_ctx* c, const EwArgs& a)
   int64_t cap    = (int64_t)c->sm_count * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  klaunch(k_elementwise<OP>, (unsigned)blocks, kThreads, 0, c->stream, a);
+  klaunch((k_elementwise<OP>), (unsigned)blocks, kThreads, 0, c->stream, a);
   LAUNCH_CHECK();
   const int reads = (OP == EW_LINCOMB) ? a.t.n
                     : (OP == EW_CONST) ? 0
@@ -508,24 +560,39 @@ extern "C" int b200_ewt_ss(b200_ctx* c, const double* y, double rtol, double ato
 // ---------------------------------------------------------------- reductions
 static int nccl_allreduce_inplace(b200_ctx* c, double* buf, int n, int op);
 
+// Where a reduction kernel's last block stores the result: on one rank straight into mapped pinned host memory
+// (no copy engine, no extra launch -- the host only waits for the stream); with a communicator into device memory,
+// all-reduced over the ranks and then published.
+static double* reduce_target(b200_ctx* c) { return (c->comm && c->nranks > 1) ? c->dev_result : c->host_result_dev; }
+static int reduce_fetch(b200_ctx* c, int rop, double* out)
+{
+  if (c->comm && c->nranks > 1)
+  {
+    int rc = nccl_allreduce_inplace(c, c->dev_result, 1, rop);
+    if (rc) return rc;
+    return read_small(c, out, c->dev_result, 1);
+  }
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  *out = c->host_result[0];
+  return 0;
+}
+static unsigned reduce_blocks(b200_ctx* c, int64_t n, int per_thread)
+{
+  int64_t n2     = (n + 1) >> 1;
+  int64_t blocks = (n2 + per_thread * kThreads - 1) / (per_thread * kThreads);
+  int64_t cap    = (int64_t)c->sm_count * 4;
+  if (blocks > cap) blocks = cap;
+  return (unsigned)(blocks < 1 ? 1 : blocks);
+}
+
 template <int KIND, int ROP>
 static int run_reduce(b200_ctx* c, const double* x, const double* y, int64_t n, double* result, double ys = 0.0)
 {
   if (!aligned16(x) || (y && !aligned16(y))) return fail("b200 reduce: pointer not 16-byte aligned");
-  int64_t n2     = (n + 1) >> 1;
-  int64_t blocks = (n2 + 4 * kThreads - 1) / (4 * kThreads);
-  int64_t cap    = (int64_t)c->sm_count * 4;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  klaunch(k_reduce<KIND, ROP>, (unsigned)blocks, kThreads, 0, c->stream, x, y, ys, n, c->partials, c->ticket, c->dev_result);
+  klaunch((k_reduce<KIND, ROP>), reduce_blocks(c, n, 4), kThreads, 0, c->stream, x, y, ys, n, c->partials, c->ticket, reduce_target(c));
   LAUNCH_CHECK();
   ALG_BYTES((KIND == RD_DOT || KIND == RD_WSQR) ? 2 : 1, n);
-  if (c->comm && c->nranks > 1)
-  {
-    int rc = nccl_allreduce_inplace(c, c->dev_result, 1, ROP);
-    if (rc) return rc;
-  }
-  return read_small(c, result, c->dev_result, 1);
+  return reduce_fetch(c, ROP, result);
 }
 
 extern "C" int b200_dot(b200_ctx* c, const double* x, const double* y, int64_t n, double* r)
@@ -559,9 +626,9 @@ extern "C" int b200_l1norm(b200_ctx* c, const double* x, int64_t n, double* r)
 template <int NT, uint32_t PAT>
 static void launch_march(const StageArgs& a, dim3 grid, cudaStream_t st)
 {
-  if (a.region == 2) klaunch(k_stage_march<NT, PAT, 2, false>, grid, kThreads, 0, st, a);
-  else if (a.rw) klaunch(k_stage_march<NT, PAT, 0, true>, grid, kThreads, 0, st, a);
-  else klaunch(k_stage_march<NT, PAT, 0, false>, grid, kThreads, 0, st, a);
+  if (a.region == 2) klaunch((k_stage_march<NT, PAT, 2, false>), grid, kThreads, 0, st, a);
+  else if (a.rw) klaunch((k_stage_march<NT, PAT, 0, true>), grid, kThreads, 0, st, a);
+  else klaunch((k_stage_march<NT, PAT, 0, false>), grid, kThreads, 0, st, a);
 }
 
 // pick the compiled pattern for the term sequence, else the general kernel
@@ -690,6 +757,67 @@ extern "C" int b200_stencil_lincomb(b200_ctx* c, const b200_stencil_geom* g, con
   return 0;
 }
 
+// ------------------------------------------------ implicit path: fused vector work
+#include "dq_kernels.cuh"
+
+extern "C" int b200_lin2_wsqrsum(b200_ctx* c, double ca, const double* a, double cb, const double* b, const double* w,
+                                 double wscalar, double* z, int64_t n, double* result)
+{
+  if (!aligned16(a) || !aligned16(b) || !aligned16(z) || (w && !aligned16(w))) return fail("b200_lin2_wsqrsum: pointer not 16-byte aligned");
+  Lin2RedArgs r;
+  memset(&r, 0, sizeof(r));
+  r.a = a; r.b = b; r.w = w; r.ca = ca; r.cb = cb; r.ws = wscalar; r.z = z; r.n = n;
+  r.partials = c->partials; r.ticket = c->ticket; r.result = reduce_target(c);
+  if (w) klaunch((k_lin2_wsqr<true>), reduce_blocks(c, n, 2), kThreads, 0, c->stream, r);
+  else klaunch((k_lin2_wsqr<false>), reduce_blocks(c, n, 2), kThreads, 0, c->stream, r);
+  LAUNCH_CHECK();
+  ALG_BYTES(w ? 4 : 3, n);
+  return reduce_fetch(c, RED_SUM, result);
+}
+
+extern "C" int b200_prod_dot(b200_ctx* c, const double* a, const double* b, const double* cc, double* z, int64_t n, double* result)
+{
+  if (!aligned16(a) || !aligned16(b) || !aligned16(cc) || !aligned16(z)) return fail("b200_prod_dot: pointer not 16-byte aligned");
+  ProdDotArgs r;
+  memset(&r, 0, sizeof(r));
+  r.a = a; r.b = b; r.c = cc; r.z = z; r.n = n;
+  r.partials = c->partials; r.ticket = c->ticket; r.result = reduce_target(c);
+  klaunch(k_prod_dot, reduce_blocks(c, n, 2), kThreads, 0, c->stream, r);
+  LAUNCH_CHECK();
+  ALG_BYTES((cc == a || cc == b) ? 3 : 4, n);
+  return reduce_fetch(c, RED_SUM, result);
+}
+
+extern "C" int b200_stencil_dq(b200_ctx* c, const b200_stencil_geom* g, const double* v, const double* y, const double* fy,
+                               double sigma, double siginv, int outer, double ca, double cb, double* z, double* dot_result)
+{
+  if (g->halo_w || g->halo_e || g->halo_s || g->halo_n) return fail("b200_stencil_dq: one periodic rank only");
+  if ((g->nx & 1) || g->nx < 2 || g->ny < 2) return fail("b200_stencil_dq: needs even nx >= 2 and ny >= 2");
+  if (g->ny >= (int64_t)1 << 31) return fail("b200_stencil_dq: ny too large");
+  if (!aligned16(v) || !aligned16(y) || !aligned16(fy) || !aligned16(z) || !aligned16(g->cxw) || !aligned16(g->cxe))
+    return fail("b200_stencil_dq: pointer not 16-byte aligned");
+  if (z == v || z == y || z == fy) return fail("b200_stencil_dq: z aliases an input");
+  DqArgs a;
+  memset(&a, 0, sizeof(a));
+  a.nx = g->nx; a.ny = g->ny; a.cxw = g->cxw; a.cxe = g->cxe; a.cys = g->cys; a.cyn = g->cyn;
+  a.v = v; a.y = y; a.fy = fy; a.sigma = sigma; a.siginv = siginv; a.ca = ca; a.cb = cb; a.outer = outer;
+  a.want_dot = dot_result ? 1 : 0;
+  a.z = z;
+  a.rows        = g_rows_per_block;
+  int64_t gx    = (a.nx / 2 + kThreads - 1) / kThreads;
+  int64_t gy    = (a.ny + a.rows - 1) / a.rows;
+  if (gy > 65535) { a.rows = (int)((a.ny + 65534) / 65535); gy = (a.ny + a.rows - 1) / a.rows; }
+  if (dot_result && gx * gy > kMaxPartials) return fail("b200_stencil_dq: too many blocks for the fused dot product");
+  a.partials = c->partials; a.ticket = c->ticket; a.result = reduce_target(c);
+  dim3 grid((unsigned)gx, (unsigned)gy);
+  if (dot_result) klaunch((k_dq_march<true>), grid, kThreads, 0, c->stream, a);
+  else klaunch((k_dq_march<false>), grid, kThreads, 0, c->stream, a);
+  LAUNCH_CHECK();
+  ALG_BYTES(4, a.nx * a.ny);
+  if (dot_result) return reduce_fetch(c, RED_SUM, dot_result);
+  return 0;
+}
+
 // ------------------------------------------- temporally blocked STS stages
 #include "chain_march.cuh"
 #include "chain_quad.cuh"
@@ -704,7 +832,7 @@ static int launch_chain_k(const ChainArgs& a, dim3 grid, cudaStream_t st)
     CU_TRY(cudaFuncSetAttribute(k_chain_march<K, PF, HALO, FMA, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  klaunch(k_chain_march<K, PF, HALO, FMA, UNI>, grid, kChainThreads, smem, st, a);
+  klaunch((k_chain_march<K, PF, HALO, FMA, UNI>), grid, kChainThreads, smem, st, a);
   return 0;
 }
 
@@ -742,7 +870,7 @@ static int launch_quad_k(const ChainArgs& a, dim3 grid, cudaStream_t st)
     CU_TRY(cudaFuncSetAttribute(k_chain_quad<K, PF, HALO, FMA, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  klaunch(k_chain_quad<K, PF, HALO, FMA, MINB>, grid, kQuadThreads, smem, st, a);
+  klaunch((k_chain_quad<K, PF, HALO, FMA, MINB>), grid, kQuadThreads, smem, st, a);
   return 0;
 }
 template <int K, int PF, int MINB>
@@ -1032,13 +1160,13 @@ static int launch_adr(b200_ctx* c, AdrArgs& a, int mode)
   dim3 grid((unsigned)gx, (unsigned)gy);
   switch (mode)
   {
-  case 1: klaunch(k_adr_march<1>, grid, kThreads, 0, c->stream, a); break;
-  case 2: klaunch(k_adr_march<2>, grid, kThreads, 0, c->stream, a); break;
-  case 3: klaunch(k_adr_march<3>, grid, kThreads, 0, c->stream, a); break;
-  case 4: klaunch(k_adr_march<4>, grid, kThreads, 0, c->stream, a); break;
-  case 5: klaunch(k_adr_march<5>, grid, kThreads, 0, c->stream, a); break;
-  case 6: klaunch(k_adr_march<6>, grid, kThreads, 0, c->stream, a); break;
-  default: klaunch(k_adr_march<7>, grid, kThreads, 0, c->stream, a); break;
+  case 1: klaunch((k_adr_march<1>), grid, kThreads, 0, c->stream, a); break;
+  case 2: klaunch((k_adr_march<2>), grid, kThreads, 0, c->stream, a); break;
+  case 3: klaunch((k_adr_march<3>), grid, kThreads, 0, c->stream, a); break;
+  case 4: klaunch((k_adr_march<4>), grid, kThreads, 0, c->stream, a); break;
+  case 5: klaunch((k_adr_march<5>), grid, kThreads, 0, c->stream, a); break;
+  case 6: klaunch((k_adr_march<6>), grid, kThreads, 0, c->stream, a); break;
+  default: klaunch((k_adr_march<7>), grid, kThreads, 0, c->stream, a); break;
   }
   LAUNCH_CHECK();
   return 0;
@@ -1108,7 +1236,7 @@ static int launch_adr_chain_k(const AdrChainArgs& a, dim3 grid, cudaStream_t st)
     CU_TRY(cudaFuncSetAttribute(k_adr_chain<K, kAdrChainPF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  klaunch(k_adr_chain<K, kAdrChainPF>, grid, kAdrChainThreads, smem, st, a);
+  klaunch((k_adr_chain<K, kAdrChainPF>), grid, kAdrChainThreads, smem, st, a);
   return 0;
 }
 

@@ -352,6 +352,20 @@ int rhs_chain(void* self, b200_ctx* ctx, int nstages, const double* x, const dou
   return b200_stencil_chain_halo(ctx, &g, nstages, x, prev2, yn, fn, coeffs, z_out, halos, kHaloRows, kHaloCols);
 }
 
+// arkLsATimes o arkLsDQJtimes around diffusion() in one stencil pass (one periodic rank, even width)
+int rhs_dq(void* self, b200_ctx* ctx, const double* v, const double* y, const double* fy, double sigma, double siginv,
+           int outer, double ca, double cb, double* z, double* dot_result)
+{
+  UserData* ud = static_cast<UserData*>(self);
+  if (ud->npx > 1 || ud->npy > 1 || (ud->nx_loc & 1) || ud->nx_loc < 2 || ud->ny_loc < 2) return 1;
+  b200_stencil_geom g;
+  memset(&g, 0, sizeof(g));
+  g.nx = ud->nx_loc; g.ny = ud->ny_loc;
+  g.cxw = ud->cxw; g.cxe = ud->cxe; g.cys = ud->cys; g.cyn = ud->cyn;
+  ud->rhs_calls++;
+  return b200_stencil_dq(ctx, &g, v, y, fy, sigma, siginv, outer, ca, cb, z, dot_result) ? -1 : 0;
+}
+
 double* halo_slot_alloc(void* self) { return b200_peer_halo_slot_alloc(static_cast<UserData*>(self)->peer_halo); }
 void halo_slot_free(void* self, double* h)
 {
@@ -682,6 +696,7 @@ extern "C" int b200_d2d_create(int argc, const char* const* argv, int rank, int 
   p->ud.rhs_op.self = &p->ud;
   p->ud.rhs_op.fused = rhs_fused;
   p->ud.rhs_op.chain = nullptr;
+  p->ud.rhs_op.dq    = (getenv("B200_NO_DQ_FUSION") || p->uo.no_fusion) ? nullptr : rhs_dq;
   p->ud.rhs_op.chain_max = 0;
   p->ud.rhs_op.halo_doubles = 0;
   p->ud.force_halo          = p->uo.force_halo || getenv("B200_FORCE_HALO") != nullptr;
@@ -871,6 +886,8 @@ extern "C" int b200_d2d_get_stats(b200_d2d* p, b200_d2d_stats* s)
   s->buffers_allocated  = vs.buffers_allocated - p->vs0.buffers_allocated;
   s->chain_launches     = vs.chain_launches - p->vs0.chain_launches;
   s->chain_stages       = vs.chain_stages - p->vs0.chain_stages;
+  s->dq_fused           = vs.dq_fused - p->vs0.dq_fused;
+  s->ew_fused           = vs.ew_fused - p->vs0.ew_fused;
   s->kernel_launches    = b200_launch_count() - p->launches0;
   s->nx = p->ud.nx; s->ny = p->ud.ny; s->nx_loc = p->ud.nx_loc; s->ny_loc = p->ud.ny_loc;
   s->is = p->ud.is; s->js = p->ud.js; s->npx = p->ud.npx; s->npy = p->ud.npy;
@@ -1048,6 +1065,8 @@ extern "C" int b200_d2d_main(int argc, char** argv)
     printf("B200 fused stage evaluations  = %ld\n", s.fused_launches);
     printf("B200 chained launches/stages  = %ld / %ld\n", s.chain_launches, s.chain_stages);
     printf("B200 plain RHS launches       = %ld\n", s.plain_rhs_launches);
+    printf("B200 fused DQ matvecs         = %ld\n", s.dq_fused);
+    printf("B200 fused vector+reduce ops  = %ld\n", s.ew_fused);
     printf("B200 aliased copies           = %ld\n", s.aliased_copies);
     printf("B200 fused WRMS norms         = %ld\n", s.wrms_fused);
     printf("B200 kernel launches          = %llu\n", (unsigned long long)s.kernel_launches);

@@ -45,7 +45,7 @@ namespace {
   }                                     \
   while (0)
 
-B200VecStats g_stats = {0, 0, 0, 0, 0, 0, 0};
+B200VecStats g_stats = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 bool g_lazy          = true;
 int g_chain_max      = 4; // stages per temporally blocked launch (1 = off)
 
@@ -75,6 +75,16 @@ struct StageRec
   int depth;               // 1 for the first stage of a chain
 };
 
+// a requested-but-not-evaluated elementwise result (the implicit path's vector work): evaluated when something
+// reads it -- alone, or inside the reduction / stencil kernel that consumes it
+enum EwKind { EWK_LIN2 = 1, EWK_SCALESUM, EWK_SCALEDIFF, EWK_PROD };
+struct EwRec
+{
+  int kind;       // LIN2: ca*a + cb*b ; SCALESUM / SCALEDIFF: ca*(a +- b) ; PROD: a.*b
+  Value *a, *b;   // one reference held on each
+  double ca, cb;
+};
+
 struct Value
 {
   int refs;
@@ -82,6 +92,7 @@ struct Value
   const B200RhsOp* op; // deferred: value = op(src)
   Value* src;
   StageRec* st;        // pending stage (d == nullptr, op == nullptr)
+  EwRec* ew;           // pending elementwise result (d == nullptr, op == nullptr, st == nullptr)
   bool is_const;       // every entry equals cval (N_VConst); the buffer is only filled if somebody needs one
   double cval;
   double* halo;        // deep halo of this value (multi-rank temporal blocking), filled on demand
@@ -137,6 +148,13 @@ void value_release(Shared* sh, Value* v)
     }
     if (v->wrms_w) value_release(sh, v->wrms_w);
     Value* next = v->src; // a deferred value owns a reference on its source
+    if (v->ew)
+    { // a pending elementwise result that was never needed
+      EwRec* e = v->ew;
+      value_release(sh, e->b);
+      next = e->a;
+      delete e;
+    }
     if (v->st)
     { // a pending stage that was never needed: drop its operands
       StageRec* r = v->st;
@@ -159,6 +177,7 @@ Value* value_new(Shared* sh, bool with_buffer)
   v->op        = nullptr;
   v->src       = nullptr;
   v->st        = nullptr;
+  v->ew        = nullptr;
   v->is_const  = false;
   v->cval      = 0.0;
   v->halo      = nullptr;
@@ -180,6 +199,7 @@ void assign(Content* c, Value* nv) // takes ownership of one reference on nv
 }
 
 void materialise(Shared* sh, Value* v);
+void force_ew(Shared* sh, Value* v);
 
 // make sure the host mirror (if it was handed out) is reflected on the device
 void sync_from_host(Content* c)
@@ -358,6 +378,7 @@ void materialise(Shared* sh, Value* v)
 {
   if (v->d) return;
   if (v->st) { launch_chain(sh, v); return; }
+  if (v->ew) { force_ew(sh, v); return; }
   if (v->is_const)
   { // a constant that somebody wants to read element by element after all
     v->d = pool_get(sh);
@@ -380,6 +401,119 @@ void materialise(Shared* sh, Value* v)
   v->src = nullptr;
   value_release(sh, src);
   g_stats.plain_rhs_launches++;
+}
+
+// ---------------------------------------------------------------- pending elementwise results
+bool is_ew(const Value* v) { return !v->d && v->ew; }
+bool is_rhs(const Value* v) { return !v->d && v->op; }
+
+Value* ew_new(Shared* sh, int kind, double ca, Value* a, double cb, Value* b)
+{
+  Value* out = value_new(sh, false);
+  EwRec* e   = new EwRec();
+  e->kind = kind; e->a = a; e->b = b; e->ca = ca; e->cb = cb;
+  a->refs++;
+  b->refs++;
+  out->ew = e;
+  return out;
+}
+
+void ew_retire(Shared* sh, Value* v) // v->d has been filled: drop the record
+{
+  EwRec* e = v->ew;
+  v->ew    = nullptr;
+  value_release(sh, e->a);
+  value_release(sh, e->b);
+  delete e;
+}
+
+// The difference-quotient pattern of arkLsATimes / arkLsDQJtimes (arkode_ls.c:2316-2372, :2839-2877):
+//   top = LIN2(ca, V, cb, J) [outer] or J itself,  J = SCALEDIFF(siginv, F, FY),  F = deferred op(W),
+//   W = LIN2(sigma, V, 1, Y).  All leaves V, Y, FY are (made) materialised; nothing in between is stored.
+struct DqMatch
+{
+  bool ok = false;
+  int outer = 0;
+  double ca = 0, cb = 0, sigma = 0, siginv = 0;
+  Value *V = nullptr, *Y = nullptr, *FY = nullptr, *F = nullptr;
+};
+DqMatch match_dq(const Value* top)
+{
+  DqMatch m;
+  if (!is_ew(top)) return m;
+  const Value* J = top;
+  if (top->ew->kind == EWK_LIN2 && is_ew(top->ew->b) && top->ew->b->ew->kind == EWK_SCALEDIFF)
+  {
+    m.outer = 1; m.ca = top->ew->ca; m.cb = top->ew->cb;
+    J = top->ew->b;
+  }
+  if (J->ew->kind != EWK_SCALEDIFF) return m;
+  Value* F = J->ew->a;
+  if (!is_rhs(F) || !F->op->dq) return m;
+  Value* W = F->src;
+  if (!is_ew(W) || W->ew->kind != EWK_LIN2 || W->ew->cb != 1.0) return m;
+  m.V = W->ew->a; m.Y = W->ew->b; m.FY = J->ew->b; m.F = F;
+  m.sigma = W->ew->ca; m.siginv = J->ew->ca;
+  if (m.outer && top->ew->a != m.V) return m;
+  m.ok = true;
+  return m;
+}
+
+// evaluate the difference-quotient pattern in one stencil pass; dot_result != nullptr: also <top, V>
+bool run_dq(Shared* sh, Value* top, const DqMatch& m, double* dot_result)
+{
+  materialise(sh, m.V);
+  materialise(sh, m.Y);
+  materialise(sh, m.FY);
+  double* out = pool_get(sh);
+  int rc = m.F->op->dq(m.F->op->self, sh->ctx, m.V->d, m.Y->d, m.FY->d, m.sigma, m.siginv, m.outer, m.ca, m.cb, out, dot_result);
+  if (rc != 0)
+  {
+    sh->free_bufs.push_back(out);
+    if (rc < 0) die("B200RhsOp::dq", rc);
+    return false;
+  }
+  top->d = out;
+  ew_retire(sh, top);
+  g_stats.dq_fused++;
+  g_stats.fused_launches++;
+  return true;
+}
+
+void force_ew(Shared* sh, Value* v)
+{
+  {
+    DqMatch m = match_dq(v);
+    if (m.ok && run_dq(sh, v, m, nullptr)) return;
+  }
+  EwRec* e = v->ew;
+  materialise(sh, e->a);
+  materialise(sh, e->b);
+  double* out = pool_get(sh);
+  switch (e->kind)
+  {
+  case EWK_LIN2:
+  {
+    const double cf[2]  = {e->ca, e->cb};
+    const double* vp[2] = {e->a->d, e->b->d};
+    DEV(b200_lincomb(sh->ctx, 2, cf, vp, out, sh->nloc));
+    break;
+  }
+  case EWK_SCALESUM: DEV(b200_scale_sumdiff(sh->ctx, e->ca, e->a->d, e->b->d, +1, out, sh->nloc)); break;
+  case EWK_SCALEDIFF: DEV(b200_scale_sumdiff(sh->ctx, e->ca, e->a->d, e->b->d, -1, out, sh->nloc)); break;
+  default: DEV(b200_prod(sh->ctx, e->a->d, e->b->d, out, sh->nloc)); break;
+  }
+  v->d = out;
+  ew_retire(sh, v);
+}
+
+// operands of a new pending elementwise result: anything that is not plain data is evaluated first, except the two
+// shapes the fused kernels consume (keep_a / keep_b say which operand may stay pending)
+void ew_operand(Shared* sh, Value* x, bool keep)
+{
+  if (x->d) return;
+  if (keep && (is_ew(x) || is_rhs(x))) return;
+  materialise(sh, x);
 }
 
 // z = sum_k cf[k]*X[k], left to right; handles deferred operands by fusion
@@ -526,13 +660,39 @@ void op_linearsum(sunrealtype a, N_Vector x, sunrealtype b, N_Vector y, N_Vector
   // nvector_parallel.c:424-517: every branch except a==+-b (|a| != 1) evaluates
   // (a*x) + (b*y) with exact +-1 products; those two evaluate a*(x +- y).
   const bool unit = (a == 1.0 || a == -1.0 || b == 1.0 || b == -1.0);
+  Content* zc = C(z);
+  Shared* sh  = zc->sh;
+  if (g_lazy)
+  { // nothing is launched: z becomes a pending elementwise result (see EwRec)
+    sync_from_host(C(x));
+    sync_from_host(C(y));
+    Value* xv = C(x)->val;
+    Value* yv = C(y)->val;
+    if (!unit && (a == b || a == -b))
+    {
+      // Jv = siginv*(F(y + sig*v) - fy), arkode_ls.c:2874: F stays deferred, its argument stays pending
+      const bool keepx = is_rhs(xv) && xv->op->dq && is_ew(xv->src) && xv->src->ew->kind == EWK_LIN2;
+      ew_operand(sh, xv, keepx);
+      ew_operand(sh, yv, false);
+      assign(zc, ew_new(sh, (a == b) ? EWK_SCALESUM : EWK_SCALEDIFF, a, xv, 0.0, yv));
+      return;
+    }
+    const bool sts_x = is_rhs(xv) || (!xv->d && xv->st), sts_y = is_rhs(yv) || (!yv->d && yv->st);
+    if (!sts_x && !sts_y)
+    { // (deferred right-hand sides and pending stages take the stage-fusion path below)
+      const bool keepy = is_ew(yv) && yv->ew->kind == EWK_SCALEDIFF && is_rhs(yv->ew->a); // z = v - gamma*Jv, :2366
+      ew_operand(sh, xv, false);
+      ew_operand(sh, yv, keepy);
+      assign(zc, ew_new(sh, EWK_LIN2, a, xv, b, yv));
+      return;
+    }
+  }
   if (!unit && (a == b || a == -b))
   {
     const double* xd = mat(x);
     const double* yd = mat(y);
-    Content* zc      = C(z);
-    Value* out       = value_new(zc->sh, true);
-    DEV(b200_scale_sumdiff(zc->sh->ctx, a, xd, yd, (a == b) ? +1 : -1, out->d, zc->sh->nloc));
+    Value* out       = value_new(sh, true);
+    DEV(b200_scale_sumdiff(sh->ctx, a, xd, yd, (a == b) ? +1 : -1, out->d, sh->nloc));
     assign(zc, out);
     return;
   }
@@ -562,8 +722,21 @@ void op_const(sunrealtype c, N_Vector z)
     DEV(KERNEL(zc->sh->ctx, xd, yd, out->d, zc->sh->nloc));          \
     assign(zc, out);                                                 \
   }
-BINARY_OP(op_prod, b200_prod)
+BINARY_OP(op_prod_now, b200_prod)
 BINARY_OP(op_div, b200_div)
+
+void op_prod(N_Vector x, N_Vector y, N_Vector z)
+{
+  if (!g_lazy) { op_prod_now(x, y, z); return; }
+  sync_from_host(C(x));
+  sync_from_host(C(y));
+  Value* xv  = C(x)->val;
+  Value* yv  = C(y)->val;
+  Shared* sh = C(z)->sh;
+  ew_operand(sh, xv, is_ew(xv) && xv->ew->kind == EWK_LIN2); // Ap = r.*s with r = r - alpha*Ap pending, sunlinsol_pcg.c:543-551
+  ew_operand(sh, yv, false);
+  assign(C(z), ew_new(sh, EWK_PROD, 0.0, xv, 0.0, yv));
+}
 
 void op_scale(sunrealtype c, N_Vector x, N_Vector z)
 {
@@ -603,12 +776,79 @@ void op_addconst(N_Vector x, sunrealtype b, N_Vector z)
   assign(zc, out);
 }
 
+// z = ca*A + cb*B pending: evaluate it inside the weighted-square-sum kernel (w: vector or constant)
+double lin2_wsqr(Shared* sh, Value* z, Value* w)
+{
+  EwRec* e = z->ew;
+  materialise(sh, e->a);
+  materialise(sh, e->b);
+  const bool wc = w->is_const && !w->d;
+  if (!wc) materialise(sh, w);
+  double* out = pool_get(sh);
+  double r    = 0.0;
+  DEV(b200_lin2_wsqrsum(sh->ctx, e->ca, e->a->d, e->cb, e->b->d, wc ? nullptr : w->d, wc ? w->cval : 0.0, out, sh->nloc, &r));
+  z->d = out;
+  ew_retire(sh, z);
+  g_stats.ew_fused++;
+  return r;
+}
+
 sunrealtype op_dotprod(N_Vector x, N_Vector y)
 {
+  Shared* sh = C(x)->sh;
+  if (g_lazy)
+  {
+    sync_from_host(C(x));
+    sync_from_host(C(y));
+    Value* xv = C(x)->val;
+    Value* yv = C(y)->val;
+    for (int swap = 0; swap < 2; swap++)
+    { // <Ap, p> with Ap = A*p pending as the difference-quotient pattern around p (sunlinsol_pcg.c:519)
+      Value* a  = swap ? yv : xv;
+      Value* b  = swap ? xv : yv;
+      DqMatch m = match_dq(a);
+      double r  = 0.0;
+      if (m.ok && m.V == b && run_dq(sh, a, m, &r)) return r;
+    }
+    if (xv == yv && is_ew(xv) && xv->ew->kind == EWK_PROD)
+    { // <r.*s, r.*s> (:543-552): a weighted square sum of r; the product itself is never needed
+      Value* A = xv->ew->a;
+      Value* W = xv->ew->b;
+      if (is_ew(A) && A->ew->kind == EWK_LIN2) return lin2_wsqr(sh, A, W);
+      materialise(sh, A);
+      double r = 0.0;
+      if (W->is_const && !W->d) { DEV(b200_wsqrsum_scalar(sh->ctx, A->d, W->cval, sh->nloc, &r)); }
+      else
+      {
+        materialise(sh, W);
+        DEV(b200_wsqrsum(sh->ctx, A->d, W->d, sh->nloc, &r));
+      }
+      return r;
+    }
+    for (int swap = 0; swap < 2; swap++)
+    { // <r, z> with z = P^-1 r = diag.*r pending (:571-589)
+      Value* zv = swap ? yv : xv;
+      Value* u  = swap ? xv : yv;
+      if (zv != u && is_ew(zv) && zv->ew->kind == EWK_PROD)
+      {
+        EwRec* e = zv->ew;
+        materialise(sh, u);
+        materialise(sh, e->a);
+        materialise(sh, e->b);
+        double* out = pool_get(sh);
+        double r    = 0.0;
+        DEV(b200_prod_dot(sh->ctx, e->a->d, e->b->d, u->d, out, sh->nloc, &r));
+        zv->d = out;
+        ew_retire(sh, zv);
+        g_stats.ew_fused++;
+        return r;
+      }
+    }
+  }
   const double* xd = mat(x);
   const double* yd = mat(y);
   double r         = 0.0;
-  DEV(b200_dot(C(x)->sh->ctx, xd, yd, C(x)->sh->nloc, &r));
+  DEV(b200_dot(sh->ctx, xd, yd, sh->nloc, &r));
   return r;
 }
 
@@ -624,8 +864,14 @@ sunrealtype wsqrsum(N_Vector x, N_Vector w)
 {
   Content* xc      = C(x);
   Shared* sh       = xc->sh;
-  const double* xd = mat(x);
+  sync_from_host(xc);
   sync_from_host(C(w));
+  if (g_lazy && is_ew(xc->val) && xc->val->ew->kind == EWK_LIN2)
+  { // p = z + beta*p, then sig = 1/||p||_wrms in arkLsDQJtimes (sunlinsol_pcg.c:596, arkode_ls.c:2852)
+    Value* wv0 = C(w)->val;
+    return lin2_wsqr(sh, xc->val, wv0);
+  }
+  const double* xd = mat(x);
   Value* wv        = C(w)->val;
   const bool wc    = wv->is_const && !wv->d; // constant weight that was never stored: pass the number
   const double* wd = wc ? nullptr : mat(w);

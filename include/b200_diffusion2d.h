@@ -41,6 +41,8 @@ typedef struct b200_d2d_stats
   int64_t nx, ny, nx_loc, ny_loc, is, js;
   int npx, npy, rank, nranks;
   long chain_launches, chain_stages; /* temporally blocked launches and the stages they covered */
+  long dq_fused, ew_fused;           /* difference-quotient matvecs in one stencil pass; elementwise results produced
+                                        inside the reduction kernel that consumes them (implicit path) */
 } b200_d2d_stats;
 
 /* Build the problem from reference-style arguments, e.g.

@@ -110,6 +110,19 @@ int b200_wsqrsum(b200_ctx* ctx, const double* x, const double* w, int64_t n, dou
 /* the same with ONE weight w for every entry (a constant-valued weight vector, e.g. the ewt = N_VConst(SUN_SMALL_REAL)
    of fixed-step explicit runs, SUN/src/arkode/arkode.c:2985-2990): w is never read from memory */
 int b200_wsqrsum_scalar(b200_ctx* ctx, const double* x, double w, int64_t n, double* result);
+/* B200_TRACE_LAUNCHES=1 in the environment: per-kernel launch counts and wall times (each launch bracketed by stream
+   synchronisations) and the host time between launches, printed to stderr by this call and at b200_ctx_destroy. */
+void b200_trace_report(void);
+
+/* Fused forms of the implicit path's vector work (SUN/src/sunlinsol/pcg/sunlinsol_pcg.c:499-601).  Each stores z exactly
+   as the separate N_VLinearSum / N_VProd would and returns the reduction N_VDotProd / N_VWrmsNorm takes of it next:
+     b200_lin2_wsqrsum  z = ca*a + cb*b ; result = sum_i (z_i w_i)^2   (w == NULL: the scalar weight wscalar)
+                        -- r = r - alpha*Ap with rho = <r.*s, r.*s> (:543-559), p = z + beta*p with the WRMS norm of
+                           arkLsDQJtimes (arkode_ls.c:2852)
+     b200_prod_dot      z = a .* b ; result = sum_i c_i z_i              -- z = P^-1 r (Jacobi), rz = <r, z> (:571-589) */
+int b200_lin2_wsqrsum(b200_ctx* ctx, double ca, const double* a, double cb, const double* b, const double* w,
+                      double wscalar, double* z, int64_t n, double* result);
+int b200_prod_dot(b200_ctx* ctx, const double* a, const double* b, const double* c, double* z, int64_t n, double* result);
 int b200_maxnorm(b200_ctx* ctx, const double* x, int64_t n, double* result);                   /* N_VMaxNorm :689 */
 int b200_min(b200_ctx* ctx, const double* x, int64_t n, double* result);                       /* N_VMin :780 */
 int b200_l1norm(b200_ctx* ctx, const double* x, int64_t n, double* result);                    /* N_VL1Norm :815 */
@@ -232,6 +245,15 @@ double* b200_peer_halo_slot_alloc(b200_peer_halo* ph);            /* NULL when t
 int b200_peer_halo_slot_free(b200_peer_halo* ph, double* slot);
 int b200_peer_halo_exchange(b200_peer_halo* ph, int nfields, const double* const* fields, double* const* slots);
 int b200_peer_halo_stats(const b200_peer_halo* ph, uint64_t* exchanges, uint64_t* doubles_pushed);
+/* The matrix-free linear operator of the implicit path in ONE stencil pass (one periodic rank, even nx):
+     outer = 1:  z = ca*v + cb*( siginv*( L(sigma*v + y) - fy ) )   = arkLsATimes o arkLsDQJtimes with ca = 1, cb = -gamma
+                 (SUN/src/arkode/arkode_ls.c:2316-2372, :2839-2877)
+     outer = 0:  z = siginv*( L(sigma*v + y) - fy )                  = arkLsDQJtimes / lsrkStep_DQJtimes
+                 (SUN/src/arkode/arkode_lsrkstep.c:2408-2431)
+   element by element the instruction sequence of the separate N_VLinearSum / RHS / N_VLinearSum calls.  With
+   dot_result != NULL also returns sum_i z_i v_i (PCG's <Ap, p>, sunlinsol_pcg.c:519). */
+int b200_stencil_dq(b200_ctx* ctx, const b200_stencil_geom* g, const double* v, const double* y, const double* fy,
+                    double sigma, double siginv, int outer, double ca, double cb, double* z, double* dot_result);
 /* rows of output each thread block of the chain kernel marches over; 0 (default) = automatic: 128
    where that leaves at least 4 waves of blocks, else 64, else 32.  Results do not depend on it. */
 int b200_set_chain_rows(int rows);

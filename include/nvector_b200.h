@@ -59,6 +59,13 @@ typedef struct B200RhsOp
      into (b200_peer_halo_*).  Every rank must see the same sequence of calls. */
   double* (*halo_alloc)(void* self);
   void (*halo_free)(void* self, double* halo);
+  /* Optional (NULL = not available): the difference-quotient Jacobian-vector product around F in one pass,
+       outer = 1:  z = ca*v + cb*( siginv*( F(sigma*v + y) - fy ) )      (arkLsATimes o arkLsDQJtimes)
+       outer = 0:  z = siginv*( F(sigma*v + y) - fy )                     (arkLsDQJtimes, lsrkStep_DQJtimes)
+     and, if dot_result != NULL, sum_i z_i v_i.  Return 0 = done, 1 = not handled here (the vector then evaluates
+     the pieces one by one), < 0 = error. */
+  int (*dq)(void* self, b200_ctx* ctx, const double* v, const double* y, const double* fy, double sigma,
+            double siginv, int outer, double ca, double cb, double* z, double* dot_result);
 } B200RhsOp;
 
 /* Create a vector: local_length entries on this rank's GPU, global_length overall
@@ -99,6 +106,8 @@ typedef struct B200VecStats
   long wrms_fused;        /* WRMS norms answered from a fused partial */
   long chain_launches;    /* temporally blocked launches (>= 2 stages each) */
   long chain_stages;      /* stages covered by those launches */
+  long dq_fused;          /* difference-quotient matvecs evaluated in one stencil pass (B200RhsOp::dq) */
+  long ew_fused;          /* elementwise results produced inside a reduction kernel (lin2+wsqr, prod+dot) */
 } B200VecStats;
 SUNDIALS_EXPORT void N_VGetStats_B200(B200VecStats* s);
 

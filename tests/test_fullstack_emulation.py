@@ -132,6 +132,30 @@ def test_temporal_blocking_and_deep_halo_paths_do_not_change_a_bit(emu, args):
     emu.sundials_lib().N_VSetStageChain_B200(4)
 
 
+def test_implicit_path_vector_work_is_fused(emu, monkeypatch):
+    """DIRK3 + PCG + Jacobi (BASELINE configs[4] at 64^2): arkLsATimes o arkLsDQJtimes runs as ONE stencil launch that
+    also returns <Ap, p>; r -= alpha*Ap with its weighted norm, z = P^-1 r with <r, z>, and p = z + beta*p with the WRMS
+    norm of the next matvec are one kernel each -- about 5 launches per PCG iteration instead of ~18, same
+    statistics as the reference fixture, state within its bar; with the fusion off the old launch count is back."""
+    meta, ref = load_golden("dirk3_pcg_64")
+    st, u = run_d2d(emu, meta["args"])
+    check_stats(meta, st, True)
+    assert st["lin_iters"] <= st["dq_fused"] <= st["lin_iters"] + st["nonlin_iters"] and st["ew_fused"] >= 2 * st["lin_iters"]
+    assert st["kernel_launches"] <= 7.5 * st["lin_iters"], (st["kernel_launches"], st["lin_iters"])
+    rel = float(np.linalg.norm(u - ref) / np.linalg.norm(ref))
+    assert rel <= max(REL_L2_TOL, 3.0 * meta["ref_np1_vs_np4_rel_l2"]), rel
+    st0, u0 = run_d2d(emu, meta["args"] + ["--no-fusion"])
+    emu.sundials_lib().N_VSetLazyFusion_B200(1)
+    check_stats(meta, st0, True)
+    assert st0["dq_fused"] == 0 and st0["kernel_launches"] > 2 * st["kernel_launches"]
+    assert float(np.linalg.norm(u - u0) / np.linalg.norm(u0)) <= max(REL_L2_TOL, 3.0 * meta["ref_np1_vs_np4_rel_l2"])
+    # the power iteration's difference quotients (--internaleig, lsrkStep_DQJtimes) take the same kernel
+    meta, ref = load_golden("rkl_internaleig_64")
+    st, u = run_d2d(emu, meta["args"])
+    check_stats(meta, st, False)
+    assert st["dq_fused"] >= st["dee_rhs_evals"] > 0
+
+
 def test_lazy_fusion_off_is_the_same_bits(emu):
     args = ["--nx", 96, "--ny", 64, "--kx", "1.0", "--ky", "0.5", "--inhomogeneous", "--integrator", "rkc",
             "--fixedstep", "0.0009765625", "--tf", "0.00390625"]
