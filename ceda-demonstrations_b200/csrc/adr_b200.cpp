@@ -89,7 +89,8 @@ struct AdrOptions
   bool linear = false, calc_error = false, write_solution = false;
   int output = 1, nout = 1;
   bool no_fusion = false; // B200 extra
-  int sts_chain  = 1;     // B200 extra: temporal-blocking depth of the STS diffusion stages (1 = off)
+  int sts_chain  = 4;     // B200 extra: temporal-blocking depth of the STS diffusion stages (1 = off; 4 measured best
+                          // at 2048^2 on the B200: 1.52 ms per Strang step against 2.86 ms with one launch per stage)
 };
 
 int adr_fused(void* self, b200_ctx* ctx, const double* y, int nterms, const double* c, const int* src,

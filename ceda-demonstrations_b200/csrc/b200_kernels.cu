@@ -775,6 +775,19 @@ extern "C" int b200_lin2_wsqrsum(b200_ctx* c, double ca, const double* a, double
   return reduce_fetch(c, RED_SUM, result);
 }
 
+extern "C" int b200_ewt_ss_wsqrsum(b200_ctx* c, const double* y, double rtol, double atol, double* ewt, int64_t n, double* result)
+{
+  if (!aligned16(y) || !aligned16(ewt)) return fail("b200_ewt_ss_wsqrsum: pointer not 16-byte aligned");
+  EwtArgs r;
+  memset(&r, 0, sizeof(r));
+  r.y = y; r.rtol = rtol; r.atol = atol; r.ewt = ewt; r.n = n;
+  r.partials = c->partials; r.ticket = c->ticket; r.result = reduce_target(c);
+  klaunch(k_ewt_wsqr, reduce_blocks(c, n, 2), kThreads, 0, c->stream, r);
+  LAUNCH_CHECK();
+  ALG_BYTES(2, n);
+  return reduce_fetch(c, RED_SUM, result);
+}
+
 extern "C" int b200_prod_dot(b200_ctx* c, const double* a, const double* b, const double* cc, double* z, int64_t n, double* result)
 {
   if (!aligned16(a) || !aligned16(b) || !aligned16(cc) || !aligned16(z)) return fail("b200_prod_dot: pointer not 16-byte aligned");

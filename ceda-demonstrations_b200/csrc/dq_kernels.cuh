@@ -53,6 +53,48 @@ __global__ void __launch_bounds__(kThreads) k_lin2_wsqr(const Lin2RedArgs a)
   grid_finish<RED_SUM>(v, gridDim.x, blockIdx.x, a.partials, a.ticket, a.result, smem);
 }
 
+// ewt = 1 / (rtol*|y| + atol) stored (arkEwtSetSS: N_VAbs, N_VScale, N_VAddConst, N_VInv, SUN/src/arkode/arkode.c:2932-2944,
+// the rounding sequence of the four separate kernels) and, in the same pass, sum (y_i*ewt_i)^2 -- the "too much accuracy"
+// norm ARKODE takes of the new y_n with the new weights at the top of the next step (arkode.c:835)
+struct EwtArgs
+{
+  const double* y;
+  double rtol, atol;
+  double* ewt;
+  int64_t n;
+  double *partials, *result;
+  unsigned* ticket;
+};
+
+__global__ void __launch_bounds__(kThreads) k_ewt_wsqr(const EwtArgs a)
+{
+  __shared__ double smem[32];
+  const int64_t n2     = a.n >> 1;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  double acc0 = 0.0, acc1 = 0.0;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n2; p += stride)
+  {
+    const double2 y = ld_keep2(a.y + 2 * p);
+    double2 w;
+    w.x = __ddiv_rn(1.0, DADD(DMUL(a.rtol, fabs(y.x)), a.atol));
+    w.y = __ddiv_rn(1.0, DADD(DMUL(a.rtol, fabs(y.y)), a.atol));
+    *reinterpret_cast<double2*>(a.ewt + 2 * p) = w;
+    const double q0 = DMUL(y.x, w.x), q1 = DMUL(y.y, w.y);
+    acc0 = DADD(acc0, DMUL(q0, q0));
+    acc1 = DADD(acc1, DMUL(q1, q1));
+  }
+  if ((a.n & 1) && blockIdx.x == 0 && threadIdx.x == 0)
+  {
+    const int64_t i = a.n - 1;
+    const double w  = __ddiv_rn(1.0, DADD(DMUL(a.rtol, fabs(a.y[i])), a.atol));
+    a.ewt[i]        = w;
+    const double q  = DMUL(a.y[i], w);
+    acc0            = DADD(acc0, DMUL(q, q));
+  }
+  const double v = block_reduce<RED_SUM>(DADD(acc0, acc1), smem);
+  grid_finish<RED_SUM>(v, gridDim.x, blockIdx.x, a.partials, a.ticket, a.result, smem);
+}
+
 struct ProdDotArgs
 {
   const double *a, *b, *c;

@@ -77,10 +77,11 @@ struct StageRec
 
 // a requested-but-not-evaluated elementwise result (the implicit path's vector work): evaluated when something
 // reads it -- alone, or inside the reduction / stencil kernel that consumes it
-enum EwKind { EWK_LIN2 = 1, EWK_SCALESUM, EWK_SCALEDIFF, EWK_PROD };
+enum EwKind { EWK_LIN2 = 1, EWK_SCALESUM, EWK_SCALEDIFF, EWK_PROD, EWK_ABS, EWK_SCALE, EWK_ADDCONST, EWK_INV, EWK_EWT };
 struct EwRec
 {
   int kind;       // LIN2: ca*a + cb*b ; SCALESUM / SCALEDIFF: ca*(a +- b) ; PROD: a.*b
+                  // unary (b == nullptr): ABS |a| ; SCALE ca*a ; ADDCONST a + cb ; INV 1/a ; EWT 1/(ca*|a| + cb)
   Value *a, *b;   // one reference held on each
   double ca, cb;
 };
@@ -151,7 +152,7 @@ void value_release(Shared* sh, Value* v)
     if (v->ew)
     { // a pending elementwise result that was never needed
       EwRec* e = v->ew;
-      value_release(sh, e->b);
+      if (e->b) value_release(sh, e->b);
       next = e->a;
       delete e;
     }
@@ -413,7 +414,7 @@ Value* ew_new(Shared* sh, int kind, double ca, Value* a, double cb, Value* b)
   EwRec* e   = new EwRec();
   e->kind = kind; e->a = a; e->b = b; e->ca = ca; e->cb = cb;
   a->refs++;
-  b->refs++;
+  if (b) b->refs++;
   out->ew = e;
   return out;
 }
@@ -423,8 +424,22 @@ void ew_retire(Shared* sh, Value* v) // v->d has been filled: drop the record
   EwRec* e = v->ew;
   v->ew    = nullptr;
   value_release(sh, e->a);
-  value_release(sh, e->b);
+  if (e->b) value_release(sh, e->b);
   delete e;
+}
+
+// 1/(rtol*|y| + atol) requested as N_VAbs, N_VScale, N_VAddConst, N_VInv (arkEwtSetSS, arkode.c:2932-2944): the chain
+// INV(ADDCONST(SCALE(ABS(y)))) collapses into one EWT node as it is built
+Value* ewt_source(const Value* v, double* rtol, double* atol)
+{
+  if (!is_ew(v) || v->ew->kind != EWK_ADDCONST) return nullptr;
+  const Value* s = v->ew->a;
+  if (!is_ew(s) || s->ew->kind != EWK_SCALE) return nullptr;
+  const Value* a = s->ew->a;
+  if (!is_ew(a) || a->ew->kind != EWK_ABS) return nullptr;
+  *rtol = s->ew->ca;
+  *atol = v->ew->cb;
+  return a->ew->a;
 }
 
 // The difference-quotient pattern of arkLsATimes / arkLsDQJtimes (arkode_ls.c:2316-2372, :2839-2877):
@@ -488,10 +503,20 @@ void force_ew(Shared* sh, Value* v)
   }
   EwRec* e = v->ew;
   materialise(sh, e->a);
-  materialise(sh, e->b);
+  if (e->b) materialise(sh, e->b);
   double* out = pool_get(sh);
   switch (e->kind)
   {
+  case EWK_ABS: DEV(b200_abs(sh->ctx, e->a->d, out, sh->nloc)); break;
+  case EWK_SCALE:
+  {
+    const double* vp[1] = {e->a->d};
+    DEV(b200_lincomb(sh->ctx, 1, &e->ca, vp, out, sh->nloc));
+    break;
+  }
+  case EWK_ADDCONST: DEV(b200_addconst(sh->ctx, e->a->d, e->cb, out, sh->nloc)); break;
+  case EWK_INV: DEV(b200_inv(sh->ctx, e->a->d, out, sh->nloc)); break;
+  case EWK_EWT: DEV(b200_ewt_ss(sh->ctx, e->a->d, e->ca, e->cb, out, sh->nloc)); break;
   case EWK_LIN2:
   {
     const double cf[2]  = {e->ca, e->cb};
@@ -738,6 +763,8 @@ void op_prod(N_Vector x, N_Vector y, N_Vector z)
   assign(C(z), ew_new(sh, EWK_PROD, 0.0, xv, 0.0, yv));
 }
 
+bool unary_pending(int kind, double ca, N_Vector x, double cb, N_Vector z, bool keep_operand);
+
 void op_scale(sunrealtype c, N_Vector x, N_Vector z)
 {
   if (c == 1.0)
@@ -750,6 +777,9 @@ void op_scale(sunrealtype c, N_Vector x, N_Vector z)
     g_stats.aliased_copies++;
     return;
   }
+  if (g_lazy && C(x)->val && is_ew(C(x)->val) && C(x)->val->ew->kind == EWK_ABS &&
+      unary_pending(EWK_SCALE, c, x, 0.0, z, true))
+    return; // rtol*|y| of arkEwtSetSS
   double cf[1]  = {c};
   N_Vector X[1] = {x};
   eval_lincomb(1, cf, X, z);
@@ -764,10 +794,54 @@ void op_scale(sunrealtype c, N_Vector x, N_Vector z)
     DEV(KERNEL(zc->sh->ctx, xd, out->d, zc->sh->nloc));         \
     assign(zc, out);                                            \
   }
-UNARY_OP(op_abs, b200_abs)
-UNARY_OP(op_inv, b200_inv)
+UNARY_OP(op_abs_now, b200_abs)
+UNARY_OP(op_inv_now, b200_inv)
 
+// pending unary result over a plain operand (a pending operand of one of the shapes below is kept: arkEwtSetSS)
+bool unary_pending(int kind, double ca, N_Vector x, double cb, N_Vector z, bool keep_operand)
+{
+  if (!g_lazy) return false;
+  Content* xc = C(x);
+  sync_from_host(xc);
+  Value* xv  = xc->val;
+  Shared* sh = C(z)->sh;
+  if (is_rhs(xv) || (!xv->d && xv->st)) return false; // stage fusion paths take these
+  ew_operand(sh, xv, keep_operand);
+  assign(C(z), ew_new(sh, kind, ca, xv, cb, nullptr));
+  return true;
+}
+
+void op_abs(N_Vector x, N_Vector z)
+{
+  if (!unary_pending(EWK_ABS, 0.0, x, 0.0, z, false)) op_abs_now(x, z);
+}
+
+void op_inv(N_Vector x, N_Vector z)
+{
+  if (g_lazy)
+  {
+    sync_from_host(C(x));
+    double rtol = 0.0, atol = 0.0;
+    Value* y = ewt_source(C(x)->val, &rtol, &atol);
+    if (y)
+    { // 1/(rtol*|y| + atol): one node over y; the three intermediate results are never evaluated
+      Shared* sh = C(z)->sh;
+      materialise(sh, y);
+      assign(C(z), ew_new(sh, EWK_EWT, rtol, y, atol, nullptr));
+      return;
+    }
+  }
+  if (!unary_pending(EWK_INV, 0.0, x, 0.0, z, false)) op_inv_now(x, z);
+}
+
+void op_addconst_now(N_Vector x, sunrealtype b, N_Vector z);
 void op_addconst(N_Vector x, sunrealtype b, N_Vector z)
+{
+  const bool keep = g_lazy && C(x)->val && is_ew(C(x)->val) && C(x)->val->ew->kind == EWK_SCALE;
+  if (!unary_pending(EWK_ADDCONST, 0.0, x, b, z, keep)) op_addconst_now(x, b, z);
+}
+
+void op_addconst_now(N_Vector x, sunrealtype b, N_Vector z)
 {
   const double* xd = mat(x);
   Content* zc      = C(z);
@@ -860,16 +934,48 @@ sunrealtype op_maxnorm(N_Vector x)
   return r;
 }
 
+// bookkeeping of the speculative fused WRMS norm: remember the weight of the most recent norm, and learn which
+// launch signatures a norm with that weight follows
+void note_norm(Shared* sh, Value* xv, Value* wv)
+{
+  // learn: x came out of a fused launch issued while w was already the most recent
+  // norm weight, i.e. fusing the norm into that launch would have hit -> do so next time
+  if (xv->sig && g_last_weight == wv && xv->seq > g_last_weight_seq) sh->spec_sigs[xv->sig] = true;
+  if (g_last_weight != wv)
+  {
+    if (g_last_weight) value_release(g_last_weight_sh, g_last_weight);
+    g_last_weight     = wv;
+    g_last_weight_sh  = sh;
+    g_last_weight_seq = g_seq;
+    wv->refs++;
+  }
+}
+
 sunrealtype wsqrsum(N_Vector x, N_Vector w)
 {
   Content* xc      = C(x);
   Shared* sh       = xc->sh;
   sync_from_host(xc);
   sync_from_host(C(w));
+  if (g_lazy && is_ew(C(w)->val) && C(w)->val->ew->kind == EWK_EWT && C(w)->val->ew->a == xc->val && xc->val->d)
+  { // ||y_n||_wrms with the error weights just requested for y_n (arkode.c:835): weights and norm in one pass over y_n
+    Value* wv0  = C(w)->val;
+    EwRec* e    = wv0->ew;
+    double* out = pool_get(sh);
+    double r    = 0.0;
+    DEV(b200_ewt_ss_wsqrsum(sh->ctx, xc->val->d, e->ca, e->cb, out, sh->nloc, &r));
+    wv0->d = out;
+    ew_retire(sh, wv0);
+    g_stats.ew_fused++;
+    note_norm(sh, xc->val, wv0);
+    return r;
+  }
   if (g_lazy && is_ew(xc->val) && xc->val->ew->kind == EWK_LIN2)
   { // p = z + beta*p, then sig = 1/||p||_wrms in arkLsDQJtimes (sunlinsol_pcg.c:596, arkode_ls.c:2852)
-    Value* wv0 = C(w)->val;
-    return lin2_wsqr(sh, xc->val, wv0);
+    Value* wv0     = C(w)->val;
+    const double r = lin2_wsqr(sh, xc->val, wv0);
+    note_norm(sh, xc->val, wv0);
+    return r;
   }
   const double* xd = mat(x);
   Value* wv        = C(w)->val;
@@ -887,17 +993,7 @@ sunrealtype wsqrsum(N_Vector x, N_Vector w)
   }
   else if (wc) { DEV(b200_wsqrsum_scalar(sh->ctx, xd, wv->cval, sh->nloc, &r)); }
   else { DEV(b200_wsqrsum(sh->ctx, xd, wd, sh->nloc, &r)); }
-  // learn: x came out of a fused launch issued while w was already the most recent
-  // norm weight, i.e. fusing the norm into that launch would have hit -> do so next time
-  if (xv->sig && g_last_weight == wv && xv->seq > g_last_weight_seq) sh->spec_sigs[xv->sig] = true;
-  if (g_last_weight != wv)
-  {
-    if (g_last_weight) value_release(g_last_weight_sh, g_last_weight);
-    g_last_weight     = wv;
-    g_last_weight_sh  = sh;
-    g_last_weight_seq = g_seq;
-    wv->refs++;
-  }
+  note_norm(sh, xv, wv);
   return r;
 }
 

@@ -123,6 +123,10 @@ void b200_trace_report(void);
 int b200_lin2_wsqrsum(b200_ctx* ctx, double ca, const double* a, double cb, const double* b, const double* w,
                       double wscalar, double* z, int64_t n, double* result);
 int b200_prod_dot(b200_ctx* ctx, const double* a, const double* b, const double* c, double* z, int64_t n, double* result);
+/* ewt = 1/(rtol*|y| + atol) as b200_ewt_ss, and in the same pass result = sum_i (y_i ewt_i)^2: the new error weights
+   (arkEwtSetSS, SUN/src/arkode/arkode.c:2932-2944) together with the norm ARKODE takes of y_n with them at the top of
+   the next step (arkode.c:835) */
+int b200_ewt_ss_wsqrsum(b200_ctx* ctx, const double* y, double rtol, double atol, double* ewt, int64_t n, double* result);
 int b200_maxnorm(b200_ctx* ctx, const double* x, int64_t n, double* result);                   /* N_VMaxNorm :689 */
 int b200_min(b200_ctx* ctx, const double* x, int64_t n, double* result);                       /* N_VMin :780 */
 int b200_l1norm(b200_ctx* ctx, const double* x, int64_t n, double* result);                    /* N_VL1Norm :815 */
