@@ -74,41 +74,79 @@ def workload_args(local_n, npx, npy, method="rkc", base_n=None):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons during the timed region (B200_PROFILING.md's clocks line).  Sampled through
+    NVML in this process (nvidia_ml_py): spawning nvidia-smi several times inside a 0.3 s timed region stalled the
+    launching thread for tens of milliseconds (round-2 measurement: 52 -> 83 ms per step with 4 nvidia-smi calls inside
+    the region); nvidia-smi remains the fallback when NVML cannot be loaded."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.samples = []
+        self.samples = []  # (sm_mhz, sm_max_mhz, set of active reasons)
         self._stop_evt = threading.Event()
+        self.source = "nvidia-smi"
+        self._nvml = self._handle = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            handle = None
+            try:
+                import torch
+
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._nvml, self._handle, self.source = pynvml, handle, "nvml"
+        except Exception:
+            pass
+
+    def _sample_nvml(self):
+        nv, h = self._nvml, self._handle
+        sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        try:
+            mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        self.samples.append((int(sm), int(mx), {n for n, b in self.BITS.items() if mask & b}))
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        parts = [p.strip() for p in out.strip().split(",")]
+        if len(parts) >= 7 and parts[0].replace(".", "").isdigit() and parts[1].replace(".", "").isdigit():
+            self.samples.append((int(float(parts[0])), int(float(parts[1])),
+                                 {n for k, n in enumerate(self.NAMES) if parts[3 + k].lower().startswith("active")}))
 
     def run(self):
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 7:
-                    self.samples.append(parts)
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.05 if self._nvml is not None else 0.5)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=6)
 
     def summary(self):
-        sm = sorted(int(float(s[0])) for s in self.samples if s[0].replace(".", "").isdigit())
-        mx = [int(float(s[1])) for s in self.samples if s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(s[3 + k].lower().startswith("active") for s in self.samples)]
+        sm = sorted(s[0] for s in self.samples)
+        mx = [s[1] for s in self.samples]
+        reasons = [n for n in self.NAMES if any(n in s[2] for s in self.samples)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+                "reasons": reasons, "samples": len(self.samples), "source": self.source}
 
 
 # ------------------------------------------------------------------------------ reference arm

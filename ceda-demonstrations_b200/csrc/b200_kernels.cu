@@ -85,8 +85,11 @@ template <class... KArgs, class... Args>
 static inline void klaunch_named(const char* name, void (*kern)(KArgs...), dim3 grid, unsigned block, size_t smem, cudaStream_t st, Args&&... args)
 {
 #ifdef B200_HOST_EMU
-  (void)st; (void)name;
+  (void)st;
+  if (!trace_on()) { emu::launch_body(grid, block, smem, [&]() { kern(args...); }); return; }
+  const double t0 = trace_now_ms();
   emu::launch_body(grid, block, smem, [&]() { kern(args...); });
+  const double t1 = trace_now_ms();
 #else
   if (!trace_on()) { kern<<<grid, block, smem, st>>>(args...); return; }
   cudaStreamSynchronize(st);
@@ -96,11 +99,11 @@ static inline void klaunch_named(const char* name, void (*kern)(KArgs...), dim3 
   cudaStreamSynchronize(st);
   const double t1 = trace_now_ms();
   g_trace.last_end = t1;
+#endif
   const void* key = reinterpret_cast<const void*>(kern); // one row per instantiation (the label is the call site's spelling)
   for (auto& r : g_trace.rows)
     if (r.key == key) { r.n++; r.ms += t1 - t0; return; }
   g_trace.rows.push_back({name, key, 1, t1 - t0, grid.x, grid.y, block, smem});
-#endif
 }
 #define klaunch(kern, ...) klaunch_named(#kern, kern, __VA_ARGS__)
 
@@ -251,6 +254,16 @@ extern "C" int b200_free(b200_ctx* c, double* dptr)
 extern "C" int b200_host_alloc(int64_t n, double** hptr)
 {
   CU_TRY(cudaMallocHost((void**)hptr, sizeof(double) * (size_t)(n > 0 ? n : 1)));
+  return 0;
+}
+
+// pinned host memory that kernels can write directly (mapped): results a kernel's last block stores there are
+// visible to the host after b200_ctx_sync, without a copy or a publishing launch
+extern "C" int b200_mapped_alloc(b200_ctx* c, int64_t n, double** hptr, double** dptr)
+{
+  CU_TRY(cudaSetDevice(c->device));
+  CU_TRY(cudaHostAlloc((void**)hptr, sizeof(double) * (size_t)(n > 0 ? n : 1), cudaHostAllocMapped));
+  CU_TRY(cudaHostGetDevicePointer((void**)dptr, *hptr, 0));
   return 0;
 }
 

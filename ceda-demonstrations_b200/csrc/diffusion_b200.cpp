@@ -739,7 +739,13 @@ extern "C" int b200_d2d_create(int argc, const char* const* argv, int rank, int 
   }
   {
     int depth = p->uo.chain;
-    if (depth <= 0) { const char* e = getenv("B200_CHAIN"); depth = e ? atoi(e) : 4; }
+    // default: 4 stages per launch (measured best at 4096^2 .. 16384^2); blocks of at most 512^2 cells are
+    // bound by launch latency, not by HBM or the FP64 pipe, and take the deepest chain the kernels offer
+    if (depth <= 0)
+    {
+      const char* e = getenv("B200_CHAIN");
+      depth         = e ? atoi(e) : (p->ud.nodes_loc <= 512 * 512 ? B200_MAX_CHAIN : 4);
+    }
     N_VSetStageChain_B200(depth);
   }
   if (p->uo.rows_per_block > 0) b200_set_rows_per_block(p->uo.rows_per_block);

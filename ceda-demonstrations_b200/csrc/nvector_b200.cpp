@@ -58,7 +58,8 @@ struct Shared
   std::vector<double*> free_bufs;
   std::vector<double*> free_halos; // deep-halo buffers (one size per problem)
   int64_t halo_doubles;
-  double* wrms_slots; // device scalars for fused WRMS partial sums
+  double* wrms_slots; // scalars the fused WRMS partial sums are stored to (device memory, or the device alias of wrms_host)
+  double* wrms_host;  // one rank: the slots live in mapped pinned host memory and are read after a stream sync
   int next_slot;
   bool spec_sigs[96]; // fused-launch signatures whose result a matching WRMS norm followed
 };
@@ -647,7 +648,8 @@ void op_destroy(N_Vector v)
       b200_ctx_sync(sh->ctx);
       for (double* p : sh->free_bufs) b200_free(sh->ctx, p);
       for (double* p : sh->free_halos) b200_free(sh->ctx, p);
-      if (sh->wrms_slots) b200_free(sh->ctx, sh->wrms_slots);
+      if (sh->wrms_host) b200_host_free(sh->wrms_host);
+      else if (sh->wrms_slots) b200_free(sh->ctx, sh->wrms_slots);
       delete sh;
     }
     delete c;
@@ -805,7 +807,7 @@ bool unary_pending(int kind, double ca, N_Vector x, double cb, N_Vector z, bool 
   sync_from_host(xc);
   Value* xv  = xc->val;
   Shared* sh = C(z)->sh;
-  if (is_rhs(xv) || (!xv->d && xv->st)) return false; // stage fusion paths take these
+  if (is_rhs(xv) || (!xv->d && xv->st)) materialise(sh, xv); // a deferred right-hand side / pending stage chain goes out now
   ew_operand(sh, xv, keep_operand);
   assign(C(z), ew_new(sh, kind, ca, xv, cb, nullptr));
   return true;
@@ -986,8 +988,16 @@ sunrealtype wsqrsum(N_Vector x, N_Vector w)
   if (xv->wrms_w == wv && xv->wrms_slot >= 0)
   { // the fused kernel that produced x already reduced sum (x*w)^2
     double* slot = sh->wrms_slots + xv->wrms_slot;
-    DEV(b200_allreduce(sh->ctx, slot, 1, 0));
-    DEV(b200_d2h(sh->ctx, &r, slot, 1));
+    if (sh->wrms_host)
+    { // the kernel stored the sum into mapped host memory: wait for the stream, read it
+      DEV(b200_ctx_sync(sh->ctx));
+      r = sh->wrms_host[xv->wrms_slot];
+    }
+    else
+    {
+      DEV(b200_allreduce(sh->ctx, slot, 1, 0));
+      DEV(b200_d2h(sh->ctx, &r, slot, 1));
+    }
     xv->wrms_slot = -1; // the all-reduce is in place: do not reuse
     g_stats.wrms_fused++;
   }
@@ -1122,7 +1132,13 @@ N_Vector N_VNew_B200(b200_ctx* ctx, sunindextype local_length, sunindextype glob
   sh->halo_doubles = 0;
   sh->next_slot  = 0;
   memset(sh->spec_sigs, 0, sizeof(sh->spec_sigs));
-  DEV(b200_malloc(ctx, kSlots, &sh->wrms_slots));
+  sh->wrms_host = nullptr;
+  {
+    int rank = 0, nranks = 1;
+    b200_comm_rank(ctx, &rank, &nranks);
+    if (nranks <= 1) DEV(b200_mapped_alloc(ctx, kSlots, &sh->wrms_host, &sh->wrms_slots));
+    else DEV(b200_malloc(ctx, kSlots, &sh->wrms_slots));
+  }
   Content* c    = new Content();
   c->sh         = sh;
   c->val        = nullptr;

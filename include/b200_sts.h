@@ -54,6 +54,9 @@ int b200_malloc(b200_ctx* ctx, int64_t n_doubles, double** dptr);
 int b200_free(b200_ctx* ctx, double* dptr);
 int b200_host_alloc(int64_t n_doubles, double** hptr);
 int b200_host_free(double* hptr);
+/* n doubles of pinned host memory mapped into the device's address space: *dptr is what kernels write through
+   (e.g. the wrms_result of b200_stage_extras), *hptr what the host reads after b200_ctx_sync.  Free with b200_host_free. */
+int b200_mapped_alloc(b200_ctx* ctx, int64_t n, double** hptr, double** dptr);
 int b200_h2d(b200_ctx* ctx, double* dst_dev, const double* src_host, int64_t n);
 /* n <= 64: read back through mapped pinned memory written by a 1-block kernel (no DMA copy, so a
    scalar never queues behind a bulk transfer on the copy engine); larger n: cudaMemcpyAsync + sync */
