@@ -66,6 +66,7 @@ oracle:
 ifneq ($(HAVE_REF),)
 	@$(MAKE) -s -C oracle ref
 	@$(MAKE) -s -C oracle nvsuite
+	@$(MAKE) -s -C oracle refmain
 endif
 
 clean:

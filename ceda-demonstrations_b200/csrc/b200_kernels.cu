@@ -1638,7 +1638,8 @@ extern "C" int b200_peer_halo_exchange(b200_peer_halo* ph, int nfields, const do
   a.timeout_ns = 20ull * 1000000000ull;
   const int64_t total = 2 * (int64_t)ph->g * ph->nx + 2 * ph->ny * ph->g2 + 4 * (int64_t)ph->g * ph->g2;
   int64_t blocks      = (total + kThreads - 1) / kThreads;
-  if (blocks > 2 * (int64_t)c->sm_count) blocks = 2 * (int64_t)c->sm_count;
+  if (blocks > (int64_t)c->sm_count / 2) blocks = (int64_t)c->sm_count / 2; // a few MB: latency-, not bandwidth-bound
+  if (blocks < 1) blocks = 1;
   klaunch(k_peer_exchange, dim3((unsigned)blocks, (unsigned)nfields), kThreads, 0, c->stream, a);
   LAUNCH_CHECK();
   ph->exchanges++;

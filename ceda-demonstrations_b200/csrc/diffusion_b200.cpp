@@ -32,6 +32,7 @@
 #include <thread>
 #include <vector>
 
+#include "b200_callbacks.h"
 #include "b200_diffusion2d.h"
 #include "b200_sts.h"
 #include "nvector_b200.h"
@@ -506,6 +507,100 @@ int parse_args(std::vector<std::string> args, UserData& ud, UserOptions& uo, boo
 
 extern "C" int b200_set_rows_per_block(int r);
 
+// Wire a set-up UserData (setup() done) to its device context: operator callbacks, eligibility of temporal blocking
+// (a collective decision), the deep-halo ring of a decomposed rank, coefficient tables.
+static int problem_attach(UserData& ud, b200_ctx* ctx, int nranks, bool overlap, bool force_halo, bool halo_nccl, bool no_fusion)
+{
+  ud.ctx         = ctx;
+  ud.overlap     = overlap;
+  ud.rhs_op.self = &ud;
+  ud.rhs_op.fused = rhs_fused;
+  ud.rhs_op.chain = nullptr;
+  ud.rhs_op.dq    = (getenv("B200_NO_DQ_FUSION") || no_fusion) ? nullptr : rhs_dq;
+  ud.rhs_op.chain_max = 0;
+  ud.rhs_op.halo_doubles = 0;
+  ud.force_halo          = force_halo;
+  // Temporal blocking is a collective decision: a temporally blocked launch is preceded by a deep halo
+  // exchange that every rank must join, so it is enabled only if EVERY block of the decomposition
+  // qualifies (even width >= 128, >= 16 rows) -- judged from the global sizes, which all ranks share,
+  // not from this rank's extent (uneven splits give neighbouring blocks of different parity).
+  const int64_t qx_min = ud.nx / ud.npx, qy_min = ud.ny / ud.npy;
+  const bool all_even  = (ud.nx % ud.npx == 0) && (qx_min % 2 == 0);
+  if (all_even && qx_min >= 128 && qy_min >= 16)
+  { // index wrap on one periodic rank, deep halos on a rank of a decomposition
+    ud.rhs_op.chain     = rhs_chain;
+    ud.rhs_op.chain_max = B200_MAX_CHAIN;
+    if (nranks > 1 || ud.force_halo)
+    {
+      ud.rhs_op.halo_doubles = b200_deep_halo_doubles(ud.nx_loc, ud.ny_loc, kHaloRows, kHaloCols);
+      if (!halo_nccl)
+      { // the eight neighbours of this block in the periodic process grid, and the heights of the rows of blocks
+        // below / above it (remainder rows go to the low coordinates, diffusion_2D.cpp:286-317)
+        UserData& u = ud;
+        auto height = [&](int cy) {
+          cy = ((cy % u.npy) + u.npy) % u.npy;
+          return u.ny / u.npy + (cy < u.ny % u.npy ? 1 : 0);
+        };
+        const int nbr[8] = {cart_rank(u.idx - 1, u.idy, u.npx, u.npy),     cart_rank(u.idx + 1, u.idy, u.npx, u.npy),
+                            cart_rank(u.idx, u.idy - 1, u.npx, u.npy),     cart_rank(u.idx, u.idy + 1, u.npx, u.npy),
+                            cart_rank(u.idx - 1, u.idy - 1, u.npx, u.npy), cart_rank(u.idx + 1, u.idy - 1, u.npx, u.npy),
+                            cart_rank(u.idx - 1, u.idy + 1, u.npx, u.npy), cart_rank(u.idx + 1, u.idy + 1, u.npx, u.npy)};
+        const int64_t ny_max = u.ny / u.npy + (u.ny % u.npy ? 1 : 0);
+        if (b200_peer_halo_create(ctx, nbr, u.nx_loc, u.ny_loc, height(u.idy - 1), height(u.idy + 1), ny_max, kHaloRows,
+                                  kHaloCols, 16, &u.peer_halo))
+        {
+          fprintf(stderr, "b200 diffusion_2D: %s\n", b200_last_error());
+          return -1;
+        }
+        u.rhs_op.halo_alloc = halo_slot_alloc;
+        u.rhs_op.halo_free  = halo_slot_free;
+      }
+    }
+  }
+  return ud.upload_tables();
+}
+
+// ------------------------------------------------- the callbacks' user_data for a foreign main()
+struct b200_d2d_problem
+{
+  UserData ud;
+};
+
+extern "C" int b200_d2d_problem_create(b200_ctx* ctx, long long nx, long long ny, double xl, double xu, double yl, double yu,
+                                       double kx, double ky, int inhomogeneous, int npx, int npy, int rank, int nranks,
+                                       N_Vector diag, b200_d2d_problem** out)
+{
+  if (!ctx || !out || nx < 2 || ny < 2) return -1;
+  b200_d2d_problem* p = new b200_d2d_problem();
+  UserData& ud        = p->ud;
+  ud.nx = nx; ud.ny = ny; ud.xl = xl; ud.xu = xu; ud.yl = yl; ud.yu = yu; ud.kx = kx; ud.ky = ky;
+  ud.inhomogeneous = inhomogeneous != 0;
+  ud.npx = npx; ud.npy = npy;
+  ud.nodes = ud.nx * ud.ny;                 // diffusion_2D.cpp:156-160
+  ud.dx    = (ud.xu - ud.xl) / (ud.nx - 1);
+  ud.dy    = (ud.yu - ud.yl) / (ud.ny - 1);
+  ud.diag  = diag;
+  if (ud.setup(rank, nranks) || problem_attach(ud, ctx, nranks, true, getenv("B200_FORCE_HALO") != nullptr,
+                                               getenv("B200_HALO_NCCL") != nullptr, false))
+  {
+    delete p;
+    return -1;
+  }
+  *out = p;
+  return 0;
+}
+
+extern "C" void* b200_d2d_problem_user_data(b200_d2d_problem* p) { return p ? static_cast<void*>(&p->ud) : nullptr; }
+
+extern "C" int b200_d2d_problem_destroy(b200_d2d_problem* p)
+{
+  if (!p) return 0;
+  p->ud.free_device();
+  if (p->ud.peer_halo) b200_peer_halo_destroy(p->ud.peer_halo);
+  delete p; // (diag belongs to the caller, like udata.diag in the reference)
+  return 0;
+}
+
 // ------------------------------------------------------------------- session
 struct b200_d2d
 {
@@ -691,52 +786,9 @@ extern "C" int b200_d2d_create(int argc, const char* const* argv, int rank, int 
       return -1;
     }
   }
-  p->ud.ctx         = p->ctx;
-  p->ud.overlap     = !p->uo.no_overlap;
-  p->ud.rhs_op.self = &p->ud;
-  p->ud.rhs_op.fused = rhs_fused;
-  p->ud.rhs_op.chain = nullptr;
-  p->ud.rhs_op.dq    = (getenv("B200_NO_DQ_FUSION") || p->uo.no_fusion) ? nullptr : rhs_dq;
-  p->ud.rhs_op.chain_max = 0;
-  p->ud.rhs_op.halo_doubles = 0;
-  p->ud.force_halo          = p->uo.force_halo || getenv("B200_FORCE_HALO") != nullptr;
-  // Temporal blocking is a collective decision: a temporally blocked launch is preceded by a deep halo
-  // exchange that every rank must join, so it is enabled only if EVERY block of the decomposition
-  // qualifies (even width >= 128, >= 16 rows) -- judged from the global sizes, which all ranks share,
-  // not from this rank's extent (uneven splits give neighbouring blocks of different parity).
-  const int64_t qx_min = p->ud.nx / p->ud.npx, qy_min = p->ud.ny / p->ud.npy;
-  const bool all_even  = (p->ud.nx % p->ud.npx == 0) && (qx_min % 2 == 0);
-  if (all_even && qx_min >= 128 && qy_min >= 16)
-  { // index wrap on one periodic rank, deep halos on a rank of a decomposition
-    p->ud.rhs_op.chain     = rhs_chain;
-    p->ud.rhs_op.chain_max = B200_MAX_CHAIN;
-    if (nranks > 1 || p->ud.force_halo)
-    {
-      p->ud.rhs_op.halo_doubles = b200_deep_halo_doubles(p->ud.nx_loc, p->ud.ny_loc, kHaloRows, kHaloCols);
-      if (!(p->uo.halo_nccl || getenv("B200_HALO_NCCL")))
-      { // the eight neighbours of this block in the periodic process grid, and the heights of the rows of blocks
-        // below / above it (remainder rows go to the low coordinates, diffusion_2D.cpp:286-317)
-        UserData& u = p->ud;
-        auto height = [&](int cy) {
-          cy = ((cy % u.npy) + u.npy) % u.npy;
-          return u.ny / u.npy + (cy < u.ny % u.npy ? 1 : 0);
-        };
-        const int nbr[8] = {cart_rank(u.idx - 1, u.idy, u.npx, u.npy),     cart_rank(u.idx + 1, u.idy, u.npx, u.npy),
-                            cart_rank(u.idx, u.idy - 1, u.npx, u.npy),     cart_rank(u.idx, u.idy + 1, u.npx, u.npy),
-                            cart_rank(u.idx - 1, u.idy - 1, u.npx, u.npy), cart_rank(u.idx + 1, u.idy - 1, u.npx, u.npy),
-                            cart_rank(u.idx - 1, u.idy + 1, u.npx, u.npy), cart_rank(u.idx + 1, u.idy + 1, u.npx, u.npy)};
-        const int64_t ny_max = u.ny / u.npy + (u.ny % u.npy ? 1 : 0);
-        if (b200_peer_halo_create(p->ctx, nbr, u.nx_loc, u.ny_loc, height(u.idy - 1), height(u.idy + 1), ny_max, kHaloRows,
-                                  kHaloCols, 16, &u.peer_halo))
-        {
-          fprintf(stderr, "b200_d2d_create: %s\n", b200_last_error());
-          return -1;
-        }
-        u.rhs_op.halo_alloc = halo_slot_alloc;
-        u.rhs_op.halo_free  = halo_slot_free;
-      }
-    }
-  }
+  if (problem_attach(p->ud, p->ctx, nranks, !p->uo.no_overlap, p->uo.force_halo || getenv("B200_FORCE_HALO") != nullptr,
+                     p->uo.halo_nccl || getenv("B200_HALO_NCCL") != nullptr, p->uo.no_fusion))
+    return -1;
   {
     int depth = p->uo.chain;
     // default: 4 stages per launch (measured best at 4096^2 .. 16384^2); blocks of at most 512^2 cells are
@@ -765,7 +817,6 @@ extern "C" int b200_d2d_create(int argc, const char* const* argv, int rank, int 
     b200_set_contract(ar == "fma");
   }
   N_VSetLazyFusion_B200(p->uo.no_fusion ? 0 : 1);
-  if (p->ud.upload_tables()) return -1;
   if (SUNContext_Create(SUN_COMM_NULL, &p->sunctx)) return -1;
   if (configure(p)) return -1;
   *out = p;

@@ -20,6 +20,21 @@ extern "C" {
 #endif
 
 /* ---- diffusion_2D ---------------------------------------------------------------- */
+/* The `user_data` object of the b200_diffusion_* callbacks, built from the fields of the reference's own UserData
+ * (diffusion_2D/diffusion_2D.hpp:66-216) AFTER its setup(): grid, domain, coefficients and the position of this rank
+ * in the process grid.  This is what lets the reference's main.cpp keep its UserData / UserOptions / UserOutput and
+ * its whole ARKODE call sequence and swap only the vector constructor, the callbacks and the user_data pointer
+ * (tests/native/patch_reference_main.py builds exactly that program).
+ * ctx: the device context the vectors were created on (with b200_comm_init done when nranks > 1).
+ * diag: the vector PSetup fills and PSolve multiplies by (udata.diag = N_VClone(u), main.cpp:227), or NULL. */
+struct b200_ctx;
+typedef struct b200_d2d_problem b200_d2d_problem;
+int b200_d2d_problem_create(struct b200_ctx* ctx, long long nx, long long ny, double xl, double xu, double yl, double yu,
+                            double kx, double ky, int inhomogeneous, int npx, int npy, int rank, int nranks,
+                            N_Vector diag, b200_d2d_problem** out);
+void* b200_d2d_problem_user_data(b200_d2d_problem* p); /* pass to ARKodeSetUserData */
+int b200_d2d_problem_destroy(b200_d2d_problem* p);
+
 /* ARKRhsFn: diffusion(), diffusion_2D/diffusion_2D.cpp:23-35 -> laplacian(), diffusion.cpp:9-209 */
 int b200_diffusion_rhs(sunrealtype t, N_Vector u, N_Vector f, void* user_data);
 /* ARKDomEigFn: dom_eig(), diffusion_2D/main.cpp:536-550 */
