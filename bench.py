@@ -89,6 +89,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index = index
         self.samples = []  # (sm_mhz, sm_max_mhz, set of active reasons)
+        self.extra = []    # (mem_mhz, gpu_temp_C, power_W) when NVML is available
         self._stop_evt = threading.Event()
         self.source = "nvidia-smi"
         self._nvml = self._handle = None
@@ -117,6 +118,12 @@ class ClockSampler(threading.Thread):
         except Exception:
             mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
         self.samples.append((int(sm), int(mx), {n for n, b in self.BITS.items() if mask & b}))
+        try:
+            self.extra.append((int(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_MEM)),
+                               int(nv.nvmlDeviceGetTemperature(h, nv.NVML_TEMPERATURE_GPU)),
+                               nv.nvmlDeviceGetPowerUsage(h) / 1000.0))
+        except Exception:
+            pass
 
     def _sample_smi(self):
         out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
@@ -135,7 +142,7 @@ class ClockSampler(threading.Thread):
                     self._sample_smi()
             except Exception:
                 pass
-            self._stop_evt.wait(0.05 if self._nvml is not None else 0.5)
+            self._stop_evt.wait(0.1 if self._nvml is not None else 0.5)
 
     def stop(self):
         self._stop_evt.set()
@@ -145,8 +152,13 @@ class ClockSampler(threading.Thread):
         sm = sorted(s[0] for s in self.samples)
         mx = [s[1] for s in self.samples]
         reasons = [n for n in self.NAMES if any(n in s[2] for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples), "source": self.source}
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "reasons": reasons, "samples": len(self.samples), "source": self.source}
+        if self.extra:
+            out["mem_mhz"] = sorted(e[0] for e in self.extra)[len(self.extra) // 2]
+            out["gpu_temp_c"] = max(e[1] for e in self.extra)
+            out["power_w"] = round(sorted(e[2] for e in self.extra)[len(self.extra) // 2], 1)
+        return out
 
 
 # ------------------------------------------------------------------------------ reference arm
@@ -510,7 +522,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--chain", type=int, default=0, help="temporal-blocking depth (0 = library default)")
-    ap.add_argument("--chain-variant", type=int, default=-1, help="0 = k_chain_march, 1 = k_chain_quad (default)")
+    ap.add_argument("--chain-variant", type=int, default=-1, help="0 = k_chain_march (default), 1 = k_chain_quad")
     ap.add_argument("--arith", default=DEFAULT_ARITH, choices=["exact", "fma"],
                     help="exact = bit-identical to the reference's baseline x86-64 build; fma = contracted multiply-adds")
     ap.add_argument("--e2e-mode", default="pipelined", choices=["pipelined", "sequential"])

@@ -180,6 +180,7 @@ struct b200_adr
   SUNLinearSolver LS        = nullptr;
   double t = 0.0, evolve_seconds = 0.0;
   B200VecStats vs0{};
+  bool settings_held = false; // N_VAcquireSettings_B200 succeeded for this session
   uint64_t launches0 = 0;
 };
 
@@ -541,6 +542,8 @@ int setup_strang(b200_adr* p)
 
 } // namespace
 
+extern "C" int b200_adr_destroy(b200_adr* p);
+
 extern "C" int b200_adr_create(int argc, const char* const* argv, int device, void* stream, b200_adr** out)
 {
   b200_adr* p = new b200_adr();
@@ -568,18 +571,20 @@ extern "C" int b200_adr_create(int argc, const char* const* argv, int device, vo
     p->ud.ops[m].op.halo_free    = nullptr;
     p->ud.ops[m].op.dq           = nullptr;
   }
+  int depth = -1; // -1: this session does not care about the process-wide chain depth
   if (p->uo.sts_chain >= 2 && p->ud.nx >= 64 && p->ud.ny >= 16)
-  { // opt-in: the pure diffusion operator (Strang's STS partition) may be chained
-    const int depth              = p->uo.sts_chain > B200_MAX_CHAIN ? B200_MAX_CHAIN : p->uo.sts_chain;
-    p->ud.ops[2].op.chain        = adr_chain_cb;
-    p->ud.ops[2].op.chain_max    = depth;
-    N_VSetStageChain_B200(depth);
+  { // the pure diffusion operator (Strang's STS partition) may be chained
+    depth                     = p->uo.sts_chain > B200_MAX_CHAIN ? B200_MAX_CHAIN : p->uo.sts_chain;
+    p->ud.ops[2].op.chain     = adr_chain_cb;
+    p->ud.ops[2].op.chain_max = depth;
   }
-  N_VSetLazyFusion_B200(p->uo.no_fusion ? 0 : 1);
-  if (SUNContext_Create(SUN_COMM_NULL, &p->sunctx)) return -1;
+  // process-wide switches: refuse to change them under another live session (nvector_b200.h)
+  if (N_VAcquireSettings_B200(p->uo.no_fusion ? 0 : 1, depth, -1, -1)) { b200_adr_destroy(p); return -1; }
+  p->settings_held = true;
+  if (SUNContext_Create(SUN_COMM_NULL, &p->sunctx)) { b200_adr_destroy(p); return -1; }
   p->y = N_VNew_B200(p->ctx, p->ud.neq, p->ud.neq, p->sunctx); // ...2d.cpp:83
-  if (!p->y) return -1;
-  if (set_ic(p->y, p->ud)) return -1;                           // ...2d.cpp:86
+  if (!p->y) { b200_adr_destroy(p); return -1; }
+  if (set_ic(p->y, p->ud)) { b200_adr_destroy(p); return -1; }                           // ...2d.cpp:86
   int rc = -1;
   switch (p->uo.integrator)
   { // ...2d.cpp:125-134
@@ -588,7 +593,7 @@ extern "C" int b200_adr_create(int argc, const char* const* argv, int device, vo
   case 2: rc = setup_extsts(p); break;
   case 3: rc = setup_strang(p); break;
   }
-  if (rc) return -1;
+  if (rc) { b200_adr_destroy(p); return -1; }
   *out = p;
   return 0;
 }
@@ -617,6 +622,7 @@ extern "C" int b200_adr_destroy(b200_adr* p)
   if (p->y) N_VDestroy(p->y);
   if (p->sunctx) SUNContext_Free(&p->sunctx);
   if (p->ctx) b200_ctx_destroy(p->ctx);
+  if (p->settings_held) N_VReleaseSettings_B200();
   delete p;
   return 0;
 }

@@ -848,11 +848,22 @@ extern "C" int b200_stencil_dq(b200_ctx* c, const b200_stencil_geom* g, const do
 #include "chain_march.cuh"
 #include "chain_quad.cuh"
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute of a kernel: remember what was configured per
+// (instantiation, device); each instantiation has its own table (a static of the template function)
+static const int kMaxDevices = 64;
+static int current_device()
+{
+  int d = 0;
+  cudaGetDevice(&d);
+  return (d >= 0 && d < kMaxDevices) ? d : 0;
+}
+
 template <int K, int PF, bool HALO, bool FMA, bool UNI>
 static int launch_chain_k(const ChainArgs& a, dim3 grid, cudaStream_t st)
 {
   const size_t smem = chain_march_smem(K, PF, a.rows);
-  static size_t configured = 0;
+  static size_t configured_on[kMaxDevices] = {};
+  size_t& configured = configured_on[current_device()];
   if (smem > configured)
   {
     CU_TRY(cudaFuncSetAttribute(k_chain_march<K, PF, HALO, FMA, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -890,7 +901,8 @@ template <int K, int PF, bool HALO, bool FMA, int MINB>
 static int launch_quad_k(const ChainArgs& a, dim3 grid, cudaStream_t st)
 {
   const size_t smem = chain_quad_smem(K, PF, a.rows);
-  static size_t configured = 0;
+  static size_t configured_on[kMaxDevices] = {};
+  size_t& configured = configured_on[current_device()];
   if (smem > configured)
   {
     CU_TRY(cudaFuncSetAttribute(k_chain_quad<K, PF, HALO, FMA, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1256,7 +1268,8 @@ template <int K>
 static int launch_adr_chain_k(const AdrChainArgs& a, dim3 grid, cudaStream_t st)
 {
   const size_t smem = adr_chain_smem(K, kAdrChainPF);
-  static bool configured = false;
+  static bool configured_on[kMaxDevices] = {};
+  bool& configured = configured_on[current_device()];
   if (!configured)
   {
     CU_TRY(cudaFuncSetAttribute(k_adr_chain<K, kAdrChainPF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -620,6 +620,7 @@ struct b200_d2d
   B200VecStats vs0{};          // process-wide counters at creation (stats are reported per session)
   uint64_t launches0 = 0;
   b200_pipe* pipe    = nullptr; // staging for b200_d2d_run_batches (created on first use)
+  bool settings_held = false;   // N_VAcquireSettings_B200 succeeded for this session
 };
 
 #define CHK(call, name)                                                       \
@@ -762,6 +763,8 @@ static int configure(b200_d2d* p)
   return 0;
 }
 
+extern "C" int b200_d2d_destroy(b200_d2d* p);
+
 extern "C" int b200_d2d_create(int argc, const char* const* argv, int rank, int nranks,
                                const unsigned char* nccl_id, int device, void* stream, b200_d2d** out)
 {
@@ -779,16 +782,16 @@ extern "C" int b200_d2d_create(int argc, const char* const* argv, int rank, int 
   }
   if (nranks > 1)
   {
-    if (!nccl_id) { fprintf(stderr, "b200_d2d_create: nranks > 1 needs an NCCL id\n"); return -1; }
+    if (!nccl_id) { fprintf(stderr, "b200_d2d_create: nranks > 1 needs an NCCL id\n"); b200_d2d_destroy(p); return -1; }
     if (b200_comm_init(p->ctx, rank, nranks, nccl_id))
     {
       fprintf(stderr, "b200_d2d_create: %s\n", b200_last_error());
-      return -1;
+      { b200_d2d_destroy(p); return -1; }
     }
   }
   if (problem_attach(p->ud, p->ctx, nranks, !p->uo.no_overlap, p->uo.force_halo || getenv("B200_FORCE_HALO") != nullptr,
                      p->uo.halo_nccl || getenv("B200_HALO_NCCL") != nullptr, p->uo.no_fusion))
-    return -1;
+    { b200_d2d_destroy(p); return -1; }
   {
     int depth = p->uo.chain;
     // default: 4 stages per launch (measured best at 4096^2 .. 16384^2); blocks of at most 512^2 cells are
@@ -798,27 +801,33 @@ extern "C" int b200_d2d_create(int argc, const char* const* argv, int rank, int 
       const char* e = getenv("B200_CHAIN");
       depth         = e ? atoi(e) : (p->ud.nodes_loc <= 512 * 512 ? B200_MAX_CHAIN : 4);
     }
-    N_VSetStageChain_B200(depth);
-  }
-  if (p->uo.rows_per_block > 0) b200_set_rows_per_block(p->uo.rows_per_block);
-  if (p->uo.chain_variant >= 0 && b200_set_chain_variant(p->uo.chain_variant))
-  {
-    fprintf(stderr, "ERROR: --chain-variant must be 0 or 1\n");
-    return -1;
-  }
-  {
+    if (depth < 1) depth = 1;
+    if (depth > B200_MAX_CHAIN) depth = B200_MAX_CHAIN;
+    if (p->uo.chain_variant > 1)
+    {
+      fprintf(stderr, "ERROR: --chain-variant must be 0 or 1\n");
+      b200_d2d_destroy(p);
+      return -1;
+    }
     std::string ar = p->uo.arith;
     if (ar.empty()) { const char* e = getenv("B200_ARITH"); ar = e ? e : "exact"; }
     if (ar != "exact" && ar != "fma")
     {
       fprintf(stderr, "ERROR: --arith must be exact or fma\n");
+      b200_d2d_destroy(p);
       return -1;
     }
-    b200_set_contract(ar == "fma");
+    // process-wide switches: refuse to change them under another live session (nvector_b200.h)
+    if (N_VAcquireSettings_B200(p->uo.no_fusion ? 0 : 1, depth, ar == "fma" ? 1 : 0, p->uo.chain_variant))
+    {
+      b200_d2d_destroy(p);
+      return -1;
+    }
+    p->settings_held = true;
   }
-  N_VSetLazyFusion_B200(p->uo.no_fusion ? 0 : 1);
-  if (SUNContext_Create(SUN_COMM_NULL, &p->sunctx)) return -1;
-  if (configure(p)) return -1;
+  if (p->uo.rows_per_block > 0) b200_set_rows_per_block(p->uo.rows_per_block);
+  if (SUNContext_Create(SUN_COMM_NULL, &p->sunctx)) { b200_d2d_destroy(p); return -1; }
+  if (configure(p)) { b200_d2d_destroy(p); return -1; }
   *out = p;
   return 0;
 }
@@ -841,6 +850,7 @@ extern "C" int b200_d2d_destroy(b200_d2d* p)
   if (p->ud.peer_halo) { b200_peer_halo_destroy(p->ud.peer_halo); p->ud.peer_halo = nullptr; }
   if (p->sunctx) SUNContext_Free(&p->sunctx);
   if (p->ctx) b200_ctx_destroy(p->ctx);
+  if (p->settings_held) N_VReleaseSettings_B200();
   delete p;
   return 0;
 }
@@ -868,6 +878,11 @@ extern "C" int b200_d2d_step(b200_d2d* p, int nsteps)
       return -1;
     }
   }
+  // ARKODE's last stages may still be pending (lazy chains): enqueue them, so that whoever times this call on the
+  // stream -- bench.py's CUDA events -- sees all of the steps' work, and wait for the device so that evolve_seconds
+  // is device-inclusive like the reference's simtime
+  (void)N_VGetDeviceArrayPointer_B200(p->u);
+  b200_ctx_sync(p->ctx);
   p->evolve_seconds += wall_seconds() - t0;
   return 0;
 }

@@ -61,6 +61,7 @@ struct Shared
   double* wrms_slots; // scalars the fused WRMS partial sums are stored to (device memory, or the device alias of wrms_host)
   double* wrms_host;  // one rank: the slots live in mapped pinned host memory and are read after a stream sync
   int next_slot;
+  long slot_owner[8]; // creation number of the value whose partial sum the slot holds (the ring is reused)
   bool spec_sigs[96]; // fused-launch signatures whose result a matching WRMS norm followed
 };
 const int kSlots = 8;
@@ -267,6 +268,7 @@ void launch_fused(Shared* sh, Value* L, int nterms, const double* cf, Value* con
       out->wrms_w = wv;
       wv->refs++;
       out->wrms_slot = slot;
+      sh->slot_owner[slot] = out->seq;
     }
   }
   if (store_f)
@@ -985,8 +987,8 @@ sunrealtype wsqrsum(N_Vector x, N_Vector w)
   const double* wd = wc ? nullptr : mat(w);
   Value* xv        = xc->val;
   double r         = 0.0;
-  if (xv->wrms_w == wv && xv->wrms_slot >= 0)
-  { // the fused kernel that produced x already reduced sum (x*w)^2
+  if (xv->wrms_w == wv && xv->wrms_slot >= 0 && sh->slot_owner[xv->wrms_slot] == xv->seq)
+  { // the fused kernel that produced x already reduced sum (x*w)^2 (and no later launch has taken the slot over)
     double* slot = sh->wrms_slots + xv->wrms_slot;
     if (sh->wrms_host)
     { // the kernel stored the sum into mapped host memory: wait for the stream, read it
@@ -1131,6 +1133,7 @@ N_Vector N_VNew_B200(b200_ctx* ctx, sunindextype local_length, sunindextype glob
   sh->wrms_slots = nullptr;
   sh->halo_doubles = 0;
   sh->next_slot  = 0;
+  for (int k = 0; k < kSlots; k++) sh->slot_owner[k] = -1;
   memset(sh->spec_sigs, 0, sizeof(sh->spec_sigs));
   sh->wrms_host = nullptr;
   {
@@ -1202,5 +1205,37 @@ void N_VSetStageChain_B200(int depth)
 }
 int N_VGetStageChain_B200(void) { return g_chain_max; }
 void N_VGetStats_B200(B200VecStats* s) { *s = g_stats; }
+
+static int g_live_sessions = 0;
+static int g_session_set[4] = {-1, -1, -1, -1}; // lazy, chain depth, fma, variant of the sessions that are alive
+
+int N_VAcquireSettings_B200(int lazy, int chain_depth, int fma_arithmetic, int chain_variant)
+{
+  const int want[4] = {lazy, chain_depth, fma_arithmetic, chain_variant};
+  if (g_live_sessions > 0)
+    for (int k = 0; k < 4; k++)
+      if (want[k] >= 0 && g_session_set[k] >= 0 && want[k] != g_session_set[k])
+      {
+        static const char* what[4] = {"lazy fusion", "stage chain depth", "arithmetic (exact / fma)", "chain kernel variant"};
+        fprintf(stderr, "nvector_b200: another session is alive with %s = %d; this one asks for %d (process-wide setting)\n",
+                what[k], g_session_set[k], want[k]);
+        return -1;
+      }
+  if (g_live_sessions == 0)
+    for (int k = 0; k < 4; k++) g_session_set[k] = -1;
+  for (int k = 0; k < 4; k++)
+    if (want[k] >= 0) g_session_set[k] = want[k];
+  if (lazy >= 0) N_VSetLazyFusion_B200(lazy);
+  if (chain_depth >= 1) N_VSetStageChain_B200(chain_depth);
+  if (fma_arithmetic >= 0) b200_set_contract(fma_arithmetic);
+  if (chain_variant >= 0) b200_set_chain_variant(chain_variant);
+  g_live_sessions++;
+  return 0;
+}
+
+void N_VReleaseSettings_B200(void)
+{
+  if (g_live_sessions > 0) g_live_sessions--;
+}
 
 } // extern "C"

@@ -111,6 +111,14 @@ typedef struct B200VecStats
 } B200VecStats;
 SUNDIALS_EXPORT void N_VGetStats_B200(B200VecStats* s);
 
+/* Lazy fusion, the chain depth, the arithmetic flavour and the chain-kernel variant are PROCESS-wide switches.  A
+   session (b200_d2d_create / b200_adr_create) registers what it runs with; a second session created while the first is
+   alive must ask for the same values (-1 = "whatever is set"), else N_VAcquireSettings_B200 returns -1 and the
+   constructor fails instead of silently changing the other session's arithmetic or fusion.  Returns 0 and applies the
+   values otherwise.  Every successful acquire is paired with one N_VReleaseSettings_B200. */
+SUNDIALS_EXPORT int N_VAcquireSettings_B200(int lazy, int chain_depth, int fma_arithmetic, int chain_variant);
+SUNDIALS_EXPORT void N_VReleaseSettings_B200(void);
+
 #ifdef __cplusplus
 }
 #endif
