@@ -480,6 +480,75 @@ int orc_step_ssps3(orc_step_ws* w, orc_rhs_fn f, void* user, double tn, double h
   return stages;
 }
 
+/* lsrkStep_TakeStepSSP43, arkode_lsrkstep.c:1610-1796: the 4-stage, 3rd-order SSP method with its 2nd-order
+ * embedding accumulated in tempv1 (h/4 times every stage value). */
+int orc_step_ssp43(orc_step_ws* w, orc_rhs_fn f, void* user, double tn, double h, double* dsm)
+{
+  const double rs = 4.0, p5 = 0.5;
+  *dsm = 0.0;
+  orc_linear_sum(1.0, w->yn, h * p5, w->fn, w->ycur, w->n);                          /* :1655 */
+  if (!w->fixedstep) orc_linear_sum(1.0, w->yn, h / rs, w->fn, w->tempv1, w->n);
+  if (f(tn + h * p5, w->ycur, w->tempv3, user)) return -1;                           /* :1676 */
+  w->nfe++;
+  orc_linear_sum(1.0, w->ycur, h * p5, w->tempv3, w->ycur, w->n);
+  if (!w->fixedstep) orc_linear_sum(1.0, w->tempv1, h / rs, w->tempv3, w->tempv1, w->n);
+  if (f(tn + h, w->ycur, w->tempv3, user)) return -1;                                /* :1711 */
+  w->nfe++;
+  double c[3]        = {1.0 / 3.0, 2.0 / 3.0, 1.0 / 6.0 * h};
+  const double* X[3] = {w->ycur, w->yn, w->tempv3};
+  orc_linear_combination(3, c, X, w->ycur, w->n);                                    /* :1726-1732 */
+  if (!w->fixedstep) orc_linear_sum(1.0, w->tempv1, h / rs, w->tempv3, w->tempv1, w->n);
+  if (f(tn + h * p5, w->ycur, w->tempv3, user)) return -1;                           /* :1758 */
+  w->nfe++;
+  orc_linear_sum(1.0, w->ycur, h * p5, w->tempv3, w->ycur, w->n);
+  if (!w->fixedstep)
+  {
+    orc_linear_sum(1.0, w->tempv1, h / rs, w->tempv3, w->tempv1, w->n);
+    orc_linear_sum(1.0, w->ycur, -1.0, w->tempv1, w->tempv1, w->n);
+    *dsm = orc_wrmsnorm(w->tempv1, w->ewt, w->n, w->nglobal);
+  }
+  return 4;
+}
+
+/* lsrkStep_TakeStepSSP104, arkode_lsrkstep.c:1816-2023: the 10-stage, 4th-order SSP method (two sweeps of
+ * five sixth-steps joined by the 1/25, 9/25 | 15, -5 recombination) and its embedding in tempv1. */
+int orc_step_ssp104(orc_step_ws* w, orc_rhs_fn f, void* user, double tn, double h, double* dsm)
+{
+  const double onesixth = 1.0 / 6.0, onefifth = 1.0 / 5.0;
+  *dsm = 0.0;
+  orc_scale(1.0, w->yn, w->tempv2, w->n);                                            /* :1858 */
+  orc_linear_sum(1.0, w->yn, onesixth * h, w->fn, w->ycur, w->n);
+  if (!w->fixedstep) orc_linear_sum(1.0, w->yn, onefifth * h, w->fn, w->tempv1, w->n);
+  for (int j = 2; j <= 5; j++)
+  {                                                                                  /* :1871-1911 */
+    if (f(tn + ((double)j - 1.0) * onesixth * h, w->ycur, w->tempv3, user)) return -1;
+    w->nfe++;
+    orc_linear_sum(1.0, w->ycur, onesixth * h, w->tempv3, w->ycur, w->n);
+    if (j == 4 && !w->fixedstep) orc_linear_sum(1.0, w->tempv1, 0.3 * h, w->tempv3, w->tempv1, w->n);
+  }
+  orc_linear_sum(1.0 / 25.0, w->tempv2, 9.0 / 25.0, w->ycur, w->tempv2, w->n);       /* :1916-1920 */
+  orc_linear_sum(15.0, w->tempv2, -5.0, w->ycur, w->ycur, w->n);
+  for (int j = 6; j <= 9; j++)
+  {                                                                                  /* :1922-1968 */
+    if (f(tn + ((double)j - 4.0) * onesixth * h, w->ycur, w->tempv3, user)) return -1;
+    w->nfe++;
+    orc_linear_sum(1.0, w->ycur, onesixth * h, w->tempv3, w->ycur, w->n);
+    if (j == 7 && !w->fixedstep) orc_linear_sum(1.0, w->tempv1, onefifth * h, w->tempv3, w->tempv1, w->n);
+    if (j == 9 && !w->fixedstep) orc_linear_sum(1.0, w->tempv1, 0.3 * h, w->tempv3, w->tempv1, w->n);
+  }
+  if (f(tn + h, w->ycur, w->tempv3, user)) return -1;                                /* :1984 */
+  w->nfe++;
+  double c[3]        = {0.6, 1.0, 0.1 * h};
+  const double* X[3] = {w->ycur, w->tempv2, w->tempv3};
+  orc_linear_combination(3, c, X, w->ycur, w->n);                                    /* :1996-2002 */
+  if (!w->fixedstep)
+  {
+    orc_linear_sum(1.0, w->ycur, -1.0, w->tempv1, w->tempv1, w->n);
+    *dsm = orc_wrmsnorm(w->tempv1, w->ewt, w->n, w->nglobal);
+  }
+  return 10;
+}
+
 /* ------------------------------ fixed-step driver ------------------------------ */
 static int lap_rhs(double t, const double* y, double* f, void* user)
 {

@@ -87,6 +87,8 @@ int orc_step_rkc(orc_step_ws* w, orc_rhs_fn f, void* user, double tn, double h, 
 int orc_step_rkl(orc_step_ws* w, orc_rhs_fn f, void* user, double tn, double h, double spectral_radius, double* dsm); /* :846-1106 */
 int orc_step_ssps2(orc_step_ws* w, orc_rhs_fn f, void* user, double tn, double h, int stages, double* dsm);          /* :1128-1300 */
 int orc_step_ssps3(orc_step_ws* w, orc_rhs_fn f, void* user, double tn, double h, int stages, double* dsm);          /* :1326-1584 */
+int orc_step_ssp43(orc_step_ws* w, orc_rhs_fn f, void* user, double tn, double h, double* dsm);                       /* :1610-1796 */
+int orc_step_ssp104(orc_step_ws* w, orc_rhs_fn f, void* user, double tn, double h, double* dsm);                      /* :1816-2023 */
 
 /* Fixed-step diffusion_2D run on one periodic rank: nsteps RKC (method 0) or RKL
    (method 1) steps of size h from the initial condition, analytic dom_eig with the

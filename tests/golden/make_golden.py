@@ -4,7 +4,7 @@
 Two sources, both the reference's own:
 
 1. SUNDIALS' committed known-answer logs for the LSRKStep stage recurrences
-   /root/reference/deps/sundials/test/unit_tests/logging/test_logging_arkode_lsrkstep_lvl5_{0..3}.out
+   /root/reference/deps/sundials/test/unit_tests/logging/test_logging_arkode_lsrkstep_lvl5_{0..5}.out
    (RKC2, RKL2, SSP(s,2), SSP(s,3) on the scalar Prothero-Robinson problem prv.hpp).  Only the
    numbers are extracted -> lsrk_logging_golden.json.
 
@@ -143,10 +143,10 @@ def parse_lsrk_log(path):
 
 
 def main(only_missing=False):
-    out = {"source": "deps/sundials/test/unit_tests/logging/test_logging_arkode_lsrkstep_lvl5_{0..3}.out",
+    out = {"source": "deps/sundials/test/unit_tests/logging/test_logging_arkode_lsrkstep_lvl5_{0..5}.out",
            "problem": "prv.hpp: y' = L(t)(y - atan t) + 1/(1+t^2), L(t) = -1000 - 10 cos((10-t)/10 pi); dom_eig = L(t)",
            "rtol": 1e-6, "atol": 1e-10, "methods": {}}
-    for idx, name in enumerate(["rkc", "rkl", "ssps2", "ssps3"]):
+    for idx, name in enumerate(["rkc", "rkl", "ssps2", "ssps3", "ssp43", "ssp104"]):
         out["methods"][name] = parse_lsrk_log(os.path.join(LOGDIR, "test_logging_arkode_lsrkstep_lvl5_%d.out" % idx))
     with open(os.path.join(HERE, "lsrk_logging_golden.json"), "w") as f:
         json.dump(out, f, indent=1)

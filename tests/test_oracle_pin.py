@@ -2,7 +2,7 @@
 
 (a) SUNDIALS' golden stage logs for RKC2 / RKL2 / SSP(s,2) / SSP(s,3)
     (tests/golden/lsrk_logging_golden.json, extracted from
-    deps/sundials/test/unit_tests/logging/test_logging_arkode_lsrkstep_lvl5_{0..3}.out);
+    deps/sundials/test/unit_tests/logging/test_logging_arkode_lsrkstep_lvl5_{0..5}.out);
 (b) final states written by the unmodified reference driver (tests/golden/d2d_*.npy);
 (c) when the reference binary is present (build container), a live run of it;
 (e) SUNDIALS' known answers for the power iteration
@@ -53,6 +53,9 @@ def run_scalar_step(orc, method, st, rtol, atol):
         assert sr == pytest.approx(st["spectral_radius"], rel=1e-12)
         fn = orc.orc_step_rkc if method == "rkc" else orc.orc_step_rkl
         s = fn(ctypes.byref(ws), cb, None, tn, h, ctypes.c_double(sr), ctypes.byref(dsm))
+    elif method in ("ssp43", "ssp104"):
+        fn = orc.orc_step_ssp43 if method == "ssp43" else orc.orc_step_ssp104
+        s = fn(ctypes.byref(ws), cb, None, tn, h, ctypes.byref(dsm))
     else:
         nst = len(st["F"])  # F_0 .. F_{s-1}
         fn = orc.orc_step_ssps2 if method == "ssps2" else orc.orc_step_ssps3
@@ -61,7 +64,7 @@ def run_scalar_step(orc, method, st, rtol, atol):
     return s, vec["ycur"][0], calls, dsm.value
 
 
-@pytest.mark.parametrize("method", ["rkc", "rkl", "ssps2", "ssps3"])
+@pytest.mark.parametrize("method", ["rkc", "rkl", "ssps2", "ssps3", "ssp43", "ssp104"])
 def test_lsrk_golden_stage_logs(orc, method):
     with open(os.path.join(GOLDEN, "lsrk_logging_golden.json")) as f:
         gold = json.load(f)
