@@ -31,6 +31,7 @@ struct ChainArgs
   const double* fn;
   double c[B200_MAX_CHAIN][5];
   double* out[B200_MAX_CHAIN];
+  double* f_out; // HEAD flavour: where L(x) = f(t_n, y_n) goes (the fn of all later stages)
   int rows;
   // multi-rank (HALO = true): per-operand deep-halo buffers, layout of b200_deep_halo_exchange
   const double *hx, *hp, *hy, *hf;
@@ -90,7 +91,9 @@ struct ChainState
 // issue group(ir) = { x row ir+1, prev2 / yn / fn row ir } into the ring and advance the running
 // source pointers by one row; the pointers are recomputed only where the source changes
 // (rows 0 and ny: wrap-around, or field <-> S/N halo)
-template <int K, int PF, bool HALO>
+// HEAD flavour (the chain starts with stage 1 of the step, z_1 = y_n + c L(y_n)): only x (= y_n) is streamed -- there is
+// no z_{-1}, and f_n = L(y_n) is produced by level 1 of this very launch, which writes it into the fn ring itself.
+template <int K, int PF, bool HALO, bool HEAD>
 __device__ __forceinline__ void chain_issue(const ChainArgs& a, ChainState& st, double2* rx, double2* rp,
                                             double2* ry, double2* rf, int64_t nx, int ny, bool issue)
 {
@@ -98,9 +101,9 @@ __device__ __forceinline__ void chain_issue(const ChainArgs& a, ChainState& st, 
   if (issue)
   {
     cp_async16(rx + st.sx_issue * kChainThreads, st.px);
-    cp_async16(rp + st.sx_issue * kChainThreads, st.pp);
+    if (!HEAD) cp_async16(rp + st.sx_issue * kChainThreads, st.pp);
     cp_async16(ry + st.sy_issue * kChainThreads, st.py);
-    cp_async16(rf + st.sy_issue * kChainThreads, st.pf);
+    if (!HEAD) cp_async16(rf + st.sy_issue * kChainThreads, st.pf);
   }
   cp_async_commit();
   st.sx_issue = (st.sx_issue + 1 == DX) ? 0 : st.sx_issue + 1;
@@ -108,16 +111,20 @@ __device__ __forceinline__ void chain_issue(const ChainArgs& a, ChainState& st, 
   const int r = ++st.ir;
   if (r == 0 || r == ny)
   {
-    st.pp = row_ptr<HALO>(a.prev2, a.hp, r, st.we, st.lane_col, nx, ny, a.g, a.g2);
+    if (!HEAD) st.pp = row_ptr<HALO>(a.prev2, a.hp, r, st.we, st.lane_col, nx, ny, a.g, a.g2);
     st.py = row_ptr<HALO>(a.yn, a.hy, r, st.we, st.lane_col, nx, ny, a.g, a.g2);
-    st.pf = row_ptr<HALO>(a.fn, a.hf, r, st.we, st.lane_col, nx, ny, a.g, a.g2);
+    if (!HEAD) st.pf = row_ptr<HALO>(a.fn, a.hf, r, st.we, st.lane_col, nx, ny, a.g, a.g2);
   }
-  else { st.pp += st.pstep; st.py += st.pstep; st.pf += st.pstep; }
+  else
+  {
+    st.py += st.pstep;
+    if (!HEAD) { st.pp += st.pstep; st.pf += st.pstep; }
+  }
   if (r + 1 == 0 || r + 1 == ny) st.px = row_ptr<HALO>(a.x, a.hx, r + 1, st.we, st.lane_col, nx, ny, a.g, a.g2);
   else st.px += st.pstep;
 }
 
-template <int K, int PF, int PH, bool CHECK, bool HALO, bool FMA, bool UNI>
+template <int K, int PF, int PH, bool CHECK, bool HALO, bool FMA, bool UNI, bool HEAD>
 __device__ __forceinline__ void chain_row(const ChainArgs& a, ChainState& st, double2 (&W)[K][3],
                                           double2* rx, double2* rp, double2* ry, double2* rf,
                                           const double2* ytab, const double* stab, int64_t nx, int ny,
@@ -126,11 +133,11 @@ __device__ __forceinline__ void chain_row(const ChainArgs& a, ChainState& st, do
 {
   constexpr int DX = PF + 1, DY = PF + K;
   constexpr int IO = PH % 3, IM = (PH + 1) % 3, IC = (PH + 2) % 3; // oldest (overwritten), then um, uc ; up = IO
-  chain_issue<K, PF, HALO>(a, st, rx, rp, ry, rf, nx, ny, issue); // group(r1 + PF)
+  chain_issue<K, PF, HALO, HEAD>(a, st, rx, rp, ry, rf, nx, ny, issue); // group(r1 + PF)
   cp_async_wait<PF>(); // all but the PF newest groups have landed: group(r1) is ready
 
   W[0][IO]        = rx[st.sx_use * kChainThreads]; // x row r1+1 replaces the oldest row
-  const double2 P = rp[st.sx_use * kChainThreads];
+  const double2 P = HEAD ? make_double2(0.0, 0.0) : rp[st.sx_use * kChainThreads];
   int64_t so      = st.soff;
 #pragma unroll
   for (int l = 1; l <= K; l++)
@@ -157,19 +164,35 @@ __device__ __forceinline__ void chain_row(const ChainArgs& a, ChainState& st, do
     const double2 p2 = (l == 1) ? P : W[(l >= 2) ? l - 2 : 0][IM];
     int sl = st.sy_use - (l - 1); // yn / fn of row r1-(l-1)
     if (sl < 0) sl += DY;
-    const double2 yv = ry[sl * kChainThreads], fv = rf[sl * kChainThreads];
     const double* cf = a.c[l - 1];
     double2 z;
-    z.x = DMUL(cf[0], L0);               z.y = DMUL(cf[0], L1);
-    z.x = mad<FMA>(cf[1], p2.x, z.x);  z.y = mad<FMA>(cf[1], p2.y, z.y);
-    z.x = mad<FMA>(cf[2], yv.x, z.x);  z.y = mad<FMA>(cf[2], yv.y, z.y);
-    z.x = mad<FMA>(cf[3], uc.x, z.x);  z.y = mad<FMA>(cf[3], uc.y, z.y);
-    z.x = mad<FMA>(cf[4], fv.x, z.x);  z.y = mad<FMA>(cf[4], fv.y, z.y);
     bool doit = (smask >> (l - 1)) & 1u;
     if (CHECK)
     {
       const int rl = r1 - (l - 1);
       doit         = doit && rl >= j0 && rl < j1;
+    }
+    if (HEAD && l == 1)
+    { // stage 1 of the step, z_1 = 1*y_n + (h mu~_1)*f_n (N_VLinearSum, arkode_lsrkstep.c:640 / :930), in the order of
+      // the one-stage kernel's PAT2(C,S): acc = 1*x ; acc += c*L -- and f_n = L(y_n) itself, with the reference's
+      // "f = 0; f += ..." (0 + L: a -0 becomes +0, and unlike further down this value is stored)
+      L0 = DADD(0.0, L0);
+      L1 = DADD(0.0, L1);
+      rf[sl * kChainThreads] = make_double2(L0, L1); // the later levels read f_n of the rows behind from this ring
+      z.x = mad<FMA>(cf[0], L0, DMUL(1.0, uc.x));
+      z.y = mad<FMA>(cf[0], L1, DMUL(1.0, uc.y));
+      bool dof = (smask >> K) & 1u; // store_ok of this lane
+      if (CHECK) dof = dof && r1 >= j0 && r1 < j1;
+      if (dof) *reinterpret_cast<double2*>(a.f_out + so) = make_double2(L0, L1);
+    }
+    else
+    {
+      const double2 yv = ry[sl * kChainThreads], fv = rf[sl * kChainThreads];
+      z.x = DMUL(cf[0], L0);               z.y = DMUL(cf[0], L1);
+      z.x = mad<FMA>(cf[1], p2.x, z.x);  z.y = mad<FMA>(cf[1], p2.y, z.y);
+      z.x = mad<FMA>(cf[2], yv.x, z.x);  z.y = mad<FMA>(cf[2], yv.y, z.y);
+      z.x = mad<FMA>(cf[3], uc.x, z.x);  z.y = mad<FMA>(cf[3], uc.y, z.y);
+      z.x = mad<FMA>(cf[4], fv.x, z.x);  z.y = mad<FMA>(cf[4], fv.y, z.y);
     }
     if (doit) *reinterpret_cast<double2*>(a.out[l - 1] + so) = z;
     so -= nx;
@@ -181,7 +204,7 @@ __device__ __forceinline__ void chain_row(const ChainArgs& a, ChainState& st, do
   st.sy_use = (st.sy_use + 1 == DY) ? 0 : st.sy_use + 1;
 }
 
-template <int K, int PF, bool HALO, bool FMA, bool UNI = false>
+template <int K, int PF, bool HALO, bool FMA, bool UNI = false, bool HEAD = false>
 __global__ void __launch_bounds__(kChainThreads, 2) k_chain_march(const ChainArgs a)
 {
   constexpr int HL   = (K + 1) / 2;  // halo lanes per side (2 cells each): 2*HL >= K
@@ -225,6 +248,7 @@ __global__ void __launch_bounds__(kChainThreads, 2) k_chain_march(const ChainArg
 #pragma unroll
   for (int l = 0; l < K; l++)
     if (store_ok && a.out[l]) smask |= 1u << l;
+  if (HEAD && store_ok) smask |= 1u << K; // f_out
 
   ChainState st;
   int64_t ic = col_u; // column used for stores and (wrap mode) loads
@@ -261,9 +285,13 @@ __global__ void __launch_bounds__(kChainThreads, 2) k_chain_march(const ChainArg
   st.trow     = K - 1;
   st.ir       = rstart;
   st.px = row_ptr<HALO>(a.x, a.hx, rstart + 1, st.we, st.lane_col, nx, ny, a.g, a.g2);
-  st.pp = row_ptr<HALO>(a.prev2, a.hp, rstart, st.we, st.lane_col, nx, ny, a.g, a.g2);
   st.py = row_ptr<HALO>(a.yn, a.hy, rstart, st.we, st.lane_col, nx, ny, a.g, a.g2);
-  st.pf = row_ptr<HALO>(a.fn, a.hf, rstart, st.we, st.lane_col, nx, ny, a.g, a.g2);
+  st.pp = st.pf = st.py; // (not streamed in the HEAD flavour)
+  if (!HEAD)
+  {
+    st.pp = row_ptr<HALO>(a.prev2, a.hp, rstart, st.we, st.lane_col, nx, ny, a.g, a.g2);
+    st.pf = row_ptr<HALO>(a.fn, a.hf, rstart, st.we, st.lane_col, nx, ny, a.g, a.g2);
+  }
 
   double2 W[K][3];
 #pragma unroll
@@ -274,10 +302,10 @@ __global__ void __launch_bounds__(kChainThreads, 2) k_chain_march(const ChainArg
 
   // prologue of the pipeline: groups rstart .. rstart+PF-1
 #pragma unroll
-  for (int q = 0; q < PF; q++) chain_issue<K, PF, HALO>(a, st, rx, rp, ry, rf, nx, ny, true);
+  for (int q = 0; q < PF; q++) chain_issue<K, PF, HALO, HEAD>(a, st, rx, rp, ry, rf, nx, ny, true);
 
 #define ROW(PH, CHECK, R1) \
-  chain_row<K, PF, PH, CHECK, HALO, FMA, UNI>(a, st, W, rx, rp, ry, rf, ytab, stab, nx, ny, cw, ce, sx0, sx1, smask, R1, j0, j1, (R1) + PF < rend)
+  chain_row<K, PF, PH, CHECK, HALO, FMA, UNI, HEAD>(a, st, W, rx, rp, ry, rf, ytab, stab, nx, ny, cw, ce, sx0, sx1, smask, R1, j0, j1, (R1) + PF < rend)
 
   // phases: [rstart, s0) checked warm-up in whole triples, [s0, s1) unchecked steady state in
   // triples, [s1, rend3) checked drain; rend3 rounds the trip count up to a multiple of 3 (the
