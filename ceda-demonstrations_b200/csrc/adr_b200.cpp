@@ -570,6 +570,7 @@ extern "C" int b200_adr_create(int argc, const char* const* argv, int device, vo
     p->ud.ops[m].op.halo_alloc   = nullptr;
     p->ud.ops[m].op.halo_free    = nullptr;
     p->ud.ops[m].op.dq           = nullptr;
+    p->ud.ops[m].op.chain_head   = nullptr;
   }
   int depth = -1; // -1: this session does not care about the process-wide chain depth
   if (p->uo.sts_chain >= 2 && p->ud.nx >= 64 && p->ud.ny >= 16)

@@ -858,7 +858,7 @@ static int current_device()
   return (d >= 0 && d < kMaxDevices) ? d : 0;
 }
 
-template <int K, int PF, bool HALO, bool FMA, bool UNI>
+template <int K, int PF, bool HALO, bool FMA, bool UNI, bool HEAD>
 static int launch_chain_k(const ChainArgs& a, dim3 grid, cudaStream_t st)
 {
   const size_t smem = chain_march_smem(K, PF, a.rows);
@@ -866,10 +866,10 @@ static int launch_chain_k(const ChainArgs& a, dim3 grid, cudaStream_t st)
   size_t& configured = configured_on[current_device()];
   if (smem > configured)
   {
-    CU_TRY(cudaFuncSetAttribute(k_chain_march<K, PF, HALO, FMA, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_TRY(cudaFuncSetAttribute(k_chain_march<K, PF, HALO, FMA, UNI, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  klaunch((k_chain_march<K, PF, HALO, FMA, UNI>), grid, kChainThreads, smem, st, a);
+  klaunch((k_chain_march<K, PF, HALO, FMA, UNI, HEAD>), grid, kChainThreads, smem, st, a);
   return 0;
 }
 
@@ -884,10 +884,15 @@ extern "C" int b200_set_contract(int on)
 }
 extern "C" int b200_get_contract(void) { return g_contract; }
 
+template <int K, int PF, bool HALO, bool FMA, bool UNI>
+static int launch_chain_h(const ChainArgs& a, dim3 grid, cudaStream_t st)
+{ // HEAD: the chain begins with stage 1 of the step (f_out set)
+  return a.f_out ? launch_chain_k<K, PF, HALO, FMA, UNI, true>(a, grid, st) : launch_chain_k<K, PF, HALO, FMA, UNI, false>(a, grid, st);
+}
 template <int K, int PF, bool HALO, bool FMA>
 static int launch_chain_u(const ChainArgs& a, dim3 grid, cudaStream_t st, bool uni)
 {
-  return uni ? launch_chain_k<K, PF, HALO, FMA, true>(a, grid, st) : launch_chain_k<K, PF, HALO, FMA, false>(a, grid, st);
+  return uni ? launch_chain_h<K, PF, HALO, FMA, true>(a, grid, st) : launch_chain_h<K, PF, HALO, FMA, false>(a, grid, st);
 }
 template <int K, int PF>
 static int launch_chain(const ChainArgs& a, dim3 grid, cudaStream_t st, bool uni)
@@ -973,9 +978,10 @@ extern "C" int b200_set_chain_rows(int r)
 static int stencil_chain_common(b200_ctx* c, const b200_stencil_geom* g, int nstages, const double* x,
                                 const double* prev2, const double* yn, const double* fn,
                                 const double* coeffs, double* const* z_out, const double* const* halos,
-                                int hg, int hg2)
+                                int hg, int hg2, double* f_out = nullptr)
 {
   if (nstages < 2 || nstages > B200_MAX_CHAIN) return fail("b200_stencil_chain: nstages must be 2..B200_MAX_CHAIN");
+  if (f_out && (f_out == x || !aligned16(f_out))) return fail("b200_stencil_chain_head: bad f_out");
   if (g->halo_w || g->halo_e || g->halo_s || g->halo_n)
     return fail("b200_stencil_chain: the one-deep halo buffers of b200_stencil_geom are not used here");
   if ((g->nx & 1) || g->nx < 128 || g->ny < 16) return fail("b200_stencil_chain: needs even nx >= 128 and ny >= 16");
@@ -1013,12 +1019,14 @@ static int stencil_chain_common(b200_ctx* c, const b200_stencil_geom* g, int nst
     {
       any = true;
       if (!aligned16(a.out[l])) return fail("b200_stencil_chain: output not 16-byte aligned");
-      if (a.out[l] == x || a.out[l] == prev2 || a.out[l] == yn || a.out[l] == fn)
+      if (a.out[l] == x || a.out[l] == prev2 || a.out[l] == yn || a.out[l] == fn || a.out[l] == f_out)
         return fail("b200_stencil_chain: an output aliases an input");
     }
   }
   if (!any || !a.out[nstages - 1]) return fail("b200_stencil_chain: the last stage must be stored");
-  const bool use_quad = b200_get_chain_variant() == 1 && chain_quad_supported(a.nx, a.ny, nstages, halos ? hg2 : -1);
+  a.f_out = f_out;
+  // (k_chain_quad has no stage-1 flavour: a chain that begins the step runs on k_chain_march)
+  const bool use_quad = !f_out && b200_get_chain_variant() == 1 && chain_quad_supported(a.nx, a.ny, nstages, halos ? hg2 : -1);
   a.rows              = g_chain_rows > 0 ? g_chain_rows : chain_rows_auto(c, a.nx, a.ny, nstages, use_quad);
   int rc = 0;
   if (use_quad)
@@ -1050,11 +1058,27 @@ static int stencil_chain_common(b200_ctx* c, const b200_stencil_geom* g, int nst
   if (rc) return rc;
   LAUNCH_CHECK();
   {
-    int touches = 4; // x, prev2, yn, fn
+    int touches = f_out ? 2 : 4; // x, prev2, yn, fn -- or x and the stored f_n when the chain begins the step
     for (int l = 0; l < nstages; l++) touches += (a.out[l] != nullptr);
     ALG_BYTES(touches, a.nx * a.ny);
   }
   return 0;
+}
+
+// The chain that BEGINS a step: stage 1 is z_1 = x + c1 L(x) (x = y_n; coeffs[0] = c1, coeffs[1..4] unused) and
+// f_n = L(x) is written to f_out and used by the later stages straight from the kernel's ring -- y_n is read once,
+// no z_{-1}, no f_n stream.
+extern "C" int b200_stencil_chain_head(b200_ctx* c, const b200_stencil_geom* g, int nstages, const double* x,
+                                       const double* coeffs, double* const* z_out, double* f_out,
+                                       const double* halo_x, int halo_rows, int halo_cols)
+{
+  if (!f_out) return fail("b200_stencil_chain_head: f_out missing");
+  if (halo_x)
+  {
+    const double* halos[4] = {halo_x, halo_x, halo_x, halo_x};
+    return stencil_chain_common(c, g, nstages, x, x, x, x, coeffs, z_out, halos, halo_rows, halo_cols, f_out);
+  }
+  return stencil_chain_common(c, g, nstages, x, x, x, x, coeffs, z_out, nullptr, 0, 0, f_out);
 }
 
 extern "C" int b200_stencil_chain(b200_ctx* c, const b200_stencil_geom* g, int nstages,

@@ -353,6 +353,42 @@ int rhs_chain(void* self, b200_ctx* ctx, int nstages, const double* x, const dou
   return b200_stencil_chain_halo(ctx, &g, nstages, x, prev2, yn, fn, coeffs, z_out, halos, kHaloRows, kHaloCols);
 }
 
+// the chain that begins a step (stage 1 folded in, f_n produced by the launch): B200RhsOp::chain_head
+int rhs_chain_head(void* self, b200_ctx* ctx, int nstages, const double* x, const double* coeffs, double* const* z_out,
+                   double* f_out, double* halo_x, int halo_x_valid)
+{
+  UserData* ud = static_cast<UserData*>(self);
+  b200_stencil_geom g;
+  memset(&g, 0, sizeof(g));
+  g.nx = ud->nx_loc; g.ny = ud->ny_loc;
+  if (ud->uniform_coeffs)
+  {
+    g.uniform = 1;
+    g.u_cxw = ud->u_coeff[0]; g.u_cxe = ud->u_coeff[1]; g.u_cys = ud->u_coeff[2]; g.u_cyn = ud->u_coeff[3];
+  }
+  ud->rhs_calls += nstages;
+  if (!halo_x)
+  {
+    g.cxw = ud->cxw; g.cxe = ud->cxe; g.cys = ud->cys; g.cyn = ud->cyn;
+    return b200_stencil_chain_head(ctx, &g, nstages, x, coeffs, z_out, f_out, nullptr, 0, 0);
+  }
+  if (!halo_x_valid)
+  {
+    const double* xf[1] = {x};
+    double* xh[1]       = {halo_x};
+    int rc;
+    if (ud->peer_halo) rc = b200_peer_halo_exchange(ud->peer_halo, 1, xf, xh);
+    else
+    {
+      const int peers[4] = {ud->ipW, ud->ipE, ud->ipS, ud->ipN};
+      rc = b200_deep_halo_exchange(ctx, peers, ud->npx > 1, ud->npy > 1, g.nx, g.ny, kHaloRows, kHaloCols, 1, xf, xh);
+    }
+    if (rc) return rc;
+  }
+  g.cxw = ud->cxw_ext; g.cxe = ud->cxe_ext; g.cys = ud->cys_ext; g.cyn = ud->cyn_ext;
+  return b200_stencil_chain_head(ctx, &g, nstages, x, coeffs, z_out, f_out, halo_x, kHaloRows, kHaloCols);
+}
+
 // arkLsATimes o arkLsDQJtimes around diffusion() in one stencil pass (one periodic rank, even width)
 int rhs_dq(void* self, b200_ctx* ctx, const double* v, const double* y, const double* fy, double sigma, double siginv,
            int outer, double ca, double cb, double* z, double* dot_result)
@@ -516,6 +552,7 @@ static int problem_attach(UserData& ud, b200_ctx* ctx, int nranks, bool overlap,
   ud.rhs_op.self = &ud;
   ud.rhs_op.fused = rhs_fused;
   ud.rhs_op.chain = nullptr;
+  ud.rhs_op.chain_head = nullptr;
   ud.rhs_op.dq    = (getenv("B200_NO_DQ_FUSION") || no_fusion) ? nullptr : rhs_dq;
   ud.rhs_op.chain_max = 0;
   ud.rhs_op.halo_doubles = 0;
@@ -529,6 +566,7 @@ static int problem_attach(UserData& ud, b200_ctx* ctx, int nranks, bool overlap,
   if (all_even && qx_min >= 128 && qy_min >= 16)
   { // index wrap on one periodic rank, deep halos on a rank of a decomposition
     ud.rhs_op.chain     = rhs_chain;
+    ud.rhs_op.chain_head = getenv("B200_NO_CHAIN_HEAD") ? nullptr : rhs_chain_head;
     ud.rhs_op.chain_max = B200_MAX_CHAIN;
     if (nranks > 1 || ud.force_halo)
     {

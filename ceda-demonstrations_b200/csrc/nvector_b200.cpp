@@ -75,6 +75,7 @@ struct StageRec
   Value *x, *p2, *yn, *fn; // one reference held on each
   double c[5];
   int depth;               // 1 for the first stage of a chain
+  bool head;               // stage 1 of a step: z = x + c[0] L(x); fn is the deferred value L(x) itself (yn == p2 == x)
 };
 
 // a requested-but-not-evaluated elementwise result (the implicit path's vector work): evaluated when something
@@ -292,10 +293,14 @@ void launch_chain(Shared* sh, Value* top)
     for (int k = 0; k < n; k++) lv[k] = rev[n - 1 - k];
   }
   StageRec* first = lv[0]->st;
+  const bool head = first->head; // the chain begins the step: f_n = L(x) is produced by this launch
   materialise(sh, first->x); // (only reachable if a chain longer than B200_MAX_CHAIN was built)
-  materialise(sh, first->p2);
-  materialise(sh, first->yn);
-  materialise(sh, first->fn);
+  if (!head)
+  {
+    materialise(sh, first->p2);
+    materialise(sh, first->yn);
+    materialise(sh, first->fn);
+  }
   // a level must be stored iff somebody outside this chain still points at it: chain-internal
   // references are the next stage's x and the stage after that's p2
   double* outs[B200_MAX_CHAIN];
@@ -309,19 +314,33 @@ void launch_chain(Shared* sh, Value* top)
     outs[k]         = keep ? pool_get(sh) : nullptr;
     for (int q = 0; q < 5; q++) cf[5 * k + q] = lv[k]->st->c[q];
   }
+  Value* F            = head ? first->fn : nullptr; // the deferred value L(x) that ARKODE keeps as fn
+  double* f_out       = head ? pool_get(sh) : nullptr;
+  const bool f_extra  = head && F->d != nullptr; // somebody evaluated f_n in the meantime: ours is scratch
   if (n == 1)
   {
-    int srcs[5]         = {B200_SRC_STENCIL, B200_SRC_VECTOR, B200_SRC_VECTOR, B200_SRC_CENTRE, B200_SRC_VECTOR};
-    const double* vp[5] = {nullptr, first->p2->d, first->yn->d, nullptr, first->fn->d};
-    int wdone           = 0;
-    DEV(first->op->fused(first->op->self, sh->ctx, first->x->d, 5, cf, srcs, vp, outs[0], nullptr, nullptr, nullptr,
-                         &wdone));
+    int wdone = 0;
+    if (head)
+    { // a lone stage 1: the ordinary fused launch z = 1*x + c*L(x) that also stores L(x)
+      const double c2[2]  = {first->c[3], first->c[0]};
+      int srcs[2]         = {B200_SRC_CENTRE, B200_SRC_STENCIL};
+      const double* vp[2] = {nullptr, nullptr};
+      DEV(first->op->fused(first->op->self, sh->ctx, first->x->d, 2, c2, srcs, vp, outs[0], f_out, nullptr, nullptr, &wdone));
+    }
+    else
+    {
+      int srcs[5]         = {B200_SRC_STENCIL, B200_SRC_VECTOR, B200_SRC_VECTOR, B200_SRC_CENTRE, B200_SRC_VECTOR};
+      const double* vp[5] = {nullptr, first->p2->d, first->yn->d, nullptr, first->fn->d};
+      DEV(first->op->fused(first->op->self, sh->ctx, first->x->d, 5, cf, srcs, vp, outs[0], nullptr, nullptr, nullptr,
+                           &wdone));
+    }
   }
   else
   {
     double* halos[4] = {nullptr, nullptr, nullptr, nullptr};
     int valid[4]     = {1, 1, 1, 1};
     Value* opv[4]    = {first->x, first->p2, first->yn, first->fn};
+    const int nop    = head ? 1 : 4; // a chain that begins the step reads x only
     const bool deep  = first->op->halo_doubles > 0;
     if (deep)
     { // multi-rank: each operand carries a deep halo, exchanged by the operator when stale
@@ -331,7 +350,7 @@ void launch_chain(Shared* sh, Value* top)
         sh->free_halos.clear();
         sh->halo_doubles = first->op->halo_doubles;
       }
-      for (int q = 0; q < 4; q++)
+      for (int q = 0; q < nop; q++)
       {
         if (!opv[q]->halo)
         {
@@ -351,12 +370,27 @@ void launch_chain(Shared* sh, Value* top)
           if (opv[e] == opv[q]) valid[q] = 1; // same value twice: exchange it once
       }
     }
-    DEV(first->op->chain(first->op->self, sh->ctx, n, first->x->d, first->p2->d, first->yn->d, first->fn->d, cf, outs,
-                         deep ? halos : nullptr, valid));
+    if (head)
+      DEV(first->op->chain_head(first->op->self, sh->ctx, n, first->x->d, cf, outs, f_out, deep ? halos[0] : nullptr, valid[0]));
+    else
+      DEV(first->op->chain(first->op->self, sh->ctx, n, first->x->d, first->p2->d, first->yn->d, first->fn->d, cf, outs,
+                           deep ? halos : nullptr, valid));
     if (deep)
-      for (int q = 0; q < 4; q++) opv[q]->halo_valid = true;
+      for (int q = 0; q < nop; q++) opv[q]->halo_valid = true;
     g_stats.chain_launches++;
     g_stats.chain_stages += n;
+  }
+  if (head)
+  {
+    if (f_extra) sh->free_bufs.push_back(f_out);
+    else
+    { // f_n is now plain data (as after a fused launch with f_out)
+      Value* src = F->src;
+      F->d   = f_out;
+      F->op  = nullptr;
+      F->src = nullptr;
+      value_release(sh, src);
+    }
   }
   // retire the records bottom-up; values nobody points at any more disappear with them
   for (int k = 0; k < n; k++) lv[k]->refs++; // pin while we rewire
@@ -568,6 +602,26 @@ void eval_lincomb(int nterms, const double* cf, N_Vector* Xv, N_Vector zv)
   // F itself must be kept if anything other than z will still point at it
   const bool store_f = L && (L->refs - (zc->val == L ? 1 : 0)) > 0;
 
+  // Stage 1 of an STS step, z_1 = 1*y_n + c*L(y_n) with L(y_n) = f_n kept by ARKODE (arkode_lsrkstep.c:640 / :930):
+  // pending as the HEAD of a chain -- if stage 2 extends it, one launch produces f_n and the stages together
+  if (L && g_chain_max >= 2 && nterms == 2 && store_f && L->op->chain_head && L->op->chain_max >= 2 && X[1] == L &&
+      X[0] == L->src && cf[0] == 1.0)
+  {
+    Value* xin = L->src;
+    materialise(sh, xin);
+    Value* out  = value_new(sh, false);
+    StageRec* r = new StageRec();
+    r->op = L->op; r->x = xin; r->p2 = xin; r->yn = xin; r->fn = L;
+    r->x->refs++; r->p2->refs++; r->yn->refs++; r->fn->refs++;
+    r->c[0] = cf[1]; r->c[1] = r->c[2] = r->c[4] = 0.0; r->c[3] = 1.0;
+    r->depth = 1;
+    r->head  = true;
+    out->st  = r;
+    assign(zc, out);
+    g_stats.fused_launches++;
+    return;
+  }
+
   // STS stage pattern [L(x), p, yn, x, fn]: defer it as a pending stage (temporal blocking)
   if (L && g_chain_max >= 2 && nterms == 5 && !store_f && L->op->chain && L->op->chain_max >= 2 && X[0] == L &&
       X[3] == L->src && X[1] != L && X[2] != L && X[4] != L && X[1] != X[3])
@@ -582,15 +636,20 @@ void eval_lincomb(int nterms, const double* cf, N_Vector* Xv, N_Vector zv)
       else materialise(sh, xin);
     }
     else materialise(sh, xin);
-    if (depth == 1) materialise(sh, X[1]);
-    materialise(sh, X[2]);
-    materialise(sh, X[4]);
+    if (depth == 1)
+    { // a new chain: its operands must be plain data (an extended chain shares the operands of its first stage --
+      // for a chain that begins the step f_n is the still-deferred L(y_n), which the launch itself will produce)
+      materialise(sh, X[1]);
+      materialise(sh, X[2]);
+      materialise(sh, X[4]);
+    }
     Value* out  = value_new(sh, false);
     StageRec* r = new StageRec();
     r->op = L->op; r->x = xin; r->p2 = X[1]; r->yn = X[2]; r->fn = X[4];
     r->x->refs++; r->p2->refs++; r->yn->refs++; r->fn->refs++;
     for (int q = 0; q < 5; q++) r->c[q] = cf[q];
     r->depth = depth;
+    r->head  = false;
     out->st  = r;
     // Not launched even at full depth: ARKODE still holds z_{j-2} in tempv1 at this point and
     // drops it right after (pointer swap + N_VScale, arkode_lsrkstep.c:742-746); launching lazily,

@@ -220,6 +220,14 @@ int b200_stencil_chain_halo(b200_ctx* ctx, const b200_stencil_geom* g, int nstag
                             const double* x, const double* prev2, const double* yn,
                             const double* fn, const double* coeffs, double* const* z_out,
                             const double* const* halos, int halo_rows, int halo_cols);
+/* The chain that BEGINS an STS step (stage 1 folded in): z_1 = x + c_1 L(x) with x = y_n (N_VLinearSum(ONE, yn, h*mus, fn,
+   ..), arkode_lsrkstep.c:640 / :930; coeffs[0][0] = c_1, the other four entries of row 0 are ignored), stages 2..nstages
+   as above with z_0 = y_n = x and f_n = L(x).  f_n is stored to f_out (it is the vector ARKODE keeps as fn) and the
+   later stages take it from the kernel's own ring: y_n is streamed once, there is no z_{-1} and no f_n stream.
+   halo_x: deep halo of x on a rank of a decomposition (NULL on one periodic rank). */
+int b200_stencil_chain_head(b200_ctx* ctx, const b200_stencil_geom* g, int nstages, const double* x,
+                            const double* coeffs, double* const* z_out, double* f_out,
+                            const double* halo_x, int halo_rows, int halo_cols);
 /* Deep halo of one nx*ny field, `rows` deep in y and `cols` deep in x, corners included:
      [ S: rows x nx | N: rows x nx | W: (ny+2 rows) x cols | E: (ny+2 rows) x cols ]
    S = rows -rows..-1, N = rows ny..ny+rows-1, W / E = columns -cols..-1 / nx..nx+cols-1

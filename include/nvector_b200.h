@@ -49,6 +49,12 @@ typedef struct B200RhsOp
                const double* yn, const double* fn, const double* coeffs, double* const* z_out,
                double* const* halos, const int* halo_valid);
   int chain_max;
+  /* Optional (NULL = not available): the chain that BEGINS a step.  Stage 1 of the STS methods is
+     z_1 = x + c_1 F(x) with x = y_n (arkode_lsrkstep.c:640 / :930) and F(x) is the f_n of every later stage, so the
+     kernel produces f_n itself (stored to f_out) and streams only x: coeffs row 0 = { c_1, -, -, -, - }, rows
+     1..nstages-1 as for `chain` with z_0 = y_n = x.  halo_x / halo_x_valid: as halos[0] / halo_valid[0] of `chain`. */
+  int (*chain_head)(void* self, b200_ctx* ctx, int nstages, const double* x, const double* coeffs,
+                    double* const* z_out, double* f_out, double* halo_x, int halo_x_valid);
   /* > 0: the operator runs on one rank of a decomposition and `chain` needs a deep halo
      (this many doubles) for each of x, prev2, yn, fn.  The vector owns and caches the
      buffers per value; `chain` receives halos[4] and halo_valid[4] and must fill (exchange)

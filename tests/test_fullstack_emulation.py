@@ -132,6 +132,25 @@ def test_temporal_blocking_and_deep_halo_paths_do_not_change_a_bit(emu, args):
     emu.sundials_lib().N_VSetStageChain_B200(4)
 
 
+@pytest.mark.parametrize("extra", [[], ["--force-halo"]], ids=["wrap", "deep_halo"])
+def test_stage_one_is_the_head_of_the_first_chain(emu, monkeypatch, extra):
+    """Fixed-step STS: stage 1 (z_1 = y_n + c L(y_n), arkode_lsrkstep.c:640 / :930) and f_n = L(y_n) come out of the
+    first chain launch of the step (HEAD flavour of k_chain_march) -- one launch less per step, every stage of the
+    step inside a chain, and not a bit changes against the separate stage-1 launch (B200_NO_CHAIN_HEAD)."""
+    for args in CHAIN_ARGS[:2]:
+        monkeypatch.setenv("B200_NO_CHAIN_HEAD", "1")
+        st0, u0 = run_d2d(emu, args + extra)
+        monkeypatch.delenv("B200_NO_CHAIN_HEAD")
+        st1, u1 = run_d2d(emu, args + extra)
+        assert np.array_equal(u0, u1)
+        assert st0["rhs_evals"] == st1["rhs_evals"] and st0["steps"] == st1["steps"]
+        assert st0["chain_stages"] == st0["steps"] * (st0["max_stages"] - 1)  # stages 2..s
+        assert st1["chain_stages"] == st1["steps"] * st1["max_stages"]        # stages 1..s: the whole step
+        assert st1["chain_launches"] == st0["chain_launches"]
+        if not extra:
+            assert st1["kernel_launches"] == st0["kernel_launches"] - st0["steps"]
+
+
 def test_implicit_path_vector_work_is_fused(emu, monkeypatch):
     """DIRK3 + PCG + Jacobi (BASELINE configs[4] at 64^2): arkLsATimes o arkLsDQJtimes runs as ONE stencil launch that
     also returns <Ap, p>; r -= alpha*Ap with its weighted norm, z = P^-1 r with <r, z>, and p = z + beta*p with the WRMS
