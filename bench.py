@@ -615,6 +615,31 @@ def main():
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms_max = float(tms.item())
     value = evals * ncell_global / (ms_max * 1e-3)
+    # per-rank view of the timed region (device time, SM clock, board power of every GPU): the job runs in lockstep
+    # through the halo exchanges, so one slow GPU (a lower power-capped clock) sets everybody's time
+    per_rank = None
+    if dist is not None:
+        cs = sampler.summary()
+        mine = torch.tensor([ms, float(cs.get("sm_mhz") or 0), float(cs.get("power_w") or 0), float(cs.get("gpu_temp_c") or 0)],
+                            dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        rows = [r.cpu().tolist() for r in allr]
+        per_rank = {"ms": [round(r[0], 2) for r in rows], "sm_mhz": [int(r[1]) for r in rows],
+                    "power_w": [round(r[2], 1) for r in rows], "gpu_temp_c": [int(r[3]) for r in rows]}
+
+    # diagnostic (B200_BENCH_PER_STEP=1, outside the timed region): the same steps once more, one call and one event
+    # pair per step, so that a periodic hiccup or a slow first step shows up
+    step_ms = None
+    if os.environ.get("B200_BENCH_PER_STEP"):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+        barrier()
+        evs[0].record()
+        for i in range(args.steps):
+            prob.step(1)
+            evs[i + 1].record()
+        barrier()
+        step_ms = [round(evs[i].elapsed_time(evs[i + 1]), 2) for i in range(args.steps)]
 
     # ---- e2e: host buffers, H2D + step + D2H every step ---------------------------------------
     # Every timed step starts from a state in pinned HOST memory and ends with its result back in
@@ -758,6 +783,10 @@ def main():
         "clocks": sampler.summary(),
         "stage_chain_depth": depth,
     }
+    if per_rank is not None:
+        line["per_rank"] = per_rank
+    if step_ms is not None:
+        line["step_ms_rank0_diagnostic"] = step_ms
     emit(line)
     if dist is not None:
         dist.destroy_process_group()
