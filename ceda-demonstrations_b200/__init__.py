@@ -54,6 +54,8 @@ class StageExtras(ctypes.Structure):
         ("send_w", ctypes.c_void_p), ("send_e", ctypes.c_void_p),
         ("send_s", ctypes.c_void_p), ("send_n", ctypes.c_void_p),
         ("wrms_w", ctypes.c_void_p), ("wrms_result", ctypes.c_void_p),
+        ("ewt_out", ctypes.c_void_p), ("ewt_rtol", ctypes.c_double), ("ewt_atol", ctypes.c_double),
+        ("ewt_result", ctypes.c_void_p),
     ]
 
 

@@ -564,6 +564,7 @@ extern "C" int b200_adr_create(int argc, const char* const* argv, int device, vo
     p->ud.ops[m].mode     = m;
     p->ud.ops[m].op.self  = &p->ud.ops[m];
     p->ud.ops[m].op.fused = adr_fused;
+    p->ud.ops[m].op.fused_ewt = nullptr;
     p->ud.ops[m].op.chain        = nullptr;
     p->ud.ops[m].op.chain_max    = 0;
     p->ud.ops[m].op.halo_doubles = 0;

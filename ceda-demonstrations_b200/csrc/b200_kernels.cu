@@ -639,9 +639,10 @@ extern "C" int b200_l1norm(b200_ctx* c, const double* x, int64_t n, double* r)
 template <int NT, uint32_t PAT>
 static void launch_march(const StageArgs& a, dim3 grid, cudaStream_t st)
 {
-  if (a.region == 2) klaunch((k_stage_march<NT, PAT, 2, false>), grid, kThreads, 0, st, a);
-  else if (a.rw) klaunch((k_stage_march<NT, PAT, 0, true>), grid, kThreads, 0, st, a);
-  else klaunch((k_stage_march<NT, PAT, 0, false>), grid, kThreads, 0, st, a);
+  if (a.region == 2) klaunch((k_stage_march<NT, PAT, 2, 0>), grid, kThreads, 0, st, a);
+  else if (a.rw && a.ewt_out) klaunch((k_stage_march<NT, PAT, 0, 2>), grid, kThreads, 0, st, a);
+  else if (a.rw) klaunch((k_stage_march<NT, PAT, 0, 1>), grid, kThreads, 0, st, a);
+  else klaunch((k_stage_march<NT, PAT, 0, 0>), grid, kThreads, 0, st, a);
 }
 
 // pick the compiled pattern for the term sequence, else the general kernel
@@ -714,6 +715,12 @@ extern "C" int b200_stencil_lincomb(b200_ctx* c, const b200_stencil_geom* g, con
     a.rw = ex->wrms_w;
     a.result = ex->wrms_result;
     if (a.f_out == x) return fail("b200_stencil_lincomb: f_out must not alias the stencil input");
+    if (ex->ewt_out)
+    {
+      if (!a.rw || !ex->ewt_result) return fail("b200_stencil_lincomb: ewt_out needs the fused WRMS norm and ewt_result");
+      if (ex->ewt_out == x || ex->ewt_out == z || !aligned16(ex->ewt_out)) return fail("b200_stencil_lincomb: bad ewt_out");
+      a.ewt_out = ex->ewt_out; a.ewt_rtol = ex->ewt_rtol; a.ewt_atol = ex->ewt_atol; a.result2 = ex->ewt_result;
+    }
   }
   if (a.rw && region != 0) return fail("b200_stencil_lincomb: fused WRMS needs region 0");
   if (a.rw && !a.result) return fail("b200_stencil_lincomb: wrms_result missing");
@@ -748,7 +755,7 @@ extern "C" int b200_stencil_lincomb(b200_ctx* c, const b200_stencil_geom* g, con
       a.rows = (int)((a.ny + 65534) / 65535);
       gy     = (a.ny + a.rows - 1) / a.rows;
     }
-    if (a.rw && gx * gy > kMaxPartials) return fail("b200_stencil_lincomb: too many blocks for fused WRMS");
+    if (a.rw && gx * gy * (a.ewt_out ? 2 : 1) > kMaxPartials) return fail("b200_stencil_lincomb: too many blocks for fused WRMS");
     dim3 grid((unsigned)gx, (unsigned)gy);
     dispatch_march(a, grid, c->stream);
     LAUNCH_CHECK();
@@ -757,13 +764,13 @@ extern "C" int b200_stencil_lincomb(b200_ctx* c, const b200_stencil_geom* g, con
   {
     int64_t gx = (a.nx + kThreads - 1) / kThreads;
     if (a.ny > 65535) return fail("b200_stencil_lincomb: generic path supports ny <= 65535");
-    if (a.rw && gx * a.ny > kMaxPartials) return fail("b200_stencil_lincomb: too many blocks for fused WRMS");
+    if (a.rw && gx * a.ny * (a.ewt_out ? 2 : 1) > kMaxPartials) return fail("b200_stencil_lincomb: too many blocks for fused WRMS");
     dim3 grid((unsigned)gx, (unsigned)a.ny);
     klaunch(k_stage_generic, grid, kThreads, 0, c->stream, a);
     LAUNCH_CHECK();
   }
   {
-    int touches = 2 + (a.f_out ? 1 : 0) + (a.rw ? 1 : 0); // x, z
+    int touches = 2 + (a.f_out ? 1 : 0) + (a.rw ? 1 : 0) + (a.ewt_out ? 1 : 0); // x, z
     for (int k = 0; k < nterms; k++) touches += (src[k] == B200_SRC_VECTOR);
     ALG_BYTES(touches, a.nx * a.ny);
   }
@@ -938,6 +945,13 @@ static int chain_rows_auto(const b200_ctx* c, int64_t nx, int64_t ny, int nstage
   const int cand[3]   = {128, 64, 32};
   for (int r : cand)
     if (gx * ((ny + r - 1) / r) >= waves) return r;
+  // Small grids: every block is resident at once and the launch takes as long as ONE block needs for its
+  // rows + 2(K-1) row steps, so the fewest rows that still fit the machine in one wave win (128^2, K = 6: 16 blocks
+  // of 8 rows = 18 row steps instead of 4 blocks of 42).
+  const int64_t resident = 2 * (int64_t)(c->sm_count > 0 ? c->sm_count : 148);
+  const int small[2]     = {8, 16};
+  for (int r : small)
+    if (gx * ((ny + r - 1) / r) <= resident) return r;
   return 32;
 }
 static int g_chain_uniform = 1; // honour b200_stencil_geom.uniform (0: always load the tables; for A/B tests)

@@ -265,11 +265,28 @@ void UserData::free_device()
 // ----------------------------------------------------------------- callbacks
 // The deferred operator behind diffusion(): start_exchange + interior + end_exchange
 // + faces of diffusion.cpp:9-209, fused with whatever linear combination consumes f.
+int rhs_fused_ewt(void* self, b200_ctx* ctx, const double* y, int nterms, const double* c,
+                  const int* src, const double* const* v, double* z, double* f_out,
+                  const double* wrms_w, double* wrms_result, int* wrms_done,
+                  double rtol, double atol, double* ewt_out, double* ewt_result, int* ewt_done);
+
 int rhs_fused(void* self, b200_ctx* ctx, const double* y, int nterms, const double* c,
               const int* src, const double* const* v, double* z, double* f_out,
               const double* wrms_w, double* wrms_result, int* wrms_done)
 {
+  int ewt_done = 0;
+  return rhs_fused_ewt(self, ctx, y, nterms, c, src, v, z, f_out, wrms_w, wrms_result, wrms_done, 0.0, 0.0, nullptr, nullptr,
+                       &ewt_done);
+}
+
+// B200RhsOp::fused_ewt: the fused stage, optionally with the error weights of y itself and their norm (one periodic rank)
+int rhs_fused_ewt(void* self, b200_ctx* ctx, const double* y, int nterms, const double* c,
+                  const int* src, const double* const* v, double* z, double* f_out,
+                  const double* wrms_w, double* wrms_result, int* wrms_done,
+                  double rtol, double atol, double* ewt_out, double* ewt_result, int* ewt_done)
+{
   UserData* ud = static_cast<UserData*>(self);
+  *ewt_done    = 0;
   b200_stencil_geom g;
   memset(&g, 0, sizeof(g));
   g.nx = ud->nx_loc; g.ny = ud->ny_loc;
@@ -283,6 +300,11 @@ int rhs_fused(void* self, b200_ctx* ctx, const double* y, int nterms, const doub
   if (!xs && !ys)
   { // one periodic rank: the halo is this rank's own opposite edge -> index wrap
     if (wrms_w) { ex.wrms_w = wrms_w; ex.wrms_result = wrms_result; *wrms_done = 1; }
+    if (wrms_w && ewt_out && ewt_result)
+    {
+      ex.ewt_out = ewt_out; ex.ewt_rtol = rtol; ex.ewt_atol = atol; ex.ewt_result = ewt_result;
+      *ewt_done = 1;
+    }
     return b200_stencil_lincomb(ctx, &g, y, nterms, c, src, v, z, &ex, 0);
   }
   // pack_buffers + start_exchange (buffers.cpp:20-43, diffusion_2D.cpp:400-507)
@@ -551,6 +573,7 @@ static int problem_attach(UserData& ud, b200_ctx* ctx, int nranks, bool overlap,
   ud.overlap     = overlap;
   ud.rhs_op.self = &ud;
   ud.rhs_op.fused = rhs_fused;
+  ud.rhs_op.fused_ewt = (getenv("B200_NO_SPEC_EWT") || no_fusion) ? nullptr : rhs_fused_ewt;
   ud.rhs_op.chain = nullptr;
   ud.rhs_op.chain_head = nullptr;
   ud.rhs_op.dq    = (getenv("B200_NO_DQ_FUSION") || no_fusion) ? nullptr : rhs_dq;

@@ -63,6 +63,11 @@ struct Shared
   int next_slot;
   long slot_owner[8]; // creation number of the value whose partial sum the slot holds (the ring is reused)
   bool spec_sigs[96]; // fused-launch signatures whose result a matching WRMS norm followed
+  // the next step's error weights, speculatively (see launch_fused): signatures of fused launches whose stencil input
+  // ARKODE then asked the error weights of, and the tolerances of the most recent such request
+  bool spec_ewt_sigs[96];
+  bool ewt_seen;
+  double ewt_rtol, ewt_atol;
 };
 const int kSlots = 8;
 
@@ -107,6 +112,9 @@ struct Value
   int wrms_slot;
   int sig;  // signature of the fused launch that produced it (0 = none)
   long seq; // creation order
+  int centre_sig;       // signature of the fused launch this value was the stencil input (and a term) of
+  bool spec_ewt;        // this value is 1/(e_rtol*|y| + e_atol) of the value y whose wrms_w it is (computed ahead of the request)
+  double e_rtol, e_atol;
 };
 
 struct Content
@@ -191,6 +199,9 @@ Value* value_new(Shared* sh, bool with_buffer)
   v->wrms_slot = -1;
   v->sig       = 0;
   v->seq       = ++g_seq;
+  v->centre_sig = 0;
+  v->spec_ewt  = false;
+  v->e_rtol = v->e_atol = 0.0;
   return v;
 }
 
@@ -258,9 +269,38 @@ void launch_fused(Shared* sh, Value* L, int nterms, const double* cf, Value* con
       wres = sh->wrms_slots + slot;
     }
   }
-  int wdone = 0;
-  DEV(L->op->fused(L->op->self, sh->ctx, src->d, nterms, cf, srcs, vp, out ? out->d : nullptr, f_out,
-                   w, wres, &wdone));
+  // The closing stage of an adaptive STS step (arkode_lsrkstep.c:768-796) has the candidate y_{n+1} as its stencil
+  // input; if the step is accepted ARKODE next asks for ewt = 1/(rtol |y_{n+1}| + atol) and ||y_{n+1}||_wrms
+  // (arkode.c:2985, :835).  Once that has been seen to follow a launch of this signature, the launch produces both as
+  // well: no launch and no host synchronisation between two steps.
+  bool centre = false;
+  for (int k = 0; k < nterms; k++) centre = centre || (X[k] == src);
+  Value* E   = nullptr;
+  int slot2  = -1;
+  int edone  = 0;
+  int wdone  = 0;
+  if (w && centre && L->op->fused_ewt && sh->ewt_seen && sh->spec_ewt_sigs[sig] && !src->wrms_w && src->wrms_slot < 0)
+  {
+    E      = value_new(sh, true);
+    slot2  = sh->next_slot;
+    sh->next_slot = (sh->next_slot + 1) % kSlots;
+    DEV(L->op->fused_ewt(L->op->self, sh->ctx, src->d, nterms, cf, srcs, vp, out->d, f_out, w, wres, &wdone, sh->ewt_rtol,
+                         sh->ewt_atol, E->d, sh->wrms_slots + slot2, &edone));
+    if (edone && wdone)
+    {
+      E->spec_ewt = true;
+      E->e_rtol = sh->ewt_rtol; E->e_atol = sh->ewt_atol;
+      src->wrms_w    = E; // (takes over the creation reference)
+      src->wrms_slot = slot2;
+      sh->slot_owner[slot2] = src->seq;
+      g_stats.ew_fused++;
+    }
+    else value_release(sh, E);
+  }
+  else
+    DEV(L->op->fused(L->op->self, sh->ctx, src->d, nterms, cf, srcs, vp, out ? out->d : nullptr, f_out,
+                     w, wres, &wdone));
+  if (centre) src->centre_sig = sig;
   if (out)
   {
     out->sig = sig;
@@ -889,6 +929,15 @@ void op_inv(N_Vector x, N_Vector z)
     if (y)
     { // 1/(rtol*|y| + atol): one node over y; the three intermediate results are never evaluated
       Shared* sh = C(z)->sh;
+      if (y->centre_sig > 0 && y->centre_sig < 96) sh->spec_ewt_sigs[y->centre_sig] = true;
+      sh->ewt_seen = true;
+      sh->ewt_rtol = rtol; sh->ewt_atol = atol;
+      if (y->wrms_w && y->wrms_w->spec_ewt && y->wrms_w->d && y->wrms_w->e_rtol == rtol && y->wrms_w->e_atol == atol)
+      { // the launch that consumed y already produced exactly this vector (launch_fused)
+        y->wrms_w->refs++;
+        assign(C(z), y->wrms_w);
+        return;
+      }
       materialise(sh, y);
       assign(C(z), ew_new(sh, EWK_EWT, rtol, y, atol, nullptr));
       return;
@@ -1194,6 +1243,9 @@ N_Vector N_VNew_B200(b200_ctx* ctx, sunindextype local_length, sunindextype glob
   sh->next_slot  = 0;
   for (int k = 0; k < kSlots; k++) sh->slot_owner[k] = -1;
   memset(sh->spec_sigs, 0, sizeof(sh->spec_sigs));
+  memset(sh->spec_ewt_sigs, 0, sizeof(sh->spec_ewt_sigs));
+  sh->ewt_seen = false;
+  sh->ewt_rtol = sh->ewt_atol = 0.0;
   sh->wrms_host = nullptr;
   {
     int rank = 0, nranks = 1;

@@ -105,3 +105,37 @@ __device__ __forceinline__ void grid_finish(double block_val, unsigned nblocks,
   }
 }
 
+
+// Two sums finished together (one ticket): partials[bid] / partials[nblocks + bid] -> result[0] / result2[0].
+__device__ __forceinline__ void grid_finish2(double v0, double v1, unsigned nblocks, unsigned bid, double* partials,
+                                             unsigned* ticket, double* result, double* result2, double* smem)
+{
+  __shared__ bool is_last2;
+  if (threadIdx.x == 0)
+  {
+    partials[bid]           = v0;
+    partials[nblocks + bid] = v1;
+    __threadfence();
+    unsigned t = atomicAdd(ticket, 1u);
+    is_last2   = (t == nblocks - 1);
+  }
+  __syncthreads();
+  if (is_last2)
+  {
+    __threadfence();
+    double a0 = 0.0, a1 = 0.0;
+    for (unsigned k = threadIdx.x; k < nblocks; k += blockDim.x)
+    {
+      a0 = DADD(a0, ((volatile double*)partials)[k]);
+      a1 = DADD(a1, ((volatile double*)partials)[nblocks + k]);
+    }
+    a0 = block_reduce<RED_SUM>(a0, smem);
+    a1 = block_reduce<RED_SUM>(a1, smem);
+    if (threadIdx.x == 0)
+    {
+      *result  = a0;
+      *result2 = a1;
+      *ticket  = 0;
+    }
+  }
+}

@@ -18,6 +18,12 @@ struct StageArgs
   double* partials;
   unsigned* ticket;
   double* result;
+  // RED == 2: also the error weights of the stencil input itself, e = 1/(rtol*|x| + atol) (arkEwtSetSS,
+  // arkode.c:2932-2944: N_VAbs, N_VScale, N_VAddConst, N_VInv) stored to ewt_out, and sum (x*e)^2 into result2 --
+  // what ARKODE asks for next if x becomes y_{n+1}
+  double* ewt_out;
+  double ewt_rtol, ewt_atol;
+  double* result2;
   int rows;   // rows marched per block
   int region; // 0 all, 1 ring, 2 interior
 };
@@ -38,7 +44,7 @@ __device__ __forceinline__ double lap5(double dxw, double dxe, double dys, doubl
 }
 
 // one cell, generic neighbour access (ring kernel, odd-width fallback)
-__device__ __forceinline__ void stage_cell(const StageArgs& a, int64_t i, int64_t j, double* wr_acc)
+__device__ __forceinline__ void stage_cell(const StageArgs& a, int64_t i, int64_t j, double* wr_acc, double* we_acc = nullptr)
 {
   const int64_t nx = a.nx, ny = a.ny;
   const int64_t id = j * nx + i;
@@ -70,6 +76,13 @@ __device__ __forceinline__ void stage_cell(const StageArgs& a, int64_t i, int64_
     const double p = DMUL(acc, a.rw[id]);
     *wr_acc        = DADD(*wr_acc, DMUL(p, p));
   }
+  if (we_acc)
+  {
+    const double e = __ddiv_rn(1.0, DADD(DMUL(a.ewt_rtol, fabs(uc)), a.ewt_atol));
+    a.ewt_out[id]  = e;
+    const double q = DMUL(uc, e);
+    *we_acc        = DADD(*we_acc, DMUL(q, q));
+  }
 }
 
 // Generic kernel: one thread per cell, any nx/ny; region-aware.
@@ -78,14 +91,21 @@ __global__ void __launch_bounds__(kThreads) k_stage_generic(const StageArgs a)
   __shared__ double smem[32];
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t j = blockIdx.y;
-  double wr       = 0.0;
+  double wr = 0.0, we = 0.0;
   if (i < a.nx)
   {
     const bool ring = (i == 0 || i == a.nx - 1 || j == 0 || j == a.ny - 1);
     if (a.region == 0 || (a.region == 1 && ring) || (a.region == 2 && !ring))
-      stage_cell(a, i, j, a.rw ? &wr : nullptr);
+      stage_cell(a, i, j, a.rw ? &wr : nullptr, a.ewt_out ? &we : nullptr);
   }
-  if (a.rw)
+  if (a.rw && a.ewt_out)
+  {
+    double v  = block_reduce<RED_SUM>(wr, smem);
+    double v2 = block_reduce<RED_SUM>(we, smem);
+    grid_finish2(v, v2, gridDim.x * gridDim.y, blockIdx.y * gridDim.x + blockIdx.x, a.partials, a.ticket, a.result,
+                 a.result2, smem);
+  }
+  else if (a.rw)
   {
     double v = block_reduce<RED_SUM>(wr, smem);
     grid_finish<RED_SUM>(v, gridDim.x * gridDim.y, blockIdx.y * gridDim.x + blockIdx.x,
@@ -126,7 +146,8 @@ __global__ void __launch_bounds__(kThreads) k_stage_ring(const StageArgs a)
 #define PAT4(a, b, c, d) (uint32_t)((a) | ((b) << 2) | ((c) << 4) | ((d) << 6))
 #define PAT5(a, b, c, d, e) (uint32_t)((a) | ((b) << 2) | ((c) << 4) | ((d) << 6) | ((e) << 8))
 
-template <int NT, uint32_t PAT, int REGION, bool HAS_RED>
+// HAS_RED: 0 = no reduction, 1 = sum (z*w)^2, 2 = that and the error weights of x with their own norm (StageArgs::ewt_out)
+template <int NT, uint32_t PAT, int REGION, int HAS_RED>
 __global__ void __launch_bounds__(kThreads, 4) k_stage_march(const StageArgs a)
 {
   __shared__ double smem[32];
@@ -183,7 +204,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_stage_march(const StageArgs a)
     xm = ld_keep2(below);
     xc = ld_keep2(xrow);
   }
-  double wr = 0.0;
+  double wr = 0.0, we = 0.0;
   // loop-invariant switches (all uniform or per-thread constants)
   const bool has_f  = (a.f_out != nullptr);
   const bool do_sw  = (REGION == 0) && a.send_w && wedge;
@@ -268,6 +289,14 @@ __global__ void __launch_bounds__(kThreads, 4) k_stage_march(const StageArgs a)
         const double q0 = DMUL(acc.x, w.x), q1 = DMUL(acc.y, w.y);
         wr = DADD(wr, DADD(DMUL(q0, q0), DMUL(q1, q1)));
       }
+      if (HAS_RED == 2)
+      {
+        const double e0 = __ddiv_rn(1.0, DADD(DMUL(a.ewt_rtol, fabs(xc.x)), a.ewt_atol));
+        const double e1 = __ddiv_rn(1.0, DADD(DMUL(a.ewt_rtol, fabs(xc.y)), a.ewt_atol));
+        *reinterpret_cast<double2*>(a.ewt_out + off) = make_double2(e0, e1);
+        const double s0 = DMUL(xc.x, e0), s1 = DMUL(xc.y, e1);
+        we = DADD(we, DADD(DMUL(s0, s0), DMUL(s1, s1)));
+      }
     }
     xm = xc;
     xc = xp;
@@ -277,7 +306,14 @@ __global__ void __launch_bounds__(kThreads, 4) k_stage_march(const StageArgs a)
     eptr += estep;
   }
 #undef SRC_OF
-  if (HAS_RED)
+  if (HAS_RED == 2)
+  {
+    double v  = block_reduce<RED_SUM>(wr, smem);
+    double v2 = block_reduce<RED_SUM>(we, smem);
+    grid_finish2(v, v2, gridDim.x * gridDim.y, blockIdx.y * gridDim.x + blockIdx.x, a.partials, a.ticket, a.result,
+                 a.result2, smem);
+  }
+  else if (HAS_RED)
   {
     double v = block_reduce<RED_SUM>(wr, smem);
     grid_finish<RED_SUM>(v, gridDim.x * gridDim.y, blockIdx.y * gridDim.x + blockIdx.x,

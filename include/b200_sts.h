@@ -180,6 +180,13 @@ typedef struct b200_stage_extras
   double* send_n;       /* [nx] pack z's north row     (buffers.cpp:40-42)  */
   const double* wrms_w; /* fuse sum_i (z_i*w_i)^2 (N_VWSqrSumLocal) ...      */
   double* wrms_result;  /* ... into this DEVICE double                       */
+  /* With wrms_w: also the error weights OF THE STENCIL INPUT x, ewt_i = 1/(rtol*|x_i| + atol) -- the N_VAbs, N_VScale,
+     N_VAddConst, N_VInv sequence of arkEwtSetSS (SUN/src/arkode/arkode.c:2932-2944), same roundings -- stored to ewt_out,
+     and sum_i (x_i*ewt_i)^2 into the device double ewt_result: what ARKODE computes next (arkode.c:835, :2985) if x is
+     accepted as y_{n+1}, i.e. when this launch is the closing stage of an adaptive STS step. */
+  double* ewt_out;
+  double ewt_rtol, ewt_atol;
+  double* ewt_result;
 } b200_stage_extras;
 
 /* The fused STS stage:  z = sum_k c[k]*T_k, left to right, where T_k is a

@@ -41,6 +41,14 @@ typedef struct B200RhsOp
   int (*fused)(void* self, b200_ctx* ctx, const double* y, int nterms, const double* c,
                const int* src, const double* const* v, double* z, double* f_out,
                const double* wrms_w, double* wrms_result, int* wrms_done);
+  /* Optional (NULL = not available): `fused` with a fused norm that ALSO produces the error weights of y itself,
+     ewt_i = 1/(rtol*|y_i| + atol) (arkEwtSetSS, arkode.c:2932-2944) into ewt_out and sum_i (y_i ewt_i)^2 into the device
+     double ewt_result -- requested speculatively when the launch looks like the closing stage of an adaptive step,
+     whose y is the candidate y_{n+1}.  Sets *ewt_done = 1 if it did so (only together with *wrms_done = 1). */
+  int (*fused_ewt)(void* self, b200_ctx* ctx, const double* y, int nterms, const double* c,
+                   const int* src, const double* const* v, double* z, double* f_out,
+                   const double* wrms_w, double* wrms_result, int* wrms_done,
+                   double rtol, double atol, double* ewt_out, double* ewt_result, int* ewt_done);
   /* Optional (NULL / 0 = not available): temporal blocking of `nstages` <= chain_max
      consecutive STS stages  z_l = c[l][0] F(z_{l-1}) + c[l][1] z_{l-2} + c[l][2] yn +
      c[l][3] z_{l-1} + c[l][4] fn  (z_0 = x, z_{-1} = prev2) in one kernel; coeffs is

@@ -15,9 +15,10 @@ namespace
 template <int NT, uint32_t PAT>
 void run_stage(const StageArgs& a, dim3 grid)
 {
-  if (a.region == 2) emu::launch(k_stage_march<NT, PAT, 2, false>, grid, kThreads, 0, a);
-  else if (a.rw) emu::launch(k_stage_march<NT, PAT, 0, true>, grid, kThreads, 0, a);
-  else emu::launch(k_stage_march<NT, PAT, 0, false>, grid, kThreads, 0, a);
+  if (a.region == 2) emu::launch(k_stage_march<NT, PAT, 2, 0>, grid, kThreads, 0, a);
+  else if (a.rw && a.ewt_out) emu::launch(k_stage_march<NT, PAT, 0, 2>, grid, kThreads, 0, a);
+  else if (a.rw) emu::launch(k_stage_march<NT, PAT, 0, 1>, grid, kThreads, 0, a);
+  else emu::launch(k_stage_march<NT, PAT, 0, 0>, grid, kThreads, 0, a);
 }
 
 template <int K, int PF, bool HALO, bool FMA>
@@ -114,6 +115,15 @@ extern "C" __attribute__((visibility("default"))) int emu_stencil_chain(int vari
 // (region 1 -> k_stage_ring; even nx -> k_stage_march with the compiled pattern for the LSRKStep
 // sequences, else the runtime pattern; odd nx or force_generic -> k_stage_generic).
 // wrms_w / wrms_result: fused sum((z*w)^2) or NULL.  Returns 0, or -1 for a bad argument.
+// b200_stage_extras.ewt_* for the NEXT emu_stencil_lincomb call (which must carry wrms_w)
+static double* g_ewt_out    = nullptr;
+static double* g_ewt_result = nullptr;
+static double g_ewt_rtol = 0.0, g_ewt_atol = 0.0;
+extern "C" __attribute__((visibility("default"))) void emu_set_next_ewt(double* ewt_out, double rtol, double atol, double* result)
+{
+  g_ewt_out = ewt_out; g_ewt_rtol = rtol; g_ewt_atol = atol; g_ewt_result = result;
+}
+
 extern "C" __attribute__((visibility("default"))) int emu_stencil_lincomb(
   int64_t nx, int64_t ny, const double* cxw, const double* cxe, const double* cys, const double* cyn,
   const double* hw, const double* he, const double* hs, const double* hn, const double* x, int nterms,
@@ -138,6 +148,11 @@ extern "C" __attribute__((visibility("default"))) int emu_stencil_lincomb(
   a.f_out = f_out;
   a.send_w = send_w; a.send_e = send_e; a.send_s = send_s; a.send_n = send_n;
   a.rw = wrms_w; a.result = wrms_result;
+  if (g_ewt_out && wrms_w)
+  {
+    a.ewt_out = g_ewt_out; a.ewt_rtol = g_ewt_rtol; a.ewt_atol = g_ewt_atol; a.result2 = g_ewt_result;
+  }
+  g_ewt_out = nullptr;
   a.region = region;
   std::vector<double> partials(1 << 16);
   unsigned ticket = 0;

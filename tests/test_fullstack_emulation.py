@@ -151,6 +151,27 @@ def test_stage_one_is_the_head_of_the_first_chain(emu, monkeypatch, extra):
             assert st1["kernel_launches"] == st0["kernel_launches"] - st0["steps"]
 
 
+@pytest.mark.parametrize("args", [
+    ["--nx", 128, "--ny", 64, "--integrator", "rkc", "--tf", "0.05"],
+    ["--nx", 32, "--ny", 32, "--integrator", "rkl", "--inhomogeneous", "--kx", "1", "--ky", "0.1", "--rtol", "1e-4", "--tf", "0.02"],
+    ["--nx", 75, "--ny", 51, "--integrator", "rkc", "--tf", "0.03"],
+], ids=["rkc_128x64", "rkl_inhom_32", "rkc_odd_75x51"])
+def test_next_step_error_weights_come_out_of_the_closing_stage(emu, monkeypatch, args):
+    """Adaptive STS: the closing-stage launch of a step also produces ewt(y_{n+1}) and ||y_{n+1}||_wrms
+    (arkode.c:2985 / :835), so an accepted step costs no k_ewt_wsqr launch and one host synchronisation less.  The
+    weights are the same bits and the norm only feeds the tolsf > 1 test, so the run is bit-identical to the one
+    with the speculation off (B200_NO_SPEC_EWT)."""
+    monkeypatch.setenv("B200_NO_SPEC_EWT", "1")
+    st0, u0 = run_d2d(emu, args)
+    monkeypatch.delenv("B200_NO_SPEC_EWT")
+    st1, u1 = run_d2d(emu, args)
+    for k in ("steps", "step_attempts", "err_test_fails", "rhs_evals", "max_stages", "dom_eig_updates"):
+        assert st0[k] == st1[k], k
+    assert np.array_equal(u0, u1)
+    # the first step learns the pattern; every later accepted step saves the ewt launch
+    assert st1["kernel_launches"] <= st0["kernel_launches"] - (st0["steps"] - 3)
+
+
 def test_implicit_path_vector_work_is_fused(emu, monkeypatch):
     """DIRK3 + PCG + Jacobi (BASELINE configs[4] at 64^2): arkLsATimes o arkLsDQJtimes runs as ONE stencil launch that
     also returns <Ap, p>; r -= alpha*Ap with its weighted norm, z = P^-1 r with <r, z>, and p = z + beta*p with the WRMS

@@ -337,6 +337,37 @@ def test_stage_kernel_fused_wrms(emu, orc, size):
     assert res == pytest.approx(want, rel=1e-13)
 
 
+@pytest.mark.parametrize("size", [(64, 20), (1024, 12), (75, 11), (32, 32)], ids=lambda s: "%dx%d" % s)
+@pytest.mark.parametrize("pat", ["sts_embed", "general3"])
+def test_stage_kernel_fused_next_error_weights(emu, orc, size, pat):
+    """StageArgs::ewt_out: the closing stage of an adaptive step also writes ewt = 1/(rtol |x| + atol) of its stencil input
+    (bit for bit the N_VAbs / N_VScale / N_VAddConst / N_VInv sequence of arkEwtSetSS, arkode.c:2932-2944 = orc_ewt_ss) and
+    reduces sum (x ewt)^2 next to sum (z w)^2 (grid_finish2: two sums, one ticket); z itself is untouched."""
+    nx, ny = size
+    n = nx * ny
+    rng = np.random.default_rng(5 + nx)
+    x = rng.standard_normal(n)
+    x[::13] = 0.0
+    srcs = STAGE_PATTERNS[pat]
+    vecs = [rng.standard_normal(n) if s == 0 else None for s in srcs]
+    coeffs = list(rng.standard_normal(len(srcs)))
+    w = rng.random(n) + 0.1
+    rtol, atol = 1e-4, 1e-11
+    g = make_grid(nx, ny)
+    tabs = [np.zeros(nx), np.zeros(nx), np.zeros(ny), np.zeros(ny)]
+    orc.orc_coeff_tables(ctypes.byref(g), *[P(t) for t in tabs])
+    want_z, _ = oracle_stage(orc, g, x, coeffs, srcs, vecs, None)
+    want_e, tmp = np.empty(n), np.empty(n)
+    orc.orc_ewt_ss(P(x), ctypes.c_double(rtol), ctypes.c_double(atol), P(tmp), P(want_e), ctypes.c_int64(n))
+    for generic in ((0, 1) if nx % 2 == 0 else (0,)):
+        e, r2 = np.full(n, np.nan), np.zeros(1)
+        emu.emu_set_next_ewt(P(e), ctypes.c_double(rtol), ctypes.c_double(atol), P(r2))
+        z, _, _, res = emu_stage(emu, nx, ny, tabs, None, x, coeffs, srcs, vecs, wrms_w=w, rows=4, force_generic=generic)
+        assert np.array_equal(z, want_z) and np.array_equal(e, want_e)
+        assert res == pytest.approx(orc.orc_wsqrsum(P(want_z), P(w), ctypes.c_int64(n)), rel=1e-13)
+        assert float(r2[0]) == pytest.approx(orc.orc_wsqrsum(P(x), P(want_e), ctypes.c_int64(n)), rel=1e-13)
+
+
 # ------------------------------------------------- the vector / halo / Jacobi / adr kernels on the emulator
 # (csrc/vector_kernels.cuh, halo_kernels.cuh, adr_kernels.cuh; entry points tests/emu/emu_kernels.cpp)
 def _aligned(a):

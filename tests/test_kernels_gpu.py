@@ -200,6 +200,38 @@ def test_fused_wrms_matches_separate_norm(ctx, b200, orc, size):
     assert float(host(res)[0]) == pytest.approx(want, rel=1e-13)
 
 
+@pytest.mark.parametrize("size", [(64, 48), (1024, 64), (75, 51), (32, 32)], ids=lambda s: "%dx%d" % s)
+def test_fused_next_error_weights_match_arkEwtSetSS(ctx, b200, orc, size):
+    """The closing stage of an adaptive step with the error weights of its stencil input fused in
+    (b200_stage_extras.ewt_out): ewt = 1/(rtol |x| + atol) bit for bit as the N_VAbs / N_VScale / N_VAddConst / N_VInv
+    sequence of arkEwtSetSS (arkode.c:2932-2944, oracle orc_ewt_ss), its norm sum (x ewt)^2 to reduction-order
+    rounding, and z / the WRMS sum of z unchanged."""
+    nx, ny = size
+    n = nx * ny
+    rng = np.random.default_rng(7 + nx)
+    x = rng.standard_normal(n)
+    x[::17] = 0.0
+    yn, fn, w = rng.standard_normal(n), rng.standard_normal(n), rng.random(n) + 0.1
+    srcs, coeffs = [0, 1, 0, 2], [0.8, -0.8, 0.4e-3, 0.4e-3]
+    rtol, atol = 1e-5, 1e-10
+    g, geom, keep = geometry(b200, orc, nx, ny)
+    want_z, _ = expected_stage(orc, g, x, coeffs, srcs, [yn, None, fn, None], None)
+    want_e, tmp = np.empty(n), np.empty(n)
+    orc.orc_ewt_ss(P(x), ctypes.c_double(rtol), ctypes.c_double(atol), P(tmp), P(want_e), ctypes.c_int64(n))
+    z = torch.empty(n, dtype=torch.float64, device="cuda")
+    e = torch.full((n,), float("nan"), dtype=torch.float64, device="cuda")
+    res = torch.zeros(2, dtype=torch.float64, device="cuda")
+    dw = dev(w)
+    ex = b200.StageExtras(None, None, None, None, None, dw.data_ptr(), res.data_ptr(), e.data_ptr(), rtol, atol,
+                          res.data_ptr() + 8)
+    ctx.stencil_lincomb(geom, dev(x), coeffs, srcs, [dev(yn), None, dev(fn), None], z, ex)
+    assert np.array_equal(host(z), want_z)
+    assert np.array_equal(host(e), want_e)
+    r = host(res)
+    assert float(r[0]) == pytest.approx(orc.orc_wsqrsum(P(want_z), P(w), ctypes.c_int64(n)), rel=1e-13)
+    assert float(r[1]) == pytest.approx(orc.orc_wsqrsum(P(x), P(want_e), ctypes.c_int64(n)), rel=1e-13)
+
+
 def test_stage_chain_equals_oracle_rkc_step(ctx, b200, orc):
     """Drive the fused kernel exactly as LSRKStep's RKC loop does (coefficients from the oracle's
     restatement of arkode_lsrkstep.c:629-717) and compare the whole step with orc_step_rkc."""
