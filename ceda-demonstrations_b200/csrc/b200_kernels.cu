@@ -65,8 +65,45 @@ static bool trace_on()
   if (g_trace.on < 0) g_trace.on = getenv("B200_TRACE_LAUNCHES") ? 1 : 0;
   return g_trace.on == 1;
 }
+#if defined(__x86_64__) || defined(__i386__)
+#define B200_CPU_RELAX() __builtin_ia32_pause()
+#else
+#define B200_CPU_RELAX() do { } while (0)
+#endif
+// B200_HOST_PROFILE=1: host time spent inside kernel launches and inside stream synchronisations (nothing is
+// serialised, two clock reads per call); reported with the trace report.  Tells launch-bound small-grid runs apart
+// from sync-bound ones.
+struct HostProfile
+{
+  int on = -1;
+  uint64_t launches = 0, syncs = 0;
+  double launch_ms = 0.0, sync_ms = 0.0;
+};
+static HostProfile g_hprof;
+static bool hprof_on()
+{
+  if (g_hprof.on < 0) g_hprof.on = getenv("B200_HOST_PROFILE") ? 1 : 0;
+  return g_hprof.on == 1;
+}
+static inline cudaError_t stream_sync_profiled(cudaStream_t st)
+{
+  if (!hprof_on()) return cudaStreamSynchronize(st);
+  const double t0 = trace_now_ms();
+  cudaError_t e   = cudaStreamSynchronize(st);
+  g_hprof.sync_ms += trace_now_ms() - t0;
+  g_hprof.syncs++;
+  return e;
+}
 extern "C" void b200_trace_report(void)
 {
+  if (hprof_on() && g_hprof.launches)
+  {
+    fprintf(stderr, "[b200 host profile] %llu launches: %.3f ms inside the launch calls (%.2f us each); %llu stream syncs: %.3f ms (%.2f us each)\n",
+            (unsigned long long)g_hprof.launches, g_hprof.launch_ms, 1e3 * g_hprof.launch_ms / (double)g_hprof.launches,
+            (unsigned long long)g_hprof.syncs, g_hprof.sync_ms, g_hprof.syncs ? 1e3 * g_hprof.sync_ms / (double)g_hprof.syncs : 0.0);
+    g_hprof.launches = g_hprof.syncs = 0;
+    g_hprof.launch_ms = g_hprof.sync_ms = 0.0;
+  }
   if (!trace_on() || g_trace.rows.empty()) return;
   double total = 0.0;
   uint64_t n   = 0;
@@ -91,7 +128,15 @@ static inline void klaunch_named(const char* name, void (*kern)(KArgs...), dim3 
   emu::launch_body(grid, block, smem, [&]() { kern(args...); });
   const double t1 = trace_now_ms();
 #else
-  if (!trace_on()) { kern<<<grid, block, smem, st>>>(args...); return; }
+  if (!trace_on())
+  {
+    if (!hprof_on()) { kern<<<grid, block, smem, st>>>(args...); return; }
+    const double h0 = trace_now_ms();
+    kern<<<grid, block, smem, st>>>(args...);
+    g_hprof.launch_ms += trace_now_ms() - h0;
+    g_hprof.launches++;
+    return;
+  }
   cudaStreamSynchronize(st);
   const double t0 = trace_now_ms();
   if (g_trace.last_end > 0.0) g_trace.gap_ms += t0 - g_trace.last_end;
@@ -233,7 +278,7 @@ extern "C" void* b200_ctx_stream(b200_ctx* c) { return (void*)c->stream; }
 
 extern "C" int b200_ctx_sync(b200_ctx* c)
 {
-  CU_TRY(cudaStreamSynchronize(c->stream));
+  CU_TRY(stream_sync_profiled(c->stream));
   return 0;
 }
 
@@ -576,7 +621,23 @@ static int nccl_allreduce_inplace(b200_ctx* c, double* buf, int n, int op);
 // Where a reduction kernel's last block stores the result: on one rank straight into mapped pinned host memory
 // (no copy engine, no extra launch -- the host only waits for the stream); with a communicator into device memory,
 // all-reduced over the ranks and then published.
-static double* reduce_target(b200_ctx* c) { return (c->comm && c->nranks > 1) ? c->dev_result : c->host_result_dev; }
+// One rank: the host does not wait for the stream (cudaStreamSynchronize costs several microseconds after the kernel
+// has ended) but for the value itself: the slot is armed with a NaN bit pattern no reduction produces, the last block's
+// 8-byte store replaces it, the host spins on the (cache-coherent, pinned) word.  Falls back to the stream
+// synchronisation after ~2 ms of spinning (long queues of large kernels) -- or always, with B200_NO_POLL.
+static const unsigned long long kArmed = 0x7ff8dead0000beefULL;
+static int g_poll = -1;
+static bool poll_on()
+{
+  if (g_poll < 0) g_poll = getenv("B200_NO_POLL") ? 0 : 1;
+  return g_poll == 1;
+}
+static double* reduce_target(b200_ctx* c)
+{
+  if (c->comm && c->nranks > 1) return c->dev_result;
+  *reinterpret_cast<volatile unsigned long long*>(c->host_result) = kArmed;
+  return c->host_result_dev;
+}
 static int reduce_fetch(b200_ctx* c, int rop, double* out)
 {
   if (c->comm && c->nranks > 1)
@@ -585,7 +646,23 @@ static int reduce_fetch(b200_ctx* c, int rop, double* out)
     if (rc) return rc;
     return read_small(c, out, c->dev_result, 1);
   }
-  CU_TRY(cudaStreamSynchronize(c->stream));
+  volatile unsigned long long* w = reinterpret_cast<volatile unsigned long long*>(c->host_result);
+  if (poll_on())
+  {
+    const double t0 = hprof_on() ? trace_now_ms() : 0.0;
+    for (int spin = 0; spin < 40000; spin++)
+    {
+      const unsigned long long b = *w;
+      if (b != kArmed)
+      {
+        memcpy(out, &b, sizeof(double));
+        if (hprof_on()) { g_hprof.sync_ms += trace_now_ms() - t0; g_hprof.syncs++; }
+        return 0;
+      }
+      B200_CPU_RELAX();
+    }
+  }
+  CU_TRY(stream_sync_profiled(c->stream));
   *out = c->host_result[0];
   return 0;
 }
@@ -893,8 +970,8 @@ extern "C" int b200_get_contract(void) { return g_contract; }
 
 template <int K, int PF, bool HALO, bool FMA, bool UNI>
 static int launch_chain_h(const ChainArgs& a, dim3 grid, cudaStream_t st)
-{ // HEAD: the chain begins with stage 1 of the step (f_out set)
-  return a.f_out ? launch_chain_k<K, PF, HALO, FMA, UNI, true>(a, grid, st) : launch_chain_k<K, PF, HALO, FMA, UNI, false>(a, grid, st);
+{ // HEAD: the chain begins with stage 1 of the step
+  return a.head ? launch_chain_k<K, PF, HALO, FMA, UNI, true>(a, grid, st) : launch_chain_k<K, PF, HALO, FMA, UNI, false>(a, grid, st);
 }
 template <int K, int PF, bool HALO, bool FMA>
 static int launch_chain_u(const ChainArgs& a, dim3 grid, cudaStream_t st, bool uni)
@@ -992,7 +1069,7 @@ extern "C" int b200_set_chain_rows(int r)
 static int stencil_chain_common(b200_ctx* c, const b200_stencil_geom* g, int nstages, const double* x,
                                 const double* prev2, const double* yn, const double* fn,
                                 const double* coeffs, double* const* z_out, const double* const* halos,
-                                int hg, int hg2, double* f_out = nullptr)
+                                int hg, int hg2, double* f_out = nullptr, bool head = false)
 {
   if (nstages < 2 || nstages > B200_MAX_CHAIN) return fail("b200_stencil_chain: nstages must be 2..B200_MAX_CHAIN");
   if (f_out && (f_out == x || !aligned16(f_out))) return fail("b200_stencil_chain_head: bad f_out");
@@ -1039,8 +1116,9 @@ static int stencil_chain_common(b200_ctx* c, const b200_stencil_geom* g, int nst
   }
   if (!any || !a.out[nstages - 1]) return fail("b200_stencil_chain: the last stage must be stored");
   a.f_out = f_out;
+  a.head  = head ? 1 : 0;
   // (k_chain_quad has no stage-1 flavour: a chain that begins the step runs on k_chain_march)
-  const bool use_quad = !f_out && b200_get_chain_variant() == 1 && chain_quad_supported(a.nx, a.ny, nstages, halos ? hg2 : -1);
+  const bool use_quad = !head && b200_get_chain_variant() == 1 && chain_quad_supported(a.nx, a.ny, nstages, halos ? hg2 : -1);
   a.rows              = g_chain_rows > 0 ? g_chain_rows : chain_rows_auto(c, a.nx, a.ny, nstages, use_quad);
   int rc = 0;
   if (use_quad)
@@ -1072,7 +1150,7 @@ static int stencil_chain_common(b200_ctx* c, const b200_stencil_geom* g, int nst
   if (rc) return rc;
   LAUNCH_CHECK();
   {
-    int touches = f_out ? 2 : 4; // x, prev2, yn, fn -- or x and the stored f_n when the chain begins the step
+    int touches = head ? (f_out ? 2 : 1) : 4; // x, prev2, yn, fn -- or x (and the stored f_n) when the chain begins the step
     for (int l = 0; l < nstages; l++) touches += (a.out[l] != nullptr);
     ALG_BYTES(touches, a.nx * a.ny);
   }
@@ -1086,13 +1164,12 @@ extern "C" int b200_stencil_chain_head(b200_ctx* c, const b200_stencil_geom* g, 
                                        const double* coeffs, double* const* z_out, double* f_out,
                                        const double* halo_x, int halo_rows, int halo_cols)
 {
-  if (!f_out) return fail("b200_stencil_chain_head: f_out missing");
   if (halo_x)
   {
     const double* halos[4] = {halo_x, halo_x, halo_x, halo_x};
-    return stencil_chain_common(c, g, nstages, x, x, x, x, coeffs, z_out, halos, halo_rows, halo_cols, f_out);
+    return stencil_chain_common(c, g, nstages, x, x, x, x, coeffs, z_out, halos, halo_rows, halo_cols, f_out, true);
   }
-  return stencil_chain_common(c, g, nstages, x, x, x, x, coeffs, z_out, nullptr, 0, 0, f_out);
+  return stencil_chain_common(c, g, nstages, x, x, x, x, coeffs, z_out, nullptr, 0, 0, f_out, true);
 }
 
 extern "C" int b200_stencil_chain(b200_ctx* c, const b200_stencil_geom* g, int nstages,

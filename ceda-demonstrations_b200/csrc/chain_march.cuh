@@ -31,7 +31,8 @@ struct ChainArgs
   const double* fn;
   double c[B200_MAX_CHAIN][5];
   double* out[B200_MAX_CHAIN];
-  double* f_out; // HEAD flavour: where L(x) = f(t_n, y_n) goes (the fn of all later stages)
+  double* f_out; // HEAD flavour: where L(x) = f(t_n, y_n) goes (the fn of all later stages); NULL = it is stored already
+  int head;      // the chain begins the step (HEAD flavour)
   int rows;
   // multi-rank (HALO = true): per-operand deep-halo buffers, layout of b200_deep_halo_exchange
   const double *hx, *hp, *hy, *hf;
@@ -248,7 +249,7 @@ __global__ void __launch_bounds__(kChainThreads, 2) k_chain_march(const ChainArg
 #pragma unroll
   for (int l = 0; l < K; l++)
     if (store_ok && a.out[l]) smask |= 1u << l;
-  if (HEAD && store_ok) smask |= 1u << K; // f_out
+  if (HEAD && store_ok && a.f_out) smask |= 1u << K; // f_out
 
   ChainState st;
   int64_t ic = col_u; // column used for stores and (wrap mode) loads

@@ -112,6 +112,10 @@ struct Value
   int wrms_slot;
   int sig;  // signature of the fused launch that produced it (0 = none)
   long seq; // creation order
+  // provenance of stored data: d holds prov_op(prov_src), bit for bit as the operator's kernels compute it (one
+  // reference held on prov_src).  Lets an adaptive STS step start its first chain from y_n alone (launch_chain, HEAD).
+  const B200RhsOp* prov_op;
+  Value* prov_src;
   int centre_sig;       // signature of the fused launch this value was the stencil input (and a term) of
   bool spec_ewt;        // this value is 1/(e_rtol*|y| + e_atol) of the value y whose wrms_w it is (computed ahead of the request)
   double e_rtol, e_atol;
@@ -132,6 +136,38 @@ Value* g_last_weight     = nullptr;
 Shared* g_last_weight_sh = nullptr;
 long g_last_weight_seq   = 0;
 long g_seq               = 0;
+
+// Fused WRMS results on one rank live in mapped pinned memory.  The host waits for the VALUE, not for the stream: a
+// slot is armed with a NaN bit pattern no sum produces when it is handed to a launch, and read_slot spins on the word
+// until the kernel's last block has stored the result (a stream synchronisation costs several microseconds after the
+// kernel has ended, every adaptive step); after ~2 ms of spinning, or with B200_NO_POLL, it synchronises instead.
+const unsigned long long kArmed = 0x7ff8dead0000beefULL;
+int g_poll = -1;
+void arm_slot(Shared* sh, int slot)
+{
+  if (sh->wrms_host) *reinterpret_cast<volatile unsigned long long*>(sh->wrms_host + slot) = kArmed;
+}
+double read_slot(Shared* sh, int slot)
+{
+  if (g_poll < 0) g_poll = getenv("B200_NO_POLL") ? 0 : 1;
+  volatile unsigned long long* w = reinterpret_cast<volatile unsigned long long*>(sh->wrms_host + slot);
+  if (g_poll == 1)
+    for (int spin = 0; spin < 40000; spin++)
+    {
+      const unsigned long long b = *w;
+      if (b != kArmed)
+      {
+        double r;
+        memcpy(&r, &b, sizeof(r));
+        return r;
+      }
+#if defined(__x86_64__) || defined(__i386__)
+      __builtin_ia32_pause();
+#endif
+    }
+  DEV(b200_ctx_sync(sh->ctx));
+  return sh->wrms_host[slot];
+}
 
 double* pool_get(Shared* sh)
 {
@@ -159,6 +195,7 @@ void value_release(Shared* sh, Value* v)
       else sh->free_halos.push_back(v->halo);
     }
     if (v->wrms_w) value_release(sh, v->wrms_w);
+    if (v->prov_src) value_release(sh, v->prov_src);
     Value* next = v->src; // a deferred value owns a reference on its source
     if (v->ew)
     { // a pending elementwise result that was never needed
@@ -199,6 +236,8 @@ Value* value_new(Shared* sh, bool with_buffer)
   v->wrms_slot = -1;
   v->sig       = 0;
   v->seq       = ++g_seq;
+  v->prov_op   = nullptr;
+  v->prov_src  = nullptr;
   v->centre_sig = 0;
   v->spec_ewt  = false;
   v->e_rtol = v->e_atol = 0.0;
@@ -267,6 +306,7 @@ void launch_fused(Shared* sh, Value* L, int nterms, const double* cf, Value* con
       slot = sh->next_slot;
       sh->next_slot = (sh->next_slot + 1) % kSlots;
       wres = sh->wrms_slots + slot;
+      arm_slot(sh, slot);
     }
   }
   // The closing stage of an adaptive STS step (arkode_lsrkstep.c:768-796) has the candidate y_{n+1} as its stencil
@@ -284,6 +324,7 @@ void launch_fused(Shared* sh, Value* L, int nterms, const double* cf, Value* con
     E      = value_new(sh, true);
     slot2  = sh->next_slot;
     sh->next_slot = (sh->next_slot + 1) % kSlots;
+    arm_slot(sh, slot2);
     DEV(L->op->fused_ewt(L->op->self, sh->ctx, src->d, nterms, cf, srcs, vp, out->d, f_out, w, wres, &wdone, sh->ewt_rtol,
                          sh->ewt_atol, E->d, sh->wrms_slots + slot2, &edone));
     if (edone && wdone)
@@ -313,10 +354,11 @@ void launch_fused(Shared* sh, Value* L, int nterms, const double* cf, Value* con
     }
   }
   if (store_f)
-  { // L is now a plain materialised value
+  { // L is now a plain materialised value (that remembers what it is the image of: its reference on src stays)
+    L->prov_op  = L->op;
+    L->prov_src = src;
     L->op  = nullptr;
     L->src = nullptr;
-    value_release(sh, src);
   }
 }
 
@@ -354,13 +396,19 @@ void launch_chain(Shared* sh, Value* top)
     outs[k]         = keep ? pool_get(sh) : nullptr;
     for (int q = 0; q < 5; q++) cf[5 * k + q] = lv[k]->st->c[q];
   }
-  Value* F            = head ? first->fn : nullptr; // the deferred value L(x) that ARKODE keeps as fn
-  double* f_out       = head ? pool_get(sh) : nullptr;
-  const bool f_extra  = head && F->d != nullptr; // somebody evaluated f_n in the meantime: ours is scratch
+  Value* F            = head ? first->fn : nullptr; // the value L(x) that ARKODE keeps as fn: still deferred, or stored
+  const bool have_f   = head && F->d != nullptr;    // (an adaptive step: it came out of the previous closing stage)
+  double* f_out       = (head && !have_f) ? pool_get(sh) : nullptr;
   if (n == 1)
   {
     int wdone = 0;
-    if (head)
+    if (head && have_f)
+    { // a lone stage 1 whose f_n is stored: the plain two-term combination
+      const double c2[2]  = {first->c[3], first->c[0]};
+      const double* vp[2] = {first->x->d, F->d};
+      DEV(b200_lincomb(sh->ctx, 2, c2, vp, outs[0], sh->nloc));
+    }
+    else if (head)
     { // a lone stage 1: the ordinary fused launch z = 1*x + c*L(x) that also stores L(x)
       const double c2[2]  = {first->c[3], first->c[0]};
       int srcs[2]         = {B200_SRC_CENTRE, B200_SRC_STENCIL};
@@ -420,17 +468,13 @@ void launch_chain(Shared* sh, Value* top)
     g_stats.chain_launches++;
     g_stats.chain_stages += n;
   }
-  if (head)
-  {
-    if (f_extra) sh->free_bufs.push_back(f_out);
-    else
-    { // f_n is now plain data (as after a fused launch with f_out)
-      Value* src = F->src;
-      F->d   = f_out;
-      F->op  = nullptr;
-      F->src = nullptr;
-      value_release(sh, src);
-    }
+  if (head && !have_f)
+  { // f_n is now plain data (as after a fused launch with f_out)
+    F->d        = f_out;
+    F->prov_op  = F->op;
+    F->prov_src = F->src; // (keeps the reference)
+    F->op  = nullptr;
+    F->src = nullptr;
   }
   // retire the records bottom-up; values nobody points at any more disappear with them
   for (int k = 0; k < n; k++) lv[k]->refs++; // pin while we rewire
@@ -475,9 +519,10 @@ void materialise(Shared* sh, Value* v)
   int wdone            = 0;
   DEV(v->op->fused(v->op->self, sh->ctx, src->d, 1, &one, srcs, vp, v->d, nullptr, nullptr, nullptr, &wdone));
   (void)X;
+  v->prov_op  = v->op;
+  v->prov_src = src; // (keeps the reference)
   v->op  = nullptr;
   v->src = nullptr;
-  value_release(sh, src);
   g_stats.plain_rhs_launches++;
 }
 
@@ -618,6 +663,13 @@ void ew_operand(Shared* sh, Value* x, bool keep)
   materialise(sh, x);
 }
 
+// z = 1*y + c*F with F stored and known to be op(y) for an operator that can begin a chain (see eval_lincomb)
+bool head_from_provenance(int nterms, const double* cf, Value* const* X)
+{
+  return g_lazy && g_chain_max >= 2 && nterms == 2 && cf[0] == 1.0 && X[0]->d && X[1]->d && X[1]->prov_op &&
+         X[1]->prov_op->chain_head && X[1]->prov_op->chain_max >= 2 && X[1]->prov_src == X[0] && X[1] != X[0];
+}
+
 // z = sum_k cf[k]*X[k], left to right; handles deferred operands by fusion
 void eval_lincomb(int nterms, const double* cf, N_Vector* Xv, N_Vector zv)
 {
@@ -643,15 +695,20 @@ void eval_lincomb(int nterms, const double* cf, N_Vector* Xv, N_Vector zv)
   const bool store_f = L && (L->refs - (zc->val == L ? 1 : 0)) > 0;
 
   // Stage 1 of an STS step, z_1 = 1*y_n + c*L(y_n) with L(y_n) = f_n kept by ARKODE (arkode_lsrkstep.c:640 / :930):
-  // pending as the HEAD of a chain -- if stage 2 extends it, one launch produces f_n and the stages together
-  if (L && g_chain_max >= 2 && nterms == 2 && store_f && L->op->chain_head && L->op->chain_max >= 2 && X[1] == L &&
-      X[0] == L->src && cf[0] == 1.0)
+  // pending as the HEAD of a chain -- if stage 2 extends it, one launch produces f_n and the stages together.
+  // f_n may also be stored already and known to be L(y_n) (provenance: an adaptive step, whose f_n the previous step's
+  // closing stage wrote): the chain then recomputes it from y_n instead of streaming it.
+  const bool head_prov = head_from_provenance(nterms, cf, X);
+  if (g_chain_max >= 2 && nterms == 2 && cf[0] == 1.0 &&
+      ((L && store_f && L->op->chain_head && L->op->chain_max >= 2 && X[1] == L && X[0] == L->src) || head_prov))
   {
-    Value* xin = L->src;
+    Value* F            = X[1];
+    const B200RhsOp* op = head_prov ? F->prov_op : F->op;
+    Value* xin          = X[0];
     materialise(sh, xin);
     Value* out  = value_new(sh, false);
     StageRec* r = new StageRec();
-    r->op = L->op; r->x = xin; r->p2 = xin; r->yn = xin; r->fn = L;
+    r->op = op; r->x = xin; r->p2 = xin; r->yn = xin; r->fn = F;
     r->x->refs++; r->p2->refs++; r->yn->refs++; r->fn->refs++;
     r->c[0] = cf[1]; r->c[1] = r->c[2] = r->c[4] = 0.0; r->c[3] = 1.0;
     r->depth = 1;
@@ -806,7 +863,9 @@ void op_linearsum(sunrealtype a, N_Vector x, sunrealtype b, N_Vector y, N_Vector
       return;
     }
     const bool sts_x = is_rhs(xv) || (!xv->d && xv->st), sts_y = is_rhs(yv) || (!yv->d && yv->st);
-    if (!sts_x && !sts_y)
+    Value* XY[2]     = {xv, yv};
+    const double ab[2] = {a, b};
+    if (!sts_x && !sts_y && !head_from_provenance(2, ab, XY))
     { // (deferred right-hand sides and pending stages take the stage-fusion path below)
       const bool keepy = is_ew(yv) && yv->ew->kind == EWK_SCALEDIFF && is_rhs(yv->ew->a); // z = v - gamma*Jv, :2366
       ew_operand(sh, xv, false);
@@ -1099,9 +1158,8 @@ sunrealtype wsqrsum(N_Vector x, N_Vector w)
   { // the fused kernel that produced x already reduced sum (x*w)^2 (and no later launch has taken the slot over)
     double* slot = sh->wrms_slots + xv->wrms_slot;
     if (sh->wrms_host)
-    { // the kernel stored the sum into mapped host memory: wait for the stream, read it
-      DEV(b200_ctx_sync(sh->ctx));
-      r = sh->wrms_host[xv->wrms_slot];
+    { // the kernel stores the sum into mapped host memory: wait for it
+      r = read_slot(sh, xv->wrms_slot);
     }
     else
     {

@@ -229,8 +229,10 @@ int b200_stencil_chain_halo(b200_ctx* ctx, const b200_stencil_geom* g, int nstag
                             const double* const* halos, int halo_rows, int halo_cols);
 /* The chain that BEGINS an STS step (stage 1 folded in): z_1 = x + c_1 L(x) with x = y_n (N_VLinearSum(ONE, yn, h*mus, fn,
    ..), arkode_lsrkstep.c:640 / :930; coeffs[0][0] = c_1, the other four entries of row 0 are ignored), stages 2..nstages
-   as above with z_0 = y_n = x and f_n = L(x).  f_n is stored to f_out (it is the vector ARKODE keeps as fn) and the
-   later stages take it from the kernel's own ring: y_n is streamed once, there is no z_{-1} and no f_n stream.
+   as above with z_0 = y_n = x and f_n = L(x).  f_n is stored to f_out (it is the vector ARKODE keeps as fn; NULL when
+   the caller holds it already -- an adaptive step whose f_n came out of the previous step's closing stage: the kernel
+   recomputes the same bits rather than stream them) and the later stages take it from the kernel's own ring: y_n is
+   streamed once, there is no z_{-1} and no f_n stream.
    halo_x: deep halo of x on a rank of a decomposition (NULL on one periodic rank). */
 int b200_stencil_chain_head(b200_ctx* ctx, const b200_stencil_geom* g, int nstages, const double* x,
                             const double* coeffs, double* const* z_out, double* f_out,

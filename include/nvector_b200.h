@@ -60,7 +60,9 @@ typedef struct B200RhsOp
   /* Optional (NULL = not available): the chain that BEGINS a step.  Stage 1 of the STS methods is
      z_1 = x + c_1 F(x) with x = y_n (arkode_lsrkstep.c:640 / :930) and F(x) is the f_n of every later stage, so the
      kernel produces f_n itself (stored to f_out) and streams only x: coeffs row 0 = { c_1, -, -, -, - }, rows
-     1..nstages-1 as for `chain` with z_0 = y_n = x.  halo_x / halo_x_valid: as halos[0] / halo_valid[0] of `chain`. */
+     1..nstages-1 as for `chain` with z_0 = y_n = x.  f_out == NULL: F(x) is stored already (the vector knows that the
+     f_n it holds is F of exactly this x), the kernel only recomputes it.  halo_x / halo_x_valid: as halos[0] /
+     halo_valid[0] of `chain`. */
   int (*chain_head)(void* self, b200_ctx* ctx, int nstages, const double* x, const double* coeffs,
                     double* const* z_out, double* f_out, double* halo_x, int halo_x_valid);
   /* > 0: the operator runs on one rank of a decomposition and `chain` needs a deep halo

@@ -151,6 +151,24 @@ def test_stage_one_is_the_head_of_the_first_chain(emu, monkeypatch, extra):
             assert st1["kernel_launches"] == st0["kernel_launches"] - st0["steps"]
 
 
+@pytest.mark.parametrize("extra", [[], ["--force-halo"]], ids=["wrap", "deep_halo"])
+def test_adaptive_steps_start_their_first_chain_from_yn_alone(emu, monkeypatch, extra):
+    """Adaptive STS: f_n is stored (the previous step's closing stage wrote it) and the vector knows it is L(y_n)
+    (provenance), so stage 1 -- an elementwise y_n + c f_n in the reference (arkode_lsrkstep.c:640) -- joins the first
+    chain, which recomputes f_n from y_n: no elementwise launch, same bits, same statistics."""
+    args = CHAIN_ARGS[2] + extra
+    monkeypatch.setenv("B200_NO_CHAIN_HEAD", "1")
+    st0, u0 = run_d2d(emu, args)
+    monkeypatch.delenv("B200_NO_CHAIN_HEAD")
+    st1, u1 = run_d2d(emu, args)
+    for k in ("steps", "step_attempts", "err_test_fails", "rhs_evals", "max_stages"):
+        assert st0[k] == st1[k], k
+    assert np.array_equal(u0, u1)
+    assert st1["chain_stages"] >= st0["chain_stages"] + st0["steps"] - 2  # stage 1 of (nearly) every step is in a chain
+    if not extra:
+        assert st1["kernel_launches"] <= st0["kernel_launches"] - (st0["steps"] - 2)
+
+
 @pytest.mark.parametrize("args", [
     ["--nx", 128, "--ny", 64, "--integrator", "rkc", "--tf", "0.05"],
     ["--nx", 32, "--ny", 32, "--integrator", "rkl", "--inhomogeneous", "--kx", "1", "--ky", "0.1", "--rtol", "1e-4", "--tf", "0.02"],
