@@ -29,6 +29,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <vector>
 
 namespace {
@@ -151,6 +152,9 @@ double read_slot(Shared* sh, int slot)
 {
   if (g_poll < 0) g_poll = getenv("B200_NO_POLL") ? 0 : 1;
   volatile unsigned long long* w = reinterpret_cast<volatile unsigned long long*>(sh->wrms_host + slot);
+  const bool prof = b200_host_profile_on() != 0;
+  timespec t0;
+  if (prof) clock_gettime(CLOCK_MONOTONIC, &t0);
   if (g_poll == 1)
     for (int spin = 0; spin < 40000; spin++)
     {
@@ -159,6 +163,12 @@ double read_slot(Shared* sh, int slot)
       {
         double r;
         memcpy(&r, &b, sizeof(r));
+        if (prof)
+        {
+          timespec t1;
+          clock_gettime(CLOCK_MONOTONIC, &t1);
+          b200_host_profile_wait(1e3 * (double)(t1.tv_sec - t0.tv_sec) + 1e-6 * (double)(t1.tv_nsec - t0.tv_nsec));
+        }
         return r;
       }
 #if defined(__x86_64__) || defined(__i386__)

@@ -302,6 +302,13 @@ const char* b200_last_chain_kernel(void);
 int b200_set_contract(int on);
 int b200_get_contract(void);
 
+/* Diagnostics.  B200_TRACE_LAUNCHES=1 serialises every launch and times it per kernel; B200_HOST_PROFILE=1 only
+   accumulates the host time spent inside launch calls and in waits for a reduction result; both are printed by
+   b200_trace_report (declared above; also called when a context is destroyed).  b200_host_profile_wait adds a wait that
+   happened in a caller. */
+int b200_host_profile_on(void);
+void b200_host_profile_wait(double ms);
+
 /* Tuning knob: rows of the sub-domain each thread block of the fused kernel marches over
    (default 8).  Results do not depend on it. */
 int b200_set_rows_per_block(int rows);

@@ -15,3 +15,12 @@ wait
 timeout 400 python bench.py --steps 20 --warmup 5 --no-e2e --no-cpu-baseline > $O/r2j_n1_alone.json 2> $O/r2j_n1_alone.err
 B200_HALO_NCCL=1 timeout 400 $TR bench.py --gpus 8 --steps 20 --warmup 5 --no-e2e > $O/r2j_scale_n8_nccl.json 2> $O/r2j_scale_n8_nccl.err
 ls -la $O | tail -14
+# (same box, one GPU) small grids with the adaptive rows of the one-stage kernels, host profile
+D=./ceda-demonstrations_b200/bin/diffusion_2D_b200
+{
+for n in 32 128; do
+echo "=== ${n}^2 rkc tf=1"
+for rep in 1 2 3 4; do timeout 300 $D --nx $n --ny $n --integrator rkc --tf 1 --nout 1 --output 1 | grep -E "Total simulation|B200 kernel launches"; done
+B200_HOST_PROFILE=1 timeout 300 $D --nx $n --ny $n --integrator rkc --tf 1 --nout 1 --output 1 2>&1 | grep -E "Total simulation|host profile"
+done
+} > $O/r2j_small_grids.log 2>&1
