@@ -42,8 +42,8 @@ $(LIB)/libb200sts.so: $(SRC)/b200_kernels.cu $(wildcard $(SRC)/*.cuh) include/b2
 	@mkdir -p $(LIB)
 	$(NVCC) $(NVFLAGS) -shared -Iinclude $< -o $@ -ldl
 
-HOST_SRC := $(SRC)/nvector_b200.cpp $(SRC)/diffusion_b200.cpp $(SRC)/adr_b200.cpp
-$(LIB)/libb200sts_sundials.so: $(HOST_SRC) include/nvector_b200.h include/b200_diffusion2d.h include/b200_adr2d.h include/b200_callbacks.h include/b200_sts.h $(LIB)/libb200sts.so
+HOST_SRC := $(SRC)/nvector_b200.cpp $(SRC)/diffusion_b200.cpp $(SRC)/adr_b200.cpp $(SRC)/blockdiag_b200.cpp
+$(LIB)/libb200sts_sundials.so: $(HOST_SRC) include/nvector_b200.h include/b200_diffusion2d.h include/b200_adr2d.h include/b200_callbacks.h include/b200_blockdiag.h include/b200_sts.h $(LIB)/libb200sts.so
 	@mkdir -p $(LIB)
 	$(CXX) $(CXXFLAGS) -shared -Iinclude $(SUNINC) $(HOST_SRC) -o $@ \
 	  -L$(LIB) -lb200sts -L$(SUNOUT)/lib -lsundials_host \

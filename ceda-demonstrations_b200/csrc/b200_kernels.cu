@@ -1465,6 +1465,54 @@ extern "C" int b200_adr_chain(b200_ctx* c, const b200_adr_params* p, int nstages
   return 0;
 }
 
+// ------------------------------------- adr: implicit reaction (block-diagonal Newton systems)
+#include "react_kernels.cuh"
+
+static unsigned blocks_for(int64_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
+
+extern "C" int b200_adr_jac_reaction(b200_ctx* c, const b200_adr_params* p, const double* y, double* J)
+{
+  if (!aligned16(y) || !aligned16(J)) return fail("b200_adr_jac_reaction: pointer not 16-byte aligned");
+  const int64_t npts = p->nx * p->ny;
+  if (npts < 1) return fail("b200_adr_jac_reaction: empty grid");
+  const AdrConsts k = adr_consts(*p);
+  klaunch(k_adr_jac_reaction, blocks_for(npts), kThreads, 0, c->stream, npts, k.B, k.Bp1, y, J);
+  LAUNCH_CHECK();
+  ALG_BYTES(3, 2 * npts);
+  return 0;
+}
+extern "C" int b200_blk2_scale_add_i(b200_ctx* c, double cc, double* A, int64_t npts)
+{
+  if (!aligned16(A) || npts < 1) return fail("b200_blk2_scale_add_i: bad argument");
+  klaunch(k_blk2_scale_add_i, blocks_for(npts), kThreads, 0, c->stream, npts, cc, A);
+  LAUNCH_CHECK();
+  ALG_BYTES(4, 2 * npts);
+  return 0;
+}
+// *info = 0, or the 1-based column of the first zero pivot (what SUNDlsMat_bandGBTRF returns); synchronises
+extern "C" int b200_blk2_factor(b200_ctx* c, double* A, double* piv, int64_t npts, long long* info)
+{
+  if (!aligned16(A) || !piv || npts < 1 || !info) return fail("b200_blk2_factor: bad argument");
+  unsigned long long* flag_h = reinterpret_cast<unsigned long long*>(c->host_result + 1);
+  unsigned long long* flag_d = reinterpret_cast<unsigned long long*>(c->host_result_dev + 1);
+  *reinterpret_cast<volatile unsigned long long*>(flag_h) = ~0ull;
+  klaunch(k_blk2_factor, blocks_for(npts), kThreads, 0, c->stream, npts, A, piv, flag_d);
+  LAUNCH_CHECK();
+  ALG_BYTES(5, 2 * npts);
+  CU_TRY(stream_sync_profiled(c->stream));
+  const unsigned long long f = *reinterpret_cast<volatile unsigned long long*>(flag_h);
+  *info = (f == ~0ull) ? 0 : (long long)f;
+  return 0;
+}
+extern "C" int b200_blk2_solve(b200_ctx* c, const double* A, const double* piv, const double* b, double* x, int64_t npts)
+{
+  if (!aligned16(A) || !aligned16(b) || !aligned16(x) || !piv || npts < 1) return fail("b200_blk2_solve: bad argument");
+  klaunch(k_blk2_solve, blocks_for(npts), kThreads, 0, c->stream, npts, A, piv, b, x);
+  LAUNCH_CHECK();
+  ALG_BYTES(5, 2 * npts);
+  return 0;
+}
+
 // --------------------------------------------------------------------- NCCL
 // NCCL is resolved at first use with dlopen("libnccl.so.2") instead of being a link-time
 // dependency: inside a Python process torch has usually loaded its own bundled NCCL

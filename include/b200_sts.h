@@ -367,6 +367,20 @@ int b200_adr_chain(b200_ctx* ctx, const b200_adr_params* p, int nstages, const d
                    const double* prev2, const double* yn, const double* fn, const double* coeffs,
                    double* const* z_out);
 
+/* ---- adr with IMPLICIT reaction (--implicit-reaction; SetupStrang / SetupExtSTS, ...2d.cpp:1207-1246, :820-854) ----
+   The reference keeps J_reaction (...2d.cpp:1523-1551) in a SUNBandMatrix(neq, 2, 2) and solves the Newton systems
+   with SUNLinSol_Band.  With the species interleaved the matrix is block diagonal (one 2 x 2 block per grid point), and
+   the banded LU with partial pivoting (SUN/src/sundials/sundials_band.c) never leaves a block; these entry points run
+   its operations per block, in its order and with its roundings.  Matrix storage: 4 doubles per grid point
+   { dU/du, dV/du, dU/dv, dV/dv }; piv: one double per grid point (1 = rows swapped). */
+int b200_adr_jac_reaction(b200_ctx* ctx, const b200_adr_params* p, const double* y, double* J);
+/* A = c*A + I (SUNMatScaleAddI_Band, SUN/src/sunmatrix/band/sunmatrix_band.c) */
+int b200_blk2_scale_add_i(b200_ctx* ctx, double c, double* A, int64_t npts);
+/* in-place LU (bandGBTRF); *info = 0 or the 1-based column of the first zero pivot.  Synchronises the stream. */
+int b200_blk2_factor(b200_ctx* ctx, double* A, double* piv, int64_t npts, long long* info);
+/* x = A^-1 b from the factors (bandGBTRS); x may alias b */
+int b200_blk2_solve(b200_ctx* ctx, const double* A, const double* piv, const double* b, double* x, int64_t npts);
+
 /* --------------------------------------------------- multi-GPU (NCCL, NVLink) */
 /* One process per GPU.  rank 0 calls b200_comm_unique_id and distributes the 128
    bytes out of band (torch.distributed / a file); every rank then calls

@@ -209,6 +209,12 @@ static inline double __shfl_xor_sync(unsigned, double v, int m) { return emu_shf
 static inline double __shfl_sync(unsigned, double v, int src) { return emu_shfl(v, src & 31); }
 
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned long long atomicMin(unsigned long long* p, unsigned long long v)
+{ // (blocks of one launch run on one OS thread at a time in the emulator; the CAS loop is for form)
+  unsigned long long old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+  while (v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+  return old;
+}
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline double __longlong_as_double(long long v)
 {
