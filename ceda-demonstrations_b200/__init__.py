@@ -110,6 +110,8 @@ class AdrStats(ctypes.Structure):
         ("aliased_copies", ctypes.c_long), ("buffers_allocated", ctypes.c_long),
         ("kernel_launches", ctypes.c_uint64),
         ("nx", ctypes.c_int64), ("ny", ctypes.c_int64), ("neq", ctypes.c_int64),
+        ("ark_rhs_evals_implicit", ctypes.c_long), ("nls_iters", ctypes.c_long),
+        ("ls_setups", ctypes.c_long), ("jac_evals", ctypes.c_long),
     ]
 
     def as_dict(self):

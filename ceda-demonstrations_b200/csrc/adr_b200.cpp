@@ -9,9 +9,10 @@
 // it.  ARKODE (SplittingStep, MRIStep, LSRKStep, ARKStep, ERKStep, SPGMR, Newton) is linked
 // unchanged.
 //
-// Explicit reactions only.  --implicit-reaction (serial band matrix + BBD preconditioner on host
-// arrays) and --calc_error (4th-order ARK reference with the same band machinery) are rejected
-// loudly; SURVEY.md section 2.1 marks them out of scope.
+// --implicit-reaction is available for the two STS integrators (--integrator 2 ExtSTS, 3 Strang): the reference's
+// SUNBandMatrix + SUNLinSol_Band pair is replaced by the block-diagonal pair of b200_blockdiag.h on device data
+// (J_reaction -> b200_adr_J_reaction).  With --integrator 1 it needs the reference's BBD preconditioner on host arrays
+// and stays rejected, as does --calc_error (4th-order ARK reference run); SURVEY.md section 2.1.
 
 #include <arkode/arkode_arkstep.h>
 #include <arkode/arkode_erkstep.h>
@@ -30,6 +31,7 @@
 #include <vector>
 
 #include "b200_adr2d.h"
+#include "b200_blockdiag.h"
 #include "b200_callbacks.h"
 #include "b200_sts.h"
 #include "nvector_b200.h"
@@ -145,6 +147,16 @@ int b200_adr_f_diffusion_forcing(sunrealtype t, N_Vector y, N_Vector f, void* us
   return MRIStepInnerStepper_AddForcing(ud->sts_mem, t, f) < 0 ? -1 : 0;
 }
 
+// J_reaction, ...2d.cpp:1523-1551 (ARKLsJacFn), into the block-diagonal device matrix of b200_blockdiag.h
+int b200_adr_J_reaction(sunrealtype, N_Vector y, N_Vector, SUNMatrix J, void* user_data, N_Vector, N_Vector, N_Vector)
+{
+  AdrData* ud = static_cast<AdrData*>(user_data);
+  double* Jd  = SUNMatrix_B200Block2_Data(J);
+  if (!Jd || SUNMatrix_B200Block2_Points(J) != ud->nx * ud->ny) return -1;
+  const b200_adr_params p = ud->params();
+  return b200_adr_jac_reaction(ud->ctx, &p, N_VGetDeviceArrayPointer_B200(y), Jd) ? -1 : 0;
+}
+
 // diffusion_domeig, ...2d.cpp:1666-1679
 int b200_adr_domeig(sunrealtype, N_Vector, N_Vector, sunrealtype* lambdaR, sunrealtype* lambdaI,
                     void* user_data, N_Vector, N_Vector, N_Vector)
@@ -178,6 +190,7 @@ struct b200_adr
   MRIStepInnerStepper inner = nullptr;
   STSInnerContent* inner_content = nullptr;
   SUNLinearSolver LS        = nullptr;
+  SUNMatrix A               = nullptr; // implicit reaction: block-diagonal Newton matrix
   double t = 0.0, evolve_seconds = 0.0;
   B200VecStats vs0{};
   bool settings_held = false; // N_VAcquireSettings_B200 succeeded for this session
@@ -245,9 +258,9 @@ int read_inputs(const std::vector<std::string>& args, AdrData& ud, AdrOptions& u
   ud.neq = 2 * ud.nx * ud.ny;
   if (uo.integrator < 0 || uo.integrator > 3) { fprintf(stderr, "ERROR: Invalid integrator option\n"); return -1; }
   if (uo.table_id < 0 || uo.table_id > 5) { fprintf(stderr, "ERROR: Invalid ARK table ID\n"); return -1; }
-  if (ud.impl_reaction)
+  if (ud.impl_reaction && uo.integrator != 2 && uo.integrator != 3)
   {
-    fprintf(stderr, "ERROR: --implicit-reaction is not available on the B200 path (host band solver; out of scope)\n");
+    fprintf(stderr, "ERROR: --implicit-reaction is available with --integrator 2 (ExtSTS) and 3 (Strang) on the B200 path\n");
     return -1;
   }
   if (uo.calc_error || uo.write_solution)
@@ -385,18 +398,95 @@ int inner_reset(MRIStepInnerStepper stepper, sunrealtype tR, N_Vector yR)
   return ARKodeReset(content->sts_arkode_mem, tR, yR) < 0 ? 1 : 0;
 }
 
-// the explicit MRI couplings of SetupExtSTS, ...2d.cpp:883-1075
-MRIStepCoupling extsts_coupling(int method)
+// the solver block both STS set-ups share when the reaction is implicit (...2d.cpp:820-854, :1207-1246): matrix,
+// direct solver, Jacobian, set-up frequency, Newton limits, predictor
+int attach_implicit_reaction(b200_adr* p, void* mem, bool deduce_fi)
+{
+  AdrData& ud = p->ud; AdrOptions& uo = p->uo;
+  p->A = SUNMatrix_B200Block2(p->ctx, ud.nx * ud.ny, p->sunctx); // SUNBandMatrix(neq, 2, 2)
+  CHKP(p->A, "SUNMatrix_B200Block2");
+  p->LS = SUNLinSol_B200Block2(p->y, p->A, p->sunctx);           // SUNLinSol_Band
+  CHKP(p->LS, "SUNLinSol_B200Block2");
+  CHK(ARKodeSetLinearSolver(mem, p->LS, p->A), "ARKodeSetLinearSolver");
+  CHK(ARKodeSetJacFn(mem, b200_adr_J_reaction), "ARKodeSetJacFn");
+  CHK(ARKodeSetLSetupFrequency(mem, uo.ls_setup_freq), "ARKodeSetLSetupFrequency");
+  CHK(ARKodeSetMaxNonlinIters(mem, uo.maxnewt), "ARKodeSetMaxNonlinIters");
+  CHK(ARKodeSetNonlinConvCoef(mem, uo.nlscoef), "ARKodeSetNonlinConvCoef");
+  if (deduce_fi) CHK(ARKodeSetDeduceImplicitRhs(mem, SUNTRUE), "ARKodeSetDeduceImplicitRhs");
+  CHK(ARKodeSetPredictorMethod(mem, uo.predictor), "ARKodeSetPredictorMethod");
+  return 0;
+}
+
+// the implicit (G) halves of the ExtSTS couplings when the reaction is implicit, ...2d.cpp:861-1000, :1063-1086:
+// rows of { stage, column, value }
+void set_implicit_coupling(MRIStepCoupling C, int method)
+{
+  const double one = 1.0, two = 2.0, four = 4.0, eight = 8.0;
+  const double sqrt2 = std::sqrt(two);
+  if (method == 0)
+  { // ARS(2,2,2)
+    const double gamma = one - one / std::sqrt(2.0);
+    const double G[8][3] = {{1, 0, gamma}, {2, 0, -gamma}, {2, 2, gamma}, {3, 2, one - gamma},
+                            {4, 2, -gamma}, {4, 4, gamma}, {5, 2, -0.4}, {5, 4, 0.4}};
+    for (auto& g : G) C->G[0][(int)g[0]][(int)g[1]] = g[2];
+  }
+  else if (method == 1)
+  { // Giraldo
+    const double G[11][3] = {{1, 0, two - sqrt2},
+                             {2, 0, one - one / sqrt2 - (two - sqrt2)},
+                             {2, 2, one - one / sqrt2},
+                             {3, 0, one / sqrt2 - one},
+                             {3, 2, one / sqrt2},
+                             {4, 0, one / (two * sqrt2)},
+                             {4, 2, one / (two * sqrt2) - one},
+                             {4, 4, one - one / sqrt2},
+                             {6, 0, (four - sqrt2) / eight - one / (two * sqrt2)},
+                             {6, 2, (four - sqrt2) / eight - one / (two * sqrt2)},
+                             {6, 4, one / (two * sqrt2) - (one - one / sqrt2)}};
+    for (auto& g : G) C->G[0][(int)g[0]][(int)g[1]] = g[2];
+  }
+}
+
+// SSP SDIRK 2, ...2d.cpp:1063-1086 (implicit only)
+MRIStepCoupling extsts_ssp_sdirk2()
+{
+  MRIStepCoupling C = MRIStepCoupling_Alloc(1, 6, MRISTEP_IMPLICIT);
+  const double one = 1.0, two = 2.0, seven = 7.0, twelve = 12.0;
+  const double gamma = one - one / std::sqrt(two);
+  C->q = 2; C->p = 1;
+  C->c[1] = gamma; C->c[2] = gamma; C->c[3] = one - gamma; C->c[4] = one - gamma; C->c[5] = one;
+  const double G[11][3] = {{1, 0, gamma}, {2, 0, -gamma}, {2, 2, gamma}, {3, 2, one - two * gamma},
+                           {4, 2, -gamma}, {4, 4, gamma}, {5, 2, two * gamma - one / two}, {5, 4, one / two - gamma},
+                           {6, 2, two * gamma - seven / twelve}, {6, 4, seven / twelve - gamma}, {0, 0, 0.0}};
+  for (auto& g : G) C->G[0][(int)g[0]][(int)g[1]] = g[2];
+  return C;
+}
+
+// the MRI couplings of SetupExtSTS, ...2d.cpp:856-1098.  kind: MRISTEP_EXPLICIT (explicit reaction), MRISTEP_IMEX
+// (explicit advection + implicit reaction) or MRISTEP_IMPLICIT (implicit reaction, no advection): the slow-explicit
+// half W is filled unless kind is IMPLICIT, the slow-implicit half G (set_implicit_coupling) unless it is EXPLICIT
+MRIStepCoupling extsts_coupling_explicit(int method, MRISTEP_METHOD_TYPE kind);
+MRIStepCoupling extsts_coupling(int method, MRISTEP_METHOD_TYPE kind = MRISTEP_EXPLICIT)
+{
+  MRIStepCoupling C = extsts_coupling_explicit(method, kind);
+  if (C && kind != MRISTEP_EXPLICIT && method >= 0) set_implicit_coupling(C, method);
+  return C;
+}
+
+MRIStepCoupling extsts_coupling_explicit(int method, MRISTEP_METHOD_TYPE kind)
 {
   MRIStepCoupling C = nullptr;
   const double one = 1.0, two = 2.0, three = 3.0, four = 4.0, six = 6.0, eight = 8.0;
+  if (method == 4) return kind == MRISTEP_IMPLICIT ? extsts_ssp_sdirk2() : nullptr;
+  if (method >= 2 && kind != MRISTEP_EXPLICIT) return nullptr; // Ralston, Heun-Euler: explicit only
   if (method == 0)
   { // ARS(2,2,2)
-    C = MRIStepCoupling_Alloc(1, 5, MRISTEP_EXPLICIT);
+    C = MRIStepCoupling_Alloc(1, 5, kind);
     const double gamma = one - one / std::sqrt(2.0);
     const double delta = one - one / (2.0 * gamma);
     C->q = 2; C->p = 1;
     C->c[1] = gamma; C->c[2] = gamma; C->c[3] = one; C->c[4] = one;
+    if (kind == MRISTEP_IMPLICIT) return C;
     C->W[0][1][0] = gamma;
     C->W[0][3][0] = delta - gamma;
     C->W[0][3][2] = one - delta;
@@ -406,10 +496,11 @@ MRIStepCoupling extsts_coupling(int method)
   }
   else if (method == 1)
   { // Giraldo
-    C = MRIStepCoupling_Alloc(1, 6, MRISTEP_EXPLICIT);
+    C = MRIStepCoupling_Alloc(1, 6, kind);
     const double sqrt2 = std::sqrt(two);
     C->q = 2; C->p = 1;
     C->c[1] = two - sqrt2; C->c[2] = two - sqrt2; C->c[3] = one; C->c[4] = one; C->c[5] = one;
+    if (kind == MRISTEP_IMPLICIT) return C;
     C->W[0][1][0] = two - sqrt2;
     C->W[0][3][0] = (three - two * sqrt2) / six - (two - sqrt2);
     C->W[0][3][2] = (three + two * sqrt2) / six;
@@ -445,14 +536,23 @@ MRIStepCoupling extsts_coupling(int method)
   return C;
 }
 
-// SetupExtSTS, ...2d.cpp:715-1120 (explicit reaction)
+// SetupExtSTS, ...2d.cpp:715-1120
 int setup_extsts(b200_adr* p)
 {
   AdrData& ud = p->ud; AdrOptions& uo = p->uo;
-  ARKRhsFn fe = ud.advection ? b200_adr_f_adv_react : b200_adr_f_reaction;
-  if (uo.extsts_method == 4)
+  // ...2d.cpp:724-733: who treats advection / reaction
+  ARKRhsFn fi = ud.impl_reaction ? b200_adr_f_reaction : nullptr;
+  ARKRhsFn fe = ud.advection ? (ud.impl_reaction ? b200_adr_f_advection : b200_adr_f_adv_react)
+                             : (ud.impl_reaction ? nullptr : b200_adr_f_reaction);
+  const MRISTEP_METHOD_TYPE kind = !ud.impl_reaction ? MRISTEP_EXPLICIT : (ud.advection ? MRISTEP_IMEX : MRISTEP_IMPLICIT);
+  if (uo.extsts_method == 4 && kind != MRISTEP_IMPLICIT)
   {
-    fprintf(stderr, "ERROR: --extsts_method 4 (SSP SDIRK 2) is implicit-only; not available on the B200 path\n");
+    fprintf(stderr, "ERROR: --extsts_method 4 (SSP SDIRK 2) is implicit-only: it needs --implicit-reaction --no-advection\n");
+    return -1;
+  }
+  if ((uo.extsts_method == 2 || uo.extsts_method == 3) && ud.impl_reaction)
+  {
+    fprintf(stderr, "ERROR: --extsts_method %d is explicit-only (no --implicit-reaction)\n", uo.extsts_method);
     return -1;
   }
   void* sts = LSRKStepCreateSTS(b200_adr_f_diffusion_forcing, 0.0, p->y, p->sunctx);
@@ -474,14 +574,15 @@ int setup_extsts(b200_adr* p)
   CHK(MRIStepInnerStepper_SetResetFn(p->inner, inner_reset), "MRIStepInnerStepper_SetResetFn");
   ud.sts_mem = p->inner;
 
-  p->arkode_mem = MRIStepCreate(fe, nullptr, 0.0, p->y, p->inner, p->sunctx);
+  p->arkode_mem = MRIStepCreate(fe, fi, 0.0, p->y, p->inner, p->sunctx);
   CHKP(p->arkode_mem, "MRIStepCreate");
   void* mem = p->arkode_mem;
   if (uo.fixed_h > 0.0) CHK(ARKodeSetFixedStep(mem, uo.fixed_h), "ARKodeSetFixedStep");
   else CHK(ARKodeSetErrorBias(mem, uo.error_bias), "ARKodeSetErrorBias");
   CHK(ARKodeSStolerances(mem, uo.rtol, uo.atol), "ARKodeSStolerances");
   CHK(ARKodeSetUserData(mem, &ud), "ARKodeSetUserData");
-  MRIStepCoupling C = extsts_coupling(uo.extsts_method);
+  if (ud.impl_reaction && attach_implicit_reaction(p, mem, false)) return -1; // ...2d.cpp:820-854
+  MRIStepCoupling C = extsts_coupling(uo.extsts_method, kind);
   if (!C) { fprintf(stderr, "ERROR: Invalid extsts method %d\n", uo.extsts_method); return -1; }
   CHK(MRIStepSetCoupling(mem, C), "MRIStepSetCoupling");
   MRIStepCoupling_Free(C);
@@ -491,11 +592,14 @@ int setup_extsts(b200_adr* p)
   return 0;
 }
 
-// SetupStrang, ...2d.cpp:1122-1333 (explicit reaction)
+// SetupStrang, ...2d.cpp:1122-1333
 int setup_strang(b200_adr* p)
 {
   AdrData& ud = p->ud; AdrOptions& uo = p->uo;
-  ARKRhsFn fe = ud.advection ? b200_adr_f_adv_react : b200_adr_f_reaction;
+  // ...2d.cpp:1131-1140
+  ARKRhsFn fi = ud.impl_reaction ? b200_adr_f_reaction : nullptr;
+  ARKRhsFn fe = ud.advection ? (ud.impl_reaction ? b200_adr_f_advection : b200_adr_f_adv_react)
+                             : (ud.impl_reaction ? nullptr : b200_adr_f_reaction);
   if (!(uo.fixed_h > 0.0))
   {
     fprintf(stderr, "ERROR: Fixed step size must be specified for Strang splitting.\n");
@@ -514,16 +618,23 @@ int setup_strang(b200_adr* p)
   CHK(ARKodeSetMaxNumSteps(ls, uo.maxsteps), "ARKodeSetMaxNumSteps");
   CHK(ARKodeSetInterpolantType(ls, ARK_INTERP_NONE), "ARKodeSetInterpolantType");
   CHK(ARKodeCreateSUNStepper(ls, &p->steppers[0]), "ARKodeCreateSUNStepper");
-  // ARKStep partition: explicit ARS(2,2,2), no embedding
-  p->arkstep_mem = ARKStepCreate(fe, nullptr, 0.0, p->y, p->sunctx);
+  // ARKStep partition: ARS(2,2,2) without embedding -- the explicit table for fe, the implicit one for fi
+  p->arkstep_mem = ARKStepCreate(fe, fi, 0.0, p->y, p->sunctx);
   CHKP(p->arkstep_mem, "ARKStepCreate");
   void* as = p->arkstep_mem;
   CHK(ARKodeSetUserData(as, &ud), "ARKodeSetUserData");
   CHK(ARKodeSetFixedStep(as, uo.fixed_h), "ARKodeSetFixedStep");
   CHK(ARKodeSetMaxNumSteps(as, uo.maxsteps), "ARKodeSetMaxNumSteps");
-  ARKodeButcherTable Be = ars222_explicit(false);
-  CHK(ARKStepSetTables(as, 2, 0, nullptr, Be), "ARKStepSetTables");
-  ARKodeButcherTable_Free(Be);
+  if (ud.impl_reaction)
+  { // ...2d.cpp:1207-1246
+    CHK(ARKodeSStolerances(as, uo.rtol, uo.atol), "ARKodeSStolerances");
+    if (attach_implicit_reaction(p, as, true)) return -1;
+  }
+  ARKodeButcherTable Be = fe ? ars222_explicit(false) : nullptr;
+  ARKodeButcherTable Bi = fi ? ars222_implicit(false) : nullptr;
+  CHK(ARKStepSetTables(as, 2, 0, Bi, Be), "ARKStepSetTables");
+  if (Be) ARKodeButcherTable_Free(Be);
+  if (Bi) ARKodeButcherTable_Free(Bi);
   CHK(ARKodeCreateSUNStepper(as, &p->steppers[1]), "ARKodeCreateSUNStepper");
   // SplittingStep with Strang coefficients
   p->arkode_mem = SplittingStepCreate(p->steppers, 2, 0.0, p->y, p->sunctx);
@@ -621,6 +732,7 @@ extern "C" int b200_adr_destroy(b200_adr* p)
   }
   else if (p->arkode_mem) ARKodeFree(&p->arkode_mem);
   if (p->LS) SUNLinSolFree(p->LS);
+  if (p->A) SUNMatDestroy(p->A);
   if (p->y) N_VDestroy(p->y);
   if (p->sunctx) SUNContext_Free(&p->sunctx);
   if (p->ctx) b200_ctx_destroy(p->ctx);
@@ -689,6 +801,15 @@ extern "C" int b200_adr_get_stats(b200_adr* p, b200_adr_stats* s)
   {
     ARKodeGetNumSteps(p->arkstep_mem, &s->ark_steps);
     ARKodeGetNumRhsEvals(p->arkstep_mem, 0, &s->ark_rhs_evals);
+    if (p->ud.impl_reaction) ARKodeGetNumRhsEvals(p->arkstep_mem, 1, &s->ark_rhs_evals_implicit);
+  }
+  if (p->uo.integrator == 2 && p->ud.impl_reaction) ARKodeGetNumRhsEvals(mem, 1, &s->rhs_evals_implicit);
+  if (p->uo.integrator == 1 || p->ud.impl_reaction)
+  {
+    void* im = (p->uo.integrator == 3) ? p->arkstep_mem : mem; // who owns the implicit partition
+    ARKodeGetNumNonlinSolvIters(im, &s->nls_iters);
+    ARKodeGetNumLinSolvSetups(im, &s->ls_setups);
+    ARKodeGetNumJacEvals(im, &s->jac_evals);
   }
   B200VecStats vs;
   N_VGetStats_B200(&vs);

@@ -9,9 +9,10 @@
  *   --integrator 2  SetupExtSTS  ...2d.cpp:715-1120   MRIStep + LSRKStep inner stepper
  *   --integrator 3  SetupStrang  ...2d.cpp:1122-1333  SplittingStep: LSRKStep . ARS(2,2,2)
  * and the same callbacks (...2d.cpp:1406-1699), which enqueue sm_100a kernels through
- * b200_sts.h instead of looping over the grid on the host.  Explicit reactions only:
- * `--implicit-reaction` needs the reference's serial band solver on host data and is
- * rejected (out of scope); `--calc_error` likewise.
+ * b200_sts.h instead of looping over the grid on the host.  `--implicit-reaction` is
+ * available with the two STS integrators (2, 3): the reference's SUNBandMatrix +
+ * SUNLinSol_Band become the block-diagonal device pair of b200_blockdiag.h; with
+ * --integrator 1 (BBD preconditioner on host arrays) it is rejected, as is `--calc_error`.
  *
  * The callbacks themselves -- ARKRhsFn / ARKDomEigFn signatures, SUNDIALS types -- are
  * declared in b200_callbacks.h.
@@ -42,6 +43,10 @@ typedef struct b200_adr_stats
   long fused_launches, plain_rhs_launches, aliased_copies, buffers_allocated;
   uint64_t kernel_launches;
   int64_t nx, ny, neq;
+  /* the implicitly treated partition (IMEX ARK: diffusion; --implicit-reaction: the reaction) */
+  long ark_rhs_evals_implicit; /* Strang: fi evaluations of the ARKStep partition */
+  long nls_iters, ls_setups, jac_evals; /* Newton iterations, linear-solver set-ups, Jacobian evaluations of the
+                                           integrator that owns the implicit partition */
 } b200_adr_stats;
 
 /* Build the problem from reference-style arguments, e.g.

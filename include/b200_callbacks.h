@@ -12,6 +12,7 @@
 #ifndef B200_CALLBACKS_H
 #define B200_CALLBACKS_H
 
+#include <sundials/sundials_matrix.h>
 #include <sundials/sundials_nvector.h>
 #include <sundials/sundials_types.h>
 
@@ -56,6 +57,10 @@ int b200_adr_f_adv_react(sunrealtype t, N_Vector y, N_Vector f, void* user_data)
 int b200_adr_f_diff_react(sunrealtype t, N_Vector y, N_Vector f, void* user_data);     /* :1582-1599 */
 int b200_adr_f_adv_diff_react(sunrealtype t, N_Vector y, N_Vector f, void* user_data); /* :1622-1646 */
 int b200_adr_f_diffusion_forcing(sunrealtype t, N_Vector y, N_Vector f, void* user_data); /* :1649-1663 */
+/* ARKLsJacFn: J_reaction(), :1523-1551 -- J must be a SUNMatrix_B200Block2 (b200_blockdiag.h), which stands in for the
+   reference's SUNBandMatrix(neq, 2, 2) when the reaction is implicit */
+int b200_adr_J_reaction(sunrealtype t, N_Vector y, N_Vector fy, SUNMatrix J, void* user_data, N_Vector tmp1,
+                        N_Vector tmp2, N_Vector tmp3);
 /* ARKDomEigFn: diffusion_domeig(), :1666-1679 */
 int b200_adr_domeig(sunrealtype t, N_Vector y, N_Vector fn, sunrealtype* lambdaR,
                     sunrealtype* lambdaI, void* user_data, N_Vector temp1, N_Vector temp2,

@@ -100,6 +100,19 @@ ADR_CASES = {
                                     "--extsts_method", "3", "--d", "0.1", "--fixed_h", "0.002", "--tf", "0.02"],
     "ark_ars_adaptive_48": ["--nx", "48", "--ny", "48", "--integrator", "1", "--table_id", "1", "--rtol", "1e-4", "--tf", "0.02"],
     "ark_default_adaptive_48": ["--nx", "48", "--ny", "48", "--integrator", "1", "--order", "3", "--rtol", "1e-5", "--tf", "0.02"],
+    # --implicit-reaction: Newton + band LU of I - gamma*J_reaction in the reference (SetupStrang / SetupExtSTS)
+    "strang_rkc_implreact_48": ["--nx", "48", "--ny", "48", "--integrator", "3", "--sts_method", "0", "--fixed_h", "0.01",
+                                "--tf", "0.05", "--implicit-reaction"],
+    "strang_rkl_implreact_noadv_40x32": ["--nx", "40", "--ny", "32", "--integrator", "3", "--sts_method", "1", "--fixed_h", "0.005",
+                                         "--tf", "0.03", "--implicit-reaction", "--no-advection"],
+    "extsts_ars_implreact_fixed_48": ["--nx", "48", "--ny", "48", "--integrator", "2", "--sts_method", "0", "--extsts_method", "0",
+                                      "--fixed_h", "0.005", "--tf", "0.05", "--implicit-reaction"],
+    "extsts_giraldo_implreact_noadv_48": ["--nx", "48", "--ny", "48", "--integrator", "2", "--sts_method", "1", "--extsts_method", "1",
+                                          "--rtol", "1e-4", "--tf", "0.05", "--implicit-reaction", "--no-advection"],
+    "extsts_sdirk_implreact_fixed_64x32": ["--nx", "64", "--ny", "32", "--integrator", "2", "--sts_method", "0", "--extsts_method", "4",
+                                           "--fixed_h", "0.005", "--tf", "0.05", "--implicit-reaction", "--no-advection"],
+    "extsts_giraldo_implreact_fixed_64": ["--nx", "64", "--ny", "64", "--integrator", "2", "--sts_method", "0", "--extsts_method", "1",
+                                          "--fixed_h", "0.004", "--tf", "0.04", "--implicit-reaction"],
 }
 
 
@@ -175,10 +188,12 @@ def main(only_missing=False):
         print("%-32s steps=%s evals=%s np1-vs-np4=%.2e" % (name, stats.get("steps"), stats.get("rhs_evals", stats.get("rhs_evals_i")), spread))
 
 
-def main_adr():
+def main_adr(only_missing=False):
     import compare_adr as ca
 
     for name, args in ADR_CASES.items():
+        if only_missing and os.path.exists(os.path.join(HERE, "adr_%s.json" % name)):
+            continue
         full = args + ["--nout", "1", "--output", "1"]
         nx, ny = int(ca.get_arg(full, "--nx", 400)), int(ca.get_arg(full, "--ny", 400))
         wd, text = ca.run(ca.REF_BIN, full)
@@ -193,6 +208,8 @@ def main_adr():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "adr":
         main_adr()
+    elif len(sys.argv) > 1 and sys.argv[1] == "adr-missing":
+        main_adr(only_missing=True)
     elif len(sys.argv) > 1 and sys.argv[1] == "missing":
         main(only_missing=True)
     else:

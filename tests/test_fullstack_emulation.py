@@ -254,6 +254,108 @@ def fmt15(a):
     return np.array(["%.15g" % v for v in np.asarray(a).ravel()])
 
 
+def test_block_solver_kernels_repeat_the_band_lu(emu):
+    """b200_adr_jac_reaction / b200_blk2_scale_add_i / b200_blk2_factor / b200_blk2_solve against the reference's own
+    sequence on the FULL banded matrix: J_reaction (...2d.cpp:1523-1551), SUNMatScaleAddI_Band, bandGBTRF, bandGBTRS
+    (tests/band_lu_restatement.py) -- bit for bit, including blocks whose rows are swapped and a zero pivot."""
+    from band_lu_restatement import band_gbtrf, band_gbtrs
+
+    lib = emu.kernel_lib()
+    ctx = ctypes.c_void_p()
+    assert lib.b200_ctx_create(0, None, ctypes.byref(ctx)) == 0
+    nx, ny = 6, 5
+    npts, n = nx * ny, 2 * nx * ny
+    rng = np.random.default_rng(11)
+    y = rng.standard_normal(n) * 2.0
+    B, gamma = 1.0, 0.37
+    prm = emu.AdrParams(nx, ny, 1.0 / nx, 1.0 / ny, -0.5, 1.0, 0.4, 0.7, 1e-2, 1.3, B)
+    J = np.full(4 * npts, np.nan)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    assert lib.b200_adr_jac_reaction(ctx, ctypes.byref(prm), P(y), P(J)) == 0
+    dense = np.zeros((n, n))
+    for p_ in range(npts):
+        u, v = y[2 * p_], y[2 * p_ + 1]
+        dense[2 * p_, 2 * p_] = 2.0 * u * v - (B + 1.0)
+        dense[2 * p_ + 1, 2 * p_] = B - 2.0 * u * v
+        dense[2 * p_, 2 * p_ + 1] = u * u
+        dense[2 * p_ + 1, 2 * p_ + 1] = -u * u
+    want = np.stack([dense[0::2, 0::2].diagonal(), dense[1::2, 0::2].diagonal(), dense[0::2, 1::2].diagonal(),
+                     dense[1::2, 1::2].diagonal()], axis=1).ravel()
+    assert np.array_equal(J, want)
+    # A = I - gamma*J (SUNMatScaleAddI(-gamma, A)): every stored band entry times c, then the diagonal + 1
+    assert lib.b200_blk2_scale_add_i(ctx, ctypes.c_double(-gamma), P(J), ctypes.c_int64(npts)) == 0
+    A = dense * (-gamma)
+    A[np.arange(n), np.arange(n)] += 1.0
+    got = np.stack([A[0::2, 0::2].diagonal(), A[1::2, 0::2].diagonal(), A[0::2, 1::2].diagonal(), A[1::2, 1::2].diagonal()],
+                   axis=1).ravel()
+    assert np.array_equal(J, got)
+    piv = np.full(npts, np.nan)
+    info = ctypes.c_longlong(-1)
+    assert lib.b200_blk2_factor(ctx, P(J), P(piv), ctypes.c_int64(npts), ctypes.byref(info)) == 0
+    pv, winfo = band_gbtrf(A, 2, 4)
+    assert info.value == winfo == 0
+    swapped = pv[0::2] != np.arange(0, n, 2)
+    assert swapped.any() and not swapped.all()  # both branches of the pivot search are exercised
+    assert np.array_equal(piv != 0.0, swapped) and np.all(pv[1::2] == np.arange(1, n, 2))
+    got = np.stack([A[0::2, 0::2].diagonal(), A[1::2, 0::2].diagonal(), A[0::2, 1::2].diagonal(), A[1::2, 1::2].diagonal()],
+                   axis=1).ravel()
+    assert np.array_equal(J, got)
+    off = A.copy()
+    for p_ in range(npts):
+        off[2 * p_:2 * p_ + 2, 2 * p_:2 * p_ + 2] = 0.0
+    assert not off.any()  # the band elimination never left the blocks
+    b = rng.standard_normal(n)
+    x = np.full(n, np.nan)
+    assert lib.b200_blk2_solve(ctx, P(J), P(piv), P(b), P(x), ctypes.c_int64(npts)) == 0
+    assert np.array_equal(x, band_gbtrs(A, 2, 4, pv, b.copy()))
+    # a zero pivot: bandGBTRF's 1-based column number comes back
+    Z = J.copy()
+    Z[4 * 7:4 * 7 + 2] = 0.0
+    Zd = np.zeros((n, n))
+    for p_ in range(npts):
+        Zd[2 * p_, 2 * p_], Zd[2 * p_ + 1, 2 * p_], Zd[2 * p_, 2 * p_ + 1], Zd[2 * p_ + 1, 2 * p_ + 1] = Z[4 * p_:4 * p_ + 4]
+    assert lib.b200_blk2_factor(ctx, P(Z), P(piv), ctypes.c_int64(npts), ctypes.byref(info)) == 0
+    assert info.value == band_gbtrf(Zd, 2, 4)[1] == 15
+    lib.b200_ctx_destroy(ctx)
+
+
+ADR_IMPLICIT_CASES = ["strang_rkc_implreact_48", "strang_rkl_implreact_noadv_40x32", "extsts_ars_implreact_fixed_48",
+                      "extsts_giraldo_implreact_noadv_48", "extsts_sdirk_implreact_fixed_64x32",
+                      "extsts_giraldo_implreact_fixed_64"]
+
+
+@pytest.mark.parametrize("name", ADR_IMPLICIT_CASES)
+def test_adr_implicit_reaction_fixture_parity_through_the_emulated_stack(emu, name):
+    """--implicit-reaction (SetupStrang / SetupExtSTS with fi = f_reaction): ARKODE's Newton iteration over the
+    block-diagonal device matrix / direct solver of b200_blockdiag.h, which repeat the reference's band LU
+    (SUNBandMatrix(neq, 2, 2) + SUNLinSol_Band) block by block -- same Newton / RHS / step counters as the unmodified
+    reference, fixed-step states equal to every printed digit."""
+    with open(os.path.join(GOLDEN, "adr_%s.json" % name)) as f:
+        meta = json.load(f)
+    ref = np.load(os.path.join(GOLDEN, "adr_%s.npy" % name))
+    args = [str(a) for a in meta["args"]]
+    tf = float(args[args.index("--tf") + 1])
+    prob = emu.Adr2D(args + ["--nout", "1", "--output", "0"], device=0, stream=None)
+    prob.evolve(tf)
+    st = prob.stats()
+    y = np.empty(st["neq"])
+    prob.get_state(y)
+    prob.close()
+    ms = meta["stats"]
+    assert st["steps"] == ms["outer.steps"] and st["lsrk_rhs_evals"] == ms["lsrk.rhs_evals"]
+    if "ark.rhs_evals_i" in ms:  # Strang: the ARKStep partition owns the reaction
+        assert st["ark_rhs_evals_implicit"] == ms["ark.rhs_evals_i"] and st["ark_rhs_evals"] == ms["ark.rhs_evals_e"]
+        assert st["nls_iters"] == ms["ark.nls_iters"]
+    else:
+        assert st["rhs_evals_implicit"] == ms["outer.rhs_evals_i"] and st["rhs_evals_explicit"] == ms["outer.rhs_evals_e"]
+        assert st["nls_iters"] == ms["outer.nls_iters"]
+    assert st["jac_evals"] >= 1 and st["ls_setups"] >= 1
+    if "--fixed_h" in args:
+        assert np.array_equal(fmt15(y), fmt15(ref))
+    else:
+        assert float(np.linalg.norm(y - ref) / np.linalg.norm(ref)) <= REL_L2_TOL
+
+
 @pytest.mark.parametrize("name", ADR_CASES)
 def test_adr_fixture_parity_through_the_emulated_stack(emu, name):
     with open(os.path.join(GOLDEN, "adr_%s.json" % name)) as f:
