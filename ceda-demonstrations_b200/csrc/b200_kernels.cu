@@ -193,9 +193,21 @@ static std::atomic<uint64_t> g_alg_bytes{0}; // modelled bytes (full-vector read
   }                                                                           \
   while (0)
 
+// B200_FAIL_AFTER_LAUNCHES=n (fault injection for the tests of the failure path): launch number n reports an error
+static long long g_fail_after = -2;
+static bool injected_failure(uint64_t launch_no)
+{
+  if (g_fail_after == -2)
+  {
+    const char* e = getenv("B200_FAIL_AFTER_LAUNCHES");
+    g_fail_after  = e ? atoll(e) : -1;
+  }
+  return g_fail_after >= 0 && (long long)launch_no == g_fail_after;
+}
 #define LAUNCH_CHECK()                                                        \
   do {                                                                        \
-    g_launches.fetch_add(1, std::memory_order_relaxed);                       \
+    const uint64_t n_ = g_launches.fetch_add(1, std::memory_order_relaxed);   \
+    if (injected_failure(n_ + 1)) return fail("injected failure (B200_FAIL_AFTER_LAUNCHES)"); \
     CU_TRY(cudaGetLastError());                                               \
   }                                                                           \
   while (0)

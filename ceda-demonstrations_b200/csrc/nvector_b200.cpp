@@ -34,10 +34,21 @@
 
 namespace {
 
+// A device failure inside a vector operation: reported once on stderr, remembered (g_failed: every later operation
+// returns at once -- the state behind the vectors can no longer be trusted), and thrown up to the boundary of this
+// library, where it becomes what the interface can express: SUN_ERR_EXT_FAIL from the fused operations (LSRKStep maps it to
+// ARK_VECTOROP_ERR, arkode_lsrkstep.c:718-723), NaN from the reductions (the step fails its error test and ARKODE
+// gives up with an error return), NULL / -1 from the accessors.  Nothing is recomputed on the host: there is no
+// fallback, only an orderly way down instead of abort().
+struct DeviceFailure
+{
+};
+bool g_failed = false;
 [[noreturn]] void die(const char* what, int rc)
 {
   fprintf(stderr, "nvector_b200: FATAL: %s failed (code %d): %s\n", what, rc, b200_last_error());
-  abort();
+  g_failed = true;
+  throw DeviceFailure();
 }
 #define DEV(call)                       \
   do {                                  \
@@ -1243,6 +1254,26 @@ void op_print(N_Vector v)
   for (sunindextype i = 0; i < C(v)->sh->nloc; i++) printf("%.16e\n", h[i]);
 }
 
+// what an operation returns after a device failure, by return type
+template <class R> R failed_result();
+template <> void failed_result<void>() {}
+template <> double failed_result<double>() { return std::nan(""); }
+template <> int failed_result<int>() { return (int)SUN_ERR_EXT_FAIL; } // SUNErrCode
+template <> double* failed_result<double*>() { return nullptr; }
+
+// the ops-table entry for f: f behind the failure boundary described at die()
+template <auto f> struct Guarded;
+template <class R, class... A, R (*f)(A...)> struct Guarded<f>
+{
+  static R call(A... a)
+  {
+    if (g_failed) return failed_result<R>();
+    try { return f(a...); }
+    catch (const DeviceFailure&) { return failed_result<R>(); }
+  }
+};
+#define GUARDED(f) Guarded<f>::call
+
 void fill_ops(N_Vector v)
 {
   v->ops->nvgetvectorid       = op_getvectorid;
@@ -1250,23 +1281,23 @@ void fill_ops(N_Vector v)
   v->ops->nvcloneempty        = op_clone;
   v->ops->nvdestroy           = op_destroy;
   v->ops->nvspace             = op_space;
-  v->ops->nvgetarraypointer   = op_getarraypointer;
+  v->ops->nvgetarraypointer   = GUARDED(op_getarraypointer);
   v->ops->nvgetlength         = op_getlength;
-  v->ops->nvlinearsum         = op_linearsum;
-  v->ops->nvconst             = op_const;
-  v->ops->nvprod              = op_prod;
-  v->ops->nvdiv               = op_div;
-  v->ops->nvscale             = op_scale;
-  v->ops->nvabs               = op_abs;
-  v->ops->nvinv               = op_inv;
-  v->ops->nvaddconst          = op_addconst;
-  v->ops->nvdotprod           = op_dotprod;
-  v->ops->nvmaxnorm           = op_maxnorm;
-  v->ops->nvwrmsnorm          = op_wrmsnorm;
-  v->ops->nvwl2norm           = op_wl2norm;
-  v->ops->nvmin               = op_min;
-  v->ops->nvl1norm            = op_l1norm;
-  v->ops->nvlinearcombination = op_linearcombination;
+  v->ops->nvlinearsum         = GUARDED(op_linearsum);
+  v->ops->nvconst             = GUARDED(op_const);
+  v->ops->nvprod              = GUARDED(op_prod);
+  v->ops->nvdiv               = GUARDED(op_div);
+  v->ops->nvscale             = GUARDED(op_scale);
+  v->ops->nvabs               = GUARDED(op_abs);
+  v->ops->nvinv               = GUARDED(op_inv);
+  v->ops->nvaddconst          = GUARDED(op_addconst);
+  v->ops->nvdotprod           = GUARDED(op_dotprod);
+  v->ops->nvmaxnorm           = GUARDED(op_maxnorm);
+  v->ops->nvwrmsnorm          = GUARDED(op_wrmsnorm);
+  v->ops->nvwl2norm           = GUARDED(op_wl2norm);
+  v->ops->nvmin               = GUARDED(op_min);
+  v->ops->nvl1norm            = GUARDED(op_l1norm);
+  v->ops->nvlinearcombination = GUARDED(op_linearcombination);
   v->ops->nvprint             = op_print;
 }
 
@@ -1318,8 +1349,15 @@ N_Vector N_VNew_B200(b200_ctx* ctx, sunindextype local_length, sunindextype glob
   {
     int rank = 0, nranks = 1;
     b200_comm_rank(ctx, &rank, &nranks);
-    if (nranks <= 1) DEV(b200_mapped_alloc(ctx, kSlots, &sh->wrms_host, &sh->wrms_slots));
-    else DEV(b200_malloc(ctx, kSlots, &sh->wrms_slots));
+    const int rc = (nranks <= 1) ? b200_mapped_alloc(ctx, kSlots, &sh->wrms_host, &sh->wrms_slots)
+                                 : b200_malloc(ctx, kSlots, &sh->wrms_slots);
+    if (rc)
+    {
+      fprintf(stderr, "N_VNew_B200: %s\n", b200_last_error());
+      delete sh;
+      N_VFreeEmpty(v);
+      return nullptr;
+    }
   }
   Content* c    = new Content();
   c->sh         = sh;
@@ -1333,40 +1371,59 @@ N_Vector N_VNew_B200(b200_ctx* ctx, sunindextype local_length, sunindextype glob
 b200_ctx* N_VGetContext_B200(N_Vector v) { return C(v)->sh->ctx; }
 sunindextype N_VGetLocalLength_B200(N_Vector v) { return C(v)->sh->nloc; }
 
-const double* N_VGetDeviceArrayPointer_B200(N_Vector v) { return mat(v); }
+// (the accessors return NULL / non-zero after a device failure -- see die())
+const double* N_VGetDeviceArrayPointer_B200(N_Vector v)
+{
+  if (g_failed) return nullptr;
+  try { return mat(v); }
+  catch (const DeviceFailure&) { return nullptr; }
+}
 
 double* N_VGetDeviceArrayPointerForWrite_B200(N_Vector v)
 {
-  Content* c = C(v);
-  Value* out = value_new(c->sh, true);
-  assign(c, out);
-  return out->d;
+  if (g_failed) return nullptr;
+  try
+  {
+    Content* c = C(v);
+    Value* out = value_new(c->sh, true);
+    assign(c, out);
+    return out->d;
+  }
+  catch (const DeviceFailure&) { return nullptr; }
 }
 
 int N_VCopyFromHost_B200(N_Vector v, const double* host)
 {
   double* d = N_VGetDeviceArrayPointerForWrite_B200(v);
+  if (!d) return -1;
   return b200_h2d(C(v)->sh->ctx, d, host, C(v)->sh->nloc);
 }
 
 int N_VCopyToHost_B200(N_Vector v, double* host)
 {
-  const double* d = mat(v);
+  const double* d = N_VGetDeviceArrayPointer_B200(v);
+  if (!d) return -1;
   return b200_d2h(C(v)->sh->ctx, host, d, C(v)->sh->nloc);
 }
+int N_VDeviceFailed_B200(void) { return g_failed ? 1 : 0; }
 
 int N_VSetDeferredRhs_B200(N_Vector f, const B200RhsOp* op, N_Vector y)
 {
   Content* fc = C(f);
   Content* yc = C(y);
   if (fc->sh != yc->sh && fc->sh->nloc != yc->sh->nloc) return -1;
-  sync_from_host(yc);
-  Value* L = value_new(fc->sh, false);
-  L->op    = op;
-  L->src   = yc->val;
-  yc->val->refs++;
-  assign(fc, L);
-  if (!g_lazy) materialise(fc->sh, L);
+  if (g_failed) return -1;
+  try
+  {
+    sync_from_host(yc);
+    Value* L = value_new(fc->sh, false);
+    L->op    = op;
+    L->src   = yc->val;
+    yc->val->refs++;
+    assign(fc, L);
+    if (!g_lazy) materialise(fc->sh, L);
+  }
+  catch (const DeviceFailure&) { return -1; }
   return 0;
 }
 

@@ -93,6 +93,11 @@ SUNDIALS_EXPORT b200_ctx* N_VGetContext_B200(N_Vector v);
 SUNDIALS_EXPORT sunindextype N_VGetLocalLength_B200(N_Vector v);
 
 /* Read access to the (materialised) device data. */
+/* 1 once a device operation behind any vector of this process has failed.  The failure is printed once; from then on
+   every vector operation returns immediately (fused operations SUN_ERR_EXT_FAIL, which LSRKStep maps to
+   ARK_VECTOROP_ERR; reductions NaN; accessors NULL / -1), so the integrator comes back with an error code instead of
+   the process being aborted.  There is no host fallback. */
+SUNDIALS_EXPORT int N_VDeviceFailed_B200(void);
 SUNDIALS_EXPORT const double* N_VGetDeviceArrayPointer_B200(N_Vector v);
 /* Give v a fresh, writable device buffer (previous value is dropped, not copied). */
 SUNDIALS_EXPORT double* N_VGetDeviceArrayPointerForWrite_B200(N_Vector v);

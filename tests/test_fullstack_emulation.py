@@ -375,3 +375,40 @@ def test_adr_fixture_parity_through_the_emulated_stack(emu, name):
         assert st["lsrk_max_stages"] == meta["stats"]["lsrk.max_stages"]
     assert st["fused_launches"] > 0
     assert np.array_equal(fmt15(y), fmt15(ref))
+
+
+FAILURE_SCRIPT = r"""
+import ctypes, importlib, os, sys
+sys.path.insert(0, {root!r})
+b200 = importlib.import_module("ceda-demonstrations_b200")
+lib = ctypes.CDLL({emu!r})
+lib.b200_last_error.restype = ctypes.c_char_p
+lib.b200_launch_count.restype = ctypes.c_uint64
+b200._kernel_lib = b200._sundials_lib = lib
+prob = b200.Diffusion2D({args!r}, device=0, stream=None)
+try:
+    prob.evolve(0.05)
+    print("EVOLVE-RETURNED-OK")
+except RuntimeError as exc:
+    print("EVOLVE-ERROR", exc)
+print("FAILED-FLAG", lib.N_VDeviceFailed_B200())
+prob.close()
+print("CLOSED")
+"""
+
+
+@pytest.mark.parametrize("args", [["--nx", "128", "--ny", "32", "--integrator", "rkc", "--tf", "0.05"],
+                                  ["--nx", "64", "--ny", "32", "--integrator", "dirk", "--order", "3", "--tf", "0.05"]],
+                         ids=["rkc", "dirk_pcg"])
+def test_a_device_failure_comes_back_as_an_error_code_not_an_abort(emu, args):
+    """A failing launch in the middle of an integration (fault injection: B200_FAIL_AFTER_LAUNCHES) is printed once,
+    turns into SUN_ERR_EXT_FAIL / NaN at the ops table, ARKodeEvolve returns an error, the session can be closed, the
+    process lives -- and nothing is computed on the host instead."""
+    import sys
+
+    code = FAILURE_SCRIPT.format(root=ROOT, emu=EMU_LIB, args=args + ["--nout", "1", "--output", "0"])
+    env = dict(os.environ, B200_FAIL_AFTER_LAUNCHES="60")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, (r.returncode, r.stdout[-2000:], r.stderr[-2000:])
+    assert "EVOLVE-ERROR" in r.stdout and "FAILED-FLAG 1" in r.stdout and "CLOSED" in r.stdout, r.stdout
+    assert "injected failure" in r.stderr and r.stderr.count("nvector_b200: FATAL") == 1, r.stderr[-2000:]
