@@ -3,7 +3,10 @@
 the reference's evaluation matrix, diffusion_2D/runtests-diffusion2d.py) and report, row by row, whether Steps / Fails /
 FEvals agree, the two accuracies and run times.  Writes the joined table as CSV.
 
-    python scripts/compare_sweep.py reference.csv b200.csv joined.csv
+    python scripts/compare_sweep.py reference.csv b200.csv joined.csv [arm-of-first-file arm-of-second-file]
+
+(arms default to reference / b200; "reference reference" joins two reference runs, e.g. 1 rank against 4 ranks: the
+reference's own spread under a different summation order)
 """
 import csv
 import sys
@@ -23,7 +26,8 @@ def num(v):
 
 
 def main():
-    ref, b2 = load(sys.argv[1], "reference"), load(sys.argv[2], "b200")
+    arm1, arm2 = (sys.argv[4], sys.argv[5]) if len(sys.argv) > 5 else ("reference", "b200")
+    ref, b2 = load(sys.argv[1], arm1), load(sys.argv[2], arm2)
     rows, equal, both_ok, close = [], 0, 0, 0
     for k in sorted(ref):
         if k not in b2:

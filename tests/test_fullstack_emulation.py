@@ -64,6 +64,8 @@ def check_stats(meta, st, implicit):
             continue
         v4 = np4.get(k, v)
         d = abs(v4 - v)
+        if d:  # (Krylov iteration counts move with the summation order of the dot products: never less than 0.1 % slack)
+            d = max(d, int(np.ceil(1e-3 * max(v, v4))))
         assert min(v, v4) - d <= st[STAT_MAP[k]] <= max(v, v4) + d, (k, st[STAT_MAP[k]], v, v4)
 
 
