@@ -978,6 +978,7 @@ static int current_device()
   return (d >= 0 && d < kMaxDevices) ? d : 0;
 }
 
+static bool g_chain_preload_only = false;
 template <int K, int PF, bool HALO, bool FMA, bool UNI, bool HEAD>
 static int launch_chain_k(const ChainArgs& a, dim3 grid, cudaStream_t st)
 {
@@ -988,6 +989,13 @@ static int launch_chain_k(const ChainArgs& a, dim3 grid, cudaStream_t st)
   {
     CU_TRY(cudaFuncSetAttribute(k_chain_march<K, PF, HALO, FMA, UNI, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
+  }
+  if (g_chain_preload_only)
+  { // b200_stencil_chain_preload: make the driver load this instantiation now (lazy module loading would do it at
+    // the first launch, milliseconds into somebody's time step), launch nothing
+    cudaFuncAttributes fa;
+    CU_TRY(cudaFuncGetAttributes(&fa, k_chain_march<K, PF, HALO, FMA, UNI, HEAD>));
+    return 0;
   }
   klaunch((k_chain_march<K, PF, HALO, FMA, UNI, HEAD>), grid, kChainThreads, smem, st, a);
   return 0;
@@ -1191,6 +1199,39 @@ static int stencil_chain_common(b200_ctx* c, const b200_stencil_geom* g, int nst
     ALG_BYTES(touches, a.nx * a.ny);
   }
   return 0;
+}
+
+// Load every k_chain_march instantiation a session with these properties can reach -- depths 2..B200_MAX_CHAIN, with
+// and without the stage-1 head -- and opt it into its shared memory.  With CUDA's lazy module loading a kernel is
+// loaded at its first launch (several milliseconds); an adaptive run changes its stage count, hence the depth of the
+// last chain of a step, at any time, and would pay that inside some time step.
+extern "C" int b200_stencil_chain_preload(b200_ctx* c, int halo, int uniform)
+{
+  CU_TRY(cudaSetDevice(c->device));
+  static const double dummy = 0.0;
+  int rc = 0;
+  g_chain_preload_only = true;
+  for (int head = 0; head < 2 && !rc; head++)
+    for (int k = 2; k <= B200_MAX_CHAIN && !rc; k++)
+    {
+      ChainArgs a;
+      memset(&a, 0, sizeof(a));
+      a.rows = 128;
+      a.head = head;
+      a.hx   = halo ? &dummy : nullptr;
+      const bool uni = uniform && g_chain_uniform;
+      const dim3 grid(1, 1);
+      switch (k)
+      {
+      case 2: rc = launch_chain<2, 4>(a, grid, c->stream, uni); break;
+      case 3: rc = launch_chain<3, 4>(a, grid, c->stream, uni); break;
+      case 4: rc = launch_chain<4, 3>(a, grid, c->stream, uni); break;
+      case 5: rc = launch_chain<5, 3>(a, grid, c->stream, uni); break;
+      default: rc = launch_chain<6, 3>(a, grid, c->stream, uni); break;
+      }
+    }
+  g_chain_preload_only = false;
+  return rc;
 }
 
 // The chain that BEGINS a step: stage 1 is z_1 = x + c1 L(x) (x = y_n; coeffs[0] = c1, coeffs[1..4] unused) and

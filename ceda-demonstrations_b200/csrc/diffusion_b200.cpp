@@ -886,6 +886,15 @@ extern "C" int b200_d2d_create(int argc, const char* const* argv, int rank, int 
     }
     p->settings_held = true;
   }
+  // (after the arithmetic is settled) load every chain-kernel instantiation this session can reach: lazy module
+  // loading would otherwise cost milliseconds inside whichever time step first meets a new chain depth
+  if (p->ud.rhs_op.chain && !p->uo.no_fusion &&
+      b200_stencil_chain_preload(p->ctx, p->ud.rhs_op.halo_doubles > 0 ? 1 : 0, p->ud.uniform_coeffs ? 1 : 0))
+  {
+    fprintf(stderr, "b200 diffusion_2D: %s\n", b200_last_error());
+    b200_d2d_destroy(p);
+    return -1;
+  }
   if (p->uo.rows_per_block > 0) b200_set_rows_per_block(p->uo.rows_per_block);
   if (SUNContext_Create(SUN_COMM_NULL, &p->sunctx)) { b200_d2d_destroy(p); return -1; }
   if (configure(p)) { b200_d2d_destroy(p); return -1; }

@@ -237,6 +237,10 @@ int b200_stencil_chain_halo(b200_ctx* ctx, const b200_stencil_geom* g, int nstag
 int b200_stencil_chain_head(b200_ctx* ctx, const b200_stencil_geom* g, int nstages, const double* x,
                             const double* coeffs, double* const* z_out, double* f_out,
                             const double* halo_x, int halo_rows, int halo_cols);
+/* Load (and opt into their shared memory) all instantiations of the chain kernel a problem with these properties can
+   reach: depths 2..B200_MAX_CHAIN, with and without the stage-1 head, for the current arithmetic (b200_set_contract).
+   CUDA loads kernels lazily at their first launch; an adaptive run may meet a new depth in any step. */
+int b200_stencil_chain_preload(b200_ctx* ctx, int halo, int uniform);
 /* Deep halo of one nx*ny field, `rows` deep in y and `cols` deep in x, corners included:
      [ S: rows x nx | N: rows x nx | W: (ny+2 rows) x cols | E: (ny+2 rows) x cols ]
    S = rows -rows..-1, N = rows ny..ny+rows-1, W / E = columns -cols..-1 / nx..nx+cols-1

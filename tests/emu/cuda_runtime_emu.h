@@ -62,6 +62,8 @@ template <class T> static inline cudaError_t cudaHostGetDevicePointer(T** d, voi
 static inline cudaError_t cudaMemset(void* p, int v, size_t n) { memset(p, v, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memmove(d, s, n); return cudaSuccess; }
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
+struct cudaFuncAttributes { int numRegs; };
+template <class F> static inline cudaError_t cudaFuncGetAttributes(cudaFuncAttributes* a, F) { a->numRegs = 0; return cudaSuccess; }
 
 // ---- NCCL: types only.  The library binds NCCL with dlopen at first use (nccl_load), so a multi-rank call in the
 // emulated build fails there with a clear message; the single-rank paths never touch it.
