@@ -19,7 +19,7 @@ BIN    := $(PKG)/bin
 SUNOUT := $(PKG)/_sundials
 NVCC   ?= nvcc
 CXX    ?= g++
-NVFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC
+NVFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -static-global-template-stub=false -diag-suppress 20279
 CXXFLAGS := -O2 -std=c++17 -fPIC -Wall -Wno-unused-function
 SUNINC := -I$(SUNOUT)/include -I$(SUN)/include
 
@@ -38,9 +38,15 @@ sundials:
 product: $(LIB)/libb200sts.so
 endif
 
-$(LIB)/libb200sts.so: $(SRC)/b200_kernels.cu $(wildcard $(SRC)/*.cuh) include/b200_sts.h
+# The chain kernel's ~100 instantiations are compiled one depth per translation unit, in parallel (csrc/chain_march_inst.cuh)
+OBJ := build/obj
+CHAIN_OBJS := $(patsubst $(SRC)/%.cu,$(OBJ)/%.o,$(wildcard $(SRC)/chain_inst_*.cu))
+$(OBJ)/%.o: $(SRC)/%.cu $(wildcard $(SRC)/*.cuh) include/b200_sts.h
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -Iinclude -I$(SRC) -c $< -o $@
+$(LIB)/libb200sts.so: $(OBJ)/b200_kernels.o $(CHAIN_OBJS)
 	@mkdir -p $(LIB)
-	$(NVCC) $(NVFLAGS) -shared -Iinclude $< -o $@ -ldl
+	$(NVCC) $(NVFLAGS) -shared $^ -o $@ -ldl
 
 HOST_SRC := $(SRC)/nvector_b200.cpp $(SRC)/diffusion_b200.cpp $(SRC)/adr_b200.cpp $(SRC)/blockdiag_b200.cpp
 $(LIB)/libb200sts_sundials.so: $(HOST_SRC) include/nvector_b200.h include/b200_diffusion2d.h include/b200_adr2d.h include/b200_callbacks.h include/b200_blockdiag.h include/b200_sts.h $(LIB)/libb200sts.so

@@ -965,7 +965,15 @@ extern "C" int b200_stencil_dq(b200_ctx* c, const b200_stencil_geom* g, const do
 }
 
 // ------------------------------------------- temporally blocked STS stages
-#include "chain_march.cuh"
+#include "chain_march_inst.cuh"
+#ifndef B200_HOST_EMU // (the emulated build is one translation unit: it instantiates the kernels implicitly)
+B200_CHAIN_K2(B200_CHAIN_DECLARE)
+B200_CHAIN_K3(B200_CHAIN_DECLARE)
+B200_CHAIN_K4(B200_CHAIN_DECLARE)
+B200_CHAIN_K4S(B200_CHAIN_DECLARE)
+B200_CHAIN_K5(B200_CHAIN_DECLARE)
+B200_CHAIN_K6(B200_CHAIN_DECLARE)
+#endif
 #include "chain_quad.cuh"
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute of a kernel: remember what was configured per
@@ -979,26 +987,53 @@ static int current_device()
 }
 
 static bool g_chain_preload_only = false;
-template <int K, int PF, bool HALO, bool FMA, bool UNI, bool HEAD>
-static int launch_chain_k(const ChainArgs& a, dim3 grid, cudaStream_t st)
+// SPLIT flavour of k_chain_march (chain_march.cuh): the upper half of the levels one row late, computed first -- two
+// independent instruction streams per row step.  Instantiated for the depth(s) listed in chain_split_available (each one costs 8 more instantiations to compile).
+static int g_chain_split = -1; // -1: not decided yet (B200_CHAIN_SPLIT, else the default below)
+static const int kChainSplitDefault = 0;
+extern "C" int b200_set_chain_split(int on)
 {
-  const size_t smem = chain_march_smem(K, PF, a.rows);
+  g_chain_split = on ? 1 : 0;
+  return 0;
+}
+extern "C" int b200_get_chain_split(void)
+{
+  if (g_chain_split < 0)
+  {
+    const char* e = getenv("B200_CHAIN_SPLIT");
+    g_chain_split = e ? (atoi(e) != 0) : kChainSplitDefault;
+  }
+  return g_chain_split;
+}
+template <int K, bool FMA> constexpr bool chain_split_available() { return !FMA && K == 4; }
+
+template <int K, int PF, bool HALO, bool FMA, bool UNI, bool HEAD, bool SPLIT>
+static int launch_chain_s(const ChainArgs& a, dim3 grid, cudaStream_t st)
+{
+  const size_t smem = chain_march_smem(K, PF, a.rows, SPLIT);
   static size_t configured_on[kMaxDevices] = {};
   size_t& configured = configured_on[current_device()];
   if (smem > configured)
   {
-    CU_TRY(cudaFuncSetAttribute(k_chain_march<K, PF, HALO, FMA, UNI, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_TRY(cudaFuncSetAttribute(k_chain_march<K, PF, HALO, FMA, UNI, HEAD, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   if (g_chain_preload_only)
   { // b200_stencil_chain_preload: make the driver load this instantiation now (lazy module loading would do it at
     // the first launch, milliseconds into somebody's time step), launch nothing
     cudaFuncAttributes fa;
-    CU_TRY(cudaFuncGetAttributes(&fa, k_chain_march<K, PF, HALO, FMA, UNI, HEAD>));
+    CU_TRY(cudaFuncGetAttributes(&fa, k_chain_march<K, PF, HALO, FMA, UNI, HEAD, SPLIT>));
     return 0;
   }
-  klaunch((k_chain_march<K, PF, HALO, FMA, UNI, HEAD>), grid, kChainThreads, smem, st, a);
+  klaunch((k_chain_march<K, PF, HALO, FMA, UNI, HEAD, SPLIT>), grid, kChainThreads, smem, st, a);
   return 0;
+}
+template <int K, int PF, bool HALO, bool FMA, bool UNI, bool HEAD>
+static int launch_chain_k(const ChainArgs& a, dim3 grid, cudaStream_t st)
+{
+  if constexpr (chain_split_available<K, FMA>())
+    if (b200_get_chain_split()) return launch_chain_s<K, PF, HALO, FMA, UNI, HEAD, true>(a, grid, st);
+  return launch_chain_s<K, PF, HALO, FMA, UNI, HEAD, false>(a, grid, st);
 }
 
 // 0: two roundings per multiply-add, bit-identical to the reference's baseline x86-64 build (default);

@@ -77,6 +77,20 @@ __device__ __forceinline__ const double* row_ptr(const double* field, const doub
 // by 3 with the 3-row register windows addressed by a compile-time phase (no rotation moves),
 // carries no row-range predicates, and uses running offsets instead of index multiplies; the
 // 2(K-1) warm-up rows and the K-1 drain rows run through the same body with CHECK = true.
+// SPLIT flavour (round 2).  In the plain order level l + 1 consumes, as its newest row, what level l produced a moment
+// ago in the SAME row step: the K levels of a step form one dependent chain of ~10 FP64 operations each, and with four
+// warps per SM sub-partition the FP64 pipe (the busiest unit at the sustained clock) runs out of independent work
+// whenever a warp or two are in their load / store phases.  SPLIT gives the upper half of the levels (H+1..K,
+// H = ceil(K/2)) ONE extra row of lag and computes it FIRST in a row step, from the windows of levels H-1 and H as the
+// PREVIOUS step left them: the two halves of a step are independent instruction streams (twice the ILP), the 3-row
+// register windows still hold every row that is needed (the newest rows of levels H-1, H are simply read one step
+// later), every cell is still produced by the same instruction sequence -> the same bits.  Costs one more yn / fn ring
+// row and one more row step per block.  chain_lag(l) = rows level l lags behind level 1.
+template <int K, bool SPLIT>
+__host__ __device__ constexpr int chain_half() { return SPLIT ? (K + 1) / 2 : K; }
+template <int K, bool SPLIT>
+__host__ __device__ constexpr int chain_lag(int l) { return (l - 1) + ((SPLIT && l > chain_half<K, SPLIT>()) ? 1 : 0); }
+
 struct ChainState
 {
   int64_t soff;      // r1*nx + ic (unwrapped; valid whenever a store can happen)
@@ -94,11 +108,11 @@ struct ChainState
 // (rows 0 and ny: wrap-around, or field <-> S/N halo)
 // HEAD flavour (the chain starts with stage 1 of the step, z_1 = y_n + c L(y_n)): only x (= y_n) is streamed -- there is
 // no z_{-1}, and f_n = L(y_n) is produced by level 1 of this very launch, which writes it into the fn ring itself.
-template <int K, int PF, bool HALO, bool HEAD>
+template <int K, int PF, bool HALO, bool HEAD, bool SPLIT>
 __device__ __forceinline__ void chain_issue(const ChainArgs& a, ChainState& st, double2* rx, double2* rp,
                                             double2* ry, double2* rf, int64_t nx, int ny, bool issue)
 {
-  constexpr int DX = PF + 1, DY = PF + K;
+  constexpr int DX = PF + 1, DY = PF + K + (SPLIT ? 1 : 0);
   if (issue)
   {
     cp_async16(rx + st.sx_issue * kChainThreads, st.px);
@@ -125,100 +139,136 @@ __device__ __forceinline__ void chain_issue(const ChainArgs& a, ChainState& st, 
   else st.px += st.pstep;
 }
 
-template <int K, int PF, int PH, bool CHECK, bool HALO, bool FMA, bool UNI, bool HEAD>
+// one level of one row step (l = 1..K); BEFORE: the window of level l-1 has not been updated in this row step yet
+// (SPLIT: level H+1 reads level H's rows one step late), so its three rows sit one slot further round
+template <int K, int PF, int PH, int L, bool CHECK, bool HALO, bool FMA, bool UNI, bool HEAD, bool SPLIT>
+__device__ __forceinline__ void chain_level(const ChainArgs& a, const ChainState& st, double2 (&W)[K][3], double2 P,
+                                            double2* ry, double2* rf, const double2* ytab, const double* stab,
+                                            int64_t nx, double2 cw, double2 ce, double sx0, double sx1,
+                                            unsigned smask, int r1, int j0, int j1)
+{
+  constexpr int DY = PF + K + (SPLIT ? 1 : 0);
+  constexpr int IO = PH % 3, IM = (PH + 1) % 3, IC = (PH + 2) % 3; // oldest (overwritten), then um, uc ; up = IO
+  constexpr int H   = chain_half<K, SPLIT>();
+  constexpr int LAG = chain_lag<K, SPLIT>(L);
+  constexpr bool BEFORE  = SPLIT && (L == H + 1);                 // level L-1 is updated AFTER this level in a row step
+  constexpr bool P2_LATE = SPLIT && (L == H + 1 || L == H + 2);   // level L-2 likewise
+  // UNI: the coefficients are kernel parameters (constant bank): no table loads, and the centre
+  // coefficient -((Dxw+Dxe)+(Dys+Dyn)) is one number for the whole field
+  const double2 dy = UNI ? make_double2(a.u_cys, a.u_cyn) : ytab[st.trow - LAG]; // (Dy_s, Dy_n) of row r1-LAG
+  const double sy  = UNI ? 0.0 : stab[st.trow - LAG]; // Dy_s + Dy_n, summed once per block when the table is filled
+  const double2 um = W[L - 1][BEFORE ? IO : IM], uc = W[L - 1][BEFORE ? IM : IC], up = W[L - 1][BEFORE ? IC : IO];
+  const double uw0 = __shfl_up_sync(0xffffffffu, uc.y, 1);
+  const double ue1 = __shfl_down_sync(0xffffffffu, uc.x, 1);
+  // diffusion.cpp:48-53, same association as k_stage_march
+  double L0 = DMUL(UNI ? a.u_ndc : -DADD(sx0, sy), uc.x);
+  double L1 = DMUL(UNI ? a.u_ndc : -DADD(sx1, sy), uc.y);
+  L0 = mad<FMA>(cw.x, uw0, L0);  L1 = mad<FMA>(cw.y, uc.x, L1);
+  L0 = mad<FMA>(ce.x, uc.y, L0); L1 = mad<FMA>(ce.y, ue1, L1);
+  L0 = mad<FMA>(dy.x, um.x, L0); L1 = mad<FMA>(dy.x, um.y, L1);
+  L0 = mad<FMA>(dy.y, up.x, L0); L1 = mad<FMA>(dy.y, up.y, L1);
+  // The reference's "f = 0; f += ..." (k_stage_march: DADD(0.0, L)) is dropped here: 0 + L differs from L only
+  // for L = -0.0, and L is consumed by z = c0*L + ... below and never stored, so the only trace it could
+  // leave is the sign of an exactly-zero z (all five terms zero) -- equal as a number, and the FP64 pipe is
+  // what bounds this kernel.
+  // z_{l-2} at this row: prev2 for the first stage, else the row of level l-2's window that holds it
+  const double2 p2 = (L == 1) ? P : W[(L >= 2) ? L - 2 : 0][P2_LATE ? IO : IM];
+  int sl = st.sy_use - LAG; // yn / fn of row r1-LAG
+  if (sl < 0) sl += DY;
+  const double* cf = a.c[L - 1];
+  const int64_t so = st.soff - (int64_t)LAG * nx;
+  double2 z;
+  bool doit = (smask >> (L - 1)) & 1u;
+  if (CHECK)
+  {
+    const int rl = r1 - LAG;
+    doit         = doit && rl >= j0 && rl < j1;
+  }
+  if (HEAD && L == 1)
+  { // stage 1 of the step, z_1 = 1*y_n + (h mu~_1)*f_n (N_VLinearSum, arkode_lsrkstep.c:640 / :930), in the order of
+    // the one-stage kernel's PAT2(C,S): acc = 1*x ; acc += c*L -- and f_n = L(y_n) itself, with the reference's
+    // "f = 0; f += ..." (0 + L: a -0 becomes +0, and unlike further down this value is stored)
+    L0 = DADD(0.0, L0);
+    L1 = DADD(0.0, L1);
+    rf[sl * kChainThreads] = make_double2(L0, L1); // the later levels read f_n of the rows behind from this ring
+    z.x = mad<FMA>(cf[0], L0, DMUL(1.0, uc.x));
+    z.y = mad<FMA>(cf[0], L1, DMUL(1.0, uc.y));
+    bool dof = (smask >> K) & 1u; // store_ok of this lane
+    if (CHECK) dof = dof && r1 >= j0 && r1 < j1;
+    if (dof) *reinterpret_cast<double2*>(a.f_out + so) = make_double2(L0, L1);
+  }
+  else
+  {
+    const double2 yv = ry[sl * kChainThreads], fv = rf[sl * kChainThreads];
+    z.x = DMUL(cf[0], L0);               z.y = DMUL(cf[0], L1);
+    z.x = mad<FMA>(cf[1], p2.x, z.x);  z.y = mad<FMA>(cf[1], p2.y, z.y);
+    z.x = mad<FMA>(cf[2], yv.x, z.x);  z.y = mad<FMA>(cf[2], yv.y, z.y);
+    z.x = mad<FMA>(cf[3], uc.x, z.x);  z.y = mad<FMA>(cf[3], uc.y, z.y);
+    z.x = mad<FMA>(cf[4], fv.x, z.x);  z.y = mad<FMA>(cf[4], fv.y, z.y);
+  }
+  if (doit) *reinterpret_cast<double2*>(a.out[L - 1] + so) = z;
+  if (L < K) W[L < K ? L : 0][IO] = z; // newest row of level l replaces its oldest
+}
+
+template <int K, int PF, int PH, int LO, int HI, bool CHECK, bool HALO, bool FMA, bool UNI, bool HEAD, bool SPLIT>
+__device__ __forceinline__ void chain_levels(const ChainArgs& a, const ChainState& st, double2 (&W)[K][3], double2 P,
+                                             double2* ry, double2* rf, const double2* ytab, const double* stab,
+                                             int64_t nx, double2 cw, double2 ce, double sx0, double sx1,
+                                             unsigned smask, int r1, int j0, int j1)
+{
+  if constexpr (LO <= HI)
+  {
+    chain_level<K, PF, PH, LO, CHECK, HALO, FMA, UNI, HEAD, SPLIT>(a, st, W, P, ry, rf, ytab, stab, nx, cw, ce, sx0, sx1,
+                                                                   smask, r1, j0, j1);
+    chain_levels<K, PF, PH, LO + 1, HI, CHECK, HALO, FMA, UNI, HEAD, SPLIT>(a, st, W, P, ry, rf, ytab, stab, nx, cw, ce,
+                                                                            sx0, sx1, smask, r1, j0, j1);
+  }
+}
+
+template <int K, int PF, int PH, bool CHECK, bool HALO, bool FMA, bool UNI, bool HEAD, bool SPLIT>
 __device__ __forceinline__ void chain_row(const ChainArgs& a, ChainState& st, double2 (&W)[K][3],
                                           double2* rx, double2* rp, double2* ry, double2* rf,
                                           const double2* ytab, const double* stab, int64_t nx, int ny,
                                           double2 cw, double2 ce, double sx0, double sx1,
                                           unsigned smask, int r1, int j0, int j1, bool issue)
 {
-  constexpr int DX = PF + 1, DY = PF + K;
-  constexpr int IO = PH % 3, IM = (PH + 1) % 3, IC = (PH + 2) % 3; // oldest (overwritten), then um, uc ; up = IO
-  chain_issue<K, PF, HALO, HEAD>(a, st, rx, rp, ry, rf, nx, ny, issue); // group(r1 + PF)
+  constexpr int DX = PF + 1, DY = PF + K + (SPLIT ? 1 : 0);
+  constexpr int IO = PH % 3;
+  constexpr int H  = chain_half<K, SPLIT>();
+  chain_issue<K, PF, HALO, HEAD, SPLIT>(a, st, rx, rp, ry, rf, nx, ny, issue); // group(r1 + PF)
   cp_async_wait<PF>(); // all but the PF newest groups have landed: group(r1) is ready
 
-  W[0][IO]        = rx[st.sx_use * kChainThreads]; // x row r1+1 replaces the oldest row
-  const double2 P = HEAD ? make_double2(0.0, 0.0) : rp[st.sx_use * kChainThreads];
-  int64_t so      = st.soff;
-#pragma unroll
-  for (int l = 1; l <= K; l++)
-  {
-    // UNI: the coefficients are kernel parameters (constant bank): no table loads, and the centre
-    // coefficient -((Dxw+Dxe)+(Dys+Dyn)) is one number for the whole field
-    const double2 dy = UNI ? make_double2(a.u_cys, a.u_cyn) : ytab[st.trow - (l - 1)]; // (Dy_s, Dy_n) of row r1-(l-1)
-    const double sy  = UNI ? 0.0 : stab[st.trow - (l - 1)]; // Dy_s + Dy_n, summed once per block when the table is filled
-    const double2 um = W[l - 1][IM], uc = W[l - 1][IC], up = W[l - 1][IO];
-    const double uw0 = __shfl_up_sync(0xffffffffu, uc.y, 1);
-    const double ue1 = __shfl_down_sync(0xffffffffu, uc.x, 1);
-    // diffusion.cpp:48-53, same association as k_stage_march
-    double L0 = DMUL(UNI ? a.u_ndc : -DADD(sx0, sy), uc.x);
-    double L1 = DMUL(UNI ? a.u_ndc : -DADD(sx1, sy), uc.y);
-    L0 = mad<FMA>(cw.x, uw0, L0);  L1 = mad<FMA>(cw.y, uc.x, L1);
-    L0 = mad<FMA>(ce.x, uc.y, L0); L1 = mad<FMA>(ce.y, ue1, L1);
-    L0 = mad<FMA>(dy.x, um.x, L0); L1 = mad<FMA>(dy.x, um.y, L1);
-    L0 = mad<FMA>(dy.y, up.x, L0); L1 = mad<FMA>(dy.y, up.y, L1);
-    // The reference's "f = 0; f += ..." (k_stage_march: DADD(0.0, L)) is dropped here: 0 + L differs from L only
-    // for L = -0.0, and L is consumed by z = c0*L + ... below and never stored, so the only trace it could
-    // leave is the sign of an exactly-zero z (all five terms zero) -- equal as a number, and the FP64 pipe is
-    // what bounds this kernel.
-    // z_{l-2} at this row: prev2 for the first stage, else the oldest row of level l-2's window
-    const double2 p2 = (l == 1) ? P : W[(l >= 2) ? l - 2 : 0][IM];
-    int sl = st.sy_use - (l - 1); // yn / fn of row r1-(l-1)
-    if (sl < 0) sl += DY;
-    const double* cf = a.c[l - 1];
-    double2 z;
-    bool doit = (smask >> (l - 1)) & 1u;
-    if (CHECK)
-    {
-      const int rl = r1 - (l - 1);
-      doit         = doit && rl >= j0 && rl < j1;
-    }
-    if (HEAD && l == 1)
-    { // stage 1 of the step, z_1 = 1*y_n + (h mu~_1)*f_n (N_VLinearSum, arkode_lsrkstep.c:640 / :930), in the order of
-      // the one-stage kernel's PAT2(C,S): acc = 1*x ; acc += c*L -- and f_n = L(y_n) itself, with the reference's
-      // "f = 0; f += ..." (0 + L: a -0 becomes +0, and unlike further down this value is stored)
-      L0 = DADD(0.0, L0);
-      L1 = DADD(0.0, L1);
-      rf[sl * kChainThreads] = make_double2(L0, L1); // the later levels read f_n of the rows behind from this ring
-      z.x = mad<FMA>(cf[0], L0, DMUL(1.0, uc.x));
-      z.y = mad<FMA>(cf[0], L1, DMUL(1.0, uc.y));
-      bool dof = (smask >> K) & 1u; // store_ok of this lane
-      if (CHECK) dof = dof && r1 >= j0 && r1 < j1;
-      if (dof) *reinterpret_cast<double2*>(a.f_out + so) = make_double2(L0, L1);
-    }
-    else
-    {
-      const double2 yv = ry[sl * kChainThreads], fv = rf[sl * kChainThreads];
-      z.x = DMUL(cf[0], L0);               z.y = DMUL(cf[0], L1);
-      z.x = mad<FMA>(cf[1], p2.x, z.x);  z.y = mad<FMA>(cf[1], p2.y, z.y);
-      z.x = mad<FMA>(cf[2], yv.x, z.x);  z.y = mad<FMA>(cf[2], yv.y, z.y);
-      z.x = mad<FMA>(cf[3], uc.x, z.x);  z.y = mad<FMA>(cf[3], uc.y, z.y);
-      z.x = mad<FMA>(cf[4], fv.x, z.x);  z.y = mad<FMA>(cf[4], fv.y, z.y);
-    }
-    if (doit) *reinterpret_cast<double2*>(a.out[l - 1] + so) = z;
-    so -= nx;
-    if (l < K) W[l][IO] = z; // newest row of level l replaces its oldest
-  }
+  const double2 xnew = rx[st.sx_use * kChainThreads]; // x row r1+1
+  const double2 P    = HEAD ? make_double2(0.0, 0.0) : rp[st.sx_use * kChainThreads];
+  // SPLIT: the upper half first, from the windows as the previous row step left them ...
+  if constexpr (SPLIT)
+    chain_levels<K, PF, PH, H + 1, K, CHECK, HALO, FMA, UNI, HEAD, SPLIT>(a, st, W, P, ry, rf, ytab, stab, nx, cw, ce, sx0,
+                                                                         sx1, smask, r1, j0, j1);
+  W[0][IO] = xnew; // x row r1+1 replaces the oldest row
+  // ... then levels 1..H (all of them without SPLIT), each from the row the level below produced a moment ago
+  chain_levels<K, PF, PH, 1, H, CHECK, HALO, FMA, UNI, HEAD, SPLIT>(a, st, W, P, ry, rf, ytab, stab, nx, cw, ce, sx0, sx1,
+                                                                    smask, r1, j0, j1);
   st.soff += nx;
   st.trow += 1;
   st.sx_use = (st.sx_use + 1 == DX) ? 0 : st.sx_use + 1;
   st.sy_use = (st.sy_use + 1 == DY) ? 0 : st.sy_use + 1;
 }
 
-template <int K, int PF, bool HALO, bool FMA, bool UNI = false, bool HEAD = false>
+template <int K, int PF, bool HALO, bool FMA, bool UNI = false, bool HEAD = false, bool SPLIT = false>
 __global__ void __launch_bounds__(kChainThreads, 2) k_chain_march(const ChainArgs a)
 {
   constexpr int HL   = (K + 1) / 2;  // halo lanes per side (2 cells each): 2*HL >= K
   constexpr int WUSE = 64 - 4 * HL;  // cells a warp stores per row
   constexpr int DX   = PF + 1;       // ring depth of x and prev2
-  constexpr int DY   = PF + K;       // ring depth of yn and fn
+  constexpr int XL   = SPLIT ? 1 : 0; // extra row of lag of the upper half of the levels
+  constexpr int DY   = PF + K + XL;  // ring depth of yn and fn
   B200_DYN_SMEM(double2, ring);
   double2* rx   = ring + threadIdx.x;                                         // [DX][threads]
   double2* rp   = ring + (size_t)DX * kChainThreads + threadIdx.x;            // [DX][threads]
   double2* ry   = ring + (size_t)2 * DX * kChainThreads + threadIdx.x;        // [DY][threads]
   double2* rf   = ring + (size_t)(2 * DX + DY) * kChainThreads + threadIdx.x; // [DY][threads]
-  double2* ytab = ring + (size_t)(2 * DX + 2 * DY) * kChainThreads;           // [rows + 3(K-1) + 2]
-  double* stab  = reinterpret_cast<double*>(ytab + (a.rows + 3 * (K - 1) + 2)); // [rows + 3(K-1) + 2]
+  double2* ytab = ring + (size_t)(2 * DX + 2 * DY) * kChainThreads;           // [rows + 3(K-1) + 2 + 2 XL]
+  double* stab  = reinterpret_cast<double*>(ytab + (a.rows + 3 * (K - 1) + 2 + 2 * XL)); // [rows + 3(K-1) + 2 + 2 XL]
 
   const int lane   = threadIdx.x & 31;
   const int64_t nx = a.nx;
@@ -228,12 +278,12 @@ __global__ void __launch_bounds__(kChainThreads, 2) k_chain_march(const ChainArg
   if (j1 > ny) j1 = ny;
   const int rstart = j0 - (K - 1), rend = j1 + (K - 1); // level-1 rows [rstart, rend)
 #define WROW(r) ((r) < 0 ? (r) + ny : ((r) >= ny ? (r) - ny : (r)))
-  // y-direction face coefficients of rows rstart-(K-1) .. rend+1 (table index 0 = row rstart-(K-1))
+  // y-direction face coefficients of rows rstart-(K-1)-XL .. rend+1+XL (table index 0 = row rstart-(K-1)-XL)
   if (!UNI)
   {
-    for (int t = threadIdx.x; t < (rend - rstart) + (K - 1) + 2; t += kChainThreads)
+    for (int t = threadIdx.x; t < (rend - rstart) + (K - 1) + 2 + 2 * XL; t += kChainThreads)
     { // HALO: the tables are extended by the caller (global periodic index), negative rows are valid
-      const int rw = HALO ? (rstart - (K - 1) + t) : WROW(rstart - (K - 1) + t);
+      const int rw = HALO ? (rstart - (K - 1) - XL + t) : WROW(rstart - (K - 1) - XL + t);
       const double ds = a.cys[rw], dn = a.cyn[rw];
       ytab[t]         = make_double2(ds, dn);
       stab[t]         = DADD(ds, dn); // diffusion.cpp:48: (Dys + Dyn)
@@ -283,7 +333,7 @@ __global__ void __launch_bounds__(kChainThreads, 2) k_chain_march(const ChainArg
 
   st.soff     = (int64_t)rstart * nx + ic;
   st.sx_issue = st.sy_issue = st.sx_use = st.sy_use = 0;
-  st.trow     = K - 1;
+  st.trow     = K - 1 + XL;
   st.ir       = rstart;
   st.px = row_ptr<HALO>(a.x, a.hx, rstart + 1, st.we, st.lane_col, nx, ny, a.g, a.g2);
   st.py = row_ptr<HALO>(a.yn, a.hy, rstart, st.we, st.lane_col, nx, ny, a.g, a.g2);
@@ -303,16 +353,17 @@ __global__ void __launch_bounds__(kChainThreads, 2) k_chain_march(const ChainArg
 
   // prologue of the pipeline: groups rstart .. rstart+PF-1
 #pragma unroll
-  for (int q = 0; q < PF; q++) chain_issue<K, PF, HALO, HEAD>(a, st, rx, rp, ry, rf, nx, ny, true);
+  for (int q = 0; q < PF; q++) chain_issue<K, PF, HALO, HEAD, SPLIT>(a, st, rx, rp, ry, rf, nx, ny, true);
 
 #define ROW(PH, CHECK, R1) \
-  chain_row<K, PF, PH, CHECK, HALO, FMA, UNI, HEAD>(a, st, W, rx, rp, ry, rf, ytab, stab, nx, ny, cw, ce, sx0, sx1, smask, R1, j0, j1, (R1) + PF < rend)
+  chain_row<K, PF, PH, CHECK, HALO, FMA, UNI, HEAD, SPLIT>(a, st, W, rx, rp, ry, rf, ytab, stab, nx, ny, cw, ce, sx0, sx1, smask, R1, j0, j1, (R1) + PF < rend)
 
   // phases: [rstart, s0) checked warm-up in whole triples, [s0, s1) unchecked steady state in
   // triples, [s1, rend3) checked drain; rend3 rounds the trip count up to a multiple of 3 (the
-  // extra rows compute garbage that is never stored and load wrapped, in-range rows).
-  const int total3 = ((rend - rstart + 2) / 3) * 3;
-  int warm         = 2 * (K - 1);
+  // extra rows compute garbage that is never stored and load wrapped, in-range rows).  SPLIT: the last level lags
+  // one row more, so the loop runs one row step longer (nothing is loaded for it: `rend` still bounds the issue).
+  const int total3 = ((rend + XL - rstart + 2) / 3) * 3;
+  int warm         = 2 * (K - 1) + XL;
   warm             = ((warm + 2) / 3) * 3;
   int steady       = (j1 - (rstart + warm)) / 3 * 3;
   if (steady < 0) steady = 0;
@@ -346,10 +397,11 @@ __global__ void __launch_bounds__(kChainThreads, 2) k_chain_march(const ChainArg
 
 
 // ---- launch geometry (host side; shared by b200_kernels.cu and the emulation harness)
-static inline size_t chain_march_smem(int K, int PF, int rows)
+static inline size_t chain_march_smem(int K, int PF, int rows, bool split = false)
 {
-  return (size_t)(2 * (PF + 1) + 2 * (PF + K)) * kChainThreads * sizeof(double2) +
-         (size_t)(rows + 3 * (K - 1) + 2) * (sizeof(double2) + sizeof(double));
+  const int xl = split ? 1 : 0;
+  return (size_t)(2 * (PF + 1) + 2 * (PF + K + xl)) * kChainThreads * sizeof(double2) +
+         (size_t)(rows + 3 * (K - 1) + 2 + 2 * xl) * (sizeof(double2) + sizeof(double));
 }
 static inline int chain_march_pf(int K) { return K <= 3 ? 4 : 3; } // prefetch depth instantiated per K
 // rows may be raised so that grid.y fits 65535

@@ -74,6 +74,7 @@ struct Shared
   double* wrms_host;  // one rank: the slots live in mapped pinned host memory and are read after a stream sync
   int next_slot;
   long slot_owner[8]; // creation number of the value whose partial sum the slot holds (the ring is reused)
+  bool slot_unread[8]; // a launch was given this slot and nobody has read (= waited for) its result yet
   bool spec_sigs[96]; // fused-launch signatures whose result a matching WRMS norm followed
   // the next step's error weights, speculatively (see launch_fused): signatures of fused launches whose stencil input
   // ARKODE then asked the error weights of, and the tolerances of the most recent such request
@@ -157,7 +158,13 @@ const unsigned long long kArmed = 0x7ff8dead0000beefULL;
 int g_poll = -1;
 void arm_slot(Shared* sh, int slot)
 {
-  if (sh->wrms_host) *reinterpret_cast<volatile unsigned long long*>(sh->wrms_host + slot) = kArmed;
+  if (!sh->wrms_host) return;
+  // The launch that had this slot before may still be queued if its result was never asked for (a speculation that
+  // missed): it would overwrite the armed word with ITS sum and the poll would take that for the new result.  Every
+  // successful wait drains the stream up to its kernel, so this is rare; when it can happen, drain first.
+  if (sh->slot_unread[slot]) DEV(b200_ctx_sync(sh->ctx));
+  *reinterpret_cast<volatile unsigned long long*>(sh->wrms_host + slot) = kArmed;
+  sh->slot_unread[slot] = true;
 }
 double read_slot(Shared* sh, int slot)
 {
@@ -174,6 +181,7 @@ double read_slot(Shared* sh, int slot)
       {
         double r;
         memcpy(&r, &b, sizeof(r));
+        for (int k = 0; k < kSlots; k++) sh->slot_unread[k] = false; // (stream order: everything launched before it is done)
         if (prof)
         {
           timespec t1;
@@ -187,6 +195,7 @@ double read_slot(Shared* sh, int slot)
 #endif
     }
   DEV(b200_ctx_sync(sh->ctx));
+  for (int k = 0; k < kSlots; k++) sh->slot_unread[k] = false;
   return sh->wrms_host[slot];
 }
 
@@ -1341,6 +1350,7 @@ N_Vector N_VNew_B200(b200_ctx* ctx, sunindextype local_length, sunindextype glob
   sh->halo_doubles = 0;
   sh->next_slot  = 0;
   for (int k = 0; k < kSlots; k++) sh->slot_owner[k] = -1;
+  for (int k = 0; k < kSlots; k++) sh->slot_unread[k] = false;
   memset(sh->spec_sigs, 0, sizeof(sh->spec_sigs));
   memset(sh->spec_ewt_sigs, 0, sizeof(sh->spec_ewt_sigs));
   sh->ewt_seen = false;

@@ -292,6 +292,11 @@ int b200_set_chain_rows(int rows);
    variable B200_CHAIN_VARIANT sets the initial value. */
 int b200_set_chain_variant(int variant);
 int b200_get_chain_variant(void);
+/* SPLIT flavour of k_chain_march (depth 4, exact arithmetic): the upper half of the levels runs one row late and
+   first in a row step, so the two halves are independent instruction streams (more work in flight for the FP64 pipe);
+   bit-identical results.  B200_CHAIN_SPLIT sets the initial value. */
+int b200_set_chain_split(int on);
+int b200_get_chain_split(void);
 /* 1 (default): honour b200_stencil_geom.uniform; 0: always load the coefficient tables (A/B tests) */
 int b200_set_chain_uniform(int on);
 /* name of the kernel the most recent chain launch used ("k_chain_quad" / "k_chain_march", "" if none) */
