@@ -1089,16 +1089,16 @@ static int launch_quad(const ChainArgs& a, dim3 grid, cudaStream_t st)
 
 static int g_chain_rows = 0; // 0 = automatic (chain_rows_auto), else what b200_set_chain_rows asked for
 // Rows each block marches over: more rows = less redundant work (a block starts K-1 rows early and the
-// K-1 rows around it are recomputed: (rows + 2(K-1)) / rows) but fewer blocks.  128 rows where that still
-// leaves >= 4 waves of blocks (2 resident blocks on each SM), else 64, else 32.  Measured at 16384^2,
-// K = 4: 62.4 / 57.5 / 54.4 ms per step for 32 / 64 / 128 rows (profiles/r01_bench_chain_rows.log).
+// K-1 rows around it are recomputed: (rows + 2(K-1)) / rows) but fewer blocks.  256 rows where that still
+// leaves >= 4 waves of blocks (2 resident blocks on each SM), else 128, else 64, else 32.  Measured at 16384^2,
+// K = 4: 62.4 / 57.5 / 54.4 / 53.6 ms per step for 32 / 64 / 128 / 256 rows (profiles/r01_bench_chain_rows.log).
 static int chain_rows_auto(const b200_ctx* c, int64_t nx, int64_t ny, int nstages, bool quad)
 {
   const int use       = quad ? 128 - 4 * ((nstages + 1) / 2) : 64 - 4 * ((nstages + 1) / 2);
   const int wpb       = quad ? kQuadThreads / 32 : kChainThreads / 32;
   const int64_t gx    = ((nx + use - 1) / use + wpb - 1) / wpb;
   const int64_t waves = 4 * 2 * (int64_t)(c->sm_count > 0 ? c->sm_count : 148);
-  const int cand[3]   = {128, 64, 32};
+  const int cand[4]   = {256, 128, 64, 32};
   for (int r : cand)
     if (gx * ((ny + r - 1) / r) >= waves) return r;
   // Small grids: every block is resident at once and the launch takes as long as ONE block needs for its
@@ -1251,7 +1251,7 @@ extern "C" int b200_stencil_chain_preload(b200_ctx* c, int halo, int uniform)
     {
       ChainArgs a;
       memset(&a, 0, sizeof(a));
-      a.rows = 128;
+      a.rows = 256;
       a.head = head;
       a.hx   = halo ? &dummy : nullptr;
       const bool uni = uniform && g_chain_uniform;

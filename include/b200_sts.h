@@ -282,8 +282,9 @@ int b200_peer_halo_stats(const b200_peer_halo* ph, uint64_t* exchanges, uint64_t
    dot_result != NULL also returns sum_i z_i v_i (PCG's <Ap, p>, sunlinsol_pcg.c:519). */
 int b200_stencil_dq(b200_ctx* ctx, const b200_stencil_geom* g, const double* v, const double* y, const double* fy,
                     double sigma, double siginv, int outer, double ca, double cb, double* z, double* dot_result);
-/* rows of output each thread block of the chain kernel marches over; 0 (default) = automatic: 128
-   where that leaves at least 4 waves of blocks, else 64, else 32.  Results do not depend on it. */
+/* rows of output each thread block of the chain kernel marches over; 0 (default) = automatic: 256
+   where that leaves at least 4 waves of blocks, else 128, else 64, else 32 (8 or 16 on grids so small that every
+   block is resident at once).  Results do not depend on it. */
 int b200_set_chain_rows(int rows);
 /* Which kernel runs a chain: 0 (default) = k_chain_march, two cells per thread; 1 = k_chain_quad,
    four cells per thread (two 64-cell halves per warp window, 120 of 128 cells useful at depth 4).
