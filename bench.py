@@ -782,6 +782,9 @@ def main():
         "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
         "clocks": sampler.summary(),
         "stage_chain_depth": depth,
+        "operand_ring": ("cp.async.bulk + mbarrier (one 512-byte copy per warp, operand and row)"
+                         if b200.kernel_lib().b200_get_chain_bulk() and args.arith == "exact" and depth == 4.0
+                         else "cp.async (16 bytes per thread, operand and row)"),
     }
     if per_rank is not None:
         line["per_rank"] = per_rank

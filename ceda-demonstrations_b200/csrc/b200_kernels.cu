@@ -971,6 +971,7 @@ B200_CHAIN_K2(B200_CHAIN_DECLARE)
 B200_CHAIN_K3(B200_CHAIN_DECLARE)
 B200_CHAIN_K4(B200_CHAIN_DECLARE)
 B200_CHAIN_K4S(B200_CHAIN_DECLARE)
+B200_CHAIN_K4B(B200_CHAIN_DECLARE_BULK)
 B200_CHAIN_K5(B200_CHAIN_DECLARE)
 B200_CHAIN_K6(B200_CHAIN_DECLARE)
 #endif
@@ -1007,30 +1008,52 @@ extern "C" int b200_get_chain_split(void)
 }
 template <int K, bool FMA> constexpr bool chain_split_available() { return !FMA && K == 4; }
 
-template <int K, int PF, bool HALO, bool FMA, bool UNI, bool HEAD, bool SPLIT>
+// BULK flavour of k_chain_march (chain_march.cuh): the operand ring is filled by cp.async.bulk (one 512-byte copy per
+// warp, operand and row, issued by one lane, completed on an mbarrier) instead of one 16-byte cp.async per thread.
+static int g_chain_bulk = -1; // -1: not decided yet (B200_CHAIN_BULK, else the default below)
+static const int kChainBulkDefault = 0;
+extern "C" int b200_set_chain_bulk(int on)
+{ // < 0: back to the initial value (B200_CHAIN_BULK, else the default)
+  g_chain_bulk = on < 0 ? -1 : (on ? 1 : 0);
+  return 0;
+}
+extern "C" int b200_get_chain_bulk(void)
+{
+  if (g_chain_bulk < 0)
+  {
+    const char* e = getenv("B200_CHAIN_BULK");
+    g_chain_bulk  = e ? (atoi(e) != 0) : kChainBulkDefault;
+  }
+  return g_chain_bulk;
+}
+template <int K, bool FMA> constexpr bool chain_bulk_available() { return !FMA && K == 4; }
+
+template <int K, int PF, bool HALO, bool FMA, bool UNI, bool HEAD, bool SPLIT, bool BULK = false>
 static int launch_chain_s(const ChainArgs& a, dim3 grid, cudaStream_t st)
 {
-  const size_t smem = chain_march_smem(K, PF, a.rows, SPLIT);
+  const size_t smem = chain_march_smem(K, PF, a.rows, SPLIT, BULK);
   static size_t configured_on[kMaxDevices] = {};
   size_t& configured = configured_on[current_device()];
   if (smem > configured)
   {
-    CU_TRY(cudaFuncSetAttribute(k_chain_march<K, PF, HALO, FMA, UNI, HEAD, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_TRY(cudaFuncSetAttribute(k_chain_march<K, PF, HALO, FMA, UNI, HEAD, SPLIT, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   if (g_chain_preload_only)
   { // b200_stencil_chain_preload: make the driver load this instantiation now (lazy module loading would do it at
     // the first launch, milliseconds into somebody's time step), launch nothing
     cudaFuncAttributes fa;
-    CU_TRY(cudaFuncGetAttributes(&fa, k_chain_march<K, PF, HALO, FMA, UNI, HEAD, SPLIT>));
+    CU_TRY(cudaFuncGetAttributes(&fa, k_chain_march<K, PF, HALO, FMA, UNI, HEAD, SPLIT, BULK>));
     return 0;
   }
-  klaunch((k_chain_march<K, PF, HALO, FMA, UNI, HEAD, SPLIT>), grid, kChainThreads, smem, st, a);
+  klaunch((k_chain_march<K, PF, HALO, FMA, UNI, HEAD, SPLIT, BULK>), grid, kChainThreads, smem, st, a);
   return 0;
 }
 template <int K, int PF, bool HALO, bool FMA, bool UNI, bool HEAD>
 static int launch_chain_k(const ChainArgs& a, dim3 grid, cudaStream_t st)
 {
+  if constexpr (chain_bulk_available<K, FMA>())
+    if (b200_get_chain_bulk()) return launch_chain_s<K, PF, HALO, FMA, UNI, HEAD, false, true>(a, grid, st);
   if constexpr (chain_split_available<K, FMA>())
     if (b200_get_chain_split()) return launch_chain_s<K, PF, HALO, FMA, UNI, HEAD, true>(a, grid, st);
   return launch_chain_s<K, PF, HALO, FMA, UNI, HEAD, false>(a, grid, st);

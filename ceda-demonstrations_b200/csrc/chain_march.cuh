@@ -101,6 +101,17 @@ struct ChainState
   int trow;          // index of row r1 in the y-coefficient table
   bool we;           // halo mode: this lane reads the W/E halo strips
   int64_t lane_col;  // column (halo mode: strip offset + column) of this lane
+  // BULK flavour.  A warp whose 64-cell window is ONE contiguous run of the field (every window but those that touch
+  // the first or last column of the block) has it copied by bulk copies: `bulk` is set and ux/up/uy/uf are the running
+  // source pointers of the WINDOW (the same in every lane -- they live in uniform registers); the edge windows keep
+  // the per-thread cp.async of the plain flavour, with their addresses computed from (row, lane_col) when needed.
+  // The four operands share one layout, and row ir+1 of this group is row ir of the next: ONE offset is computed per
+  // row step (uox), the other is handed down (uoy); uhx / uhy say whether the row lies in the S / N halo (halo mode).
+  bool bulk;
+  int64_t wcol;     // first column of the warp's window
+  int64_t uox, uoy; // element offset of the window in row ir+1 / row ir (from the field's or the halo's base)
+  bool uhx, uhy;
+  unsigned par;     // parity of the barrier phase the next wait is for
 };
 
 // issue group(ir) = { x row ir+1, prev2 / yn / fn row ir } into the ring and advance the running
@@ -108,11 +119,55 @@ struct ChainState
 // (rows 0 and ny: wrap-around, or field <-> S/N halo)
 // HEAD flavour (the chain starts with stage 1 of the step, z_1 = y_n + c L(y_n)): only x (= y_n) is streamed -- there is
 // no z_{-1}, and f_n = L(y_n) is produced by level 1 of this very launch, which writes it into the fn ring itself.
-template <int K, int PF, bool HALO, bool HEAD, bool SPLIT>
+// BULK flavour: the same group as ONE bulk copy per operand (cp.async.bulk, the TMA unit's 1-D path: 512 bytes, the
+// warp's whole window), issued by one elected lane from warp-uniform pointers and completed on the warp's mbarrier of
+// this ring slot; rxw .. rfw are the ring rows of the WARP (lane 0's slot).
+template <int K, int PF, bool HALO, bool HEAD, bool SPLIT, bool BULK>
 __device__ __forceinline__ void chain_issue(const ChainArgs& a, ChainState& st, double2* rx, double2* rp,
-                                            double2* ry, double2* rf, int64_t nx, int ny, bool issue)
+                                            double2* ry, double2* rf, double2* rxw, double2* rpw, double2* ryw,
+                                            double2* rfw, unsigned long long* bars, int64_t nx, int ny, bool issue)
 {
   constexpr int DX = PF + 1, DY = PF + K + (SPLIT ? 1 : 0);
+  if (BULK && st.bulk)
+  {
+    if (issue && elect_one())
+    {
+      unsigned long long* bar = bars + st.sx_issue;
+      mbar_arrive_expect_tx(bar, 512u * (HEAD ? 2u : 4u));
+      bulk_g2s(rxw + st.sx_issue * kChainThreads, ((HALO && st.uhx) ? a.hx : a.x) + st.uox, 512u, bar);
+      if (!HEAD) bulk_g2s(rpw + st.sx_issue * kChainThreads, ((HALO && st.uhy) ? a.hp : a.prev2) + st.uoy, 512u, bar);
+      bulk_g2s(ryw + st.sy_issue * kChainThreads, ((HALO && st.uhy) ? a.hy : a.yn) + st.uoy, 512u, bar);
+      if (!HEAD) bulk_g2s(rfw + st.sy_issue * kChainThreads, ((HALO && st.uhy) ? a.hf : a.fn) + st.uoy, 512u, bar);
+    }
+    st.sx_issue = (st.sx_issue + 1 == DX) ? 0 : st.sx_issue + 1;
+    st.sy_issue = (st.sy_issue + 1 == DY) ? 0 : st.sy_issue + 1;
+    const int r = ++st.ir; // the next group: rows r and r + 1
+    st.uoy = st.uox;
+    st.uhy = st.uhx;
+    if (r + 1 == 0 || r + 1 == ny)
+    { // row 0 of the field (wrap mode: from either side; halo mode: coming out of the S halo), or into the N halo
+      st.uhx = HALO && (r + 1 == ny);
+      st.uox = st.wcol + (st.uhx ? (int64_t)a.g * nx : 0);
+    }
+    else st.uox += nx;
+    return;
+  }
+  if (BULK)
+  { // edge window of the BULK flavour: per-thread cp.async, addresses from (row, lane_col) -- no running pointers
+    if (issue)
+    {
+      const int r = st.ir;
+      cp_async16(rx + st.sx_issue * kChainThreads, row_ptr<HALO>(a.x, a.hx, r + 1, st.we, st.lane_col, nx, ny, a.g, a.g2));
+      if (!HEAD) cp_async16(rp + st.sx_issue * kChainThreads, row_ptr<HALO>(a.prev2, a.hp, r, st.we, st.lane_col, nx, ny, a.g, a.g2));
+      cp_async16(ry + st.sy_issue * kChainThreads, row_ptr<HALO>(a.yn, a.hy, r, st.we, st.lane_col, nx, ny, a.g, a.g2));
+      if (!HEAD) cp_async16(rf + st.sy_issue * kChainThreads, row_ptr<HALO>(a.fn, a.hf, r, st.we, st.lane_col, nx, ny, a.g, a.g2));
+    }
+    cp_async_commit();
+    st.sx_issue = (st.sx_issue + 1 == DX) ? 0 : st.sx_issue + 1;
+    st.sy_issue = (st.sy_issue + 1 == DY) ? 0 : st.sy_issue + 1;
+    ++st.ir;
+    return;
+  }
   if (issue)
   {
     cp_async16(rx + st.sx_issue * kChainThreads, st.px);
@@ -225,9 +280,10 @@ __device__ __forceinline__ void chain_levels(const ChainArgs& a, const ChainStat
   }
 }
 
-template <int K, int PF, int PH, bool CHECK, bool HALO, bool FMA, bool UNI, bool HEAD, bool SPLIT>
+template <int K, int PF, int PH, bool CHECK, bool HALO, bool FMA, bool UNI, bool HEAD, bool SPLIT, bool BULK>
 __device__ __forceinline__ void chain_row(const ChainArgs& a, ChainState& st, double2 (&W)[K][3],
-                                          double2* rx, double2* rp, double2* ry, double2* rf,
+                                          double2* rx, double2* rp, double2* ry, double2* rf, double2* rxw,
+                                          double2* rpw, double2* ryw, double2* rfw, unsigned long long* bars,
                                           const double2* ytab, const double* stab, int64_t nx, int ny,
                                           double2 cw, double2 ce, double sx0, double sx1,
                                           unsigned smask, int r1, int j0, int j1, bool issue)
@@ -235,8 +291,15 @@ __device__ __forceinline__ void chain_row(const ChainArgs& a, ChainState& st, do
   constexpr int DX = PF + 1, DY = PF + K + (SPLIT ? 1 : 0);
   constexpr int IO = PH % 3;
   constexpr int H  = chain_half<K, SPLIT>();
-  chain_issue<K, PF, HALO, HEAD, SPLIT>(a, st, rx, rp, ry, rf, nx, ny, issue); // group(r1 + PF)
-  cp_async_wait<PF>(); // all but the PF newest groups have landed: group(r1) is ready
+  // BULK: the slots group(r1 + PF) goes into were last read in the previous row step, and every lane must have seen
+  // that step's barrier phase before the barrier is armed again
+  if (BULK && st.bulk) __syncwarp();
+  chain_issue<K, PF, HALO, HEAD, SPLIT, BULK>(a, st, rx, rp, ry, rf, rxw, rpw, ryw, rfw, bars, nx, ny, issue); // group(r1 + PF)
+  if (BULK && st.bulk)
+  { // group(r1) has landed when its barrier phase completes (rows at and beyond rend = j1 + K - 1 have no group)
+    if (!CHECK || r1 < j1 + (K - 1)) mbar_wait(bars + st.sx_use, st.par);
+  }
+  else cp_async_wait<PF>(); // all but the PF newest groups have landed: group(r1) is ready
 
   const double2 xnew = rx[st.sx_use * kChainThreads]; // x row r1+1
   const double2 P    = HEAD ? make_double2(0.0, 0.0) : rp[st.sx_use * kChainThreads];
@@ -252,9 +315,55 @@ __device__ __forceinline__ void chain_row(const ChainArgs& a, ChainState& st, do
   st.trow += 1;
   st.sx_use = (st.sx_use + 1 == DX) ? 0 : st.sx_use + 1;
   st.sy_use = (st.sy_use + 1 == DY) ? 0 : st.sy_use + 1;
+  if constexpr (BULK)
+    if (st.sx_use == 0) st.par ^= 1u; // every barrier has been through one more phase
 }
 
-template <int K, int PF, bool HALO, bool FMA, bool UNI = false, bool HEAD = false, bool SPLIT = false>
+// BULK flavour: element offset of a window (first column w0, inside the field) in row r, r in [-g, ny+g), from the base
+// of the field or -- *in_halo -- of its deep halo (layout at row_ptr)
+template <bool HALO>
+__device__ __forceinline__ int64_t chain_window_off(int r, int64_t w0, int64_t nx, int ny, int g, bool* in_halo)
+{
+  *in_halo = HALO && (r < 0 || r >= ny);
+  if (!HALO) return (int64_t)((r < 0) ? r + ny : ((r >= ny) ? r - ny : r)) * nx + w0;
+  if (r >= 0 && r < ny) return (int64_t)r * nx + w0;
+  return (int64_t)((r < 0) ? r + g : g + (r - ny)) * nx + w0;
+}
+
+// where the cell at unwrapped column col_u of the block comes from: wrap mode -- the field itself, periodically;
+// halo mode -- the field, or the W / E strips of the deep halo (beyond the strips: clamped, never used)
+template <bool HALO>
+__device__ __forceinline__ void chain_source(const ChainArgs& a, int64_t col_u, int64_t nx, int ny, bool* we,
+                                             int64_t* lane_col, int64_t* pstep, int64_t* ic, int64_t* xc)
+{
+  *ic    = col_u;
+  *xc    = col_u;
+  *we    = false;
+  *pstep = nx;
+  if (HALO)
+  {
+    const int64_t strip = (int64_t)(ny + 2 * a.g) * a.g2;
+    if (col_u < 0) { *we = true; *lane_col = 2 * a.g * nx + (col_u + a.g2); }
+    else if (col_u >= nx)
+    {
+      int64_t c = col_u - nx;
+      if (c > a.g2 - 2) { c = a.g2 - 2; *xc = nx + c; }
+      *we       = true;
+      *lane_col = 2 * a.g * nx + strip + c;
+    }
+    else *lane_col = col_u;
+    if (*we) *pstep = a.g2;
+  }
+  else
+  {
+    if (*ic < 0) *ic += nx;
+    else if (*ic >= nx) *ic -= nx;
+    *xc       = *ic;
+    *lane_col = *ic;
+  }
+}
+
+template <int K, int PF, bool HALO, bool FMA, bool UNI = false, bool HEAD = false, bool SPLIT = false, bool BULK = false>
 __global__ void __launch_bounds__(kChainThreads, 2) k_chain_march(const ChainArgs a)
 {
   constexpr int HL   = (K + 1) / 2;  // halo lanes per side (2 cells each): 2*HL >= K
@@ -269,6 +378,7 @@ __global__ void __launch_bounds__(kChainThreads, 2) k_chain_march(const ChainArg
   double2* rf   = ring + (size_t)(2 * DX + DY) * kChainThreads + threadIdx.x; // [DY][threads]
   double2* ytab = ring + (size_t)(2 * DX + 2 * DY) * kChainThreads;           // [rows + 3(K-1) + 2 + 2 XL]
   double* stab  = reinterpret_cast<double*>(ytab + (a.rows + 3 * (K - 1) + 2 + 2 * XL)); // [rows + 3(K-1) + 2 + 2 XL]
+  unsigned long long* bars = nullptr; // BULK: one mbarrier per warp and x-ring slot, behind stab: [warps][DX]
 
   const int lane   = threadIdx.x & 31;
   const int64_t nx = a.nx;
@@ -302,31 +412,9 @@ __global__ void __launch_bounds__(kChainThreads, 2) k_chain_march(const ChainArg
   if (HEAD && store_ok && a.f_out) smask |= 1u << K; // f_out
 
   ChainState st;
-  int64_t ic = col_u; // column used for stores and (wrap mode) loads
-  int64_t xc = col_u; // column index into the x-direction coefficient tables
-  st.we      = false;
-  st.pstep   = nx;
-  if (HALO)
-  { // columns outside [0, nx) come from the W / E halo strips; beyond the strips: clamp (never used)
-    const int64_t strip = (int64_t)(ny + 2 * a.g) * a.g2;
-    if (col_u < 0) { st.we = true; st.lane_col = 2 * a.g * nx + (col_u + a.g2); }
-    else if (col_u >= nx)
-    {
-      int64_t c = col_u - nx;
-      if (c > a.g2 - 2) { c = a.g2 - 2; xc = nx + c; }
-      st.we       = true;
-      st.lane_col = 2 * a.g * nx + strip + c;
-    }
-    else st.lane_col = col_u;
-    if (st.we) st.pstep = a.g2;
-  }
-  else
-  {
-    if (ic < 0) ic += nx;
-    else if (ic >= nx) ic -= nx;
-    xc          = ic;
-    st.lane_col = ic;
-  }
+  int64_t ic; // column used for stores and (wrap mode) loads
+  int64_t xc; // column index into the x-direction coefficient tables
+  chain_source<HALO>(a, col_u, nx, ny, &st.we, &st.lane_col, &st.pstep, &ic, &xc);
   const double2 cw = UNI ? make_double2(a.u_cxw, a.u_cxw) : ld_keep2(a.cxw + xc);
   const double2 ce = UNI ? make_double2(a.u_cxe, a.u_cxe) : ld_keep2(a.cxe + xc);
   const double sx0 = DADD(cw.x, ce.x), sx1 = DADD(cw.y, ce.y);
@@ -335,14 +423,6 @@ __global__ void __launch_bounds__(kChainThreads, 2) k_chain_march(const ChainArg
   st.sx_issue = st.sy_issue = st.sx_use = st.sy_use = 0;
   st.trow     = K - 1 + XL;
   st.ir       = rstart;
-  st.px = row_ptr<HALO>(a.x, a.hx, rstart + 1, st.we, st.lane_col, nx, ny, a.g, a.g2);
-  st.py = row_ptr<HALO>(a.yn, a.hy, rstart, st.we, st.lane_col, nx, ny, a.g, a.g2);
-  st.pp = st.pf = st.py; // (not streamed in the HEAD flavour)
-  if (!HEAD)
-  {
-    st.pp = row_ptr<HALO>(a.prev2, a.hp, rstart, st.we, st.lane_col, nx, ny, a.g, a.g2);
-    st.pf = row_ptr<HALO>(a.fn, a.hf, rstart, st.we, st.lane_col, nx, ny, a.g, a.g2);
-  }
 
   double2 W[K][3];
 #pragma unroll
@@ -351,12 +431,55 @@ __global__ void __launch_bounds__(kChainThreads, 2) k_chain_march(const ChainArg
   W[0][1] = ld_keep2(row_ptr<HALO>(a.x, a.hx, rstart - 1, st.we, st.lane_col, nx, ny, a.g, a.g2));
   W[0][2] = ld_keep2(row_ptr<HALO>(a.x, a.hx, rstart, st.we, st.lane_col, nx, ny, a.g, a.g2));
 
+  st.bulk = false;
+  st.par  = 0;
+  st.wcol = 0;
+  st.uox = st.uoy = 0;
+  st.uhx = st.uhy = false;
+  double2 *rxw = rx, *rpw = rp, *ryw = ry, *rfw = rf;
+  if constexpr (BULK)
+  { // the warp index once more, as a value the compiler knows to be the same in every lane: everything derived from
+    // it (window column, source pointers, ring rows, barriers) stays in uniform registers
+    const int wu     = warp_uniform(threadIdx.x >> 5);
+    const int64_t w0 = ((int64_t)blockIdx.x * (kChainThreads / 32) + wu) * WUSE - 2 * HL;
+    st.bulk          = (w0 >= 0) && (w0 + 64 <= nx);
+    st.wcol          = w0;
+    rxw  = ring + wu * 32;
+    rpw  = rxw + (size_t)DX * kChainThreads;
+    ryw  = rxw + (size_t)2 * DX * kChainThreads;
+    rfw  = rxw + (size_t)(2 * DX + DY) * kChainThreads;
+    bars = reinterpret_cast<unsigned long long*>(stab + (a.rows + 3 * (K - 1) + 2 + 2 * XL)) + wu * DX;
+    if (st.bulk)
+    {
+      if (elect_one())
+      {
+#pragma unroll
+        for (int q = 0; q < DX; q++) mbar_init(bars + q, 1u);
+        mbar_fence_init();
+      }
+      __syncwarp();
+      st.uoy = chain_window_off<HALO>(rstart, w0, nx, ny, a.g, &st.uhy);
+      st.uox = chain_window_off<HALO>(rstart + 1, w0, nx, ny, a.g, &st.uhx);
+    }
+  }
+  else
+  {
+    st.px = row_ptr<HALO>(a.x, a.hx, rstart + 1, st.we, st.lane_col, nx, ny, a.g, a.g2);
+    st.py = row_ptr<HALO>(a.yn, a.hy, rstart, st.we, st.lane_col, nx, ny, a.g, a.g2);
+    st.pp = st.pf = st.py; // (not streamed in the HEAD flavour)
+    if (!HEAD)
+    {
+      st.pp = row_ptr<HALO>(a.prev2, a.hp, rstart, st.we, st.lane_col, nx, ny, a.g, a.g2);
+      st.pf = row_ptr<HALO>(a.fn, a.hf, rstart, st.we, st.lane_col, nx, ny, a.g, a.g2);
+    }
+  }
+
   // prologue of the pipeline: groups rstart .. rstart+PF-1
 #pragma unroll
-  for (int q = 0; q < PF; q++) chain_issue<K, PF, HALO, HEAD, SPLIT>(a, st, rx, rp, ry, rf, nx, ny, true);
+  for (int q = 0; q < PF; q++) chain_issue<K, PF, HALO, HEAD, SPLIT, BULK>(a, st, rx, rp, ry, rf, rxw, rpw, ryw, rfw, bars, nx, ny, true);
 
 #define ROW(PH, CHECK, R1) \
-  chain_row<K, PF, PH, CHECK, HALO, FMA, UNI, HEAD, SPLIT>(a, st, W, rx, rp, ry, rf, ytab, stab, nx, ny, cw, ce, sx0, sx1, smask, R1, j0, j1, (R1) + PF < rend)
+  chain_row<K, PF, PH, CHECK, HALO, FMA, UNI, HEAD, SPLIT, BULK>(a, st, W, rx, rp, ry, rf, rxw, rpw, ryw, rfw, bars, ytab, stab, nx, ny, cw, ce, sx0, sx1, smask, R1, j0, j1, (R1) + PF < rend)
 
   // phases: [rstart, s0) checked warm-up in whole triples, [s0, s1) unchecked steady state in
   // triples, [s1, rend3) checked drain; rend3 rounds the trip count up to a multiple of 3 (the
@@ -397,11 +520,12 @@ __global__ void __launch_bounds__(kChainThreads, 2) k_chain_march(const ChainArg
 
 
 // ---- launch geometry (host side; shared by b200_kernels.cu and the emulation harness)
-static inline size_t chain_march_smem(int K, int PF, int rows, bool split = false)
+static inline size_t chain_march_smem(int K, int PF, int rows, bool split = false, bool bulk = false)
 {
   const int xl = split ? 1 : 0;
   return (size_t)(2 * (PF + 1) + 2 * (PF + K + xl)) * kChainThreads * sizeof(double2) +
-         (size_t)(rows + 3 * (K - 1) + 2 + 2 * xl) * (sizeof(double2) + sizeof(double));
+         (size_t)(rows + 3 * (K - 1) + 2 + 2 * xl) * (sizeof(double2) + sizeof(double)) +
+         (bulk ? (size_t)(kChainThreads / 32) * (PF + 1) * sizeof(unsigned long long) : 0);
 }
 static inline int chain_march_pf(int K) { return K <= 3 ? 4 : 3; } // prefetch depth instantiated per K
 // rows may be raised so that grid.y fits 65535

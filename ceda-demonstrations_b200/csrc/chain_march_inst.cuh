@@ -29,6 +29,16 @@
 #define B200_CHAIN_K5(F) B200_CHAIN_FLAVOURS(F, 5, 3, false) B200_CHAIN_FLAVOURS_FMA(F, 5, 3)
 #define B200_CHAIN_K6(F) B200_CHAIN_FLAVOURS(F, 6, 3, false) B200_CHAIN_FLAVOURS_FMA(F, 6, 3)
 
+// BULK flavours (operand ring filled by cp.async.bulk + mbarrier), exact arithmetic: FB(K, PF, HALO, UNI, HEAD)
+#define B200_CHAIN_BULK_FLAVOURS(FB, K, PF)                                                                              \
+  FB(K, PF, false, false, false) FB(K, PF, false, false, true) FB(K, PF, false, true, false) FB(K, PF, false, true, true) \
+  FB(K, PF, true, false, false)  FB(K, PF, true, false, true)  FB(K, PF, true, true, false)  FB(K, PF, true, true, true)
+#define B200_CHAIN_K4B(FB) B200_CHAIN_BULK_FLAVOURS(FB, 4, 3)
+#define B200_CHAIN_DECLARE_BULK(K, PF, HALO, UNI, HEAD) \
+  extern template __global__ void k_chain_march<K, PF, HALO, false, UNI, HEAD, false, true>(const ChainArgs);
+#define B200_CHAIN_DEFINE_BULK(K, PF, HALO, UNI, HEAD) \
+  template __global__ void k_chain_march<K, PF, HALO, false, UNI, HEAD, false, true>(const ChainArgs);
+
 #define B200_CHAIN_DECLARE(K, PF, HALO, FMA, UNI, HEAD, SPLIT) \
   extern template __global__ void k_chain_march<K, PF, HALO, FMA, UNI, HEAD, SPLIT>(const ChainArgs);
 #define B200_CHAIN_DEFINE(K, PF, HALO, FMA, UNI, HEAD, SPLIT) \

@@ -39,6 +39,63 @@ __device__ __forceinline__ void cp_async_wait()
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// Bulk asynchronous copies (the TMA unit's 1-D path, SASS UBLKCP) completed on a shared-memory mbarrier: ONE thread
+// moves a whole contiguous run of a row (16-byte aligned, a multiple of 16 bytes) global -> shared, the bytes are
+// counted down on the barrier's transaction count, and every consumer waits for the barrier's phase by parity.
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned arrivals)
+{
+  const unsigned ba = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ba), "r"(arrivals) : "memory");
+}
+// makes freshly initialised barriers visible to the async proxy (call once after the mbar_init's, before the first copy)
+__device__ __forceinline__ void mbar_fence_init()
+{
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// one arrival that also announces `bytes` of bulk-copy traffic for the current phase
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+  const unsigned ba = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ba), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, unsigned bytes, unsigned long long* bar)
+{
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  const unsigned ba = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sa),
+               "l"(gmem), "r"(bytes), "r"(ba)
+               : "memory");
+}
+// one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one()
+{
+  unsigned pred;
+  asm volatile("{\n"
+               ".reg .pred p;\n"
+               "elect.sync _|p, 0xffffffff;\n"
+               "selp.u32 %0, 1, 0, p;\n"
+               "}"
+               : "=r"(pred));
+  return pred != 0;
+}
+// a value that is the same in every lane, in a form the compiler can keep in a uniform register
+__device__ __forceinline__ int warp_uniform(int v) { return __shfl_sync(0xffffffffu, v, 0); }
+// blocks until the phase of parity `parity` has completed (try_wait suspends the warp for a while instead of spinning)
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+  const unsigned ba = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("{\n"
+               ".reg .pred p;\n"
+               "MBAR_WAIT:\n" // (labels are local to the { } block)
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+               "@p bra MBAR_DONE;\n"
+               "bra MBAR_WAIT;\n"
+               "MBAR_DONE:\n"
+               "}" ::"r"(ba),
+               "r"(parity)
+               : "memory");
+}
 
 // system-scope flag traffic of the peer-mapped halo exchange (flags live in another GPU's memory, reached over NVLink)
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v)

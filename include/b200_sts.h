@@ -298,6 +298,12 @@ int b200_get_chain_variant(void);
    bit-identical results.  B200_CHAIN_SPLIT sets the initial value. */
 int b200_set_chain_split(int on);
 int b200_get_chain_split(void);
+/* BULK flavour of k_chain_march (depth 4, exact arithmetic): the operand ring in shared memory is filled by bulk
+   asynchronous copies (cp.async.bulk, the TMA unit's 1-D path: one 512-byte copy per warp, operand and row, issued by
+   one lane and completed on an mbarrier) instead of one 16-byte cp.async per thread; bit-identical results.
+   B200_CHAIN_BULK sets the initial value; a negative argument returns to it. */
+int b200_set_chain_bulk(int on);
+int b200_get_chain_bulk(void);
 /* 1 (default): honour b200_stencil_geom.uniform; 0: always load the coefficient tables (A/B tests) */
 int b200_set_chain_uniform(int on);
 /* name of the kernel the most recent chain launch used ("k_chain_quad" / "k_chain_march", "" if none) */

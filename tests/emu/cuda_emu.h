@@ -24,6 +24,7 @@
 #include <deque>
 #include <functional>
 #include <memory>
+#include <unordered_map>
 #include <vector>
 
 struct alignas(16) double2
@@ -107,8 +108,25 @@ struct Warp
   int arrived = 0, alive = 32;
   unsigned gen = 0;
 };
+struct BulkCopy
+{
+  void* dst;
+  const void* src;
+  unsigned bytes;
+};
+// shared-memory mbarrier with a transaction count (mbar_* / bulk_g2s below); the state lives beside the block, keyed by
+// the barrier's address
+struct MBar
+{
+  unsigned count = 0;  // arrivals per phase
+  int pending    = 0;  // arrivals still missing in the current phase
+  long tx        = 0;  // bytes announced and not yet delivered
+  unsigned phase = 0;  // completed phases
+  std::vector<BulkCopy> copies; // lazy mode: bulk copies issued and not yet performed
+};
 struct Block
 {
+  std::unordered_map<const void*, MBar> bars;
   std::vector<Warp> warps;
   std::vector<Fiber> fibers;
   int arrived = 0, alive = 0;
@@ -208,6 +226,8 @@ static inline double __shfl_down_sync(unsigned, double v, int d) { return emu_sh
 static inline double __shfl_xor_sync(unsigned, double v, int m) { return emu_shfl(v, emu::cur().lane ^ m); }
 static inline double __shfl_sync(unsigned, double v, int src) { return emu_shfl(v, src & 31); }
 
+static inline void __syncwarp(unsigned = 0xffffffffu) { emu::warp_barrier(); }
+
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned long long atomicMin(unsigned long long* p, unsigned long long v)
 { // (blocks of one launch run on one OS thread at a time in the emulator; the CAS loop is for form)
@@ -262,6 +282,79 @@ static inline void cp_async_wait()
   {
     emu::run_copies(emu::cur().groups.front());
     emu::cur().groups.pop_front();
+  }
+}
+
+// mbarrier + bulk copies (kernel_prims.cuh).  Eager mode: a bulk copy happens when it is issued; lazy mode
+// (emu::cp_async_lazy): at the last legal moment, when somebody waits for the barrier it completes on -- so a slot read
+// before its wait, or refilled before it was consumed, gives wrong numbers in at least one of the two modes.
+namespace emu
+{
+inline void mbar_settle(MBar& b)
+{
+  if (b.pending == 0 && b.tx == 0)
+  {
+    b.phase++;
+    b.pending = (int)b.count;
+  }
+}
+inline MBar& mbar_of(const void* bar)
+{
+  auto it = cur_block->bars.find(bar);
+  if (it == cur_block->bars.end())
+  {
+    fprintf(stderr, "cuda_emu: mbarrier %p used before mbar_init\n", bar);
+    abort();
+  }
+  return it->second;
+}
+} // namespace emu
+static inline void mbar_init(unsigned long long* bar, unsigned arrivals)
+{
+  emu::MBar& b = emu::cur_block->bars[bar];
+  b            = emu::MBar();
+  b.count      = arrivals;
+  b.pending    = (int)arrivals;
+}
+static inline void mbar_fence_init() {}
+static inline void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+  emu::MBar& b = emu::mbar_of(bar);
+  if (b.pending <= 0) { fprintf(stderr, "cuda_emu: more arrivals than the mbarrier was initialised for\n"); abort(); }
+  b.tx += bytes;
+  b.pending--;
+  emu::mbar_settle(b);
+}
+static inline void bulk_g2s(void* smem, const void* gmem, unsigned bytes, unsigned long long* bar)
+{
+  if (((uintptr_t)smem & 15) || ((uintptr_t)gmem & 15) || (bytes & 15) || bytes == 0) abort(); // cp.async.bulk: 16-byte granules
+  emu::MBar& b = emu::mbar_of(bar);
+  if (emu::cp_async_lazy) { b.copies.push_back({smem, gmem, bytes}); return; }
+  memcpy(smem, gmem, bytes);
+  b.tx -= bytes;
+  emu::mbar_settle(b);
+}
+static inline bool elect_one() { return emu::cur().lane == 0; }
+static inline int warp_uniform(int v) { return v; }
+static inline void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+  emu::MBar& b = emu::mbar_of(bar);
+  for (long spins = 0; (b.phase & 1u) == (parity & 1u); spins++)
+  {
+    if (!b.copies.empty())
+    {
+      for (const emu::BulkCopy& c : b.copies)
+      {
+        memcpy(c.dst, c.src, c.bytes);
+        b.tx -= c.bytes;
+      }
+      b.copies.clear();
+      emu::mbar_settle(b);
+      continue;
+    }
+    if (spins > 100000) { fprintf(stderr, "cuda_emu: mbar_wait never completes (missing arrival or bytes)\n"); abort(); }
+    emu::cur_block->progress++; // the other lanes of the warp may be the ones that still have to arrive
+    emu::yield_to_scheduler();
   }
 }
 

@@ -21,9 +21,19 @@ void run_stage(const StageArgs& a, dim3 grid)
   else emu::launch(k_stage_march<NT, PAT, 0, 0>, grid, kThreads, 0, a);
 }
 
+int g_emu_bulk = 0; // emu_set_chain_bulk: the BULK flavour of k_chain_march (exact arithmetic)
+
 template <int K, int PF, bool HALO, bool FMA>
 void run_march(const ChainArgs& a, dim3 grid, bool uni)
 {
+  if constexpr (!FMA)
+    if (g_emu_bulk)
+    {
+      const size_t smem = chain_march_smem(K, PF, a.rows, false, true);
+      if (uni) emu::launch(k_chain_march<K, PF, HALO, false, true, false, false, true>, grid, kChainThreads, smem, a);
+      else emu::launch(k_chain_march<K, PF, HALO, false, false, false, false, true>, grid, kChainThreads, smem, a);
+      return;
+    }
   if (uni) emu::launch(k_chain_march<K, PF, HALO, FMA, true>, grid, kChainThreads, chain_march_smem(K, PF, a.rows), a);
   else emu::launch(k_chain_march<K, PF, HALO, FMA, false>, grid, kChainThreads, chain_march_smem(K, PF, a.rows), a);
 }
@@ -46,6 +56,8 @@ void run_quad_k(const ChainArgs& a, dim3 grid, bool halo, bool fma)
   else fma ? run_quad<K, PF, false, true>(a, grid) : run_quad<K, PF, false, false>(a, grid);
 }
 } // namespace
+
+extern "C" __attribute__((visibility("default"))) void emu_set_chain_bulk(int on) { g_emu_bulk = on; }
 
 // variant: 0 = k_chain_march (2 cells / thread), 1 = k_chain_quad (4 cells / thread)
 // halos: NULL (periodic wrap) or the four deep-halo buffers {x, prev2, yn, fn} (g rows, g2 columns)

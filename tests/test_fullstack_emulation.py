@@ -418,6 +418,26 @@ def test_a_device_failure_comes_back_as_an_error_code_not_an_abort(emu, args):
 
 @pytest.mark.parametrize("args", CHAIN_ARGS, ids=["rkc_fixed_inhom_128x48", "rkl_fixed_uniform_130x40", "rkc_adaptive_128x64"])
 @pytest.mark.parametrize("extra", [[], ["--force-halo"]], ids=["wrap", "deep_halo"])
+def test_bulk_copy_ring_does_not_change_a_bit(emu, args, extra):
+    """BULK flavour of k_chain_march (depth 4): the operand ring filled by cp.async.bulk + mbarrier (interior windows)
+    and by per-thread cp.async (the windows on the block's first and last columns); whole integrations through the
+    launchers -- tables and uniform coefficients, wrap and deep halos, head and body chains -- agree bit for bit."""
+    lib = emu.kernel_lib()
+    lib.b200_set_chain_bulk(0)
+    st0, u0 = run_d2d(emu, args + ["--chain", "4"] + extra)
+    lib.b200_set_chain_bulk(1)
+    try:
+        st1, u1 = run_d2d(emu, args + ["--chain", "4"] + extra)
+    finally:
+        lib.b200_set_chain_bulk(-1)
+    assert st0["chain_launches"] == st1["chain_launches"] > 0 and st0["chain_stages"] == st1["chain_stages"]
+    for k in ("steps", "step_attempts", "err_test_fails", "rhs_evals", "max_stages"):
+        assert st0[k] == st1[k], k
+    assert np.array_equal(u0, u1)
+
+
+@pytest.mark.parametrize("args", CHAIN_ARGS, ids=["rkc_fixed_inhom_128x48", "rkl_fixed_uniform_130x40", "rkc_adaptive_128x64"])
+@pytest.mark.parametrize("extra", [[], ["--force-halo"]], ids=["wrap", "deep_halo"])
 def test_split_level_groups_do_not_change_a_bit(emu, args, extra):
     """SPLIT flavour of k_chain_march (depth 4): the upper half of the levels runs one row late and first in a row step
     (two independent instruction streams); every cell still sees the same instruction sequence, so whole integrations

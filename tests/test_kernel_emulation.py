@@ -678,3 +678,47 @@ def test_peer_exchange_fills_every_deep_halo_of_a_process_grid(emu, npx, npy, nx
             U[np.ix_(rows(-g, ny + g), cols(-g2, 0))].ravel(),
             U[np.ix_(rows(-g, ny + g), cols(nx_loc, nx_loc + g2))].ravel()])
         assert np.array_equal(slots[rank], want), rank
+
+
+# ---- BULK flavour of k_chain_march: the operand ring filled by cp.async.bulk + mbarrier (emulated in cuda_emu.h:
+# eager = the copy lands at issue time, lazy = when somebody waits for its barrier).  Same checks as above, the switch on.
+@pytest.fixture
+def emu_bulk(emu):
+    emu.emu_set_chain_bulk(1)
+    yield emu
+    emu.emu_set_chain_bulk(0)
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "%dx%d_rows%d" % c)
+@pytest.mark.parametrize("k", [2, 3, 4])
+def test_bulk_ring_periodic_wrap_bit_exact(emu_bulk, case, k):
+    test_chain_kernels_periodic_wrap_bit_exact(emu_bulk, case, k, 0)
+
+
+@pytest.mark.parametrize("k", [5, 6])
+def test_bulk_ring_deep_levels_bit_exact(emu_bulk, k):
+    test_chain_kernels_deep_levels_bit_exact(emu_bulk, k, 0)
+
+
+@pytest.mark.parametrize("block", [(0, 0), (1, 1)], ids=["block00", "block11"])
+@pytest.mark.parametrize("k", [2, 4, 5])
+def test_bulk_ring_halo_flavour_bit_exact(emu_bulk, block, k):
+    test_chain_kernels_halo_flavour_bit_exact(emu_bulk, block, k, 0)
+
+
+@pytest.mark.parametrize("k", [3, 4])
+@pytest.mark.parametrize("halo", [False, True], ids=["wrap", "halo"])
+def test_bulk_ring_uniform_coefficients_bit_exact(emu_bulk, k, halo):
+    test_uniform_coefficient_flavour_bit_exact(emu_bulk, k, halo)
+
+
+@pytest.mark.parametrize("shape", [s for s in _random_shapes(40, 2026) if s[4] == 0],
+                         ids=lambda s: "%dx%d_rows%d_k%d_v%d_l%d" % s)
+def test_bulk_ring_random_shapes_bit_exact(emu_bulk, shape):
+    test_chain_kernels_random_shapes_bit_exact(emu_bulk, shape)
+
+
+@pytest.mark.parametrize("shape", [s for s in _random_shapes(16, 777) if s[4] == 0],
+                         ids=lambda s: "%dx%d_rows%d_k%d_v%d_l%d" % s)
+def test_bulk_ring_random_decompositions_bit_exact(emu_bulk, shape):
+    test_chain_kernels_random_decompositions_bit_exact(emu_bulk, shape)
