@@ -972,6 +972,7 @@ B200_CHAIN_K3(B200_CHAIN_DECLARE)
 B200_CHAIN_K4(B200_CHAIN_DECLARE)
 B200_CHAIN_K4S(B200_CHAIN_DECLARE)
 B200_CHAIN_K4B(B200_CHAIN_DECLARE_BULK)
+B200_CHAIN_K4P(B200_CHAIN_DECLARE)
 B200_CHAIN_K5(B200_CHAIN_DECLARE)
 B200_CHAIN_K6(B200_CHAIN_DECLARE)
 #endif
@@ -1006,7 +1007,7 @@ extern "C" int b200_get_chain_split(void)
   }
   return g_chain_split;
 }
-template <int K, bool FMA> constexpr bool chain_split_available() { return !FMA && K == 4; }
+template <int K, int PF, bool FMA> constexpr bool chain_split_available() { return !FMA && K == 4 && PF == 3; }
 
 // BULK flavour of k_chain_march (chain_march.cuh): the operand ring is filled by cp.async.bulk (one 512-byte copy per
 // warp, operand and row, issued by one lane, completed on an mbarrier) instead of one 16-byte cp.async per thread.
@@ -1014,7 +1015,7 @@ static int g_chain_bulk = -1; // -1: not decided yet (B200_CHAIN_BULK, else the 
 static const int kChainBulkDefault = 0;
 extern "C" int b200_set_chain_bulk(int on)
 { // < 0: back to the initial value (B200_CHAIN_BULK, else the default)
-  g_chain_bulk = on < 0 ? -1 : (on ? 1 : 0);
+  g_chain_bulk = on < 0 ? -1 : (on > 2 ? 2 : on); // 1: prefetch depth of the plain flavour, 2: one row deeper
   return 0;
 }
 extern "C" int b200_get_chain_bulk(void)
@@ -1022,11 +1023,12 @@ extern "C" int b200_get_chain_bulk(void)
   if (g_chain_bulk < 0)
   {
     const char* e = getenv("B200_CHAIN_BULK");
-    g_chain_bulk  = e ? (atoi(e) != 0) : kChainBulkDefault;
+    g_chain_bulk  = e ? atoi(e) : kChainBulkDefault;
+    if (g_chain_bulk < 0 || g_chain_bulk > 2) g_chain_bulk = kChainBulkDefault;
   }
   return g_chain_bulk;
 }
-template <int K, bool FMA> constexpr bool chain_bulk_available() { return !FMA && K == 4; }
+template <int K, int PF, bool FMA> constexpr bool chain_bulk_available() { return !FMA && K == 4 && PF == 3; }
 
 template <int K, int PF, bool HALO, bool FMA, bool UNI, bool HEAD, bool SPLIT, bool BULK = false>
 static int launch_chain_s(const ChainArgs& a, dim3 grid, cudaStream_t st)
@@ -1052,9 +1054,12 @@ static int launch_chain_s(const ChainArgs& a, dim3 grid, cudaStream_t st)
 template <int K, int PF, bool HALO, bool FMA, bool UNI, bool HEAD>
 static int launch_chain_k(const ChainArgs& a, dim3 grid, cudaStream_t st)
 {
-  if constexpr (chain_bulk_available<K, FMA>())
+  if constexpr (chain_bulk_available<K, PF, FMA>())
+  {
+    if (b200_get_chain_bulk() == 2) return launch_chain_s<K, PF + 1, HALO, FMA, UNI, HEAD, false, true>(a, grid, st);
     if (b200_get_chain_bulk()) return launch_chain_s<K, PF, HALO, FMA, UNI, HEAD, false, true>(a, grid, st);
-  if constexpr (chain_split_available<K, FMA>())
+  }
+  if constexpr (chain_split_available<K, PF, FMA>())
     if (b200_get_chain_split()) return launch_chain_s<K, PF, HALO, FMA, UNI, HEAD, true>(a, grid, st);
   return launch_chain_s<K, PF, HALO, FMA, UNI, HEAD, false>(a, grid, st);
 }
@@ -1080,9 +1085,30 @@ static int launch_chain_u(const ChainArgs& a, dim3 grid, cudaStream_t st, bool u
 {
   return uni ? launch_chain_h<K, PF, HALO, FMA, true>(a, grid, st) : launch_chain_h<K, PF, HALO, FMA, false>(a, grid, st);
 }
+// Depth 4, exact arithmetic, plain flavour with one more row in flight (PF = 4: the yn / fn ring is then 8 rows deep and
+// its slot arithmetic a mask).  B200_CHAIN_PF=4 / b200_set_chain_pf(4); instantiated in csrc/chain_inst_k4p.cu.
+static int g_chain_pf = -1;
+static const int kChainPfDefault = 3;
+extern "C" int b200_set_chain_pf(int pf)
+{
+  g_chain_pf = (pf == 3 || pf == 4) ? pf : -1;
+  return 0;
+}
+extern "C" int b200_get_chain_pf(void)
+{
+  if (g_chain_pf < 0)
+  {
+    const char* e = getenv("B200_CHAIN_PF");
+    g_chain_pf    = (e && atoi(e) == 4) ? 4 : ((e && atoi(e) == 3) ? 3 : kChainPfDefault);
+  }
+  return g_chain_pf;
+}
 template <int K, int PF>
 static int launch_chain(const ChainArgs& a, dim3 grid, cudaStream_t st, bool uni)
 {
+  if constexpr (K == 4 && PF == 3)
+    if (!g_contract && !b200_get_chain_bulk() && !b200_get_chain_split() && b200_get_chain_pf() == 4)
+      return a.hx ? launch_chain_u<4, 4, true, false>(a, grid, st, uni) : launch_chain_u<4, 4, false, false>(a, grid, st, uni);
   if (g_contract)
     return a.hx ? launch_chain_u<K, PF, true, true>(a, grid, st, uni) : launch_chain_u<K, PF, false, true>(a, grid, st, uni);
   return a.hx ? launch_chain_u<K, PF, true, false>(a, grid, st, uni) : launch_chain_u<K, PF, false, false>(a, grid, st, uni);

@@ -91,6 +91,24 @@ __host__ __device__ constexpr int chain_half() { return SPLIT ? (K + 1) / 2 : K;
 template <int K, bool SPLIT>
 __host__ __device__ constexpr int chain_lag(int l) { return (l - 1) + ((SPLIT && l > chain_half<K, SPLIT>()) ? 1 : 0); }
 
+// ring slot arithmetic: a depth that is a power of two costs one AND
+template <int D>
+__device__ __forceinline__ int ring_next(int s)
+{
+  if constexpr ((D & (D - 1)) == 0) return (s + 1) & (D - 1);
+  else return (s + 1 == D) ? 0 : s + 1;
+}
+template <int D>
+__device__ __forceinline__ int ring_back(int s, int lag)
+{
+  if constexpr ((D & (D - 1)) == 0) return (s - lag) & (D - 1);
+  else
+  {
+    const int t = s - lag;
+    return t < 0 ? t + D : t;
+  }
+}
+
 struct ChainState
 {
   int64_t soff;      // r1*nx + ic (unwrapped; valid whenever a store can happen)
@@ -122,7 +140,9 @@ struct ChainState
 // BULK flavour: the same group as ONE bulk copy per operand (cp.async.bulk, the TMA unit's 1-D path: 512 bytes, the
 // warp's whole window), issued by one elected lane from warp-uniform pointers and completed on the warp's mbarrier of
 // this ring slot; rxw .. rfw are the ring rows of the WARP (lane 0's slot).
-template <int K, int PF, bool HALO, bool HEAD, bool SPLIT, bool BULK>
+// WRAP = false (the steady state of the row loop, see the kernel): neither row of the NEXT group is row 0 or row ny, so
+// the running pointers just advance by one row.
+template <int K, int PF, bool HALO, bool HEAD, bool SPLIT, bool BULK, bool WRAP = true>
 __device__ __forceinline__ void chain_issue(const ChainArgs& a, ChainState& st, double2* rx, double2* rp,
                                             double2* ry, double2* rf, double2* rxw, double2* rpw, double2* ryw,
                                             double2* rfw, unsigned long long* bars, int64_t nx, int ny, bool issue)
@@ -139,12 +159,12 @@ __device__ __forceinline__ void chain_issue(const ChainArgs& a, ChainState& st, 
       bulk_g2s(ryw + st.sy_issue * kChainThreads, ((HALO && st.uhy) ? a.hy : a.yn) + st.uoy, 512u, bar);
       if (!HEAD) bulk_g2s(rfw + st.sy_issue * kChainThreads, ((HALO && st.uhy) ? a.hf : a.fn) + st.uoy, 512u, bar);
     }
-    st.sx_issue = (st.sx_issue + 1 == DX) ? 0 : st.sx_issue + 1;
-    st.sy_issue = (st.sy_issue + 1 == DY) ? 0 : st.sy_issue + 1;
+    st.sx_issue = ring_next<DX>(st.sx_issue);
+    st.sy_issue = ring_next<DY>(st.sy_issue);
     const int r = ++st.ir; // the next group: rows r and r + 1
     st.uoy = st.uox;
     st.uhy = st.uhx;
-    if (r + 1 == 0 || r + 1 == ny)
+    if (WRAP && (r + 1 == 0 || r + 1 == ny))
     { // row 0 of the field (wrap mode: from either side; halo mode: coming out of the S halo), or into the N halo
       st.uhx = HALO && (r + 1 == ny);
       st.uox = st.wcol + (st.uhx ? (int64_t)a.g * nx : 0);
@@ -163,8 +183,8 @@ __device__ __forceinline__ void chain_issue(const ChainArgs& a, ChainState& st, 
       if (!HEAD) cp_async16(rf + st.sy_issue * kChainThreads, row_ptr<HALO>(a.fn, a.hf, r, st.we, st.lane_col, nx, ny, a.g, a.g2));
     }
     cp_async_commit();
-    st.sx_issue = (st.sx_issue + 1 == DX) ? 0 : st.sx_issue + 1;
-    st.sy_issue = (st.sy_issue + 1 == DY) ? 0 : st.sy_issue + 1;
+    st.sx_issue = ring_next<DX>(st.sx_issue);
+    st.sy_issue = ring_next<DY>(st.sy_issue);
     ++st.ir;
     return;
   }
@@ -176,10 +196,10 @@ __device__ __forceinline__ void chain_issue(const ChainArgs& a, ChainState& st, 
     if (!HEAD) cp_async16(rf + st.sy_issue * kChainThreads, st.pf);
   }
   cp_async_commit();
-  st.sx_issue = (st.sx_issue + 1 == DX) ? 0 : st.sx_issue + 1;
-  st.sy_issue = (st.sy_issue + 1 == DY) ? 0 : st.sy_issue + 1;
+  st.sx_issue = ring_next<DX>(st.sx_issue);
+  st.sy_issue = ring_next<DY>(st.sy_issue);
   const int r = ++st.ir;
-  if (r == 0 || r == ny)
+  if (WRAP && (r == 0 || r == ny))
   {
     if (!HEAD) st.pp = row_ptr<HALO>(a.prev2, a.hp, r, st.we, st.lane_col, nx, ny, a.g, a.g2);
     st.py = row_ptr<HALO>(a.yn, a.hy, r, st.we, st.lane_col, nx, ny, a.g, a.g2);
@@ -190,7 +210,7 @@ __device__ __forceinline__ void chain_issue(const ChainArgs& a, ChainState& st, 
     st.py += st.pstep;
     if (!HEAD) { st.pp += st.pstep; st.pf += st.pstep; }
   }
-  if (r + 1 == 0 || r + 1 == ny) st.px = row_ptr<HALO>(a.x, a.hx, r + 1, st.we, st.lane_col, nx, ny, a.g, a.g2);
+  if (WRAP && (r + 1 == 0 || r + 1 == ny)) st.px = row_ptr<HALO>(a.x, a.hx, r + 1, st.we, st.lane_col, nx, ny, a.g, a.g2);
   else st.px += st.pstep;
 }
 
@@ -228,8 +248,7 @@ __device__ __forceinline__ void chain_level(const ChainArgs& a, const ChainState
   // what bounds this kernel.
   // z_{l-2} at this row: prev2 for the first stage, else the row of level l-2's window that holds it
   const double2 p2 = (L == 1) ? P : W[(L >= 2) ? L - 2 : 0][P2_LATE ? IO : IM];
-  int sl = st.sy_use - LAG; // yn / fn of row r1-LAG
-  if (sl < 0) sl += DY;
+  const int sl = ring_back<DY>(st.sy_use, LAG); // yn / fn of row r1-LAG
   const double* cf = a.c[L - 1];
   const int64_t so = st.soff - (int64_t)LAG * nx;
   double2 z;
@@ -294,7 +313,7 @@ __device__ __forceinline__ void chain_row(const ChainArgs& a, ChainState& st, do
   // BULK: the slots group(r1 + PF) goes into were last read in the previous row step, and every lane must have seen
   // that step's barrier phase before the barrier is armed again
   if (BULK && st.bulk) __syncwarp();
-  chain_issue<K, PF, HALO, HEAD, SPLIT, BULK>(a, st, rx, rp, ry, rf, rxw, rpw, ryw, rfw, bars, nx, ny, issue); // group(r1 + PF)
+  chain_issue<K, PF, HALO, HEAD, SPLIT, BULK, CHECK>(a, st, rx, rp, ry, rf, rxw, rpw, ryw, rfw, bars, nx, ny, issue); // group(r1 + PF)
   if (BULK && st.bulk)
   { // group(r1) has landed when its barrier phase completes (rows at and beyond rend = j1 + K - 1 have no group)
     if (!CHECK || r1 < j1 + (K - 1)) mbar_wait(bars + st.sx_use, st.par);
@@ -313,8 +332,8 @@ __device__ __forceinline__ void chain_row(const ChainArgs& a, ChainState& st, do
                                                                     smask, r1, j0, j1);
   st.soff += nx;
   st.trow += 1;
-  st.sx_use = (st.sx_use + 1 == DX) ? 0 : st.sx_use + 1;
-  st.sy_use = (st.sy_use + 1 == DY) ? 0 : st.sy_use + 1;
+  st.sx_use = ring_next<DX>(st.sx_use);
+  st.sy_use = ring_next<DY>(st.sy_use);
   if constexpr (BULK)
     if (st.sx_use == 0) st.par ^= 1u; // every barrier has been through one more phase
 }
@@ -488,7 +507,11 @@ __global__ void __launch_bounds__(kChainThreads, 2) k_chain_march(const ChainArg
   const int total3 = ((rend + XL - rstart + 2) / 3) * 3;
   int warm         = 2 * (K - 1) + XL;
   warm             = ((warm + 2) / 3) * 3;
-  int steady       = (j1 - (rstart + warm)) / 3 * 3;
+  // (the steady state also stays clear of the rows whose NEXT group touches row ny -- the group issued in row step r1
+  // is group(r1 + PF), the one after it holds rows r1 + PF + 1 and r1 + PF + 2 -- so that it needs no wrap-around /
+  // field-to-halo logic at all: only the last block rows of the field hand a few more rows to the checked drain)
+  const int lim    = (j1 < ny - (PF + 2)) ? j1 : ny - (PF + 2);
+  int steady       = (lim - (rstart + warm)) / 3 * 3;
   if (steady < 0) steady = 0;
   int r1 = rstart;
 #pragma unroll 1

@@ -26,6 +26,7 @@
 #define B200_CHAIN_K3(F) B200_CHAIN_FLAVOURS(F, 3, 4, false) B200_CHAIN_FLAVOURS_FMA(F, 3, 4)
 #define B200_CHAIN_K4(F) B200_CHAIN_FLAVOURS(F, 4, 3, false) B200_CHAIN_FLAVOURS_FMA(F, 4, 3)
 #define B200_CHAIN_K4S(F) B200_CHAIN_FLAVOURS(F, 4, 3, true)
+#define B200_CHAIN_K4P(F) B200_CHAIN_FLAVOURS(F, 4, 4, false) // one more row in flight (exact arithmetic)
 #define B200_CHAIN_K5(F) B200_CHAIN_FLAVOURS(F, 5, 3, false) B200_CHAIN_FLAVOURS_FMA(F, 5, 3)
 #define B200_CHAIN_K6(F) B200_CHAIN_FLAVOURS(F, 6, 3, false) B200_CHAIN_FLAVOURS_FMA(F, 6, 3)
 
@@ -33,7 +34,7 @@
 #define B200_CHAIN_BULK_FLAVOURS(FB, K, PF)                                                                              \
   FB(K, PF, false, false, false) FB(K, PF, false, false, true) FB(K, PF, false, true, false) FB(K, PF, false, true, true) \
   FB(K, PF, true, false, false)  FB(K, PF, true, false, true)  FB(K, PF, true, true, false)  FB(K, PF, true, true, true)
-#define B200_CHAIN_K4B(FB) B200_CHAIN_BULK_FLAVOURS(FB, 4, 3)
+#define B200_CHAIN_K4B(FB) B200_CHAIN_BULK_FLAVOURS(FB, 4, 3) B200_CHAIN_BULK_FLAVOURS(FB, 4, 4)
 #define B200_CHAIN_DECLARE_BULK(K, PF, HALO, UNI, HEAD) \
   extern template __global__ void k_chain_march<K, PF, HALO, false, UNI, HEAD, false, true>(const ChainArgs);
 #define B200_CHAIN_DEFINE_BULK(K, PF, HALO, UNI, HEAD) \

@@ -301,9 +301,14 @@ int b200_get_chain_split(void);
 /* BULK flavour of k_chain_march (depth 4, exact arithmetic): the operand ring in shared memory is filled by bulk
    asynchronous copies (cp.async.bulk, the TMA unit's 1-D path: one 512-byte copy per warp, operand and row, issued by
    one lane and completed on an mbarrier) instead of one 16-byte cp.async per thread; bit-identical results.
-   B200_CHAIN_BULK sets the initial value; a negative argument returns to it. */
+   1: the prefetch depth of the plain flavour (3 rows ahead), 2: one row deeper (4 rows, 111 KB of shared memory per
+   block).  B200_CHAIN_BULK sets the initial value; a negative argument returns to it. */
 int b200_set_chain_bulk(int on);
 int b200_get_chain_bulk(void);
+/* Rows of operands the plain flavour of k_chain_march (depth 4, exact arithmetic) keeps in flight: 3 or 4 (other
+   values: back to the initial one, B200_CHAIN_PF or the default).  Results do not depend on it. */
+int b200_set_chain_pf(int pf);
+int b200_get_chain_pf(void);
 /* 1 (default): honour b200_stencil_geom.uniform; 0: always load the coefficient tables (A/B tests) */
 int b200_set_chain_uniform(int on);
 /* name of the kernel the most recent chain launch used ("k_chain_quad" / "k_chain_march", "" if none) */

@@ -29,6 +29,13 @@ void run_march(const ChainArgs& a, dim3 grid, bool uni)
   if constexpr (!FMA)
     if (g_emu_bulk)
     {
+      if (g_emu_bulk == 2)
+      { // one row more in flight
+        const size_t smem = chain_march_smem(K, PF + 1, a.rows, false, true);
+        if (uni) emu::launch(k_chain_march<K, PF + 1, HALO, false, true, false, false, true>, grid, kChainThreads, smem, a);
+        else emu::launch(k_chain_march<K, PF + 1, HALO, false, false, false, false, true>, grid, kChainThreads, smem, a);
+        return;
+      }
       const size_t smem = chain_march_smem(K, PF, a.rows, false, true);
       if (uni) emu::launch(k_chain_march<K, PF, HALO, false, true, false, false, true>, grid, kChainThreads, smem, a);
       else emu::launch(k_chain_march<K, PF, HALO, false, false, false, false, true>, grid, kChainThreads, smem, a);

@@ -416,20 +416,30 @@ def test_a_device_failure_comes_back_as_an_error_code_not_an_abort(emu, args):
     assert "injected failure" in r.stderr and r.stderr.count("nvector_b200: FATAL") == 1, r.stderr[-2000:]
 
 
+def set_ring_flavour(lib, level):
+    """How k_chain_march (depth 4) fills its operand ring: -1 = plain cp.async, 3 rows ahead; 1 / 2 = cp.async.bulk +
+    mbarrier, 3 / 4 rows ahead; 3 = plain cp.async, 4 rows ahead; 0 = back to the library's defaults."""
+    lib.b200_set_chain_bulk({-1: 0, 0: -1, 1: 1, 2: 2, 3: 0}[level])
+    lib.b200_set_chain_pf({-1: 3, 0: 0, 1: 3, 2: 3, 3: 4}[level])
+
+
 @pytest.mark.parametrize("args", CHAIN_ARGS, ids=["rkc_fixed_inhom_128x48", "rkl_fixed_uniform_130x40", "rkc_adaptive_128x64"])
 @pytest.mark.parametrize("extra", [[], ["--force-halo"]], ids=["wrap", "deep_halo"])
-def test_bulk_copy_ring_does_not_change_a_bit(emu, args, extra):
+@pytest.mark.parametrize("level", [1, 2, 3], ids=["bulk_pf3", "bulk_pf4", "plain_pf4"])
+def test_bulk_copy_ring_does_not_change_a_bit(emu, args, extra, level):
     """BULK flavour of k_chain_march (depth 4): the operand ring filled by cp.async.bulk + mbarrier (interior windows)
     and by per-thread cp.async (the windows on the block's first and last columns); whole integrations through the
     launchers -- tables and uniform coefficients, wrap and deep halos, head and body chains -- agree bit for bit."""
     lib = emu.kernel_lib()
-    lib.b200_set_chain_bulk(0)
+    set_ring_flavour(lib, -1)
     st0, u0 = run_d2d(emu, args + ["--chain", "4"] + extra)
-    lib.b200_set_chain_bulk(1)
+    if level >= 2 and args is not CHAIN_ARGS[0]:
+        pytest.skip("the deeper prefetch is covered by the first case (suite run time)")
+    set_ring_flavour(lib, level)
     try:
         st1, u1 = run_d2d(emu, args + ["--chain", "4"] + extra)
     finally:
-        lib.b200_set_chain_bulk(-1)
+        set_ring_flavour(lib, 0)
     assert st0["chain_launches"] == st1["chain_launches"] > 0 and st0["chain_stages"] == st1["chain_stages"]
     for k in ("steps", "step_attempts", "err_test_fails", "rhs_evals", "max_stages"):
         assert st0[k] == st1[k], k

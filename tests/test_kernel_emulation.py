@@ -682,9 +682,9 @@ def test_peer_exchange_fills_every_deep_halo_of_a_process_grid(emu, npx, npy, nx
 
 # ---- BULK flavour of k_chain_march: the operand ring filled by cp.async.bulk + mbarrier (emulated in cuda_emu.h:
 # eager = the copy lands at issue time, lazy = when somebody waits for its barrier).  Same checks as above, the switch on.
-@pytest.fixture
-def emu_bulk(emu):
-    emu.emu_set_chain_bulk(1)
+@pytest.fixture(params=[1, 2], ids=["pf", "pf_plus_1"])
+def emu_bulk(emu, request):
+    emu.emu_set_chain_bulk(request.param)  # 1: the plain flavour's prefetch depth, 2: one row deeper
     yield emu
     emu.emu_set_chain_bulk(0)
 
