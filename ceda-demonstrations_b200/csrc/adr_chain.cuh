@@ -57,20 +57,22 @@ __device__ __forceinline__ const double* adr_row_ptr(const double* field, int r,
   return field + 2 * ((int64_t)rw * nx + col);
 }
 
+// WRAP = false (steady state of the row loop): neither row of the next group is row 0 or row ny
+template <bool WRAP>
 __device__ __forceinline__ void adr_half_advance(const AdrChainArgs& a, AdrHalf& q, int r, int64_t nx, int ny)
 {
-  if (r == 0 || r == ny)
+  if (WRAP && (r == 0 || r == ny))
   {
     q.pp = adr_row_ptr(a.prev2, r, q.col, nx, ny);
     q.py = adr_row_ptr(a.yn, r, q.col, nx, ny);
     q.pf = adr_row_ptr(a.fn, r, q.col, nx, ny);
   }
   else { q.pp += 2 * nx; q.py += 2 * nx; q.pf += 2 * nx; }
-  if (r + 1 == 0 || r + 1 == ny) q.px = adr_row_ptr(a.x, r + 1, q.col, nx, ny);
+  if (WRAP && (r + 1 == 0 || r + 1 == ny)) q.px = adr_row_ptr(a.x, r + 1, q.col, nx, ny);
   else q.px += 2 * nx;
 }
 
-template <int K, int PF>
+template <int K, int PF, bool WRAP = true>
 __device__ __forceinline__ void adr_chain_issue(const AdrChainArgs& a, AdrChainState& st, double2* rx, double2* rp,
                                                 double2* ry, double2* rf, int64_t nx, int ny, bool issue)
 {
@@ -87,11 +89,11 @@ __device__ __forceinline__ void adr_chain_issue(const AdrChainArgs& a, AdrChainS
     cp_async16(sf, st.h[0].pf);           cp_async16(sf + kAdrChainThreads, st.h[1].pf);
   }
   cp_async_commit();
-  st.sx_issue = (st.sx_issue + 1 == DX) ? 0 : st.sx_issue + 1;
-  st.sy_issue = (st.sy_issue + 1 == DY) ? 0 : st.sy_issue + 1;
+  st.sx_issue = ring_next<DX>(st.sx_issue);
+  st.sy_issue = ring_next<DY>(st.sy_issue);
   const int r = ++st.ir;
-  adr_half_advance(a, st.h[0], r, nx, ny);
-  adr_half_advance(a, st.h[1], r, nx, ny);
+  adr_half_advance<WRAP>(a, st.h[0], r, nx, ny);
+  adr_half_advance<WRAP>(a, st.h[1], r, nx, ny);
 }
 
 __device__ __forceinline__ double2 shfl_point(double2 v, int src_lane)
@@ -119,7 +121,7 @@ __device__ __forceinline__ void adr_chain_row(const AdrChainArgs& a, AdrChainSta
 {
   constexpr int DX = PF + 1, DY = PF + K;
   constexpr int IO = PH % 3, IM = (PH + 1) % 3, IC = (PH + 2) % 3; // oldest (overwritten), then south, centre ; north = IO
-  adr_chain_issue<K, PF>(a, st, rx, rp, ry, rf, nx, ny, issue); // group(r1 + PF)
+  adr_chain_issue<K, PF, CHECK>(a, st, rx, rp, ry, rf, nx, ny, issue); // group(r1 + PF)
   cp_async_wait<PF>();
 
   Wa[0][IO]        = rx[(2 * st.sx_use) * kAdrChainThreads]; // x row r1+1 replaces the oldest row
@@ -240,7 +242,10 @@ __global__ void __launch_bounds__(kAdrChainThreads, 2) k_adr_chain(const AdrChai
   const int total3 = ((rend - rstart + 2) / 3) * 3;
   int warm         = 2 * (K - 1);
   warm             = ((warm + 2) / 3) * 3;
-  int steady       = (j1 - (rstart + warm)) / 3 * 3;
+  // (as in k_chain_march: the steady state stays clear of the rows whose next group touches row ny, so that it carries
+  // no wrap-around logic)
+  const int lim    = (j1 < ny - (PF + 2)) ? j1 : ny - (PF + 2);
+  int steady       = (lim - (rstart + warm)) / 3 * 3;
   if (steady < 0) steady = 0;
   int r1 = rstart;
 #pragma unroll 1
