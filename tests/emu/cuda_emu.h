@@ -6,7 +6,8 @@
 //   threadIdx / blockIdx / blockDim / gridDim, dynamic and static shared memory, __syncthreads (block
 //   barrier), atomicAdd(unsigned) / __threadfence (the last-block ticket of the reductions),
 //   __shfl_{up,down,xor}_sync on doubles (per-warp exchange + barrier), exactly rounded FP64
-//   (__dmul_rn ... compile with -ffp-contract=off; DFMA = std::fma), and cp.async groups.
+//   (__dmul_rn ... compile with -ffp-contract=off; DFMA = std::fma), cp.async groups, and shared-memory mbarriers
+//   with transaction counts + bulk copies (cp.async.bulk), __syncwarp, elect.
 // cp.async has two modes (emu::cp_async_lazy): eager = the copy happens at issue time; lazy = the
 // copy happens at the last legal moment (the cp.async.wait_group that forces its group), so a
 // kernel that reads a ring slot before waiting for it, or overwrites one before it was consumed,
