@@ -1136,6 +1136,25 @@ static int launch_quad(const ChainArgs& a, dim3 grid, cudaStream_t st)
   return a.hx ? launch_quad_k<K, PF, true, false, MINB>(a, grid, st) : launch_quad_k<K, PF, false, false, MINB>(a, grid, st);
 }
 
+// A grid of slightly more than a whole number of waves (all blocks of a wave start together and, on a small grid, end
+// together) leaves a few straggler blocks running on an otherwise empty machine for one more block duration: 2048^2,
+// depth 4, 32 rows = 320 blocks for 296 slots took 0.056 ms per launch, 37 rows = 280 blocks 0.045 ms
+// (profiles/r02_kbench_chain_rows_wave_fit.log).  Where the block count exceeds w = 1..3 waves by at most a quarter
+// wave, the rows are raised until the grid fits w waves.  B200_NO_WAVE_FIT=1 switches it off (A/B).
+static int rows_fit_waves(int64_t ny, int64_t gx, int rows, int64_t resident)
+{
+  static const bool off = getenv("B200_NO_WAVE_FIT") != nullptr;
+  if (off || gx <= 0 || resident <= 0 || rows <= 0) return rows;
+  const int64_t blocks = gx * ((ny + rows - 1) / rows);
+  const int64_t w      = blocks / resident;
+  if (w < 1 || w > 3 || blocks == w * resident || 4 * (blocks - w * resident) > resident) return rows;
+  const int64_t gy = (w * resident) / gx; // block rows that fit w waves
+  if (gy < 1) return rows;
+  const int r2 = (int)((ny + gy - 1) / gy);
+  if (r2 <= rows || r2 > 2 * rows || gx * ((ny + r2 - 1) / r2) > w * resident) return rows;
+  return r2;
+}
+
 static int g_chain_rows = 0; // 0 = automatic (chain_rows_auto), else what b200_set_chain_rows asked for
 // Rows each block marches over: more rows = less redundant work (a block starts K-1 rows early and the
 // K-1 rows around it are recomputed: (rows + 2(K-1)) / rows) but fewer blocks.  256 rows where that still
@@ -1148,8 +1167,10 @@ static int chain_rows_auto(const b200_ctx* c, int64_t nx, int64_t ny, int nstage
   const int64_t gx    = ((nx + use - 1) / use + wpb - 1) / wpb;
   const int64_t waves = 4 * 2 * (int64_t)(c->sm_count > 0 ? c->sm_count : 148);
   const int cand[4]   = {256, 128, 64, 32};
+  const int64_t slots = 2 * (int64_t)(c->sm_count > 0 ? c->sm_count : 148);
   for (int r : cand)
     if (gx * ((ny + r - 1) / r) >= waves) return r;
+  if (gx * ((ny + 31) / 32) > slots) return rows_fit_waves(ny, gx, 32, slots);
   // Small grids: every block is resident at once and the launch takes as long as ONE block needs for its
   // rows + 2(K-1) row steps, so the fewest rows that still fit the machine in one wave win (128^2, K = 6: 16 blocks
   // of 8 rows = 18 row steps instead of 4 blocks of 42).
@@ -1585,6 +1606,7 @@ extern "C" int b200_adr_chain(b200_ctx* c, const b200_adr_params* p, int nstages
   a.rows              = 16;
   for (int r : {128, 64, 32})
     if (gx * ((a.ny + r - 1) / r) >= waves) { a.rows = r; break; }
+  a.rows = rows_fit_waves(a.ny, gx, a.rows, waves / 2);
   if ((a.ny + a.rows - 1) / a.rows > 65535) a.rows = (int)((a.ny + 65534) / 65535);
   dim3 grid = adr_chain_grid(a.nx, a.ny, nstages, a.rows);
   int rc    = 0;
