@@ -1231,7 +1231,9 @@ static int stencil_chain_common(b200_ctx* c, const b200_stencil_geom* g, int nst
   a.nx = g->nx; a.ny = g->ny;
   a.cxw = g->cxw; a.cxe = g->cxe; a.cys = g->cys; a.cyn = g->cyn;
   a.x = x; a.prev2 = prev2; a.yn = yn; a.fn = fn;
-  const bool uni = g->uniform != 0 && g_chain_uniform;
+  // (the uniform flavour shares the x-direction products between neighbours: it needs Dx_w == Dx_e to the bit --
+  // always the case for this problem, kx / dx^2 on both faces; anything else runs on the tables, which are still valid)
+  const bool uni = g->uniform != 0 && g_chain_uniform && memcmp(&g->u_cxw, &g->u_cxe, sizeof(double)) == 0;
   if (uni)
   { // centre coefficient in the reference's association, diffusion.cpp:48 (host IEEE adds = device DADD)
     a.u_cxw = g->u_cxw; a.u_cxe = g->u_cxe; a.u_cys = g->u_cys; a.u_cyn = g->u_cyn;

@@ -233,13 +233,27 @@ __device__ __forceinline__ void chain_level(const ChainArgs& a, const ChainState
   const double2 dy = UNI ? make_double2(a.u_cys, a.u_cyn) : ytab[st.trow - LAG]; // (Dy_s, Dy_n) of row r1-LAG
   const double sy  = UNI ? 0.0 : stab[st.trow - LAG]; // Dy_s + Dy_n, summed once per block when the table is filled
   const double2 um = W[L - 1][BEFORE ? IO : IM], uc = W[L - 1][BEFORE ? IM : IC], up = W[L - 1][BEFORE ? IC : IO];
-  const double uw0 = __shfl_up_sync(0xffffffffu, uc.y, 1);
-  const double ue1 = __shfl_down_sync(0xffffffffu, uc.x, 1);
   // diffusion.cpp:48-53, same association as k_stage_march
   double L0 = DMUL(UNI ? a.u_ndc : -DADD(sx0, sy), uc.x);
   double L1 = DMUL(UNI ? a.u_ndc : -DADD(sx1, sy), uc.y);
-  L0 = mad<FMA>(cw.x, uw0, L0);  L1 = mad<FMA>(cw.y, uc.x, L1);
-  L0 = mad<FMA>(ce.x, uc.y, L0); L1 = mad<FMA>(ce.y, ue1, L1);
+  if constexpr (UNI && !FMA)
+  { // Uniform coefficients with Dx_w == Dx_e (the launcher checks the bits; it is one number, kx / dx^2, in the
+    // reference): the product Dx * u of a cell is what BOTH its x-neighbours add, so each thread rounds the products
+    // of its own two cells once and the neighbours' come through the shuffles -- two multiplies per level and thread
+    // less, the same bits (identical operands), the sums in the reference's order (west, then east).
+    const double pa = DMUL(cw.x, uc.x), pb = DMUL(cw.x, uc.y);
+    const double pw = __shfl_up_sync(0xffffffffu, pb, 1);   // Dx_w * u(west of my first cell)
+    const double pe = __shfl_down_sync(0xffffffffu, pa, 1); // Dx_e * u(east of my second cell)
+    L0 = DADD(L0, pw); L1 = DADD(L1, pa);
+    L0 = DADD(L0, pb); L1 = DADD(L1, pe);
+  }
+  else
+  {
+    const double uw0 = __shfl_up_sync(0xffffffffu, uc.y, 1);
+    const double ue1 = __shfl_down_sync(0xffffffffu, uc.x, 1);
+    L0 = mad<FMA>(cw.x, uw0, L0);  L1 = mad<FMA>(cw.y, uc.x, L1);
+    L0 = mad<FMA>(ce.x, uc.y, L0); L1 = mad<FMA>(ce.y, ue1, L1);
+  }
   L0 = mad<FMA>(dy.x, um.x, L0); L1 = mad<FMA>(dy.x, um.y, L1);
   L0 = mad<FMA>(dy.y, up.x, L0); L1 = mad<FMA>(dy.y, up.y, L1);
   // The reference's "f = 0; f += ..." (k_stage_march: DADD(0.0, L)) is dropped here: 0 + L differs from L only

@@ -89,6 +89,7 @@ extern "C" __attribute__((visibility("default"))) int emu_stencil_chain(int vari
   a.rows = rows;
   if (halos) { a.hx = halos[0]; a.hp = halos[1]; a.hy = halos[2]; a.hf = halos[3]; a.g = g; a.g2 = g2; }
   const bool uni = uniform4 != nullptr;
+  if (uni && memcmp(&uniform4[0], &uniform4[1], sizeof(double)) != 0) return -1; // the uniform flavour needs Dx_w == Dx_e
   if (uni)
   {
     a.u_cxw = uniform4[0]; a.u_cxe = uniform4[1]; a.u_cys = uniform4[2]; a.u_cyn = uniform4[3];
