@@ -1012,7 +1012,7 @@ template <int K, int PF, bool FMA> constexpr bool chain_split_available() { retu
 // BULK flavour of k_chain_march (chain_march.cuh): the operand ring is filled by cp.async.bulk (one 512-byte copy per
 // warp, operand and row, issued by one lane, completed on an mbarrier) instead of one 16-byte cp.async per thread.
 static int g_chain_bulk = -1; // -1: not decided yet (B200_CHAIN_BULK, else the default below)
-static const int kChainBulkDefault = 0;
+static const int kChainBulkDefault = 2; // measured: profiles/r02_bench_n1_default_ab_call_aa_*, DESIGN 4.1b
 extern "C" int b200_set_chain_bulk(int on)
 { // < 0: back to the initial value (B200_CHAIN_BULK, else the default)
   g_chain_bulk = on < 0 ? -1 : (on > 2 ? 2 : on); // 1: prefetch depth of the plain flavour, 2: one row deeper
@@ -1054,13 +1054,13 @@ static int launch_chain_s(const ChainArgs& a, dim3 grid, cudaStream_t st)
 template <int K, int PF, bool HALO, bool FMA, bool UNI, bool HEAD>
 static int launch_chain_k(const ChainArgs& a, dim3 grid, cudaStream_t st)
 {
+  if constexpr (chain_split_available<K, PF, FMA>()) // (opt-in: an explicit request wins over the default ring)
+    if (b200_get_chain_split()) return launch_chain_s<K, PF, HALO, FMA, UNI, HEAD, true>(a, grid, st);
   if constexpr (chain_bulk_available<K, PF, FMA>())
   {
     if (b200_get_chain_bulk() == 2) return launch_chain_s<K, PF + 1, HALO, FMA, UNI, HEAD, false, true>(a, grid, st);
     if (b200_get_chain_bulk()) return launch_chain_s<K, PF, HALO, FMA, UNI, HEAD, false, true>(a, grid, st);
   }
-  if constexpr (chain_split_available<K, PF, FMA>())
-    if (b200_get_chain_split()) return launch_chain_s<K, PF, HALO, FMA, UNI, HEAD, true>(a, grid, st);
   return launch_chain_s<K, PF, HALO, FMA, UNI, HEAD, false>(a, grid, st);
 }
 

@@ -236,7 +236,12 @@ __device__ __forceinline__ void chain_level(const ChainArgs& a, const ChainState
   // diffusion.cpp:48-53, same association as k_stage_march
   double L0 = DMUL(UNI ? a.u_ndc : -DADD(sx0, sy), uc.x);
   double L1 = DMUL(UNI ? a.u_ndc : -DADD(sx1, sy), uc.y);
-  if constexpr (UNI && !FMA)
+#ifndef B200_NO_XSHARE // (A/B builds only)
+  constexpr bool XSHARE = UNI && !FMA;
+#else
+  constexpr bool XSHARE = false;
+#endif
+  if constexpr (XSHARE)
   { // Uniform coefficients with Dx_w == Dx_e (the launcher checks the bits; it is one number, kx / dx^2, in the
     // reference): the product Dx * u of a cell is what BOTH its x-neighbours add, so each thread rounds the products
     // of its own two cells once and the neighbours' come through the shuffles -- two multiplies per level and thread

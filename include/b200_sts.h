@@ -298,11 +298,11 @@ int b200_get_chain_variant(void);
    bit-identical results.  B200_CHAIN_SPLIT sets the initial value. */
 int b200_set_chain_split(int on);
 int b200_get_chain_split(void);
-/* BULK flavour of k_chain_march (depth 4, exact arithmetic): the operand ring in shared memory is filled by bulk
-   asynchronous copies (cp.async.bulk, the TMA unit's 1-D path: one 512-byte copy per warp, operand and row, issued by
-   one lane and completed on an mbarrier) instead of one 16-byte cp.async per thread; bit-identical results.
-   1: the prefetch depth of the plain flavour (3 rows ahead), 2: one row deeper (4 rows, 111 KB of shared memory per
-   block).  B200_CHAIN_BULK sets the initial value; a negative argument returns to it. */
+/* How k_chain_march (depth 4, exact arithmetic) fills its operand ring in shared memory.  0: one 16-byte cp.async per
+   thread, operand and row; 1 / 2: bulk asynchronous copies (cp.async.bulk, the TMA unit's 1-D path: one 512-byte copy
+   per warp, operand and row, issued by one lane from warp-uniform pointers and completed on an mbarrier) with 3 / 4
+   rows in flight.  Default 2 (111 KB of shared memory per block; measured in DESIGN.md 4.1b); bit-identical results.
+   B200_CHAIN_BULK sets the initial value; a negative argument returns to it. */
 int b200_set_chain_bulk(int on);
 int b200_get_chain_bulk(void);
 /* Rows of operands the plain flavour of k_chain_march (depth 4, exact arithmetic) keeps in flight: 3 or 4 (other
