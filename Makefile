@@ -25,7 +25,7 @@ SUNINC := -I$(SUNOUT)/include -I$(SUN)/include
 
 HAVE_REF := $(wildcard $(SUN)/src/arkode/arkode.c)
 
-.PHONY: all product oracle sundials clean
+.PHONY: all product oracle sundials clean ab
 all: product
 
 ifneq ($(HAVE_REF),)
@@ -47,6 +47,15 @@ $(OBJ)/%.o: $(SRC)/%.cu $(wildcard $(SRC)/*.cuh) include/b200_sts.h
 $(LIB)/libb200sts.so: $(OBJ)/b200_kernels.o $(CHAIN_OBJS)
 	@mkdir -p $(LIB)
 	$(NVCC) $(NVFLAGS) -shared $^ -o $@ -ldl
+
+# A/B build of the kernel library WITHOUT the shared x-direction products of the uniform flavour (measurement only:
+# scripts/gpu_r2_aa.sh swaps it in on the GPU box)
+ab: $(LIB)/libb200sts.so
+	@mkdir -p build/ab
+	$(NVCC) $(NVFLAGS) -DB200_NO_XSHARE -Iinclude -I$(SRC) -c $(SRC)/chain_inst_k4.cu -o build/ab/chain_inst_k4.o
+	$(NVCC) $(NVFLAGS) -DB200_NO_XSHARE -Iinclude -I$(SRC) -c $(SRC)/chain_inst_k4b.cu -o build/ab/chain_inst_k4b.o
+	$(NVCC) $(NVFLAGS) -shared $(OBJ)/b200_kernels.o $(filter-out $(OBJ)/chain_inst_k4.o $(OBJ)/chain_inst_k4b.o,$(CHAIN_OBJS)) \
+	  build/ab/chain_inst_k4.o build/ab/chain_inst_k4b.o -o build/ab/libb200sts_noxshare.so -ldl
 
 HOST_SRC := $(SRC)/nvector_b200.cpp $(SRC)/diffusion_b200.cpp $(SRC)/adr_b200.cpp $(SRC)/blockdiag_b200.cpp
 $(LIB)/libb200sts_sundials.so: $(HOST_SRC) include/nvector_b200.h include/b200_diffusion2d.h include/b200_adr2d.h include/b200_callbacks.h include/b200_blockdiag.h include/b200_sts.h $(LIB)/libb200sts.so

@@ -1,5 +1,6 @@
 #!/bin/bash
 # round 2, call AA (1 GPU): which flavour should be the default?  On ONE box, alternating, three repetitions:
+# (make ab builds build/ab/libb200sts_noxshare.so)
 # {plain cp.async ring, BULK ring with 4 rows in flight} x {x-direction products shared, not shared (A/B build of the
 # library, -DB200_NO_XSHARE)}
 cd "$(dirname "$0")/.."
