@@ -1160,25 +1160,37 @@ static int g_chain_rows = 0; // 0 = automatic (chain_rows_auto), else what b200_
 // K-1 rows around it are recomputed: (rows + 2(K-1)) / rows) but fewer blocks.  256 rows where that still
 // leaves >= 4 waves of blocks (2 resident blocks on each SM), else 128, else 64, else 32.  Measured at 16384^2,
 // K = 4: 62.4 / 57.5 / 54.4 / 53.6 ms per step for 32 / 64 / 128 / 256 rows (profiles/r01_bench_chain_rows.log).
-static int chain_rows_auto(const b200_ctx* c, int64_t nx, int64_t ny, int nstages, bool quad)
+static int chain_rows_auto_sm(int sm_count, int64_t nx, int64_t ny, int nstages, bool quad)
 {
+  const int64_t sms   = sm_count > 0 ? sm_count : 148;
   const int use       = quad ? 128 - 4 * ((nstages + 1) / 2) : 64 - 4 * ((nstages + 1) / 2);
   const int wpb       = quad ? kQuadThreads / 32 : kChainThreads / 32;
   const int64_t gx    = ((nx + use - 1) / use + wpb - 1) / wpb;
-  const int64_t waves = 4 * 2 * (int64_t)(c->sm_count > 0 ? c->sm_count : 148);
+  const int64_t waves = 4 * 2 * sms;
   const int cand[4]   = {256, 128, 64, 32};
-  const int64_t slots = 2 * (int64_t)(c->sm_count > 0 ? c->sm_count : 148);
+  const int64_t slots = 2 * sms;
   for (int r : cand)
     if (gx * ((ny + r - 1) / r) >= waves) return r;
   if (gx * ((ny + 31) / 32) > slots) return rows_fit_waves(ny, gx, 32, slots);
   // Small grids: every block is resident at once and the launch takes as long as ONE block needs for its
   // rows + 2(K-1) row steps, so the fewest rows that still fit the machine in one wave win (128^2, K = 6: 16 blocks
   // of 8 rows = 18 row steps instead of 4 blocks of 42).
-  const int64_t resident = 2 * (int64_t)(c->sm_count > 0 ? c->sm_count : 148);
+  const int64_t resident = 2 * sms;
   const int small[2]     = {8, 16};
   for (int r : small)
     if (gx * ((ny + r - 1) / r) <= resident) return r;
   return 32;
+}
+static int chain_rows_auto(const b200_ctx* c, int64_t nx, int64_t ny, int nstages, bool quad)
+{
+  return chain_rows_auto_sm(c->sm_count, nx, ny, nstages, quad);
+}
+// the automatic choice for an nx x ny block and a chain of nstages stages (k_chain_march) on a device with sm_count
+// multiprocessors (0: the context's own device) -- for tests and tuning scripts; launches nothing
+extern "C" int b200_chain_rows_query(b200_ctx* c, int64_t nx, int64_t ny, int nstages, int sm_count)
+{
+  if (nstages < 2 || nstages > B200_MAX_CHAIN || nx < 2 || ny < 1) return -1;
+  return chain_rows_auto_sm(sm_count > 0 ? sm_count : (c ? c->sm_count : 148), nx, ny, nstages, false);
 }
 static int g_chain_uniform = 1; // honour b200_stencil_geom.uniform (0: always load the tables; for A/B tests)
 extern "C" int b200_set_chain_uniform(int on)

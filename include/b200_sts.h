@@ -286,6 +286,9 @@ int b200_stencil_dq(b200_ctx* ctx, const b200_stencil_geom* g, const double* v, 
    where that leaves at least 4 waves of blocks, else 128, else 64, else 32 (8 or 16 on grids so small that every
    block is resident at once).  Results do not depend on it. */
 int b200_set_chain_rows(int rows);
+/* the automatic choice for an nx x ny block and a chain of nstages stages on a device with sm_count multiprocessors
+   (0: the device of ctx, which may then not be NULL); launches nothing.  -1: bad arguments. */
+int b200_chain_rows_query(b200_ctx* ctx, int64_t nx, int64_t ny, int nstages, int sm_count);
 /* Which kernel runs a chain: 0 (default) = k_chain_march, two cells per thread; 1 = k_chain_quad,
    four cells per thread (two 64-cell halves per warp window, 120 of 128 cells useful at depth 4).
    Same shape requirements, bit-identical results; at depth 4 on 16384^2 both sit at 85-90 % of the

@@ -32,6 +32,32 @@ def test_kernel_library_exports_every_declared_symbol(b200):
     b200.kernel_lib()  # dlopen succeeds without a GPU and without NCCL being loaded
 
 
+def test_chain_rows_are_fitted_to_whole_waves(b200):
+    """Rows per block of the chain kernel on a 148-SM device (host logic only, nothing is launched): the measured choices
+    of DESIGN 4.1b -- 256 rows at 16384^2 (8.0 waves), 128 at 8192^2, 32 at 4096^2, and at 2048^2 not 32 rows (320 blocks
+    for 296 slots: a straggler wave) but 35 (295 blocks); tiny grids fit one wave with the fewest rows."""
+    import ctypes
+
+    lib = b200.kernel_lib()
+    lib.b200_chain_rows_query.restype = ctypes.c_int
+    q = lambda nx, ny, k: lib.b200_chain_rows_query(None, ctypes.c_int64(nx), ctypes.c_int64(ny), k, 148)
+    assert q(16384, 16384, 4) == 256
+    assert q(8192, 8192, 4) == 128
+    assert q(4096, 4096, 4) == 32
+    assert q(2048, 2048, 4) == 35
+    assert q(128, 128, 4) == 8
+    assert q(1024, 1024, 4) == 16
+    slots = 2 * 148
+    for n in (1536, 2048, 2304, 2560, 3072):
+        r = q(n, n, 4)
+        gx = ((n + 55) // 56 + 7) // 8
+        blocks = gx * ((n + r - 1) // r)
+        waves, rest = divmod(blocks, slots)
+        assert 8 <= r <= 256
+        assert waves == 0 or waves > 3 or rest == 0 or 4 * rest > slots, (n, r, blocks)  # no straggler quarter-wave
+    assert q(4096, 4096, 1) == -1 and q(4096, 4096, 7) == -1
+
+
 def test_sundials_library_exports_every_declared_symbol(b200):
     if not os.path.exists(b200.SUNDIALS_LIB):
         pytest.skip("libb200sts_sundials.so not built (no SUNDIALS host library)")
