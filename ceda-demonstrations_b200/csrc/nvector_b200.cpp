@@ -396,7 +396,7 @@ void launch_fused(Shared* sh, Value* L, int nterms, const double* cf, Value* con
 // stage, as the ordinary fused stage launch).
 void launch_chain(Shared* sh, Value* top)
 {
-  Value* lv[B200_MAX_CHAIN]; // lv[0] = first stage of the chain ... lv[n-1] = top
+  Value* lv[B200_MAX_CHAIN] = {}; // lv[0] = first stage of the chain ... lv[n-1] = top
   int n = 0;
   {
     Value* rev[B200_MAX_CHAIN];
@@ -404,6 +404,7 @@ void launch_chain(Shared* sh, Value* top)
     while (u && !u->d && u->st && n < B200_MAX_CHAIN) { rev[n++] = u; u = u->st->x; }
     for (int k = 0; k < n; k++) lv[k] = rev[n - 1 - k];
   }
+  if (n == 0) return; // nothing pending (callers only come here with a pending stage)
   StageRec* first = lv[0]->st;
   const bool head = first->head; // the chain begins the step: f_n = L(x) is produced by this launch
   materialise(sh, first->x); // (only reachable if a chain longer than B200_MAX_CHAIN was built)
