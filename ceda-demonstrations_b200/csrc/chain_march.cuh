@@ -65,18 +65,25 @@ __device__ __forceinline__ const double* row_ptr(const double* field, const doub
   return halo + (int64_t)hr * nx + lane_col;
 }
 
-// Operands are staged through a thread-private shared-memory ring filled with cp.async
-// (LDGSTS, 16 B per thread per operand per row) PF rows ahead: the bytes in flight that keep HBM
-// busy cost no registers, and the FP64 pipe works on row r while rows r+1..r+PF stream in.
-// Every thread reads back only the slots it filled itself, so cp.async.wait_group is the only
-// synchronisation in the row loop.  Ring depths: x and prev2 PF+1 rows, yn and fn PF+K rows
+// Operands are staged through a shared-memory ring PF rows ahead: the bytes in flight that keep HBM
+// busy cost no registers, and the FP64 pipe works on row r while rows r+1..r+PF stream in.  Every
+// thread reads back its own 16 bytes of a ring row.  Two ways of filling it:
+//   plain -- every thread copies its own 16 bytes with cp.async (LDGSTS), so cp.async.wait_group is
+//            the only synchronisation in the row loop;
+//   BULK  -- a warp's ring row is 512 contiguous bytes on both sides, so one elected lane issues one
+//            cp.async.bulk (UBLKCP, the TMA unit's 1-D path) per operand and row from warp-uniform
+//            pointers, completed on an mbarrier per warp and ring slot which all 32 lanes wait for
+//            (see ChainState / chain_issue); the windows on the block's first and last columns,
+//            which are not one contiguous run, stay with cp.async.  Ring depths: x and prev2 PF+1 rows, yn and fn PF+K rows
 // (level l consumes yn/fn of row r-(l-1)).  The y-direction coefficients of the block's rows
 // sit in a small shared table (one __syncthreads before the loop).
 //
 // The row loop is issue-bound once HBM is no longer the limit, so the steady state is unrolled
 // by 3 with the 3-row register windows addressed by a compile-time phase (no rotation moves),
-// carries no row-range predicates, and uses running offsets instead of index multiplies; the
-// 2(K-1) warm-up rows and the K-1 drain rows run through the same body with CHECK = true.
+// carries no row-range predicates and no wrap-around / field-to-halo logic (the rows whose next
+// group touches row 0 or row ny belong to the checked phases), and uses running offsets instead of
+// index multiplies; the 2(K-1) warm-up rows and the drain rows run through the same body with
+// CHECK = true.
 // SPLIT flavour (round 2).  In the plain order level l + 1 consumes, as its newest row, what level l produced a moment
 // ago in the SAME row step: the K levels of a step form one dependent chain of ~10 FP64 operations each, and with four
 // warps per SM sub-partition the FP64 pipe (the busiest unit at the sustained clock) runs out of independent work
