@@ -78,6 +78,26 @@ def test_kernel_library_has_sm100a_code_and_no_nccl_link_dependency(b200):
     assert "nccl" not in ldd  # bound with dlopen at first multi-GPU use
 
 
+def test_default_chain_kernel_uses_the_tma_unit(b200):
+    """The shipped library's default instantiation of the dominant kernel -- k_chain_march<4, 4, wrap, exact, uniform,
+    body, plain order, BULK> -- fills its operand ring with bulk asynchronous copies: its SASS must hold the bulk-copy,
+    transaction-barrier and elect instructions (and, for the edge windows, the per-thread LDGSTS path), and no local
+    memory traffic (spills)."""
+    import shutil
+
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    fun = "_Z13k_chain_marchILi4ELi4ELb0ELb0ELb1ELb0ELb0ELb1EEv9ChainArgs"
+    r = subprocess.run(["cuobjdump", "-sass", "-fun", fun, b200.KERNEL_LIB], capture_output=True, text=True)
+    sass = r.stdout
+    assert "Function : " + fun in sass, r.stderr[-500:]
+    for mnemonic in ("UBLKCP.S.G", "SYNCS.ARRIVE.TRANS64", "SYNCS.PHASECHK.TRANS64.TRYWAIT", "ELECT", "LDGSTS.E.BYPASS.128"):
+        assert mnemonic in sass, mnemonic
+    assert sass.count("UBLKCP.S.G") >= 4 * 9  # 4 operands x (3 prologue groups + 3 unrolled phases x >= 2 loops)
+    assert "STL" not in sass and "LDL" not in sass
+    assert sass.count("DMUL") + sass.count("DADD") > 1000 and "DFMA" not in sass  # exact arithmetic: no contraction
+
+
 @pytest.mark.skipif(has_gpu(), reason="only meaningful where there is no GPU")
 def test_product_fails_loudly_without_a_gpu(b200):
     lib = b200.kernel_lib()
