@@ -127,9 +127,9 @@ struct ChainState
   bool we;           // halo mode: this lane reads the W/E halo strips
   int64_t lane_col;  // column (halo mode: strip offset + column) of this lane
   // BULK flavour.  A warp whose 64-cell window is ONE contiguous run of the field (every window but those that touch
-  // the first or last column of the block) has it copied by bulk copies: `bulk` is set and ux/up/uy/uf are the running
-  // source pointers of the WINDOW (the same in every lane -- they live in uniform registers); the edge windows keep
-  // the per-thread cp.async of the plain flavour, with their addresses computed from (row, lane_col) when needed.
+  // the first or last column of the block) has it copied by bulk copies: `bulk` is set and the source offsets below
+  // belong to the WINDOW (the same in every lane -- they live in uniform registers); the edge windows keep the
+  // per-thread cp.async of the plain flavour, with their addresses computed from (row, lane_col) when needed.
   // The four operands share one layout, and row ir+1 of this group is row ir of the next: ONE offset is computed per
   // row step (uox), the other is handed down (uoy); uhx / uhy say whether the row lies in the S / N halo (halo mode).
   bool bulk;
